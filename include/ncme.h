@@ -1,0 +1,176 @@
+/* ncme.h -- C ABI of libncme: the B200-native FSP right-hand-side path of NumCME.jl.
+ *
+ * Every entry point is what a Julia `ccall` (or Python ctypes) binding for the corresponding
+ * reference function would bind.  Citations are file:line under the reference repository
+ * (voduchuy/NumCME.jl v0.1.4).  See INTEGRATION.md for the Julia-side glue.
+ *
+ * Conventions
+ *   - All functions return 0 on success and a negative ncme_status on failure; the message of the
+ *     last failure on the calling thread is available from ncme_last_error().  Nothing throws.
+ *   - Indices crossing the ABI follow the reference: 1-based, 0 = "none".
+ *   - `stoich` is the reference's `Matrix{Int}` in Julia (column-major) layout: entry
+ *     (species s, reaction r) at stoich[r*ns + s].
+ *   - State lists are state-major: state i occupies states[i*ns .. i*ns+ns-1] (a Julia
+ *     Vector{MVector{NS,Int64}} is laid out exactly like this).
+ *   - Pointers named *_dev are device pointers (from ncme_dmalloc or any CUDA allocator, e.g. a
+ *     torch tensor's data_ptr); all others are host pointers.
+ *   - Kernels are launched on the context's stream; calls that return a scalar or fill a host
+ *     buffer synchronise that stream, all others are asynchronous.
+ *   - A context is not thread-safe (neither is the reference: matvec! mutates A.t_cache,
+ *     src/fspmatrix/sparse/fspsparsematrix.jl:206-210).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     NCME_ERR_CUDA.
+ */
+#ifndef NCME_H
+#define NCME_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCME_VERSION 100
+#define NCME_MAX_REACTIONS 32
+#define NCME_MAX_SPECIES 16
+
+typedef enum {
+    NCME_OK = 0,
+    NCME_ERR_ARG = -1,      /* ArgumentError / DimensionMismatch in the reference */
+    NCME_ERR_CUDA = -2,     /* CUDA runtime failure (incl. no device) */
+    NCME_ERR_NOMEM = -3,
+    NCME_ERR_KEYWIDTH = -4, /* a state component does not fit the 64-bit packed key */
+    NCME_ERR_COMM = -5,     /* NCCL failure */
+    NCME_ERR_SOLVER = -6    /* integrator failure (step size underflow, GMRES breakdown ...) */
+} ncme_status;
+
+typedef struct ncme_ctx ncme_ctx;
+typedef struct ncme_space ncme_space;
+typedef struct ncme_matrix ncme_matrix;
+typedef struct ncme_sensmatrix ncme_sensmatrix;
+
+/* reaction kinds: src/cmemodel/propensity.jl:8-153 */
+enum { NCME_TIME_INVARIANT = 0, NCME_SEPARABLE_TV = 1, NCME_JOINT_TV = 2 };
+
+int ncme_version(void);
+const char* ncme_last_error(void);
+
+/* ---------------------------------------------------------------- context / memory ----------- */
+int ncme_ctx_create(int device, ncme_ctx** out);
+int ncme_ctx_destroy(ncme_ctx* ctx);
+/* Adopt an external cudaStream_t (e.g. torch's current stream); NULL restores the context's own. */
+int ncme_ctx_set_stream(ncme_ctx* ctx, void* cuda_stream);
+int ncme_ctx_sync(ncme_ctx* ctx);
+/* info[0]=SM count, [1]=L2 bytes, [2]=total global memory bytes, [3]=compute capability*10 */
+int ncme_ctx_device_info(ncme_ctx* ctx, int64_t info[4]);
+/* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
+int ncme_ctx_launch_count(ncme_ctx* ctx, int64_t* count);
+
+int ncme_dmalloc(ncme_ctx* ctx, size_t bytes, void** dptr);
+int ncme_dfree(ncme_ctx* ctx, void* dptr);
+int ncme_h2d(ncme_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int ncme_d2h(ncme_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* page-locked host staging buffers for the end-to-end (host-buffer) path */
+int ncme_host_alloc(size_t bytes, void** hptr);
+int ncme_host_free(void* hptr);
+
+/* ---------------------------------------------------------------- StateSpaceSparse ----------- */
+/* StateSpaceSparse(stoich_matrix, initstates)      src/statespace/sparse/sparsestatespace.jl:103-124
+ * Duplicate and negative initial states are silently dropped (:221). */
+int ncme_space_create(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int64_t n0, const int64_t* states0,
+                      ncme_space** out);
+/* Import a state space built elsewhere (states + both connectivity tables, reference conventions:
+ * struct fields of sparsestatespace.jl:22-40).  The hash table is rebuilt on the device. */
+int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int64_t n, const int64_t* states,
+                         const uint32_t* state_connectivity, const uint32_t* sink_connectivity, ncme_space** out);
+int ncme_space_destroy(ncme_space* space);
+/* expand!(space, expansionlevel; onlyreactions)    sparsestatespace.jl:153-194 (+ _addstates! :208-267).
+ * onlyreactions: 1-based reaction ids, nonly = 0 means all.  New states are appended in the
+ * reference's exact insertion order (LIFO frontier, reactions ascending, first occurrence wins). */
+int ncme_space_expand(ncme_space* space, int expansionlevel, int nonly, const int32_t* onlyreactions);
+/* deleteat!(space, ids)                            sparsestatespace.jl:276-331.  ids 1-based, any order. */
+int ncme_space_delete(ncme_space* space, int64_t nids, const int64_t* ids);
+/* get_state_count / get_sink_count                 sparsestatespace.jl:55,62 */
+int ncme_space_state_count(ncme_space* space, int64_t* n);
+int ncme_space_sink_count(ncme_space* space, int64_t* r);
+/* get_states (rows [first, first+count), 0-based range)   sparsestatespace.jl:69 */
+int ncme_space_download_states(ncme_space* space, int64_t first, int64_t count, int64_t* states_out);
+/* get_state_connectivity / get_sink_connectivity   sparsestatespace.jl:78-80.  Row-major count x nr. */
+int ncme_space_download_connectivity(ncme_space* space, int64_t first, int64_t count, uint32_t* state_conn_out,
+                                     uint32_t* sink_conn_out);
+/* get(state2idx, x, 0) for m states                sparsestatespace.jl:33 (Dict lookups :221,247,258) */
+int ncme_space_lookup(ncme_space* space, int64_t m, const int64_t* states, uint32_t* idx_out);
+
+/* ---------------------------------------------------------------- FspMatrixSparse ------------ */
+/* FspMatrixSparse{Float64}(space, propensities; parameters)   src/fspmatrix/sparse/fspsparsematrix.jl:47-108
+ * kind[r]      : NCME_TIME_INVARIANT / NCME_SEPARABLE_TV / NCME_JOINT_TV for reaction r (0-based array)
+ * propvals     : host, reaction-major n x nr: propvals[r*n + i] = state factor of reaction r at state i
+ *                (f(x,p) for time-invariant, statefactor(x,p) for separable, ignored for joint --
+ *                joint terms start with all-zero values like the reference, :87,129).
+ * The matrix snapshots the space (the reference deep-copies the states, :97). */
+int ncme_matrix_create(ncme_space* space, const int32_t* kind, const double* propvals, ncme_matrix** out);
+int ncme_matrix_destroy(ncme_matrix* mat);
+/* size(A)                                          fspsparsematrix.jl:174-186 */
+int ncme_matrix_size(ncme_matrix* mat, int64_t* rows, int64_t* cols);
+/* _update_sparsematrix!(A_joint[r], states, prop, t, theta)   fspsparsematrix.jl:154-166
+ * vals[i] = f(t, x_i, theta) evaluated by the host for the 1-based joint reaction `reaction`. */
+int ncme_matrix_set_joint_values(ncme_matrix* mat, int reaction, const double* vals);
+/* matvec!(out,t,A,v) (beta=0) / matvecadd!(out,t,A,v) (beta=1)   fspsparsematrix.jl:196-247
+ * coef[r] (host, nr entries) = tfactor_r(t,theta) for separable reactions; entries of time-invariant
+ * and joint reactions are ignored (treated as 1).  x_dev,y_dev: device, length n + nr, must not alias.
+ * One fused kernel launch: all terms, diagonal and the nr sink rows. */
+int ncme_matvec(ncme_matrix* mat, const double* coef, const double* x_dev, double* y_dev, double beta);
+/* Same through host buffers (H2D of x, kernel, D2H of y inside the call; synchronous).
+ * This is what `matvec!(out::Vector, t, A, v::Vector)` binds when the vectors live in host memory. */
+int ncme_matvec_host(ncme_matrix* mat, const double* coef, const double* x_host, double* y_host, double beta);
+/* Structural counts as the reference stores them: nnz[k], k = term index in reference order
+ * (summed time-invariant matrix first if any, then separable, then joint); returns nterms.
+ * algorithmic_bytes = sum_k (8 nnz_k + 4 (nnz_k - n)) + 16 (n + nr)       (SURVEY.md 8(d)). */
+int ncme_matrix_stats(ncme_matrix* mat, int* nterms, int64_t* nnz_per_term, int64_t* algorithmic_bytes,
+                      int64_t* device_bytes);
+
+/* Launch tuning for experiments: rows each thread owns in the matvec kernel (0 = auto, 1, 2 or 4). */
+int ncme_matrix_set_tuning(ncme_matrix* mat, int rows_per_thread);
+
+/* ---------------------------------------------------------------- ForwardSensFspMatrixSparse -- */
+/* ForwardSensFspMatrixSparse{Float64}(model, space)
+ *                      src/forwardsensfspmatrix/forwardsensfspmatrixsparse/sensfspmatrixsparse.jl:31-95
+ * npar          : number of parameters P
+ * nentries      : number of (reaction, parameter) pairs of the gradient sparsity pattern
+ * ent_reaction  : 1-based reaction of each entry;  ent_param: 1-based parameter of each entry
+ * dpropvals     : host, entry-major nentries x n: d(state factor)/d(theta_param) at each state
+ *                 (d f / d theta for time-invariant; d statefactor / d theta for separable; ignored for joint) */
+int ncme_sensmatrix_create(ncme_matrix* mat, int npar, int nentries, const int32_t* ent_reaction,
+                           const int32_t* ent_param, const double* dpropvals, ncme_sensmatrix** out);
+int ncme_sensmatrix_destroy(ncme_sensmatrix* smat);
+/* joint-TV entries: host evaluates d f / d theta_param (t, x_i, theta) and uploads (entry is 0-based). */
+int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* smat, int entry, const double* vals);
+/* matvec!(out, t, SA, vs)                          sensfspmatrixsparse.jl:97-142
+ * coef[r]   : as ncme_matvec.   dcoef[e] (host, nentries): d tfactor_r / d theta_param (t,theta) for
+ * separable entries, ignored otherwise.  X_dev, Y_dev: device, (P+1)*(n+nr) doubles, block layout
+ * [p; s_1; ...; s_P].  One fused launch; A is read once for all P+1 blocks. */
+int ncme_sens_matvec(ncme_sensmatrix* smat, const double* coef, const double* dcoef, const double* X_dev,
+                     double* Y_dev);
+
+/* ---------------------------------------------------------------- device vector ops (K7) ------ */
+/* The operations an ODE integrator performs on the FSP vector (DiffEq/CVODE internals driven from
+ * src/transientcme/sparse/fspsolve.jl:158-161), so that `u` can stay device-resident. */
+int ncme_vec_fill(ncme_ctx* ctx, int64_t n, double a, double* x_dev);
+int ncme_vec_copy(ncme_ctx* ctx, int64_t n, const double* x_dev, double* y_dev);
+int ncme_vec_scale(ncme_ctx* ctx, int64_t n, double a, double* x_dev);
+int ncme_vec_axpy(ncme_ctx* ctx, int64_t n, double a, const double* x_dev, double* y_dev);
+/* out = sum_k coefs[k] * xs[k]   (k <= 8; out may alias any xs[k]) */
+int ncme_vec_lincomb(ncme_ctx* ctx, int64_t n, int k, const double* coefs, const double* const* xs_dev,
+                     double* out_dev);
+int ncme_vec_sum(ncme_ctx* ctx, int64_t n, const double* x_dev, double* out);
+int ncme_vec_dot(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* y_dev, double* out);
+/* sqrt(mean((x_i / (atol + rtol*max(|u0_i|,|u1_i|)))^2)) -- the integrator's weighted RMS error norm */
+int ncme_vec_wrms(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* u0_dev, const double* u1_dev,
+                  double atol, double rtol, double* out);
+int ncme_vec_any_nonfinite(ncme_ctx* ctx, int64_t n, const double* x_dev, int* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCME_H */

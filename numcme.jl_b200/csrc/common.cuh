@@ -1,0 +1,117 @@
+// Internal declarations shared by the libncme translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ncme.h"
+
+namespace ncme {
+
+void set_error(const char* fmt, ...);
+
+#define NCME_CUDA(expr)                                                                           \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ncme::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return NCME_ERR_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+#define NCME_TRY(expr)              \
+    do {                            \
+        int _s = (expr);            \
+        if (_s != NCME_OK) return _s; \
+    } while (0)
+
+#define NCME_REQUIRE(cond, ...)          \
+    do {                                 \
+        if (!(cond)) {                   \
+            ncme::set_error(__VA_ARGS__); \
+            return NCME_ERR_ARG;         \
+        }                                \
+    } while (0)
+
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+
+template <typename T>
+static inline T round_up(T a, T b) {
+    return (a + b - 1) / b * b;
+}
+
+}  // namespace ncme
+
+struct ncme_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    size_t total_mem = 0;
+    int cc = 100;
+    int64_t launches = 0;
+    // small device scratch for reductions (partials + counters), and a pinned host mirror
+    double* red_partials = nullptr;   // [RED_MAX_BLOCKS * 4]
+    unsigned int* red_counter = nullptr;
+    double* red_result_dev = nullptr; // [8]
+    double* red_result_host = nullptr;  // pinned [8]
+    // pinned staging for the host-buffer matvec path
+    double* stage_host = nullptr;
+    size_t stage_host_bytes = 0;
+    double* stage_dev_x = nullptr;
+    double* stage_dev_y = nullptr;
+    size_t stage_dev_bytes = 0;
+};
+
+namespace ncme {
+
+// Device array with capacity growth (contents preserved).
+template <typename T>
+struct DevArray {
+    T* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n, cudaStream_t s, bool keep = true) {
+        if (n <= cap) return NCME_OK;
+        size_t ncap = cap ? cap : 256;
+        while (ncap < n) ncap = ncap + ncap / 2 + 256;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", ncap * sizeof(T), cudaGetErrorString(e));
+            return NCME_ERR_NOMEM;
+        }
+        if (p && keep && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) {
+                set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+                return NCME_ERR_CUDA;
+            }
+        }
+        if (p) {
+            cudaStreamSynchronize(s);
+            cudaFree(p);
+        }
+        p = q;
+        cap = ncap;
+        return NCME_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---- scan / compaction primitives (scan.cu)
+// exclusive prefix sum of n uint32 flags into out (uint32), total returned on host (synchronises).
+int exclusive_scan_u32(ncme_ctx* ctx, const uint32_t* in_dev, uint32_t* out_dev, int64_t n, uint32_t* scratch_dev,
+                       size_t scratch_elems, uint64_t* total_host);
+size_t scan_scratch_elems(int64_t n);
+
+}  // namespace ncme

@@ -1,0 +1,614 @@
+// FspMatrixSparse on the device: assembly (K6) and the fused multi-term fp64 SpMV (K1).
+// Reference: src/fspmatrix/sparse/fspsparsematrix.jl  (constructor :47-108, COO generator :120-152,
+// joint refresh :154-166, matvec!/matvecadd! :196-247).
+#include "matrix.cuh"
+
+namespace ncme {
+
+constexpr int SINK_CHUNK = 2048;
+constexpr int MV_THREADS = 256;
+
+// ------------------------------------------------------------------------------ load helpers ---
+// Matrix streams are read exactly once per matvec: streaming (evict-first) loads keep L1/L2 for x.
+template <int ROWS>
+__device__ __forceinline__ void ld_stream(const double* __restrict__ p, double (&v)[ROWS]);
+template <>
+__device__ __forceinline__ void ld_stream<1>(const double* __restrict__ p, double (&v)[1]) {
+    v[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void ld_stream<2>(const double* __restrict__ p, double (&v)[2]) {
+    double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+}
+template <>
+__device__ __forceinline__ void ld_stream<4>(const double* __restrict__ p, double (&v)[4]) {
+    // 256-bit global load (sm_100+)
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+template <int ROWS>
+__device__ __forceinline__ void ld_stream(const uint32_t* __restrict__ p, uint32_t (&v)[ROWS]);
+template <>
+__device__ __forceinline__ void ld_stream<1>(const uint32_t* __restrict__ p, uint32_t (&v)[1]) {
+    v[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void ld_stream<2>(const uint32_t* __restrict__ p, uint32_t (&v)[2]) {
+    uint2 t = __ldcs(reinterpret_cast<const uint2*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+}
+template <>
+__device__ __forceinline__ void ld_stream<4>(const uint32_t* __restrict__ p, uint32_t (&v)[4]) {
+    uint4 t = __ldcs(reinterpret_cast<const uint4*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+    v[2] = t.z;
+    v[3] = t.w;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// ------------------------------------------------------------------------------ sink rows ------
+// y[n+r] = c_r * sum over the sink entries of reaction r.  One CTA per (reaction, <=SINK_CHUNK
+// entries) task writes a partial; the last CTA to finish adds the partials of each reaction in task
+// order, so the result is deterministic (no floating-point atomics).
+__device__ __forceinline__ void sink_task(const MatvecArgs& a) {
+    __shared__ double wsum[MV_THREADS / 32];
+    __shared__ bool is_last;
+    const int4 t = a.tasks[blockIdx.x];
+    double s = 0.0;
+    for (int k = t.y + (int)threadIdx.x; k < t.z; k += MV_THREADS) s += __ldcs(a.sink_val + k) * __ldg(a.x + __ldcs(a.sink_row + k));
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < MV_THREADS / 32; ++w) tot += wsum[w];
+        a.sink_partial[blockIdx.x] = tot;
+        __threadfence();
+        const unsigned prev = atomicAdd(a.sink_counter, 1u);
+        is_last = (prev == (unsigned)a.ntasks - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if ((int)threadIdx.x < a.nr) {
+        const int r = threadIdx.x;
+        double tot = 0.0;
+        const volatile double* part = a.sink_partial;
+        for (int k = a.task_ptr[r]; k < a.task_ptr[r + 1]; ++k) tot += part[k];
+        double out = a.sink_coef[r] * tot;
+        if (a.beta != 0.0) out += a.beta * a.y[a.n + r];
+        a.y[a.n + r] = out;
+    }
+    if (threadIdx.x == 0) *a.sink_counter = 0u;
+}
+
+// ------------------------------------------------------------------------------ K1 -------------
+// One thread owns ROWS consecutive rows.  Per slot it streams ROWS column indices and ROWS values
+// (vector loads), gathers x through the read-only path (neighbouring rows have neighbouring
+// predecessors, so the gathers of a warp coalesce into a few L1 lines), and finally applies the
+// time-dependent coefficients that arrive by value in the launch parameters.
+template <int S, int ROWS>
+__global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
+    if ((int)blockIdx.x < a.ntasks) {
+        sink_task(a);
+        return;
+    }
+    const int64_t i0 = ((int64_t)(blockIdx.x - a.ntasks) * MV_THREADS + threadIdx.x) * ROWS;
+    if (i0 >= a.n) return;
+
+    uint32_t c[S][ROWS];
+    double v[S][ROWS];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        ld_stream<ROWS>(a.col + (int64_t)s * a.ld + i0, c[s]);
+        ld_stream<ROWS>(a.val + (int64_t)s * a.ld + i0, v[s]);
+    }
+    double d[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) d[j] = 0.0;
+    for (int k = 0; k < a.ndiag; ++k) {
+        double t[ROWS];
+        ld_stream<ROWS>(a.diag + (int64_t)k * a.ld + i0, t);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) d[j] = fma(a.diag_coef[k], t[j], d[j]);
+    }
+    double acc[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) acc[j] = (i0 + j < a.n) ? d[j] * __ldg(a.x + i0 + j) : 0.0;
+    double g[S][ROWS];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) g[s][j] = __ldg(a.x + c[s][j]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double cs = a.slot_coef[s];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) acc[j] = fma(cs * v[s][j], g[s][j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        if (i0 + j < a.n) {
+            double out = acc[j];
+            if (a.beta != 0.0) out += a.beta * a.y[i0 + j];
+            a.y[i0 + j] = out;
+        }
+    }
+}
+
+// Generic slot count (> 16 slots): same data flow without the register tile.
+__global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_constant__ MatvecArgs a) {
+    if ((int)blockIdx.x < a.ntasks) {
+        sink_task(a);
+        return;
+    }
+    const int64_t i = (int64_t)(blockIdx.x - a.ntasks) * MV_THREADS + threadIdx.x;
+    if (i >= a.n) return;
+    double d = 0.0;
+    for (int k = 0; k < a.ndiag; ++k) d = fma(a.diag_coef[k], __ldcs(a.diag + (int64_t)k * a.ld + i), d);
+    double acc = d * __ldg(a.x + i);
+#pragma unroll 4
+    for (int s = 0; s < a.nslots; ++s) {
+        const uint32_t c = __ldcs(a.col + (int64_t)s * a.ld + i);
+        const double v = __ldcs(a.val + (int64_t)s * a.ld + i);
+        acc = fma(a.slot_coef[s] * v, __ldg(a.x + c), acc);
+    }
+    if (a.beta != 0.0) acc += a.beta * a.y[i];
+    a.y[i] = acc;
+}
+
+template <int ROWS>
+static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
+    const int64_t rows_per_block = (int64_t)MV_THREADS * ROWS;
+    const unsigned grid = (unsigned)(a.ntasks + (a.n + rows_per_block - 1) / rows_per_block);
+    cudaStream_t st = A->ctx->stream;
+    switch (a.nslots) {
+#define NCME_CASE(SS)                                              \
+    case SS:                                                       \
+        k_fsp_matvec<SS, ROWS><<<grid, MV_THREADS, 0, st>>>(a);    \
+        break;
+        NCME_CASE(1) NCME_CASE(2) NCME_CASE(3) NCME_CASE(4) NCME_CASE(5) NCME_CASE(6) NCME_CASE(7) NCME_CASE(8)
+        NCME_CASE(9) NCME_CASE(10) NCME_CASE(11) NCME_CASE(12) NCME_CASE(13) NCME_CASE(14) NCME_CASE(15) NCME_CASE(16)
+#undef NCME_CASE
+        default:
+            return -1;
+    }
+    return 0;
+}
+
+int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
+    ncme_ctx* ctx = A->ctx;
+    int rows = A->tune_rows;
+    if (rows == 0) rows = (a.nslots <= 8) ? 2 : 1;
+    // vector loads of x[i0..] / y are not used (scalar), but the matrix streams need i0 % ROWS == 0 only.
+    int rc = -1;
+    if (a.nslots >= 1 && a.nslots <= 16) {
+        if (rows == 4 && a.nslots <= 8)
+            rc = launch_rows<4>(A, a);
+        else if (rows >= 2)
+            rc = launch_rows<2>(A, a);
+        else
+            rc = launch_rows<1>(A, a);
+    }
+    if (rc != 0) {
+        const unsigned grid = (unsigned)(a.ntasks + (a.n + MV_THREADS - 1) / MV_THREADS);
+        k_fsp_matvec_generic<<<grid, MV_THREADS, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a) {
+    a->col = A->col.p;
+    a->val = A->val.p;
+    a->diag = A->diag.p;
+    a->n = A->n;
+    a->ld = A->ld;
+    a->nslots = A->nslots;
+    a->ndiag = A->ndiag;
+    a->nr = A->nr;
+    for (int s = 0; s < A->nslots; ++s) {
+        const int src = A->slot_coef_src[s];
+        a->slot_coef[s] = (src >= 0 && A->kind[src] == NCME_SEPARABLE_TV) ? coef[src] : 1.0;
+    }
+    for (int d = 0; d < A->ndiag; ++d) {
+        const int src = A->diag_coef_src[d];
+        a->diag_coef[d] = (src >= 0 && A->kind[src] == NCME_SEPARABLE_TV) ? coef[src] : 1.0;
+    }
+    for (int r = 0; r < A->nr; ++r) a->sink_coef[r] = (A->kind[r] == NCME_SEPARABLE_TV) ? coef[r] : 1.0;
+    a->sink_row = A->sink_row.p;
+    a->sink_val = A->sink_val.p;
+    a->tasks = A->tasks.p;
+    a->ntasks = A->ntasks;
+    for (int r = 0; r <= A->nr; ++r) a->task_ptr[r] = A->task_ptr[r];
+    a->sink_partial = A->sink_partial.p;
+    a->sink_counter = A->sink_counter;
+    return NCME_OK;
+}
+
+// ------------------------------------------------------------------------------ K6 assembly ----
+struct SlotReactions {
+    int count;
+    int r[NCME_MAX_REACTIONS];
+};
+
+// col/val of one slot from the predecessor table and the uploaded state factors G[r][i].
+__global__ void k_assemble_slot(const uint32_t* __restrict__ pred_r0, const double* __restrict__ G, int64_t n,
+                                SlotReactions sr, uint32_t* __restrict__ col, double* __restrict__ val, int64_t ld) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    uint32_t c = 0;
+    double v = 0.0;
+    if (i < n) {
+        const uint32_t p = pred_r0[i];
+        c = (p == NONE32) ? (uint32_t)i : p;
+        if (p != NONE32)
+            for (int k = 0; k < sr.count; ++k) v += G[(int64_t)sr.r[k] * n + p];
+    }
+    col[i] = c;
+    val[i] = v;
+}
+
+__global__ void k_assemble_diag(const double* __restrict__ G, int64_t n, SlotReactions sr, double* __restrict__ diag,
+                                int64_t ld) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    double v = 0.0;
+    if (i < n)
+        for (int k = 0; k < sr.count; ++k) v -= G[(int64_t)sr.r[k] * n + i];
+    diag[i] = v;
+}
+
+__global__ void k_bit_flags(const uint32_t* __restrict__ mask, int64_t n, int r, uint32_t* __restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (mask[i] >> r) & 1u;
+}
+
+__global__ void k_pred_flags(const uint32_t* __restrict__ pred, int64_t n, uint32_t* __restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = pred[i] != NONE32 ? 1u : 0u;
+}
+
+__global__ void k_fill_sinks(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
+                             const double* __restrict__ G_r, uint32_t* __restrict__ sink_row, double* __restrict__ sink_val) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) {
+        sink_row[pos[i]] = (uint32_t)i;
+        sink_val[pos[i]] = G_r ? G_r[i] : 0.0;
+    }
+}
+
+// _update_sparsematrix! (:154-166) for one joint reaction: vals[i] = f(t, x_i, theta).
+__global__ void k_set_joint(const double* __restrict__ vals, int64_t n, const uint32_t* __restrict__ col,
+                            double* __restrict__ val, double* __restrict__ diag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = col[i];
+    val[i] = (c == (uint32_t)i) ? 0.0 : vals[c];
+    diag[i] = -vals[i];
+}
+
+__global__ void k_set_joint_sinks(const double* __restrict__ vals, const uint32_t* __restrict__ sink_row, int64_t begin,
+                                  int64_t end, double* __restrict__ sink_val) {
+    int64_t k = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < end) sink_val[k] = vals[sink_row[k]];
+}
+
+static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+static bool same_stoich(const ncme_space* sp, int r1, int r2) {
+    for (int s = 0; s < sp->ns; ++s)
+        if (sp->stoich[(size_t)r1 * sp->ns + s] != sp->stoich[(size_t)r2 * sp->ns + s]) return false;
+    return true;
+}
+static bool zero_stoich(const ncme_space* sp, int r) {
+    for (int s = 0; s < sp->ns; ++s)
+        if (sp->stoich[(size_t)r * sp->ns + s] != 0) return false;
+    return true;
+}
+
+static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A) {
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nr = sp->nr;
+    const int64_t n = sp->n;
+    A->ctx = ctx;
+    A->ns = sp->ns;
+    A->nr = nr;
+    A->n = n;
+    A->N = n + nr;
+    A->ld = round_up<int64_t>(n > 0 ? n : 1, 64);
+    for (int r = 0; r < nr; ++r) {
+        NCME_REQUIRE(kind[r] >= 0 && kind[r] <= 2, "bad reaction kind");
+        A->kind[r] = kind[r];
+    }
+    // ---- slot / diagonal plan
+    SlotReactions slots[NCME_MAX_REACTIONS];
+    SlotReactions diags[NCME_MAX_REACTIONS + 1];
+    int nslots = 0, ndiag = 0;
+    bool any_ti = false;
+    for (int r = 0; r < nr; ++r) any_ti |= (kind[r] == NCME_TIME_INVARIANT);
+    if (any_ti) {
+        diags[0].count = 0;
+        A->diag_coef_src[0] = -1;
+        ndiag = 1;
+    }
+    for (int r = 0; r < nr; ++r) {
+        A->reaction_slot[r] = -1;
+        A->reaction_diag[r] = -1;
+        if (zero_stoich(sp, r)) continue;  // x -> x: the +a and -a entries cancel, contributes nothing
+        if (kind[r] == NCME_TIME_INVARIANT) {
+            diags[0].r[diags[0].count++] = r;
+            A->reaction_diag[r] = 0;
+            int found = -1;
+            for (int s = 0; s < nslots; ++s)
+                if (A->slot_coef_src[s] == -1 && same_stoich(sp, slots[s].r[0], r)) found = s;
+            if (found >= 0) {
+                slots[found].r[slots[found].count++] = r;
+                A->reaction_slot[r] = found;
+                continue;
+            }
+            A->slot_coef_src[nslots] = -1;
+        } else {
+            A->slot_coef_src[nslots] = r;
+            diags[ndiag].count = 1;
+            diags[ndiag].r[0] = r;
+            A->diag_coef_src[ndiag] = r;
+            A->reaction_diag[r] = ndiag;
+            ndiag++;
+        }
+        slots[nslots].count = 1;
+        slots[nslots].r[0] = r;
+        A->slot_first_reaction[nslots] = r;
+        A->reaction_slot[r] = nslots;
+        nslots++;
+    }
+    A->nslots = nslots;
+    A->ndiag = ndiag;
+
+    // ---- upload the state factors (joint reactions start at zero, :87,129)
+    DevArray<double> G;
+    NCME_TRY(G.reserve((size_t)(n > 0 ? n : 1) * nr, st, false));
+    for (int r = 0; r < nr && n > 0; ++r) {
+        if (kind[r] == NCME_JOINT_TV || !propvals)
+            NCME_CUDA(cudaMemsetAsync(G.p + (size_t)r * n, 0, (size_t)n * 8, st));
+        else
+            NCME_CUDA(cudaMemcpyAsync(G.p + (size_t)r * n, propvals + (size_t)r * n, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    }
+    NCME_TRY(A->col.reserve((size_t)A->ld * (nslots > 0 ? nslots : 1), st, false));
+    NCME_TRY(A->val.reserve((size_t)A->ld * (nslots > 0 ? nslots : 1), st, false));
+    NCME_TRY(A->diag.reserve((size_t)A->ld * (ndiag > 0 ? ndiag : 1), st, false));
+    for (int s = 0; s < nslots; ++s) {
+        k_assemble_slot<<<nblk(A->ld), 256, 0, st>>>(sp->pred.p + (size_t)slots[s].r[0] * sp->ld, G.p, n, slots[s],
+                                                     A->col.p + (size_t)s * A->ld, A->val.p + (size_t)s * A->ld, A->ld);
+        ctx->launches++;
+    }
+    for (int d = 0; d < ndiag; ++d) {
+        k_assemble_diag<<<nblk(A->ld), 256, 0, st>>>(G.p, n, diags[d], A->diag.p + (size_t)d * A->ld, A->ld);
+        ctx->launches++;
+    }
+    NCME_CUDA(cudaGetLastError());
+
+    // ---- sink lists (rows ascending inside each reaction) and structural counts
+    DevArray<uint32_t> flags, pos, scratch;
+    NCME_TRY(flags.reserve((size_t)(n > 0 ? n : 1), st, false));
+    NCME_TRY(pos.reserve((size_t)(n > 0 ? n : 1), st, false));
+    NCME_TRY(scratch.reserve(scan_scratch_elems(n > 0 ? n : 1), st, false));
+    int64_t npred[NCME_MAX_REACTIONS] = {0};
+    std::vector<uint64_t> nsink_r((size_t)nr, 0);
+    int rc = NCME_OK;
+    for (int r = 0; r < nr && n > 0 && rc == NCME_OK; ++r) {
+        k_pred_flags<<<nblk(n), 256, 0, st>>>(sp->pred.p + (size_t)r * sp->ld, n, flags.p);
+        ctx->launches++;
+        uint64_t tot = 0;
+        rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, &tot);
+        npred[r] = (int64_t)tot;
+    }
+    // two passes over the sink flags: count, then fill
+    A->sink_ptr[0] = 0;
+    for (int r = 0; r < nr && rc == NCME_OK; ++r) {
+        uint64_t tot = 0;
+        if (n > 0) {
+            k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p, n, r, flags.p);
+            ctx->launches++;
+            rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, &tot);
+        }
+        nsink_r[(size_t)r] = zero_stoich(sp, r) ? 0 : tot;
+        A->sink_ptr[r + 1] = A->sink_ptr[r] + (int64_t)nsink_r[(size_t)r];
+    }
+    if (rc == NCME_OK) {
+        A->nsink = A->sink_ptr[nr];
+        rc = A->sink_row.reserve((size_t)(A->nsink > 0 ? A->nsink : 1), st, false);
+        if (rc == NCME_OK) rc = A->sink_val.reserve((size_t)(A->nsink > 0 ? A->nsink : 1), st, false);
+    }
+    for (int r = 0; r < nr && rc == NCME_OK && n > 0; ++r) {
+        if (nsink_r[(size_t)r] == 0) continue;
+        k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p, n, r, flags.p);
+        ctx->launches++;
+        rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, nullptr);
+        k_fill_sinks<<<nblk(n), 256, 0, st>>>(flags.p, pos.p, n, G.p + (size_t)r * n, A->sink_row.p + A->sink_ptr[r],
+                                              A->sink_val.p + A->sink_ptr[r]);
+        ctx->launches++;
+    }
+    if (rc == NCME_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("matrix assembly failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = NCME_ERR_CUDA;
+    }
+    G.release();
+    flags.release();
+    pos.release();
+    scratch.release();
+    NCME_TRY(rc);
+
+    // ---- sink tasks
+    std::vector<int4> tasks;
+    for (int r = 0; r < nr; ++r) {
+        A->task_ptr[r] = (int)tasks.size();
+        int64_t b = A->sink_ptr[r], e = A->sink_ptr[r + 1];
+        do {
+            int64_t e2 = (e - b > SINK_CHUNK) ? b + SINK_CHUNK : e;
+            tasks.push_back(make_int4(r, (int)b, (int)e2, 0));
+            b = e2;
+        } while (b < e);
+    }
+    A->task_ptr[nr] = (int)tasks.size();
+    A->ntasks = (int)tasks.size();
+    NCME_REQUIRE(A->nsink < 0x7FFFFFFF, "too many sink entries");
+    NCME_TRY(A->tasks.reserve(tasks.size(), st, false));
+    NCME_TRY(A->sink_partial.reserve(tasks.size(), st, false));
+    NCME_CUDA(cudaMemcpyAsync(A->tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    NCME_CUDA(cudaMalloc(&A->sink_counter, sizeof(unsigned)));
+    NCME_CUDA(cudaMemsetAsync(A->sink_counter, 0, sizeof(unsigned), st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+
+    // ---- reference-structure statistics
+    int nt = 0;
+    if (any_ti) {
+        int64_t nnz = n;
+        for (int s = 0; s < nslots; ++s)
+            if (A->slot_coef_src[s] == -1) nnz += npred[slots[s].r[0]];
+        for (int r = 0; r < nr; ++r)
+            if (kind[r] == NCME_TIME_INVARIANT) nnz += (int64_t)nsink_r[(size_t)r];
+        A->nnz_term[nt++] = nnz;
+    }
+    for (int pass = NCME_SEPARABLE_TV; pass <= NCME_JOINT_TV; ++pass)
+        for (int r = 0; r < nr; ++r)
+            if (kind[r] == pass) A->nnz_term[nt++] = n + npred[r] + (int64_t)nsink_r[(size_t)r];
+    A->nterms = nt;
+    A->algorithmic_bytes = 16 * A->N;
+    for (int k = 0; k < nt; ++k) A->algorithmic_bytes += 8 * A->nnz_term[k] + 4 * (A->nnz_term[k] - n);
+    return NCME_OK;
+}
+
+}  // namespace ncme
+
+using namespace ncme;
+
+extern "C" {
+
+int ncme_matrix_create(ncme_space* space, const int32_t* kind, const double* propvals, ncme_matrix** out) {
+    NCME_REQUIRE(space && kind && out, "null argument");
+    NCME_REQUIRE(propvals || space->n == 0, "propvals is null");
+    ncme_matrix* A = new ncme_matrix();
+    int st = matrix_build(space, kind, propvals, A);
+    if (st != NCME_OK) {
+        ncme_matrix_destroy(A);
+        return st;
+    }
+    *out = A;
+    return NCME_OK;
+}
+
+int ncme_matrix_destroy(ncme_matrix* A) {
+    if (!A) return NCME_OK;
+    if (A->ctx) cudaStreamSynchronize(A->ctx->stream);
+    A->col.release();
+    A->val.release();
+    A->diag.release();
+    A->sink_row.release();
+    A->sink_val.release();
+    A->tasks.release();
+    A->sink_partial.release();
+    if (A->sink_counter) cudaFree(A->sink_counter);
+    delete A;
+    return NCME_OK;
+}
+
+int ncme_matrix_size(ncme_matrix* A, int64_t* rows, int64_t* cols) {
+    NCME_REQUIRE(A, "null matrix");
+    if (rows) *rows = A->N;
+    if (cols) *cols = A->N;
+    return NCME_OK;
+}
+
+int ncme_matrix_set_tuning(ncme_matrix* A, int rows_per_thread) {
+    NCME_REQUIRE(A && (rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4),
+                 "rows_per_thread must be 0, 1, 2 or 4");
+    A->tune_rows = rows_per_thread;
+    return NCME_OK;
+}
+
+int ncme_matrix_set_joint_values(ncme_matrix* A, int reaction, const double* vals) {
+    NCME_REQUIRE(A && vals, "null argument");
+    NCME_REQUIRE(reaction >= 1 && reaction <= A->nr && A->kind[reaction - 1] == NCME_JOINT_TV,
+                 "reaction %d is not a joint time-varying reaction", reaction);
+    const int r = reaction - 1;
+    const int s = A->reaction_slot[r], d = A->reaction_diag[r];
+    if (s < 0 || A->n == 0) return NCME_OK;
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    DevArray<double> tmp;
+    NCME_TRY(tmp.reserve((size_t)A->n, st, false));
+    NCME_CUDA(cudaMemcpyAsync(tmp.p, vals, (size_t)A->n * 8, cudaMemcpyHostToDevice, st));
+    k_set_joint<<<nblk(A->n), 256, 0, st>>>(tmp.p, A->n, A->col.p + (size_t)s * A->ld, A->val.p + (size_t)s * A->ld,
+                                            A->diag.p + (size_t)d * A->ld);
+    ctx->launches++;
+    const int64_t b = A->sink_ptr[r], e = A->sink_ptr[r + 1];
+    if (e > b) {
+        k_set_joint_sinks<<<nblk(e - b), 256, 0, st>>>(tmp.p, A->sink_row.p, b, e, A->sink_val.p);
+        ctx->launches++;
+    }
+    NCME_CUDA(cudaGetLastError());
+    NCME_CUDA(cudaStreamSynchronize(st));
+    tmp.release();
+    return NCME_OK;
+}
+
+int ncme_matvec(ncme_matrix* A, const double* coef, const double* x_dev, double* y_dev, double beta) {
+    NCME_REQUIRE(A && x_dev && y_dev, "null argument");
+    NCME_REQUIRE(x_dev != y_dev, "matvec!: input and output must not alias");
+    bool need_coef = false;
+    for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] == NCME_SEPARABLE_TV);
+    NCME_REQUIRE(coef || !need_coef, "coef is null but the matrix has separable time-varying reactions");
+    MatvecArgs a;
+    matvec_fill_args(A, coef, &a);
+    a.x = x_dev;
+    a.y = y_dev;
+    a.beta = beta;
+    return matvec_launch(A, a);
+}
+
+int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, double* y_host, double beta) {
+    NCME_REQUIRE(A && x_host && y_host, "null argument");
+    ncme_ctx* ctx = A->ctx;
+    const size_t bytes = (size_t)A->N * sizeof(double);
+    if (ctx->stage_dev_bytes < bytes) {
+        if (ctx->stage_dev_x) cudaFree(ctx->stage_dev_x);
+        if (ctx->stage_dev_y) cudaFree(ctx->stage_dev_y);
+        ctx->stage_dev_x = ctx->stage_dev_y = nullptr;
+        ctx->stage_dev_bytes = 0;
+        NCME_CUDA(cudaMalloc(&ctx->stage_dev_x, bytes));
+        NCME_CUDA(cudaMalloc(&ctx->stage_dev_y, bytes));
+        ctx->stage_dev_bytes = bytes;
+    }
+    cudaStream_t st = ctx->stream;
+    NCME_CUDA(cudaMemcpyAsync(ctx->stage_dev_x, x_host, bytes, cudaMemcpyHostToDevice, st));
+    if (beta != 0.0) NCME_CUDA(cudaMemcpyAsync(ctx->stage_dev_y, y_host, bytes, cudaMemcpyHostToDevice, st));
+    NCME_TRY(ncme_matvec(A, coef, ctx->stage_dev_x, ctx->stage_dev_y, beta));
+    NCME_CUDA(cudaMemcpyAsync(y_host, ctx->stage_dev_y, bytes, cudaMemcpyDeviceToHost, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    return NCME_OK;
+}
+
+int ncme_matrix_stats(ncme_matrix* A, int* nterms, int64_t* nnz_per_term, int64_t* algorithmic_bytes, int64_t* device_bytes) {
+    NCME_REQUIRE(A, "null matrix");
+    if (nterms) *nterms = A->nterms;
+    if (nnz_per_term)
+        for (int k = 0; k < A->nterms; ++k) nnz_per_term[k] = A->nnz_term[k];
+    if (algorithmic_bytes) *algorithmic_bytes = A->algorithmic_bytes;
+    if (device_bytes)
+        *device_bytes = (int64_t)A->ld * (12 * A->nslots + 8 * A->ndiag) + 12 * A->nsink + 16 * A->N;
+    return NCME_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Device layout of FspMatrixSparse (reference: src/fspmatrix/sparse/fspsparsematrix.jl:9-27).
+//
+// The reference keeps one CSC matrix per term (summed time-invariant, one per separable reaction,
+// one per joint reaction).  Here all terms live in ONE slot-major ELL structure that a single
+// kernel streams once:
+//
+//   y_i = sum_s  c_s(t) * val[s][i] * x[col[s][i]]  +  ( sum_d cd_d(t) * diag[d][i] ) * x_i        i < n
+//   y_{n+r} = c_r(t) * sum_{k in sinks(r)} sink_val[k] * x[sink_row[k]]                            r < R
+//
+// slot s   = one reaction (time-invariant reactions with identical stoichiometry share a slot, which is
+//            exactly the duplicate-summing of Julia's sparse(), :74).  col[s][i] is the predecessor of
+//            state i through the slot's stoichiometry (state_connectivity, sparsestatespace.jl:35) or i
+//            itself with val = 0 where there is none.  val[s][i] = state factor at the predecessor.
+// diag d   = d = 0: minus the sum of all time-invariant state factors (if any); then one per
+//            time-varying reaction (minus its state factor / joint value).
+// Arrays are slot-major with row stride ld (multiple of 64 rows => every slot is 256-byte aligned),
+// so a warp reads 32*ROWS consecutive values per slot: fully coalesced, vectorisable.
+#pragma once
+#include "space.cuh"
+
+struct ncme_matrix {
+    ncme_ctx* ctx = nullptr;
+    int ns = 0, nr = 0;
+    int64_t n = 0, N = 0, ld = 0;
+    int kind[NCME_MAX_REACTIONS] = {0};
+
+    int nslots = 0;
+    int slot_coef_src[NCME_MAX_REACTIONS] = {0};   // reaction whose time factor scales the slot, -1 => 1.0
+    int slot_first_reaction[NCME_MAX_REACTIONS] = {0};
+    int reaction_slot[NCME_MAX_REACTIONS] = {0};   // slot holding reaction r (-1: zero-stoichiometry, contributes nothing)
+    int ndiag = 0;
+    int diag_coef_src[NCME_MAX_REACTIONS + 1] = {0};
+    int reaction_diag[NCME_MAX_REACTIONS] = {0};   // diag array of reaction r
+
+    ncme::DevArray<uint32_t> col;   // [nslots][ld]
+    ncme::DevArray<double> val;     // [nslots][ld]
+    ncme::DevArray<double> diag;    // [ndiag][ld]
+    ncme::DevArray<uint32_t> pred_copy;  // [nr][ld] snapshot of the space's predecessor table (NONE32 kept)
+
+    // sink rows: entries grouped by reaction, rows ascending inside a reaction
+    int64_t nsink = 0;
+    int64_t sink_ptr[NCME_MAX_REACTIONS + 1] = {0};
+    ncme::DevArray<uint32_t> sink_row;
+    ncme::DevArray<double> sink_val;
+    int ntasks = 0;
+    int task_ptr[NCME_MAX_REACTIONS + 1] = {0};
+    ncme::DevArray<int4> tasks;          // (reaction, begin, end, -)
+    ncme::DevArray<double> sink_partial; // [ntasks]
+    unsigned int* sink_counter = nullptr;
+
+    // reference-structure statistics
+    int nterms = 0;
+    int64_t nnz_term[NCME_MAX_REACTIONS + 1] = {0};
+    int64_t algorithmic_bytes = 0;
+
+    // launch tuning (experiments): rows per thread (0 = auto), threads per block
+    int tune_rows = 0;
+    int tune_block = 256;
+};
+
+namespace ncme {
+
+struct MatvecArgs {
+    const uint32_t* col;
+    const double* val;
+    const double* diag;
+    int64_t n, ld;
+    int nslots, ndiag, nr;
+    double slot_coef[NCME_MAX_REACTIONS];
+    double diag_coef[NCME_MAX_REACTIONS + 1];
+    double sink_coef[NCME_MAX_REACTIONS];
+    const uint32_t* sink_row;
+    const double* sink_val;
+    const int4* tasks;
+    int ntasks;
+    int task_ptr[NCME_MAX_REACTIONS + 1];
+    double* sink_partial;
+    unsigned int* sink_counter;
+    const double* x;
+    double* y;
+    double beta;
+};
+
+int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a);
+int matvec_launch(ncme_matrix* A, const MatvecArgs& a);
+
+}  // namespace ncme

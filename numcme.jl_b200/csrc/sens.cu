@@ -1,0 +1,415 @@
+// K2: ForwardSensFspMatrixSparse -- fused block matvec over [p; s_1; ...; s_P].
+// Reference: src/forwardsensfspmatrix/forwardsensfspmatrixsparse/sensfspmatrixsparse.jl
+//   constructor :31-95, matvec! :97-142.
+//
+// The reference runs (P+1) full matvec! passes (re-reading A every time) plus one CSC pass per
+// (reaction, parameter) entry.  Here one kernel reads A's col/val/diag ONCE per row into registers,
+// applies it to all P+1 blocks, and streams each dA entry exactly once:
+//   Y_0  = A(t) p
+//   Y_ip = A(t) s_ip + sum_{e=(r,ip)} [ c_r(t) dA_e p + (d c_r/d theta_ip)(t) A_r p ]
+// dA_e has the sparsity of reaction r's slot, so it shares col[slot(r)] with A.
+#include "matrix.cuh"
+
+struct ncme_sensmatrix {
+    ncme_matrix* A = nullptr;
+    int npar = 0;
+    int nent = 0;
+    int ent_reaction[NCME_MAX_REACTIONS * 4];   // internal order: sorted by parameter
+    int ent_param[NCME_MAX_REACTIONS * 4];
+    int ent_user[NCME_MAX_REACTIONS * 4];       // internal -> user entry index
+    int user_ent[NCME_MAX_REACTIONS * 4];       // user -> internal
+    int ent_ptr[NCME_MAX_REACTIONS * 4 + 2];    // entries of parameter ip: [ent_ptr[ip], ent_ptr[ip+1])
+    ncme::DevArray<double> dval;    // [nent][ld]  d(state factor)/d theta at the predecessor
+    ncme::DevArray<double> ddiag;   // [nent][ld]  minus d(state factor)/d theta at the state itself
+    ncme::DevArray<double> dsink;   // per entry: values along the sink list of its reaction
+    int64_t dsink_ptr[NCME_MAX_REACTIONS * 4 + 1];
+    ncme::DevArray<double> partial;   // [ntasks][P+1]
+    ncme::DevArray<double> dpartial;  // [ntasks][nent]
+    unsigned int* counter = nullptr;
+    int* meta_dev = nullptr;  // ent_reaction | ent_param | ent_slot | ent_diag | ent_ptr  (device copy)
+};
+
+namespace ncme {
+
+constexpr int SMAX_ENT = NCME_MAX_REACTIONS * 4;
+constexpr int SV_THREADS = 256;
+
+struct SensArgs {
+    MatvecArgs m;          // x = X block 0, y = Y block 0
+    int npar, nent;
+    int64_t N;             // block length
+    const double* dval;
+    const double* ddiag;
+    const double* dsink;
+    const int* ent_reaction;  // device meta
+    const int* ent_param;
+    const int* ent_slot;
+    const int* ent_diag;
+    const int* ent_ptr;
+    const int64_t* dsink_ptr;  // device
+    const double* ent_c;       // device: c_r(t) per entry
+    const double* ent_dc;      // device: d c_r / d theta (t) per entry
+    double* partial;
+    double* dpartial;
+    unsigned int* counter;
+};
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// block-wide sum, result valid in thread 0
+__device__ __forceinline__ double bsum(double v, double* sh) {
+    v = wsum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < SV_THREADS / 32; ++w) t += sh[w];
+    return t;
+}
+
+__device__ void sens_sink_task(const SensArgs& a) {
+    __shared__ double sh[SV_THREADS / 32];
+    __shared__ bool is_last;
+    const MatvecArgs& m = a.m;
+    const int4 t = m.tasks[blockIdx.x];
+    const int r = t.x;
+    for (int b = 0; b <= a.npar; ++b) {
+        const double* xb = m.x + (int64_t)b * a.N;
+        double s = 0.0;
+        for (int k = t.y + (int)threadIdx.x; k < t.z; k += SV_THREADS) s += m.sink_val[k] * xb[m.sink_row[k]];
+        s = bsum(s, sh);
+        if (threadIdx.x == 0) a.partial[(int64_t)blockIdx.x * (a.npar + 1) + b] = s;
+    }
+    for (int e = 0; e < a.nent; ++e) {
+        if (a.ent_reaction[e] != r) continue;  // uniform
+        const double* ds = a.dsink + a.dsink_ptr[e];
+        const int rbeg = m.tasks[m.task_ptr[r]].y;  // first sink entry of reaction r
+        double s = 0.0;
+        for (int k = t.y + (int)threadIdx.x; k < t.z; k += SV_THREADS) s += ds[k - rbeg] * m.x[m.sink_row[k]];
+        s = bsum(s, sh);
+        if (threadIdx.x == 0) a.dpartial[(int64_t)blockIdx.x * a.nent + e] = s;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.counter, 1u) == (unsigned)m.ntasks - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const volatile double* part = a.partial;
+    const volatile double* dpart = a.dpartial;
+    for (int q = threadIdx.x; q < m.nr * (a.npar + 1); q += SV_THREADS) {
+        const int rr = q / (a.npar + 1), b = q % (a.npar + 1);
+        double tot = 0.0;
+        for (int k = m.task_ptr[rr]; k < m.task_ptr[rr + 1]; ++k) tot += part[(int64_t)k * (a.npar + 1) + b];
+        m.y[(int64_t)b * a.N + m.n + rr] = m.sink_coef[rr] * tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int e = 0; e < a.nent; ++e) {
+            const int rr = a.ent_reaction[e], ip = a.ent_param[e];
+            double dt = 0.0, s0 = 0.0;
+            for (int k = m.task_ptr[rr]; k < m.task_ptr[rr + 1]; ++k) {
+                dt += dpart[(int64_t)k * a.nent + e];
+                s0 += part[(int64_t)k * (a.npar + 1)];
+            }
+            m.y[(int64_t)(ip + 1) * a.N + m.n + rr] += a.ent_c[e] * dt + a.ent_dc[e] * s0;
+        }
+        *a.counter = 0u;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(SV_THREADS) k_sens_matvec(const __grid_constant__ SensArgs a) {
+    const MatvecArgs& m = a.m;
+    if ((int)blockIdx.x < m.ntasks) {
+        sens_sink_task(a);
+        return;
+    }
+    const int64_t i = (int64_t)(blockIdx.x - m.ntasks) * SV_THREADS + threadIdx.x;
+    if (i >= m.n) return;
+    uint32_t c[S];
+    double v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        c[s] = __ldcs(m.col + (int64_t)s * m.ld + i);
+        v[s] = m.slot_coef[s] * __ldcs(m.val + (int64_t)s * m.ld + i);
+    }
+    double d = 0.0;
+    for (int k = 0; k < m.ndiag; ++k) d = fma(m.diag_coef[k], __ldcs(m.diag + (int64_t)k * m.ld + i), d);
+    // block 0 (probabilities): keep the gathered p values, the dA terms reuse them
+    double g0[S];
+    const double p_i = __ldg(m.x + i);
+    {
+        double acc = d * p_i;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            g0[s] = __ldg(m.x + c[s]);
+            acc = fma(v[s], g0[s], acc);
+        }
+        m.y[i] = acc;
+    }
+    for (int ip = 0; ip < a.npar; ++ip) {
+        const double* xb = m.x + (int64_t)(ip + 1) * a.N;
+        double acc = d * __ldg(xb + i);
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc = fma(v[s], __ldg(xb + c[s]), acc);
+        for (int e = a.ent_ptr[ip]; e < a.ent_ptr[ip + 1]; ++e) {
+            const int s = a.ent_slot[e];
+            if (s < 0) continue;
+            double gp = 0.0;
+#pragma unroll
+            for (int q = 0; q < S; ++q)
+                if (q == s) gp = g0[q];
+            const double dv = __ldcs(a.dval + (int64_t)e * m.ld + i);
+            const double dd = __ldcs(a.ddiag + (int64_t)e * m.ld + i);
+            acc = fma(a.ent_c[e], fma(dv, gp, dd * p_i), acc);
+            const double dc = a.ent_dc[e];
+            if (dc != 0.0) {
+                // (d c_r / d theta) * A_r p : the reaction's own slot and diagonal, without c_r
+                const double wr = __ldcs(m.val + (int64_t)s * m.ld + i);
+                const double gr = __ldcs(m.diag + (int64_t)a.ent_diag[e] * m.ld + i);
+                acc = fma(dc, fma(wr, gp, gr * p_i), acc);
+            }
+        }
+        m.y[(int64_t)(ip + 1) * a.N + i] = acc;
+    }
+}
+
+__global__ void k_sens_entry_fill(const uint32_t* __restrict__ col, const double* __restrict__ dG, int64_t n, int64_t ld,
+                                  double* __restrict__ dval, double* __restrict__ ddiag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    double a = 0.0, b = 0.0;
+    if (i < n) {
+        const uint32_t c = col[i];
+        a = (c == (uint32_t)i) ? 0.0 : dG[c];
+        b = -dG[i];
+    }
+    dval[i] = a;
+    ddiag[i] = b;
+}
+
+__global__ void k_sens_sink_fill(const uint32_t* __restrict__ sink_row, int64_t begin, int64_t end,
+                                 const double* __restrict__ dG, double* __restrict__ out) {
+    int64_t k = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < end) out[k - begin] = dG[sink_row[k]];
+}
+
+static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+static int sens_fill_entry(ncme_sensmatrix* SA, int e, const double* dG_host) {
+    ncme_matrix* A = SA->A;
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const int r = SA->ent_reaction[e];
+    const int s = A->reaction_slot[r];
+    DevArray<double> tmp;
+    NCME_TRY(tmp.reserve((size_t)(A->n > 0 ? A->n : 1), st, false));
+    if (dG_host)
+        NCME_CUDA(cudaMemcpyAsync(tmp.p, dG_host, (size_t)A->n * 8, cudaMemcpyHostToDevice, st));
+    else
+        NCME_CUDA(cudaMemsetAsync(tmp.p, 0, (size_t)A->n * 8, st));
+    if (s >= 0) {
+        k_sens_entry_fill<<<nblk(A->ld), 256, 0, st>>>(A->col.p + (size_t)s * A->ld, tmp.p, A->n, A->ld,
+                                                       SA->dval.p + (size_t)e * A->ld, SA->ddiag.p + (size_t)e * A->ld);
+        ctx->launches++;
+        const int64_t b = A->sink_ptr[r], en = A->sink_ptr[r + 1];
+        if (en > b) {
+            k_sens_sink_fill<<<nblk(en - b), 256, 0, st>>>(A->sink_row.p, b, en, tmp.p, SA->dsink.p + SA->dsink_ptr[e]);
+            ctx->launches++;
+        }
+    } else {
+        NCME_CUDA(cudaMemsetAsync(SA->dval.p + (size_t)e * A->ld, 0, (size_t)A->ld * 8, st));
+        NCME_CUDA(cudaMemsetAsync(SA->ddiag.p + (size_t)e * A->ld, 0, (size_t)A->ld * 8, st));
+    }
+    NCME_CUDA(cudaGetLastError());
+    NCME_CUDA(cudaStreamSynchronize(st));
+    tmp.release();
+    return NCME_OK;
+}
+
+}  // namespace ncme
+
+using namespace ncme;
+
+extern "C" {
+
+int ncme_sensmatrix_destroy(ncme_sensmatrix* SA) {
+    if (!SA) return NCME_OK;
+    if (SA->A && SA->A->ctx) cudaStreamSynchronize(SA->A->ctx->stream);
+    SA->dval.release();
+    SA->ddiag.release();
+    SA->dsink.release();
+    SA->partial.release();
+    SA->dpartial.release();
+    if (SA->counter) cudaFree(SA->counter);
+    if (SA->meta_dev) cudaFree(SA->meta_dev);
+    delete SA;
+    return NCME_OK;
+}
+
+int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t* ent_reaction, const int32_t* ent_param,
+                           const double* dpropvals, ncme_sensmatrix** out) {
+    NCME_REQUIRE(A && out && npar >= 0 && nentries >= 0, "bad arguments");
+    NCME_REQUIRE(nentries <= SMAX_ENT, "too many (reaction, parameter) entries (max %d)", SMAX_ENT);
+    NCME_REQUIRE(npar <= SMAX_ENT, "too many parameters (max %d)", SMAX_ENT);
+    NCME_REQUIRE(nentries == 0 || (ent_reaction && ent_param && dpropvals), "null entry arrays");
+    ncme_sensmatrix* SA = new ncme_sensmatrix();
+    SA->A = A;
+    SA->npar = npar;
+    SA->nent = nentries;
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    int rc = NCME_OK;
+    do {
+        // internal order: by parameter (stable)
+        int k = 0;
+        for (int ip = 0; ip < npar; ++ip) {
+            SA->ent_ptr[ip] = k;
+            for (int e = 0; e < nentries; ++e)
+                if (ent_param[e] == ip + 1) {
+                    if (ent_reaction[e] < 1 || ent_reaction[e] > A->nr) {
+                        set_error("entry %d: reaction out of range", e);
+                        rc = NCME_ERR_ARG;
+                    }
+                    SA->ent_reaction[k] = ent_reaction[e] - 1;
+                    SA->ent_param[k] = ip;
+                    SA->ent_user[k] = e;
+                    SA->user_ent[e] = k;
+                    ++k;
+                }
+        }
+        SA->ent_ptr[npar] = k;
+        if (rc != NCME_OK) break;
+        if (k != nentries) {
+            set_error("entry parameter index out of range 1..%d", npar);
+            rc = NCME_ERR_ARG;
+            break;
+        }
+        SA->dsink_ptr[0] = 0;
+        for (int e = 0; e < nentries; ++e) {
+            const int r = SA->ent_reaction[e];
+            SA->dsink_ptr[e + 1] = SA->dsink_ptr[e] + (A->sink_ptr[r + 1] - A->sink_ptr[r]);
+        }
+        const size_t ne = (size_t)(nentries > 0 ? nentries : 1);
+        if ((rc = SA->dval.reserve(ne * A->ld, st, false)) != NCME_OK) break;
+        if ((rc = SA->ddiag.reserve(ne * A->ld, st, false)) != NCME_OK) break;
+        if ((rc = SA->dsink.reserve((size_t)SA->dsink_ptr[nentries] + 1, st, false)) != NCME_OK) break;
+        if ((rc = SA->partial.reserve((size_t)A->ntasks * (npar + 1), st, false)) != NCME_OK) break;
+        if ((rc = SA->dpartial.reserve((size_t)A->ntasks * ne, st, false)) != NCME_OK) break;
+        for (int e = 0; e < nentries && rc == NCME_OK; ++e) {
+            const int r = SA->ent_reaction[e];
+            const double* src = (A->kind[r] == NCME_JOINT_TV) ? nullptr : dpropvals + (size_t)SA->ent_user[e] * A->n;
+            rc = sens_fill_entry(SA, e, src);
+        }
+        if (rc != NCME_OK) break;
+        // device meta: ent_reaction | ent_param | ent_slot | ent_diag | ent_ptr(npar+1) ; then dsink_ptr (int64) ; then 2*nent doubles
+        std::vector<int> meta((size_t)4 * SMAX_ENT + SMAX_ENT + 2, 0);
+        for (int e = 0; e < nentries; ++e) {
+            meta[(size_t)e] = SA->ent_reaction[e];
+            meta[(size_t)SMAX_ENT + e] = SA->ent_param[e];
+            meta[(size_t)2 * SMAX_ENT + e] = A->reaction_slot[SA->ent_reaction[e]];
+            meta[(size_t)3 * SMAX_ENT + e] = A->reaction_diag[SA->ent_reaction[e]];
+        }
+        for (int ip = 0; ip <= npar; ++ip) meta[(size_t)4 * SMAX_ENT + ip] = SA->ent_ptr[ip];
+        const size_t meta_bytes = meta.size() * sizeof(int);
+        const size_t total = meta_bytes + (SMAX_ENT + 1) * sizeof(int64_t) + 2 * SMAX_ENT * sizeof(double) + 64;
+        if (cudaMalloc(&SA->meta_dev, total) != cudaSuccess || cudaMalloc(&SA->counter, sizeof(unsigned)) != cudaSuccess) {
+            set_error("cudaMalloc failed");
+            rc = NCME_ERR_NOMEM;
+            break;
+        }
+        cudaMemsetAsync(SA->counter, 0, sizeof(unsigned), st);
+        cudaMemcpyAsync(SA->meta_dev, meta.data(), meta_bytes, cudaMemcpyHostToDevice, st);
+        char* base = (char*)SA->meta_dev + round_up<size_t>(meta_bytes, 16);
+        cudaMemcpyAsync(base, SA->dsink_ptr, (SMAX_ENT + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("sens meta upload failed");
+            rc = NCME_ERR_CUDA;
+        }
+    } while (0);
+    if (rc != NCME_OK) {
+        ncme_sensmatrix_destroy(SA);
+        return rc;
+    }
+    *out = SA;
+    return NCME_OK;
+}
+
+int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* SA, int entry, const double* vals) {
+    NCME_REQUIRE(SA && vals && entry >= 0 && entry < SA->nent, "bad arguments");
+    const int e = SA->user_ent[entry];
+    NCME_REQUIRE(SA->A->kind[SA->ent_reaction[e]] == NCME_JOINT_TV, "entry %d does not belong to a joint reaction", entry);
+    return sens_fill_entry(SA, e, vals);
+}
+
+int ncme_sens_matvec(ncme_sensmatrix* SA, const double* coef, const double* dcoef, const double* X, double* Y) {
+    NCME_REQUIRE(SA && X && Y && X != Y, "bad arguments");
+    ncme_matrix* A = SA->A;
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    bool need_coef = false;
+    for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] == NCME_SEPARABLE_TV);
+    NCME_REQUIRE((coef && (dcoef || SA->nent == 0)) || !need_coef, "coef/dcoef required for separable reactions");
+    SensArgs a;
+    matvec_fill_args(A, coef, &a.m);
+    a.m.x = X;
+    a.m.y = Y;
+    a.m.beta = 0.0;
+    a.npar = SA->npar;
+    a.nent = SA->nent;
+    a.N = A->N;
+    a.dval = SA->dval.p;
+    a.ddiag = SA->ddiag.p;
+    a.dsink = SA->dsink.p;
+    const size_t meta_bytes = ((size_t)4 * SMAX_ENT + SMAX_ENT + 2) * sizeof(int);
+    a.ent_reaction = SA->meta_dev;
+    a.ent_param = SA->meta_dev + SMAX_ENT;
+    a.ent_slot = SA->meta_dev + 2 * SMAX_ENT;
+    a.ent_diag = SA->meta_dev + 3 * SMAX_ENT;
+    a.ent_ptr = SA->meta_dev + 4 * SMAX_ENT;
+    char* base = (char*)SA->meta_dev + round_up<size_t>(meta_bytes, 16);
+    a.dsink_ptr = (const int64_t*)base;
+    double* cdev = (double*)(base + (SMAX_ENT + 1) * sizeof(int64_t));
+    double hc[2 * SMAX_ENT];
+    for (int e = 0; e < SA->nent; ++e) {
+        const int r = SA->ent_reaction[e];
+        const bool sep = A->kind[r] == NCME_SEPARABLE_TV;
+        hc[e] = sep ? coef[r] : 1.0;
+        hc[SMAX_ENT + e] = sep ? dcoef[SA->ent_user[e]] : 0.0;
+    }
+    // pageable -> device copy of a few hundred bytes; ordered on the stream before the kernel
+    NCME_CUDA(cudaMemcpyAsync(cdev, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    a.ent_c = cdev;
+    a.ent_dc = cdev + SMAX_ENT;
+    a.partial = SA->partial.p;
+    a.dpartial = SA->dpartial.p;
+    a.counter = SA->counter;
+    const unsigned grid = (unsigned)(A->ntasks + (A->n + SV_THREADS - 1) / SV_THREADS);
+    switch (A->nslots) {
+#define NCME_SCASE(SS)                                   \
+    case SS:                                             \
+        k_sens_matvec<SS><<<grid, SV_THREADS, 0, st>>>(a); \
+        break;
+        NCME_SCASE(1) NCME_SCASE(2) NCME_SCASE(3) NCME_SCASE(4) NCME_SCASE(5) NCME_SCASE(6) NCME_SCASE(7) NCME_SCASE(8)
+        NCME_SCASE(9) NCME_SCASE(10) NCME_SCASE(11) NCME_SCASE(12) NCME_SCASE(13) NCME_SCASE(14) NCME_SCASE(15) NCME_SCASE(16)
+        NCME_SCASE(17) NCME_SCASE(18) NCME_SCASE(19) NCME_SCASE(20) NCME_SCASE(21) NCME_SCASE(22) NCME_SCASE(23) NCME_SCASE(24)
+        NCME_SCASE(25) NCME_SCASE(26) NCME_SCASE(27) NCME_SCASE(28) NCME_SCASE(29) NCME_SCASE(30) NCME_SCASE(31) NCME_SCASE(32)
+#undef NCME_SCASE
+        default:
+            set_error("sens matvec: unsupported slot count %d", A->nslots);
+            return NCME_ERR_ARG;
+    }
+    ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,655 @@
+// StateSpaceSparse on the device: GPU hash table (K3), frontier expansion with stream compaction (K4),
+// deletion/reindexing (K5).  Reference: src/statespace/sparse/sparsestatespace.jl
+//   constructor :103-124, expand! :153-194, _addstates! :208-267, deleteat! :276-331.
+//
+// Ordering contract: new states are appended in exactly the reference's insertion order.  The
+// reference walks the candidate list sequentially and gives the next index to the first occurrence
+// of every unseen non-negative state (:220-226).  Here every candidate c carries its position in
+// that list as a rank; duplicates race with atomicMin(rank) on the hash-table value, the winners
+// (rank == stored value) are stream-compacted in rank order, which reproduces the sequential result.
+#include "space.cuh"
+
+namespace ncme {
+
+// ------------------------------------------------------------------------------------ kernels ---
+__global__ void k_fill_u32(uint32_t* p, int64_t n, uint32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_u64(uint64_t* p, int64_t n, uint64_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// insert key -> value i for i in [first, n)
+__global__ void k_table_insert_range(HashView h, const uint64_t* __restrict__ keys, int64_t first, int64_t n) {
+    int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    uint64_t slot = hash64(key) & h.capmask;
+    while (true) {
+        uint64_t prev = atomicCAS((unsigned long long*)&h.keys[slot], (unsigned long long)EMPTY_KEY,
+                                  (unsigned long long)key);
+        if (prev == EMPTY_KEY || prev == key) {
+            h.vals[slot] = (uint32_t)i;
+            return;
+        }
+        slot = (slot + 1) & h.capmask;
+    }
+}
+
+// key of x + sign * s_r.  Returns 0 if representable, 1 if a component would be negative (not a
+// state at all), 2 if non-negative but too wide for the packed key.
+__device__ __forceinline__ int shifted_key(const KeyLayout& L, const StoichDev& S, uint64_t key, int r, int sign,
+                                           uint64_t* out) {
+    uint64_t nk = 0;
+    bool neg = false, wide = false;
+    for (int s = 0; s < L.ns; ++s) {
+        long long v = (long long)((key >> L.shift[s]) & L.mask[s]) + (long long)sign * S.s[r][s];
+        neg |= v < 0;
+        wide |= v > (long long)L.mask[s];
+        nk |= ((uint64_t)(v < 0 ? 0 : v)) << L.shift[s];
+    }
+    *out = nk;
+    return neg ? 1 : (wide ? 2 : 0);
+}
+
+// Candidate generation (expand! :176-186): candidate rank c <-> (frontier entry popped LIFO, reaction k).
+// frontier == nullptr means the frontier is the index range [fbase, fbase + F).
+__global__ void k_gen_candidates(KeyLayout L, StoichDev S, const uint64_t* __restrict__ keys,
+                                 const uint32_t* __restrict__ frontier, int64_t fbase, int64_t F, int nreact,
+                                 const int* __restrict__ reacts /*device, nreact, 0-based*/, uint64_t* __restrict__ cand_key,
+                                 int* err_flag) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F * nreact) return;
+    const int64_t f = F - 1 - c / nreact;
+    const int r = reacts[c % nreact];
+    const int64_t idx = frontier ? (int64_t)frontier[f] : fbase + f;
+    uint64_t nk;
+    const int rc = shifted_key(L, S, keys[idx], r, +1, &nk);
+    if (rc == 2) atomicExch(err_flag, 1);
+    cand_key[c] = rc == 0 ? nk : EMPTY_KEY;
+}
+
+// _addstates! first loop (:219-226), parallel: probe; existing states drop out; unseen keys are
+// inserted with value = min over duplicates of (n_old + rank).
+__global__ void k_insert_candidates(HashView h, const uint64_t* __restrict__ cand_key, int64_t ncand, uint32_t n_old,
+                                    uint32_t* __restrict__ cand_slot) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand) return;
+    const uint64_t key = cand_key[c];
+    if (key == EMPTY_KEY) {
+        cand_slot[c] = NONE32;
+        return;
+    }
+    uint64_t slot = hash64(key) & h.capmask;
+    while (true) {
+        uint64_t prev = atomicCAS((unsigned long long*)&h.keys[slot], (unsigned long long)EMPTY_KEY,
+                                  (unsigned long long)key);
+        if (prev == EMPTY_KEY || prev == key) {
+            // committed states have values < n_old and are never modified by atomicMin with >= n_old
+            uint32_t before = atomicMin(&h.vals[slot], n_old + (uint32_t)c);
+            cand_slot[c] = (before < n_old) ? NONE32 : (uint32_t)slot;
+            return;
+        }
+        slot = (slot + 1) & h.capmask;
+    }
+}
+
+__global__ void k_mark_winners(HashView h, const uint32_t* __restrict__ cand_slot, int64_t ncand, uint32_t n_old,
+                               uint32_t* __restrict__ flags) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand) return;
+    const uint32_t slot = cand_slot[c];
+    flags[c] = (slot != NONE32 && h.vals[slot] == n_old + (uint32_t)c) ? 1u : 0u;
+}
+
+__global__ void k_commit_new(HashView h, const uint64_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_slot,
+                             const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t ncand,
+                             uint32_t n_old, uint64_t* __restrict__ keys, uint32_t* __restrict__ pred, int64_t ld, int nr,
+                             uint32_t* __restrict__ sinkmask) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand || !flags[c]) return;
+    const uint32_t i = n_old + pos[c];
+    keys[i] = cand_key[c];
+    h.vals[cand_slot[c]] = i;
+    sinkmask[i] = 0u;
+    for (int r = 0; r < nr; ++r) pred[(int64_t)r * ld + i] = NONE32;
+}
+
+// _addstates! connectivity loops (:241-266), one thread per (new state, reaction).
+__global__ void k_connect_new(HashView h, KeyLayout L, StoichDev S, const uint64_t* __restrict__ keys, int64_t n_old,
+                              int64_t n_new, uint32_t* __restrict__ pred, int64_t ld, uint32_t* __restrict__ sinkmask) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nr = S.nr;
+    if (t >= (n_new - n_old) * nr) return;
+    const int64_t i = n_old + t / nr;
+    const int r = (int)(t % nr);
+    const uint64_t key = keys[i];
+    uint64_t k2;
+    if (shifted_key(L, S, key, r, -1, &k2) == 0) {  // predecessor x_i - s_r
+        uint32_t j = hash_lookup(h, k2);
+        if (j != NONE32) {
+            pred[(int64_t)r * ld + i] = j;
+            atomicAnd(&sinkmask[j], ~(1u << r));
+        }
+    }
+    const int rc = shifted_key(L, S, key, r, +1, &k2);  // successor x_i + s_r
+    if (rc == 0) {
+        uint32_t j = hash_lookup(h, k2);
+        if (j == NONE32)
+            atomicOr(&sinkmask[i], 1u << r);
+        else
+            pred[(int64_t)r * ld + j] = (uint32_t)i;
+    } else if (rc == 2) {
+        // successor is non-negative but does not fit the key: it cannot be in the space => it is a sink
+        atomicOr(&sinkmask[i], 1u << r);
+    }
+}
+
+__global__ void k_frontier_flags(const uint32_t* __restrict__ sinkmask, int64_t n, uint32_t reactmask,
+                                 uint32_t* __restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (sinkmask[i] & reactmask) ? 1u : 0u;
+}
+
+__global__ void k_compact_indices(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
+                                  uint32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = (uint32_t)i;
+}
+
+// deleteat! :283-317 -- compact keys / sink masks / predecessor table through the old->new index map.
+__global__ void k_clear_flags_at(const uint32_t* __restrict__ ids0 /*0-based*/, int64_t nids, uint32_t* __restrict__ keep) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nids) keep[ids0[k]] = 0u;
+}
+
+__global__ void k_compact_space(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, int64_t n,
+                                const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pred, int64_t ld,
+                                const uint32_t* __restrict__ sinkmask, int nr, uint64_t* __restrict__ keys2,
+                                uint32_t* __restrict__ pred2, int64_t ld2, uint32_t* __restrict__ sinkmask2) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const uint32_t j = pos[i];
+    keys2[j] = keys[i];
+    sinkmask2[j] = sinkmask[i];
+    for (int r = 0; r < nr; ++r) {
+        uint32_t p = pred[(int64_t)r * ld + i];
+        pred2[(int64_t)r * ld2 + j] = (p != NONE32 && keep[p]) ? pos[p] : NONE32;
+    }
+}
+
+// deleteat! :318-329 -- re-derive sink flags of the surviving states.
+__global__ void k_rederive_sinks(HashView h, KeyLayout L, StoichDev S, const uint64_t* __restrict__ keys, int64_t n,
+                                 uint32_t* __restrict__ sinkmask) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nr = S.nr;
+    if (t >= n * nr) return;
+    const int64_t i = t / nr;
+    const int r = (int)(t % nr);
+    if (sinkmask[i] & (1u << r)) return;
+    uint64_t k2;
+    const int rc = shifted_key(L, S, keys[i], r, +1, &k2);
+    if ((rc == 0 && hash_lookup(h, k2) == NONE32) || rc == 2) atomicOr(&sinkmask[i], 1u << r);
+}
+
+__global__ void k_lookup(HashView h, const uint64_t* __restrict__ q, int64_t m, uint32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t k = q[i];
+    uint32_t v = (k == EMPTY_KEY) ? NONE32 : hash_lookup(h, k);
+    out[i] = (v == NONE32) ? 0u : v + 1u;
+}
+
+// --------------------------------------------------------------------------------- host side ---
+static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+#define LAUNCH(ctx, kern, n, ...)                                          \
+    do {                                                                   \
+        if ((n) > 0) {                                                     \
+            kern<<<nblk(n), 256, 0, (ctx)->stream>>>(__VA_ARGS__);          \
+            (ctx)->launches++;                                             \
+            NCME_CUDA(cudaGetLastError());                                 \
+        }                                                                  \
+    } while (0)
+
+int space_pack_host(const ncme_space* sp, const int64_t* state, uint64_t* key_out) {
+    uint64_t k = 0;
+    for (int s = 0; s < sp->ns; ++s) {
+        if (state[s] < 0) return 1;
+        if ((uint64_t)state[s] > sp->layout.mask[s]) {
+            set_error("state component %lld of species %d does not fit the %d-species packed key", (long long)state[s],
+                      s + 1, sp->ns);
+            return NCME_ERR_KEYWIDTH;
+        }
+        k |= (uint64_t)state[s] << sp->layout.shift[s];
+    }
+    *key_out = k;
+    return 0;
+}
+
+int space_reserve_rows(ncme_space* sp, int64_t nrows) {
+    if (nrows <= sp->ld) return NCME_OK;
+    cudaStream_t st = sp->ctx->stream;
+    int64_t nld = sp->ld ? sp->ld : 1024;
+    while (nld < nrows) nld = nld + nld / 2;
+    nld = round_up<int64_t>(nld, 64);
+    NCME_TRY(sp->keys.reserve((size_t)nld, st));
+    NCME_TRY(sp->sinkmask.reserve((size_t)nld, st));
+    // the slot-major table changes stride: re-lay it out
+    DevArray<uint32_t> np;
+    NCME_TRY(np.reserve((size_t)nld * sp->nr, st, false));
+    for (int r = 0; r < sp->nr && sp->n > 0; ++r)
+        NCME_CUDA(cudaMemcpyAsync(np.p + (size_t)r * nld, sp->pred.p + (size_t)r * sp->ld, (size_t)sp->n * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToDevice, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    sp->pred.release();
+    sp->pred = np;
+    sp->ld = nld;
+    return NCME_OK;
+}
+
+int space_rebuild_table(ncme_space* sp, uint64_t min_slots) {
+    ncme_ctx* ctx = sp->ctx;
+    uint64_t cap = 1024;
+    while (cap < min_slots) cap <<= 1;
+    if (cap < sp->tcap) cap = sp->tcap;
+    NCME_TRY(sp->tkeys.reserve(cap, ctx->stream, false));
+    NCME_TRY(sp->tvals.reserve(cap, ctx->stream, false));
+    sp->tcap = cap;
+    NCME_CUDA(cudaMemsetAsync(sp->tkeys.p, 0xFF, cap * sizeof(uint64_t), ctx->stream));
+    NCME_CUDA(cudaMemsetAsync(sp->tvals.p, 0xFF, cap * sizeof(uint32_t), ctx->stream));
+    LAUNCH(ctx, k_table_insert_range, sp->n, sp->hview(), sp->keys.p, (int64_t)0, sp->n);
+    return NCME_OK;
+}
+
+static int ensure_scratch(ncme_space* sp, int64_t m) {
+    cudaStream_t st = sp->ctx->stream;
+    NCME_TRY(sp->cand_key.reserve((size_t)m, st, true));
+    NCME_TRY(sp->cand_slot.reserve((size_t)m, st, false));
+    NCME_TRY(sp->flags.reserve((size_t)m, st, false));
+    NCME_TRY(sp->pos.reserve((size_t)m, st, false));
+    NCME_TRY(sp->scan_scratch.reserve(scan_scratch_elems(m), st, false));
+    return NCME_OK;
+}
+
+int space_addstates(ncme_space* sp, int64_t ncand, int64_t* added) {
+    ncme_ctx* ctx = sp->ctx;
+    *added = 0;
+    if (ncand <= 0) return NCME_OK;
+    NCME_REQUIRE((uint64_t)sp->n + (uint64_t)ncand < 0xFFFFFFF0ull, "state space exceeds the 32-bit index range");
+    NCME_TRY(ensure_scratch(sp, ncand));
+    if (2 * (uint64_t)(sp->n + ncand) > sp->tcap) NCME_TRY(space_rebuild_table(sp, 4 * (uint64_t)(sp->n + ncand)));
+    const uint32_t n_old = (uint32_t)sp->n;
+    LAUNCH(ctx, k_insert_candidates, ncand, sp->hview(), sp->cand_key.p, ncand, n_old, sp->cand_slot.p);
+    LAUNCH(ctx, k_mark_winners, ncand, sp->hview(), sp->cand_slot.p, ncand, n_old, sp->flags.p);
+    uint64_t m = 0;
+    NCME_TRY(exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, ncand, sp->scan_scratch.p, sp->scan_scratch.cap, &m));
+    if (m == 0) return NCME_OK;
+    NCME_TRY(space_reserve_rows(sp, sp->n + (int64_t)m));
+    LAUNCH(ctx, k_commit_new, ncand, sp->hview(), sp->cand_key.p, sp->cand_slot.p, sp->flags.p, sp->pos.p, ncand, n_old,
+           sp->keys.p, sp->pred.p, sp->ld, sp->nr, sp->sinkmask.p);
+    const int64_t n_new = sp->n + (int64_t)m;
+    LAUNCH(ctx, k_connect_new, (int64_t)m * sp->nr, sp->hview(), sp->layout, sp->sdev, sp->keys.p, sp->n, n_new,
+           sp->pred.p, sp->ld, sp->sinkmask.p);
+    sp->n = n_new;
+    sp->version++;
+    *added = (int64_t)m;
+    return NCME_OK;
+}
+
+static int space_alloc(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, ncme_space** out) {
+    NCME_REQUIRE(ctx && out && stoich, "null argument");
+    NCME_REQUIRE(ns >= 1 && ns <= NCME_MAX_SPECIES, "species count must be in 1..%d", NCME_MAX_SPECIES);
+    NCME_REQUIRE(nr >= 1 && nr <= NCME_MAX_REACTIONS, "reaction count must be in 1..%d", NCME_MAX_REACTIONS);
+    ncme_space* sp = new ncme_space();
+    sp->ctx = ctx;
+    sp->ns = ns;
+    sp->nr = nr;
+    sp->stoich.assign(stoich, stoich + (size_t)ns * nr);
+    const int bits = 63 / ns;  // top bit stays 0 so that EMPTY_KEY is never a valid key
+    sp->layout.ns = ns;
+    for (int s = 0; s < ns; ++s) {
+        sp->layout.shift[s] = s * bits;
+        sp->layout.mask[s] = (bits >= 63) ? 0x7FFFFFFFFFFFFFFFull : ((1ull << bits) - 1);
+    }
+    sp->sdev.nr = nr;
+    sp->sdev.ns = ns;
+    for (int r = 0; r < nr; ++r)
+        for (int s = 0; s < ns; ++s) {
+            int64_t v = stoich[(size_t)r * ns + s];
+            if (v < -32768 || v > 32767) {
+                delete sp;
+                set_error("stoichiometry entry out of int16 range");
+                return NCME_ERR_ARG;
+            }
+            sp->sdev.s[r][s] = (int16_t)v;
+        }
+    cudaError_t e = cudaMalloc(&sp->err_flag, sizeof(int));
+    if (e != cudaSuccess) {
+        delete sp;
+        set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+        return NCME_ERR_CUDA;
+    }
+    cudaMemsetAsync(sp->err_flag, 0, sizeof(int), ctx->stream);
+    *out = sp;
+    return NCME_OK;
+}
+
+static int check_overflow(ncme_space* sp) {
+    int flag = 0;
+    NCME_CUDA(cudaMemcpyAsync(&flag, sp->err_flag, sizeof(int), cudaMemcpyDeviceToHost, sp->ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(sp->ctx->stream));
+    if (flag) {
+        cudaMemsetAsync(sp->err_flag, 0, sizeof(int), sp->ctx->stream);
+        set_error("a reachable state does not fit the 64-bit packed key (%d species, %d bits each)", sp->ns, 63 / sp->ns);
+        return NCME_ERR_KEYWIDTH;
+    }
+    return NCME_OK;
+}
+
+}  // namespace ncme
+
+using namespace ncme;
+
+extern "C" {
+
+int ncme_space_create(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int64_t n0, const int64_t* states0,
+                      ncme_space** out) {
+    NCME_REQUIRE(n0 >= 0 && (n0 == 0 || states0), "bad initial state list");
+    ncme_space* sp = nullptr;
+    NCME_TRY(space_alloc(ctx, ns, nr, stoich, &sp));
+    int st = NCME_OK;
+    do {
+        if ((st = space_reserve_rows(sp, n0 > 1024 ? n0 : 1024)) != NCME_OK) break;
+        if ((st = space_rebuild_table(sp, 4 * (uint64_t)(n0 + 256))) != NCME_OK) break;
+        if (n0 == 0) break;
+        std::vector<uint64_t> ck((size_t)n0);
+        for (int64_t i = 0; i < n0; ++i) {
+            int rc = space_pack_host(sp, states0 + (size_t)i * ns, &ck[(size_t)i]);
+            if (rc < 0) {
+                st = rc;
+                break;
+            }
+            if (rc == 1) ck[(size_t)i] = EMPTY_KEY;  // negative component: silently dropped (:221)
+        }
+        if (st != NCME_OK) break;
+        if ((st = sp->cand_key.reserve((size_t)n0, ctx->stream, false)) != NCME_OK) break;
+        if (cudaMemcpyAsync(sp->cand_key.p, ck.data(), (size_t)n0 * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                            ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            set_error("upload of initial states failed");
+            st = NCME_ERR_CUDA;
+            break;
+        }
+        int64_t added = 0;
+        st = space_addstates(sp, n0, &added);
+    } while (0);
+    if (st != NCME_OK) {
+        ncme_space_destroy(sp);
+        return st;
+    }
+    *out = sp;
+    return NCME_OK;
+}
+
+int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int64_t n, const int64_t* states,
+                         const uint32_t* state_connectivity, const uint32_t* sink_connectivity, ncme_space** out) {
+    NCME_REQUIRE(n >= 0 && (n == 0 || (states && state_connectivity && sink_connectivity)), "bad arguments");
+    ncme_space* sp = nullptr;
+    NCME_TRY(space_alloc(ctx, ns, nr, stoich, &sp));
+    int st = NCME_OK;
+    do {
+        if ((st = space_reserve_rows(sp, n > 1024 ? n : 1024)) != NCME_OK) break;
+        std::vector<uint64_t> hk((size_t)n);
+        std::vector<uint32_t> hm((size_t)n, 0u), hp((size_t)n * nr);
+        for (int64_t i = 0; i < n && st == NCME_OK; ++i) {
+            int rc = space_pack_host(sp, states + (size_t)i * ns, &hk[(size_t)i]);
+            if (rc != 0) {
+                if (rc == 1) set_error("negative state component in imported state space");
+                st = rc < 0 ? rc : NCME_ERR_ARG;
+            }
+            for (int r = 0; r < nr; ++r) {
+                uint32_t c = state_connectivity[(size_t)i * nr + r];
+                if (c > (uint32_t)n) {
+                    set_error("state_connectivity entry out of range");
+                    st = NCME_ERR_ARG;
+                }
+                hp[(size_t)r * n + i] = c ? c - 1 : NONE32;
+                if (sink_connectivity[(size_t)i * nr + r]) hm[(size_t)i] |= 1u << r;
+            }
+        }
+        if (st != NCME_OK) break;
+        cudaStream_t s = ctx->stream;
+        bool ok = true;
+        if (n > 0) {
+            ok &= cudaMemcpyAsync(sp->keys.p, hk.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s) == cudaSuccess;
+            ok &= cudaMemcpyAsync(sp->sinkmask.p, hm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+            for (int r = 0; r < nr; ++r)
+                ok &= cudaMemcpyAsync(sp->pred.p + (size_t)r * sp->ld, hp.data() + (size_t)r * n, (size_t)n * 4,
+                                      cudaMemcpyHostToDevice, s) == cudaSuccess;
+            ok &= cudaStreamSynchronize(s) == cudaSuccess;
+        }
+        if (!ok) {
+            set_error("upload of imported state space failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = NCME_ERR_CUDA;
+            break;
+        }
+        sp->n = n;
+        st = space_rebuild_table(sp, 4 * (uint64_t)(n + 256));
+    } while (0);
+    if (st != NCME_OK) {
+        ncme_space_destroy(sp);
+        return st;
+    }
+    *out = sp;
+    return NCME_OK;
+}
+
+int ncme_space_destroy(ncme_space* sp) {
+    if (!sp) return NCME_OK;
+    if (sp->ctx) cudaStreamSynchronize(sp->ctx->stream);
+    sp->keys.release();
+    sp->pred.release();
+    sp->sinkmask.release();
+    sp->tkeys.release();
+    sp->tvals.release();
+    sp->cand_key.release();
+    sp->cand_slot.release();
+    sp->flags.release();
+    sp->pos.release();
+    sp->scan_scratch.release();
+    sp->frontier.release();
+    if (sp->err_flag) cudaFree(sp->err_flag);
+    delete sp;
+    return NCME_OK;
+}
+
+int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32_t* onlyreactions) {
+    NCME_REQUIRE(sp, "null space");
+    if (expansionlevel <= 0 || sp->n == 0) return NCME_OK;
+    ncme_ctx* ctx = sp->ctx;
+    int reacts[NCME_MAX_REACTIONS];
+    int nreact = 0;
+    uint32_t reactmask = 0;
+    if (nonly <= 0) {
+        for (int r = 0; r < sp->nr; ++r) reacts[nreact++] = r;
+    } else {
+        NCME_REQUIRE(onlyreactions && nonly <= NCME_MAX_REACTIONS, "bad onlyreactions");
+        for (int k = 0; k < nonly; ++k) {
+            NCME_REQUIRE(onlyreactions[k] >= 1 && onlyreactions[k] <= sp->nr, "onlyreactions entry out of range");
+            reacts[nreact++] = onlyreactions[k] - 1;
+        }
+    }
+    for (int k = 0; k < nreact; ++k) reactmask |= 1u << reacts[k];
+    int* reacts_dev = nullptr;
+    NCME_CUDA(cudaMalloc(&reacts_dev, sizeof(int) * NCME_MAX_REACTIONS));
+    int st = NCME_OK;
+    do {
+        if (cudaMemcpyAsync(reacts_dev, reacts, sizeof(int) * nreact, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            set_error("cudaMemcpyAsync failed");
+            st = NCME_ERR_CUDA;
+            break;
+        }
+        // explorables = states with a sink flag on one of the expansion reactions (:165-173)
+        cudaStream_t s = ctx->stream;
+        if ((st = sp->flags.reserve((size_t)sp->n, s, false)) != NCME_OK) break;
+        if ((st = sp->pos.reserve((size_t)sp->n, s, false)) != NCME_OK) break;
+        if ((st = sp->scan_scratch.reserve(scan_scratch_elems(sp->n), s, false)) != NCME_OK) break;
+        k_frontier_flags<<<nblk(sp->n), 256, 0, s>>>(sp->sinkmask.p, sp->n, reactmask, sp->flags.p);
+        ctx->launches++;
+        uint64_t F = 0;
+        if ((st = exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, sp->n, sp->scan_scratch.p, sp->scan_scratch.cap, &F)) != NCME_OK)
+            break;
+        if (F == 0) break;
+        if ((st = sp->frontier.reserve((size_t)F, s, false)) != NCME_OK) break;
+        k_compact_indices<<<nblk(sp->n), 256, 0, s>>>(sp->flags.p, sp->pos.p, sp->n, sp->frontier.p);
+        ctx->launches++;
+        const uint32_t* frontier = sp->frontier.p;
+        int64_t fbase = 0;
+        for (int level = 0; level < expansionlevel && F > 0; ++level) {
+            const int64_t ncand = (int64_t)F * nreact;
+            if ((st = sp->cand_key.reserve((size_t)ncand, s, false)) != NCME_OK) break;
+            k_gen_candidates<<<nblk(ncand), 256, 0, s>>>(sp->layout, sp->sdev, sp->keys.p, frontier, fbase, (int64_t)F,
+                                                         nreact, reacts_dev, sp->cand_key.p, sp->err_flag);
+            ctx->launches++;
+            int64_t added = 0;
+            const int64_t n_before = sp->n;
+            if ((st = space_addstates(sp, ncand, &added)) != NCME_OK) break;
+            frontier = nullptr;
+            fbase = n_before;
+            F = (uint64_t)added;
+        }
+        if (st != NCME_OK) break;
+        if (cudaGetLastError() != cudaSuccess) {
+            set_error("kernel launch failed in expand");
+            st = NCME_ERR_CUDA;
+            break;
+        }
+        st = check_overflow(sp);
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(reacts_dev);
+    return st;
+}
+
+int ncme_space_delete(ncme_space* sp, int64_t nids, const int64_t* ids) {
+    NCME_REQUIRE(sp && (nids == 0 || ids), "bad arguments");
+    if (nids <= 0 || sp->n == 0) return NCME_OK;
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t s = ctx->stream;
+    const int64_t n = sp->n;
+    std::vector<uint32_t> ids0((size_t)nids);
+    for (int64_t k = 0; k < nids; ++k) {
+        NCME_REQUIRE(ids[k] >= 1 && ids[k] <= n, "deleteat!: index %lld out of range 1..%lld", (long long)ids[k], (long long)n);
+        ids0[(size_t)k] = (uint32_t)(ids[k] - 1);
+    }
+    NCME_TRY(sp->flags.reserve((size_t)n, s, false));
+    NCME_TRY(sp->pos.reserve((size_t)n, s, false));
+    NCME_TRY(sp->scan_scratch.reserve(scan_scratch_elems(n), s, false));
+    NCME_TRY(sp->cand_slot.reserve((size_t)nids, s, false));
+    NCME_CUDA(cudaMemcpyAsync(sp->cand_slot.p, ids0.data(), (size_t)nids * 4, cudaMemcpyHostToDevice, s));
+    LAUNCH(ctx, k_fill_u32, n, sp->flags.p, n, 1u);
+    LAUNCH(ctx, k_clear_flags_at, nids, sp->cand_slot.p, nids, sp->flags.p);
+    uint64_t m = 0;
+    NCME_TRY(exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, n, sp->scan_scratch.p, sp->scan_scratch.cap, &m));
+    // compact into fresh arrays
+    DevArray<uint64_t> k2;
+    DevArray<uint32_t> p2, m2;
+    const int64_t ld2 = round_up<int64_t>((int64_t)m > 1024 ? (int64_t)m : 1024, 64);
+    NCME_TRY(k2.reserve((size_t)ld2, s, false));
+    NCME_TRY(m2.reserve((size_t)ld2, s, false));
+    NCME_TRY(p2.reserve((size_t)ld2 * sp->nr, s, false));
+    LAUNCH(ctx, k_compact_space, n, sp->flags.p, sp->pos.p, n, sp->keys.p, sp->pred.p, sp->ld, sp->sinkmask.p, sp->nr, k2.p,
+           p2.p, ld2, m2.p);
+    NCME_CUDA(cudaStreamSynchronize(s));
+    sp->keys.release();
+    sp->pred.release();
+    sp->sinkmask.release();
+    sp->keys = k2;
+    sp->pred = p2;
+    sp->sinkmask = m2;
+    sp->ld = ld2;
+    sp->n = (int64_t)m;
+    sp->version++;
+    if (sp->n == 0) {
+        NCME_CUDA(cudaMemsetAsync(sp->tkeys.p, 0xFF, sp->tcap * sizeof(uint64_t), s));
+        NCME_CUDA(cudaMemsetAsync(sp->tvals.p, 0xFF, sp->tcap * sizeof(uint32_t), s));
+        return NCME_OK;
+    }
+    NCME_TRY(space_rebuild_table(sp, 4 * (uint64_t)(sp->n + 256)));
+    LAUNCH(ctx, k_rederive_sinks, sp->n * sp->nr, sp->hview(), sp->layout, sp->sdev, sp->keys.p, sp->n, sp->sinkmask.p);
+    NCME_CUDA(cudaStreamSynchronize(s));
+    return NCME_OK;
+}
+
+int ncme_space_state_count(ncme_space* sp, int64_t* n) {
+    NCME_REQUIRE(sp && n, "null argument");
+    *n = sp->n;
+    return NCME_OK;
+}
+
+int ncme_space_sink_count(ncme_space* sp, int64_t* r) {
+    NCME_REQUIRE(sp && r, "null argument");
+    *r = sp->nr;
+    return NCME_OK;
+}
+
+int ncme_space_download_states(ncme_space* sp, int64_t first, int64_t count, int64_t* out) {
+    NCME_REQUIRE(sp && first >= 0 && count >= 0 && first + count <= sp->n && (count == 0 || out), "bad range");
+    if (count == 0) return NCME_OK;
+    std::vector<uint64_t> hk((size_t)count);
+    NCME_CUDA(cudaMemcpyAsync(hk.data(), sp->keys.p + first, (size_t)count * 8, cudaMemcpyDeviceToHost, sp->ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(sp->ctx->stream));
+    for (int64_t i = 0; i < count; ++i)
+        for (int s = 0; s < sp->ns; ++s)
+            out[(size_t)i * sp->ns + s] = (int64_t)((hk[(size_t)i] >> sp->layout.shift[s]) & sp->layout.mask[s]);
+    return NCME_OK;
+}
+
+int ncme_space_download_connectivity(ncme_space* sp, int64_t first, int64_t count, uint32_t* sc_out, uint32_t* kc_out) {
+    NCME_REQUIRE(sp && first >= 0 && count >= 0 && first + count <= sp->n, "bad range");
+    if (count == 0) return NCME_OK;
+    cudaStream_t s = sp->ctx->stream;
+    const int nr = sp->nr;
+    std::vector<uint32_t> hp((size_t)count * nr), hm((size_t)count);
+    for (int r = 0; r < nr; ++r)
+        NCME_CUDA(cudaMemcpyAsync(hp.data() + (size_t)r * count, sp->pred.p + (size_t)r * sp->ld + first, (size_t)count * 4,
+                                  cudaMemcpyDeviceToHost, s));
+    NCME_CUDA(cudaMemcpyAsync(hm.data(), sp->sinkmask.p + first, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
+    NCME_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < count; ++i)
+        for (int r = 0; r < nr; ++r) {
+            uint32_t p = hp[(size_t)r * count + i];
+            if (sc_out) sc_out[(size_t)i * nr + r] = (p == NONE32) ? 0u : p + 1u;
+            if (kc_out) kc_out[(size_t)i * nr + r] = (hm[(size_t)i] >> r & 1u) ? (uint32_t)(r + 1) : 0u;
+        }
+    return NCME_OK;
+}
+
+int ncme_space_lookup(ncme_space* sp, int64_t m, const int64_t* states, uint32_t* idx_out) {
+    NCME_REQUIRE(sp && m >= 0 && (m == 0 || (states && idx_out)), "bad arguments");
+    if (m == 0) return NCME_OK;
+    ncme_ctx* ctx = sp->ctx;
+    std::vector<uint64_t> q((size_t)m);
+    for (int64_t i = 0; i < m; ++i) {
+        uint64_t k = EMPTY_KEY;
+        bool fits = true;
+        for (int s = 0; s < sp->ns; ++s) {
+            int64_t v = states[(size_t)i * sp->ns + s];
+            if (v < 0 || (uint64_t)v > sp->layout.mask[s]) fits = false;
+        }
+        if (fits) space_pack_host(sp, states + (size_t)i * sp->ns, &k);
+        q[(size_t)i] = k;
+    }
+    NCME_TRY(sp->cand_key.reserve((size_t)m, ctx->stream, false));
+    NCME_TRY(sp->cand_slot.reserve((size_t)m, ctx->stream, false));
+    NCME_CUDA(cudaMemcpyAsync(sp->cand_key.p, q.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_lookup, m, sp->hview(), sp->cand_key.p, m, sp->cand_slot.p);
+    NCME_CUDA(cudaMemcpyAsync(idx_out, sp->cand_slot.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NCME_OK;
+}
+
+}  // extern "C"

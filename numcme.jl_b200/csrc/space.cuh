@@ -1,0 +1,85 @@
+// Device-resident StateSpaceSparse (reference: src/statespace/sparse/sparsestatespace.jl:22-40).
+#pragma once
+#include "common.cuh"
+
+namespace ncme {
+
+// How a state (NS non-negative integers) is packed into one 64-bit hash key.
+struct KeyLayout {
+    int ns;
+    int shift[NCME_MAX_SPECIES];
+    uint64_t mask[NCME_MAX_SPECIES];
+};
+
+// Net stoichiometry, reaction-major, small integers.
+struct StoichDev {
+    int nr;
+    int ns;
+    int16_t s[NCME_MAX_REACTIONS][NCME_MAX_SPECIES];
+};
+
+__host__ __device__ inline uint64_t hash64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+struct HashView {
+    uint64_t* keys;
+    uint32_t* vals;
+    uint64_t capmask;  // capacity - 1 (capacity is a power of two)
+};
+
+__device__ inline uint32_t hash_lookup(const HashView& h, uint64_t key) {
+    uint64_t slot = hash64(key) & h.capmask;
+    while (true) {
+        uint64_t kk = h.keys[slot];
+        if (kk == key) return h.vals[slot];
+        if (kk == EMPTY_KEY) return NONE32;
+        slot = (slot + 1) & h.capmask;
+    }
+}
+
+}  // namespace ncme
+
+struct ncme_space {
+    ncme_ctx* ctx = nullptr;
+    int ns = 0, nr = 0;
+    std::vector<int64_t> stoich;  // reaction-major: stoich[r*ns + s]  (== Julia column-major Matrix)
+    ncme::KeyLayout layout{};
+    ncme::StoichDev sdev{};
+    int64_t n = 0;    // number of states
+    int64_t ld = 0;   // row stride of the slot-major pred table (capacity)
+    uint64_t version = 0;  // bumped by every mutation
+
+    ncme::DevArray<uint64_t> keys;      // [ld]      packed state of index i (insertion order)
+    ncme::DevArray<uint32_t> pred;      // [nr][ld]  pred[r][i] = j with x_i = x_j + s_r, NONE32 if absent
+    ncme::DevArray<uint32_t> sinkmask;  // [ld]      bit r set <=> x_i + s_r >= 0 and not in the space
+
+    ncme::DevArray<uint64_t> tkeys;     // open-addressing table
+    ncme::DevArray<uint32_t> tvals;
+    uint64_t tcap = 0;
+
+    // scratch for expansion / deletion
+    ncme::DevArray<uint64_t> cand_key;
+    ncme::DevArray<uint32_t> cand_slot;
+    ncme::DevArray<uint32_t> flags;
+    ncme::DevArray<uint32_t> pos;
+    ncme::DevArray<uint32_t> scan_scratch;
+    ncme::DevArray<uint32_t> frontier;
+    int* err_flag = nullptr;  // device int: key-width overflow seen
+
+    ncme::HashView hview() const { return ncme::HashView{tkeys.p, tvals.p, tcap - 1}; }
+};
+
+namespace ncme {
+// Append candidate states (packed keys in cand_key[0..ncand), EMPTY_KEY = invalid) in candidate
+// order, first occurrence wins; updates connectivity.  Returns number added through *added.
+int space_addstates(ncme_space* sp, int64_t ncand, int64_t* added);
+int space_reserve_rows(ncme_space* sp, int64_t nrows);
+int space_rebuild_table(ncme_space* sp, uint64_t min_slots);
+int space_pack_host(const ncme_space* sp, const int64_t* state, uint64_t* key_out);  // 0 ok, 1 negative, <0 error
+}  // namespace ncme

@@ -1,0 +1,163 @@
+"""FspMatrixSparse behind the reference's API; all arithmetic is the fused CUDA matvec of libncme.
+
+Reference: src/fspmatrix/sparse/fspsparsematrix.jl -- constructor :47-108, ``matvec!`` :196-217,
+``matvecadd!`` :226-247, ``matvec`` :254-258, ``*`` :262-264, ``size`` :174-186, getters :29-37.
+Julia's ``matvec!`` / ``matvecadd!`` are ``matvec_`` / ``matvecadd_`` here.
+
+Vectors may be numpy arrays (host path: H2D + kernel + D2H inside the call, what a Julia
+``Vector{Float64}`` binding does) or device-resident (``DeviceVector`` / torch CUDA float64 tensor:
+kernel only, asynchronous on the context's stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .cmemodel import JOINT_TV, SEPARABLE_TV, Propensity, eval_over_states
+from .device import DeviceVector, device_ptr, is_device, vec_len
+from .statespace import StateSpaceSparse
+
+
+class FspMatrixSparse:
+    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=()):
+        self.ctx = space.ctx
+        self.parameters = parameters
+        self.propensities = list(propensity_functions)
+        if len(self.propensities) != space.nr:
+            raise L.ArgumentError("one propensity per reaction is required")
+        for a in self.propensities:
+            if not isinstance(a, Propensity):
+                raise L.ArgumentError("propensities must be Propensity instances (see propensity())")
+        self.states = space.get_states()          # host copy, like `deepcopy(space.states)` (:97)
+        n = self.states.shape[0]
+        self.n = n
+        self.nr = space.nr
+        self.rowcount = self.colcount = n + space.get_sink_count()
+        self.kinds = np.array([a.kind_code for a in self.propensities], dtype=np.int32)
+        self.timeinvariant_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "ti"]
+        self.separabletv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "sep"]
+        self.jointtv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "joint"]
+        propvals = np.zeros((self.nr, max(n, 1)), dtype=np.float64)
+        for r, a in enumerate(self.propensities):
+            if a.kind == "ti":
+                propvals[r, :n] = eval_over_states(a.f, self.states, parameters)
+            elif a.kind == "sep":
+                propvals[r, :n] = eval_over_states(a.statefactor, self.states, parameters)
+        propvals = np.ascontiguousarray(propvals[:, :n]) if n else propvals
+        h = L.p_void()
+        L.check(L.load().ncme_matrix_create(space.handle, L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double),
+                                            C.byref(h)))
+        self._h = h
+        self.t_cache = -np.inf
+        self._coef = np.ones(self.nr, dtype=np.float64)
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- accessors (fspsparsematrix.jl:29-37)
+    def size(self, dim=None):
+        if dim is None:
+            return (self.rowcount, self.colcount)
+        if dim not in (1, 2):
+            raise L.ArgumentError("Second argument must be either 1 or 2.")
+        return self.rowcount if dim == 1 else self.colcount
+
+    def stats(self) -> dict:
+        nt = C.c_int()
+        nnz = (C.c_int64 * 40)()
+        ab = C.c_int64()
+        db = C.c_int64()
+        L.check(L.load().ncme_matrix_stats(self._h, C.byref(nt), nnz, C.byref(ab), C.byref(db)))
+        return {"nterms": nt.value, "nnz_per_term": [nnz[k] for k in range(nt.value)],
+                "algorithmic_bytes": ab.value, "device_bytes": db.value}
+
+    def set_tuning(self, rows_per_thread: int):
+        L.check(L.load().ncme_matrix_set_tuning(self._h, int(rows_per_thread)))
+
+    # -- time-dependent pieces evaluated on the host (they are opaque closures, as in the reference)
+    def coefficients(self, t: float) -> np.ndarray:
+        th = self.parameters
+        for r in self.separabletv_propensity_ids:
+            self._coef[r - 1] = float(self.propensities[r - 1].tfactor(t, th))
+        return self._coef
+
+    def _refresh_joint(self, t: float):
+        if t == self.t_cache:
+            return
+        self.t_cache = t
+        for r in self.jointtv_propensity_ids:
+            vals = eval_over_states(self.propensities[r - 1].f, self.states, self.parameters, t=t)
+            L.check(L.load().ncme_matrix_set_joint_values(self._h, r, L.ptr(vals, C.c_double)))
+
+    def _apply(self, out, t, v, beta: float):
+        N = self.rowcount
+        if vec_len(out) != N or vec_len(v) != N:
+            raise L.ArgumentError(f"DimensionMismatch: matrix is {N}x{N}, got vectors of length {vec_len(v)} and {vec_len(out)}")
+        coef = self.coefficients(float(t))
+        self._refresh_joint(float(t))
+        lib = L.load()
+        if is_device(out) and is_device(v):
+            L.check(lib.ncme_matvec(self._h, L.ptr(coef, C.c_double), C.c_void_p(device_ptr(v)), C.c_void_p(device_ptr(out)),
+                                    beta))
+            return
+        if isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous:
+            vv = np.ascontiguousarray(v, dtype=np.float64)
+            L.check(lib.ncme_matvec_host(self._h, L.ptr(coef, C.c_double), vv.ctypes.data_as(C.c_void_p),
+                                         out.ctypes.data_as(C.c_void_p), beta))
+            return
+        raise L.ArgumentError("out/v must both be device vectors or `out` a contiguous float64 numpy array")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().ncme_matrix_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.close()
+        except Exception:
+            pass
+
+    def __matmul__(self, v):
+        return matvec(0.0, self, v)
+
+    def __mul__(self, v):
+        return matvec(0.0, self, v)
+
+
+def matvec_(out, t, A, v):
+    """matvec!(out, t, A, v):  out = A(t) v   (A: FspMatrixSparse or ForwardSensFspMatrixSparse)"""
+    if not isinstance(A, FspMatrixSparse):
+        return A.matvec_(out, t, v)
+    A._apply(out, t, v, 0.0)
+
+
+def matvecadd_(out, t, A: FspMatrixSparse, v):
+    """matvecadd!(out, t, A, v):  out = out + A(t) v"""
+    A._apply(out, t, v, 1.0)
+
+
+def matvec(t, A: FspMatrixSparse, v):
+    """w = matvec(t, A, v)"""
+    if is_device(v):
+        w = DeviceVector(A.ctx, vec_len(v))
+    else:
+        w = np.empty(vec_len(v), dtype=np.float64)
+    matvec_(w, t, A, v)
+    return w
+
+
+def get_rowcount(A):
+    return A.rowcount
+
+
+def get_colcount(A):
+    return A.colcount
+
+
+def get_propensities_of(A):
+    return A.propensities

@@ -1,0 +1,108 @@
+"""ForwardSensFspMatrixSparse behind the reference's API (fused CUDA block matvec, K2).
+
+Reference: src/forwardsensfspmatrix/forwardsensfspmatrixsparse/sensfspmatrixsparse.jl
+(constructor :31-95, ``matvec!`` :97-142).  Vector layout ``[p; s_1; ...; s_P]``, each block of
+length N = n + R, exactly as the reference.
+
+Divergence (no reference test covers it): for joint time-varying reactions the
+derivative matrix is filled with d f / d theta (the mathematically correct value); the reference
+fills it with f itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .cmemodel import (CmeModelWithSensitivity, eval_over_states, get_parameters, get_propensities,
+                       get_propensity_gradients, get_gradient_sparsity_patterns)
+from .device import DeviceVector, device_ptr, is_device, vec_len
+from .fspmatrix import FspMatrixSparse
+from .statespace import StateSpaceSparse
+
+
+class ForwardSensFspMatrixSparse:
+    def __init__(self, model: CmeModelWithSensitivity, space: StateSpaceSparse):
+        self.fspmatrix = A = FspMatrixSparse(space, get_propensities(model), parameters=get_parameters(model))
+        self.ctx = A.ctx
+        self.parameters = get_parameters(model)
+        self.parameter_count = P = len(self.parameters)
+        self.propensity_gradients = get_propensity_gradients(model)
+        pattern = get_gradient_sparsity_patterns(model)
+        # entries in the reference's order: parameter-major, reactions ascending (nzrange over CSC columns)
+        ents = [(r, ip) for ip in range(P) for r in range(A.nr) if pattern[r, ip]]
+        self.entries = ents
+        n = A.n
+        dvals = np.zeros((max(len(ents), 1), max(n, 1)), dtype=np.float64)
+        for e, (r, ip) in enumerate(ents):
+            g = self.propensity_gradients[r]
+            kind = A.propensities[r].kind
+            if kind == "ti":
+                dvals[e, :n] = eval_over_states(g.pardiffs[ip], A.states, self.parameters)
+            elif kind == "sep":
+                dvals[e, :n] = eval_over_states(g.statefactor_pardiffs[ip], A.states, self.parameters)
+        dvals = np.ascontiguousarray(dvals[:, :n]) if n else dvals
+        er = np.array([r + 1 for r, _ in ents], dtype=np.int32)
+        ep = np.array([ip + 1 for _, ip in ents], dtype=np.int32)
+        h = L.p_void()
+        L.check(L.load().ncme_sensmatrix_create(A.handle, P, len(ents), L.ptr(er, C.c_int32) if ents else None,
+                                                L.ptr(ep, C.c_int32) if ents else None,
+                                                L.ptr(dvals, C.c_double), C.byref(h)))
+        self._h = h
+        self._dcoef = np.zeros(max(len(ents), 1), dtype=np.float64)
+        self._joint_entries = [e for e, (r, _) in enumerate(ents) if A.propensities[r].kind == "joint"]
+        self._stage = None
+
+    def _prepare(self, t: float):
+        A = self.fspmatrix
+        th = self.parameters
+        coef = A.coefficients(t)
+        A._refresh_joint(t)
+        for e, (r, ip) in enumerate(self.entries):
+            if A.propensities[r].kind == "sep":
+                self._dcoef[e] = float(self.propensity_gradients[r].tfactor_pardiffs[ip](t, th))
+        for e in self._joint_entries:                 # re-evaluated every call, like the reference (:137)
+            r, ip = self.entries[e]
+            vals = eval_over_states(self.propensity_gradients[r].pardiffs[ip], A.states, th, t=t)
+            L.check(L.load().ncme_sensmatrix_set_joint_values(self._h, e, L.ptr(vals, C.c_double)))
+        return coef
+
+    def matvec_(self, out, t, vs):
+        A = self.fspmatrix
+        total = A.rowcount * (self.parameter_count + 1)
+        if vec_len(out) != total or vec_len(vs) != total:
+            raise L.ArgumentError(f"DimensionMismatch: expected vectors of length {total}")
+        coef = self._prepare(float(t))
+        lib = L.load()
+        if is_device(out) and is_device(vs):
+            L.check(lib.ncme_sens_matvec(self._h, L.ptr(coef, C.c_double), L.ptr(self._dcoef, C.c_double),
+                                         C.c_void_p(device_ptr(vs)), C.c_void_p(device_ptr(out))))
+            return
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
+            raise L.ArgumentError("out must be a contiguous float64 numpy array or a device vector")
+        if self._stage is None or self._stage[0].n != total:
+            self._stage = (DeviceVector(self.ctx, total), DeviceVector(self.ctx, total))
+        dx, dy = self._stage
+        dx.upload(np.ascontiguousarray(vs, dtype=np.float64))
+        L.check(lib.ncme_sens_matvec(self._h, L.ptr(coef, C.c_double), L.ptr(self._dcoef, C.c_double),
+                                     C.c_void_p(dx.ptr), C.c_void_p(dy.ptr)))
+        out[:] = dy.to_host()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().ncme_sensmatrix_destroy(self._h)
+            self._h = None
+        self.fspmatrix.close()
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.close()
+        except Exception:
+            pass
+
+
+def sens_matvec_(out, t, SA: ForwardSensFspMatrixSparse, vs):
+    """matvec!(out, t, SA::ForwardSensFspMatrixSparse, vs)"""
+    SA.matvec_(out, t, vs)

@@ -1,0 +1,96 @@
+"""GPU parity: fused sensitivity block matvec (K2) vs the oracle pinned on test/sensmat/telegraph.jl."""
+import math
+
+import numpy as np
+import pytest
+
+from fixtures import FSPMAT_THETA, SENS_THETA, TELEGRAPH_S, fspmat_propensities, sens_telegraph
+from oracle.fspmatrix import OProp
+from oracle.sensmatrix import OGrad, SensFspMatrixOracle
+from oracle.statespace import StateSpaceOracle, StateSpaceOracleFast
+from test_gpu_matvec import _relerr, _to_pkg_props
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_pkg_grads(pkg, props, grads):
+    out = []
+    for a, g in zip(props, grads):
+        if g.kind == "ti":
+            out.append(pkg.propensitygrad(g.pardiffs))
+        elif g.kind == "sep":
+            out.append(pkg.propensitygrad_timevarying(a.tfactor, a.statefactor, g.tfactor_pardiffs, g.statefactor_pardiffs))
+        else:
+            out.append(pkg.propensitygrad_timevarying(g.pardiffs))
+    return out
+
+
+def _sensmodel(pkg, S, props, grads, pattern, theta):
+    return pkg.CmeModelWithSensitivity(pkg.CmeModel(S, _to_pkg_props(pkg, props), theta), pattern,
+                                       _to_pkg_grads(pkg, props, grads))
+
+
+@pytest.mark.parametrize("t", [10.0, 20.0, 30.0, 100.0])
+def test_sens_telegraph(pkg, ctx, t):  # test/sensmat/telegraph.jl:190-217
+    props, grads, pattern, states = sens_telegraph()
+    model = _sensmodel(pkg, TELEGRAPH_S, props, grads, pattern, SENS_THETA)
+    sp = pkg.StateSpaceSparse(TELEGRAPH_S, states)
+    SA = pkg.ForwardSensFspMatrixSparse(model, sp)
+    OS = SensFspMatrixOracle(StateSpaceOracleFast(TELEGRAPH_S, states), props, grads, pattern, SENS_THETA)
+    n = SA.fspmatrix.rowcount
+    v = np.ones(6 * n)
+    v /= v.sum()
+    out = np.empty_like(v)
+    pkg.matvec_(out, t, SA, v)
+    ref = OS.matvec(t, v)
+    assert np.abs(out - ref).max() <= n * np.finfo(float).eps          # the reference test's own tolerance
+    rng = np.random.default_rng(7)
+    v = rng.random(6 * n)
+    dv, do = pkg.DeviceVector.from_host(ctx, v), pkg.DeviceVector(ctx, 6 * n)
+    pkg.matvec_(do, t, SA, dv)
+    assert _relerr(do.to_host(), OS.matvec(t, v)) <= 1e-12
+    ones = np.ones(6 * n)
+    pkg.matvec_(out, t, SA, ones)
+    assert abs(out.sum() / ones.sum()) <= n * 6 * np.finfo(float).eps  # telegraph.jl:34-43
+
+
+def test_sens_poisson(pkg):  # test/sensmat/poisson.jl
+    S = np.array([[1], [-1]]).T
+    props = [OProp("ti", f=lambda x, p: p[0] + 0.0 * x[0]), OProp("ti", f=lambda x, p: p[1] + 0.0 * x[0])]
+    one = lambda x, p: 1.0 + 0.0 * x[0]
+    zero = lambda x, p: 0.0 * x[0]
+    grads = [OGrad("ti", pardiffs=[one, zero]), OGrad("ti", pardiffs=[zero, one])]
+    states = [[i] for i in range(1, 101)]
+    model = _sensmodel(pkg, S, props, grads, np.eye(2, dtype=bool), [10.0, 5.0])
+    SA = pkg.ForwardSensFspMatrixSparse(model, pkg.StateSpaceSparse(S, states))
+    OS = SensFspMatrixOracle(StateSpaceOracleFast(S, states), props, grads, np.eye(2, dtype=bool), [10.0, 5.0])
+    v = np.ones(3 * SA.fspmatrix.rowcount)
+    out = np.empty_like(v)
+    pkg.matvec_(out, 0.0, SA, v)
+    assert out.sum() == pytest.approx(0.0, abs=1e-9)
+    assert _relerr(out, OS.matvec(0.0, v)) <= 1e-12
+
+
+def test_sens_joint(pkg):
+    f = lambda t, x, p: (1.0 + 0.5 * math.sin(t)) * p[1] * x[1]
+    df = lambda t, x, p: (1.0 + 0.5 * math.sin(t)) * x[1]
+    zero3 = lambda t, x, p: 0.0 * x[0]
+    zero = lambda x, p: 0.0 * x[0]
+    props = fspmat_propensities("ti")
+    props[1] = OProp("joint", f=f)
+    grads = [OGrad("ti", pardiffs=[lambda x, p: 1.0 * x[0], zero, zero, zero]),
+             OGrad("joint", pardiffs=[zero3, df, zero3, zero3]),
+             OGrad("ti", pardiffs=[zero, zero, lambda x, p: 1.0 * x[1], zero]),
+             OGrad("ti", pardiffs=[zero, zero, zero, lambda x, p: 1.0 * x[2]])]
+    osp = StateSpaceOracle(TELEGRAPH_S, [1, 0, 0])
+    osp.expand(6)
+    OS = SensFspMatrixOracle(osp, props, grads, np.eye(4, dtype=bool), FSPMAT_THETA)
+    sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])
+    sp.expand_(6)
+    SA = pkg.ForwardSensFspMatrixSparse(_sensmodel(pkg, TELEGRAPH_S, props, grads, np.eye(4, dtype=bool), FSPMAT_THETA), sp)
+    rng = np.random.default_rng(3)
+    v = rng.random(5 * SA.fspmatrix.rowcount)
+    out = np.empty_like(v)
+    for t in (0.3, 1.7):
+        pkg.matvec_(out, t, SA, v)
+        assert _relerr(out, OS.matvec(t, v)) <= 1e-12
