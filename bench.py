@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- FSP matvec throughput on the M-3D workload (BASELINE.json config 5).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--levels L]
+
+A "step" is one fused FSP matvec y = A(t) x over the whole state space (n = 10 039 316 states,
+R = 6, time-varying variant: 1 041 MB algorithmic bytes per step, far larger than the 126 MB L2).
+`value` = algorithmic GB/s with x, y and A resident in HBM; `e2e` = the same metric through the
+host-buffer C-ABI entry point (pinned host x -> H2D -> kernel -> D2H y inside the timed region).
+At N > 1 (torchrun) every rank runs the same workload on its own GPU (weak scaling, replicas).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fsp_matvec_hbm_gbs"
+UNIT = "GB/s"
+CPU_SAMPLE_LEVELS = 180          # M-3D at L=180: 1 004 731 states (~104 MB) -- bounded CPU sample
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(levels, steps, warmup, time_varying=True):
+    """The reference's CPU matvec (serial CSC passes, one per term) restated in C (oracle/cpu_matvec.c),
+    on a bounded sample of the workload.  Returns (GB/s, info dict)."""
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from oracle import cbaseline
+    from oracle.fspmatrix import FspMatrixOracle
+    from oracle.statespace import StateSpaceOracleFast
+
+    model = pkg.workloads.m3d_model(time_varying=time_varying)
+    osp = StateSpaceOracleFast(model.stoich_matrix, [0, 0, 0])
+    osp.expand(levels)
+    OA = FspMatrixOracle(osp, model.propensities, model.parameters)
+    terms = cbaseline.CscTerms(OA.terms_at(2.5))
+    nbytes = OA.algorithmic_bytes()
+    rng = np.random.default_rng(0)
+    v = rng.random(OA.rowcount)
+    v /= v.sum()
+    out = np.empty_like(v)
+    for _ in range(warmup):
+        terms.matvec(v, out)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        terms.matvec(v, out)
+    dt = (time.perf_counter() - t0) / steps
+    info = {"kind": "port", "cores": 1, "unit": UNIT, "value": nbytes / dt / 1e9,
+            "sample": f"M-3D TV at L={levels} (n={osp.get_state_count()}, {nbytes/1e6:.1f} MB algorithmic bytes per matvec), "
+                      f"{steps} serial CSC matvecs (one pass per term, Int64 indices) = SparseArrays.mul! restated in C; "
+                      f"{dt*1e3:.2f} ms per matvec; host has {os.cpu_count()} cores, the reference path uses 1"}
+    return nbytes / dt / 1e9, dt, info, (OA, v, out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--levels", type=int, default=None, help="expansion depth of the M-3D simplex (default 390)")
+    ap.add_argument("--rows", type=int, default=0, help="matvec kernel variant: rows per thread (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    levels = args.levels or pkg.workloads.M3D_LEVELS
+    config = {"workload": f"M-3D three-species birth-death FSP, time-varying variant, simplex L={levels}",
+              "levels": levels, "reactions": 6, "l2_policy": "inputs (matrix ~1 GB) larger than the 126 MB L2",
+              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak scaling)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        gbs, dt, info, _ = cpu_reference_arm(CPU_SAMPLE_LEVELS, max(1, min(K, 40)), min(W, 3))
+        line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": max(1, min(K, 40)), "warmup": min(W, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": info,
+                "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    ctx = pkg.Context(local_rank)
+    ctx.use_torch_stream()
+
+    # ---- build the workload through the product path: GPU expand, host propensities, GPU assembly
+    model = pkg.workloads.m3d_model(time_varying=True)
+    t_build = time.perf_counter()
+    space = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0, 0], ctx=ctx)
+    space.expand_(levels)
+    t_expand = time.perf_counter() - t_build
+    A = pkg.FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+    t_assemble = time.perf_counter() - t_build - t_expand
+    if args.rows:
+        A.set_tuning(args.rows)
+    st = A.stats()
+    nbytes = st["algorithmic_bytes"]
+    N = A.size(1)
+    n = space.get_state_count()
+    config.update({"states": n, "algorithmic_bytes_per_step": nbytes, "nnz_per_term": st["nnz_per_term"],
+                   "expand_s": round(t_expand, 3), "assemble_s": round(t_assemble, 3)})
+    rng = np.random.default_rng(0)
+    xh = rng.random(N)
+    xh /= xh.sum()
+    x = pkg.DeviceVector.from_host(ctx, xh)
+    y = pkg.DeviceVector(ctx, N)
+    tt = 2.5
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(W):
+        pkg.matvec_(y, tt, A, x)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pkg.matvec_(y, tt, A, x)
+    e1.record()
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1) / K
+    clocks = sampler.stop()
+
+    # ---- end to end through host buffers (pinned), H2D + kernel + D2H per step
+    xp = torch.empty(N, dtype=torch.float64).pin_memory()
+    yp = torch.empty(N, dtype=torch.float64).pin_memory()
+    xp.numpy()[:] = xh
+    Ke = max(3, min(K, 20))
+    for _ in range(3):
+        pkg.matvec_(yp.numpy(), tt, A, xp.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(Ke):
+        pkg.matvec_(yp.numpy(), tt, A, xp.numpy())
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / Ke
+    wall_e2e = (time.perf_counter() - t0) / Ke * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)
+    checksum = float(yp.numpy().sum())
+
+    if world > 1:
+        tms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tms[0]), float(tms[1])
+
+    value = world * nbytes / (ms * 1e-3) / 1e9
+    e2e_value = world * nbytes / (ms_e2e * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    per_gpu = nbytes / (ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
+                    "ms_per_step": ms_e2e, "checksum_sum_y": checksum},
+            "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": UNIT, "frac": per_gpu / peak,
+                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu / 8000.0,
+                         "kernel": "k_fsp_matvec", "launch_us": ms * 1e3 / max(launches / K, 1)}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            line["roofline"]["traffic"] = json.load(open(tr)).get("k_fsp_matvec_dram_bytes_per_launch")
+        except Exception:
+            pass
+    if rank == 0 and world == 1 and not args.no_cpu:
+        gbs, dt, info, (OA, v, out) = cpu_reference_arm(CPU_SAMPLE_LEVELS, 20, 2)
+        line["cpu_baseline"] = info
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

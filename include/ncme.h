@@ -59,7 +59,9 @@ const char* ncme_last_error(void);
 /* ---------------------------------------------------------------- context / memory ----------- */
 int ncme_ctx_create(int device, ncme_ctx** out);
 int ncme_ctx_destroy(ncme_ctx* ctx);
-/* Adopt an external cudaStream_t (e.g. torch's current stream); NULL restores the context's own. */
+/* Adopt an external cudaStream_t (e.g. torch's current stream); NULL restores the context's own.
+ * The legacy default stream has handle 0, so pass NCME_STREAM_LEGACY ((void*)1 == cudaStreamLegacy) for it. */
+#define NCME_STREAM_LEGACY ((void*)0x1)
 int ncme_ctx_set_stream(ncme_ctx* ctx, void* cuda_stream);
 int ncme_ctx_sync(ncme_ctx* ctx);
 /* info[0]=SM count, [1]=L2 bytes, [2]=total global memory bytes, [3]=compute capability*10 */

@@ -42,7 +42,8 @@ class Context:
 
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         self._torch_stream = s
-        L.check(L.load().ncme_ctx_set_stream(self._h, C.c_void_p(s.cuda_stream)))
+        # torch's legacy default stream has handle 0 (== "restore own stream" in the ABI): use cudaStreamLegacy
+        L.check(L.load().ncme_ctx_set_stream(self._h, C.c_void_p(s.cuda_stream or 1)))
 
     def sync(self):
         L.check(L.load().ncme_ctx_sync(self._h))
