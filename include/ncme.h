@@ -172,6 +172,56 @@ int ncme_vec_wrms(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* u
                   double atol, double rtol, double* out);
 int ncme_vec_any_nonfinite(ncme_ctx* ctx, int64_t n, const double* x_dev, int* out);
 
+/* ---------------------------------------------------------------- prune (adapt!) --------------- */
+/* The dropstates branch of adapt!           src/transientcme/sparse/rstepadapters.jl:40-46 (RStepAdapter, strict=0:
+ * `>=`) and :93-99 (SelectiveRStepAdapter, strict=1: `>`):
+ *   pids = sortperm(p); dropcount = #{k : sum(p) - cumsum(p[pids])_k >= threshold}; deleteat!(space, sort(pids[1:dropcount]))
+ * computed on the device (key-index bitonic sort, scan, count) followed by the deletion of those states.
+ * p_dev: device, n doubles.  The compaction map of this deletion stays valid until the next mutation of the space and
+ * is applied to vectors with ncme_space_compact_vector (deleteat!(p, dropids), :45). */
+int ncme_space_prune_by_mass(ncme_space* space, const double* p_dev, double threshold, int strict, int64_t* dropcount);
+/* out_dev[newidx(i)] = in_dev[i] for every state i kept by the last ncme_space_delete / ncme_space_prune_by_mass;
+ * in_dev has the old length, out_dev the new one.  They must not alias. */
+int ncme_space_compact_vector(ncme_space* space, const double* in_dev, double* out_dev);
+
+/* ---------------------------------------------------------------- native integrator ------------ */
+/* Device-resident replacement for `DE.init(ODEProblem(fsprhs!, u, (t0,t1), theta), CVODE_BDF(...); callback, saveat)`
+ * + `DE.step!(integrator, t1 - t0, true)`      src/transientcme/sparse/fspsolve.jl:145-161
+ * selected from the host by `ode_method = nothing`.  u stays in HBM; per step only the error norm and the
+ * R sink entries of the stage vectors cross PCIe.
+ *
+ * coef_fn(t, coef, user) : host callback filling coef[r] = tfactor_r(t, theta) for separable reactions (and, for
+ *                          joint reactions, calling ncme_matrix_set_joint_values); may be NULL for time-invariant A.
+ * save_fn(t, u_host, user): called with a pinned host copy of the N-vector at every requested output time.
+ * Event (fspsolve.jl:145-156): integration stops at the first t where sum(u[n+1..n+R]) - event_slope * t crosses
+ * zero from below (event_slope = fsptol / tend), located on the dense output of the sink entries only. */
+typedef void (*ncme_coef_fn)(double t, double* coef, void* user);
+typedef void (*ncme_save_fn)(double t, const double* u_host, void* user);
+
+typedef struct ncme_solve_opts {
+    double rtol;          /* odertol */
+    double atol;          /* odeatol */
+    double event_slope;   /* fsptol / tend */
+    int check_event;      /* 0: ignore the sinks (fixed-space solve, fspsolve.jl:10-41) */
+    int save_every_step;  /* saveat = []: every accepted step (and t0) is handed to save_fn */
+    int nsave;            /* saveat times (ascending); those inside [t0, t_final] are produced by dense output */
+    const double* save_t;
+    double h_init;        /* 0 = automatic */
+    int64_t max_steps;    /* 0 = 10^8 */
+    int method;           /* 0 = Dormand-Prince 5(4) explicit; 1 = BDF/GMRES (see ncme_solve_segment docs) */
+} ncme_solve_opts;
+
+typedef struct ncme_solve_stats {
+    double t_final;
+    double h_last;
+    int event_hit;
+    int nsaved;
+    int64_t steps, rejected, rhs_evals, launches;
+} ncme_solve_stats;
+
+int ncme_solve_segment(ncme_matrix* mat, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
+                       double* u_dev, const ncme_solve_opts* opts, ncme_solve_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,4 +14,6 @@ from .statespace import (StateSpaceSparse, expand_, deleteat_, get_state_count, 
                          get_statedict, get_state_connectivity, get_sink_connectivity)
 from .fspmatrix import FspMatrixSparse, matvec_, matvecadd_, matvec, get_rowcount, get_colcount
 from .sensmatrix import ForwardSensFspMatrixSparse, sens_matvec_
+from .fspvector import FspVectorSparse, FspOutputSparse, FspOutputSliceSparse
+from .transientcme import (solve, AdaptiveFspSparse, RStepAdapter, SelectiveRStepAdapter, NativeRK45, init_, adapt_)
 from . import workloads

@@ -69,6 +69,9 @@ SIGNATURES = {
     "ncme_sensmatrix_destroy": (cint, [p_void]),
     "ncme_sensmatrix_set_joint_values": (cint, [p_void, cint, p_f64]),
     "ncme_sens_matvec": (cint, [p_void, p_f64, p_f64, p_void, p_void]),
+    "ncme_space_prune_by_mass": (cint, [p_void, p_void, f64, cint, p_i64]),
+    "ncme_space_compact_vector": (cint, [p_void, p_void, p_void]),
+    "ncme_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),
     "ncme_vec_fill": (cint, [p_void, i64, f64, p_void]),
     "ncme_vec_copy": (cint, [p_void, i64, p_void, p_void]),
     "ncme_vec_scale": (cint, [p_void, i64, f64, p_void]),
@@ -79,6 +82,21 @@ SIGNATURES = {
     "ncme_vec_wrms": (cint, [p_void, i64, p_void, p_void, p_void, f64, f64, p_f64]),
     "ncme_vec_any_nonfinite": (cint, [p_void, i64, p_void, C.POINTER(cint)]),
 }
+
+COEF_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_void_p)
+SAVE_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_void_p)
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("event_slope", C.c_double), ("check_event", C.c_int),
+                ("save_every_step", C.c_int), ("nsave", C.c_int), ("save_t", C.POINTER(C.c_double)),
+                ("h_init", C.c_double), ("max_steps", C.c_int64), ("method", C.c_int)]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("t_final", C.c_double), ("h_last", C.c_double), ("event_hit", C.c_int), ("nsaved", C.c_int),
+                ("steps", C.c_int64), ("rejected", C.c_int64), ("rhs_evals", C.c_int64), ("launches", C.c_int64)]
+
 
 _lib = None
 

@@ -59,8 +59,8 @@ struct ncme_ctx {
     // small device scratch for reductions (partials + counters), and a pinned host mirror
     double* red_partials = nullptr;   // [RED_MAX_BLOCKS * 4]
     unsigned int* red_counter = nullptr;
-    double* red_result_dev = nullptr; // [8]
-    double* red_result_host = nullptr;  // pinned [8]
+    double* red_result_dev = nullptr; // [1024]
+    double* red_result_host = nullptr;  // pinned [1024]
     // pinned staging for the host-buffer matvec path
     double* stage_host = nullptr;
     size_t stage_host_bytes = 0;
@@ -113,5 +113,7 @@ struct DevArray {
 int exclusive_scan_u32(ncme_ctx* ctx, const uint32_t* in_dev, uint32_t* out_dev, int64_t n, uint32_t* scratch_dev,
                        size_t scratch_elems, uint64_t* total_host);
 size_t scan_scratch_elems(int64_t n);
+int exclusive_scan_f64(ncme_ctx* ctx, const double* in_dev, double* out_dev, int64_t n, double* scratch_dev,
+                       size_t scratch_elems);
 
 }  // namespace ncme

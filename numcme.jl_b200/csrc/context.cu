@@ -45,8 +45,8 @@ int ncme_ctx_create(int device, ncme_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&ctx->red_partials, sizeof(double) * 4 * 4096) != cudaSuccess ||
         cudaMalloc(&ctx->red_counter, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(&ctx->red_result_dev, sizeof(double) * 8) != cudaSuccess ||
-        cudaMallocHost(&ctx->red_result_host, sizeof(double) * 8) != cudaSuccess ||
+        cudaMalloc(&ctx->red_result_dev, sizeof(double) * 1024) != cudaSuccess ||
+        cudaMallocHost(&ctx->red_result_host, sizeof(double) * 1024) != cudaSuccess ||
         cudaMemset(ctx->red_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
         set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         ncme_ctx_destroy(ctx);

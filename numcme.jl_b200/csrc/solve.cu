@@ -1,0 +1,390 @@
+// Native device-resident integrator for one FSP segment.
+// Replaces DE.init(...)/DE.step!(integrator, tend - tnow, true) + the ContinuousCallback of
+// src/transientcme/sparse/fspsolve.jl:145-161.  The FSP vector never leaves HBM: per step the host sees
+// one weighted error norm and the R sink entries of the stage vectors (for the event function).
+//
+// method 0: Dormand-Prince 5(4) with FSAL, step-size control on the weighted RMS norm
+//           sqrt(mean((err_i / (atol + rtol*max(|u_i|,|unew_i|)))^2)) and 4th-order dense output
+//           (Hairer's dopri5 continuous extension) for saveat and for locating the sink event.
+#include <math.h>
+
+#include <algorithm>
+
+#include "matrix.cuh"
+#include "vec.cuh"
+
+namespace ncme {
+
+constexpr int ST = 256;
+
+struct StepArgs {
+    int64_t N;        // vector length n + R
+    int64_t n;        // states
+    int R;
+    const double* u;
+    const double* unew;
+    const double* k[7];
+    double e[7];      // h * error coefficients
+    double atol, rtol;
+    double* partials;
+    unsigned int* counter;
+    double* result;   // [0] = sum of squares, [1 + v*R + r] = sink entry r of vector v (u, unew, k1..k7)
+};
+
+__global__ void __launch_bounds__(ST) k_rk_errnorm(const __grid_constant__ StepArgs a) {
+    __shared__ double wsum[ST / 32];
+    __shared__ bool is_last;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x; i < a.N; i += (int64_t)gridDim.x * ST) {
+        double err = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (a.e[j] != 0.0) err = fma(a.e[j], a.k[j][i], err);
+        const double w = a.atol + a.rtol * fmax(fabs(a.u[i]), fabs(a.unew[i]));
+        const double q = err / w;
+        s = fma(q, q, s);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < ST / 32; ++w) t += wsum[w];
+        a.partials[blockIdx.x] = t;
+        __threadfence();
+        is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        const volatile double* p = a.partials;
+        double t = 0.0;
+        for (unsigned k = threadIdx.x; k < gridDim.x; k += 32) t += p[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (threadIdx.x == 0) {
+            a.result[0] = t;
+            *a.counter = 0u;
+        }
+    }
+    // sink tails of the 9 vectors (the stage kernels that produced them finished before this launch)
+    for (int q = threadIdx.x; q < 9 * a.R; q += ST) {
+        const int v = q / a.R, r = q % a.R;
+        const double* src = v == 0 ? a.u : (v == 1 ? a.unew : a.k[v - 2]);
+        a.result[1 + q] = src[a.n + r];
+    }
+}
+
+struct DenseArgs {
+    int64_t N;
+    const double* u;
+    const double* unew;
+    const double* k[7];
+    double d[7];   // h * d_j
+    double h, theta;
+    double* out;
+};
+
+// Hairer's contd5: u + th*(r2 + (1-th)*(r3 + th*(r4 + (1-th)*r5)))
+__global__ void __launch_bounds__(ST) k_rk_dense(const __grid_constant__ DenseArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x;
+    if (i >= a.N) return;
+    const double u0 = a.u[i], u1 = a.unew[i];
+    const double r2 = u1 - u0;
+    const double r3 = a.h * a.k[0][i] - r2;
+    const double r4 = r2 - a.h * a.k[6][i] - r3;
+    double r5 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+        if (a.d[j] != 0.0) r5 = fma(a.d[j], a.k[j][i], r5);
+    const double th = a.theta, th1 = 1.0 - a.theta;
+    a.out[i] = u0 + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+}
+
+// ---- Dormand-Prince tableau
+static const double DP_C[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+static const double DP_A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+static const double DP_E[7] = {71.0 / 57600, 0, -71.0 / 16695, 71.0 / 1920, -17253.0 / 339200, 22.0 / 525, -1.0 / 40};
+static const double DP_D[7] = {-12715105075.0 / 11282082432.0, 0, 87487479700.0 / 32700410799.0,
+                               -10690763975.0 / 1880347072.0, 701980252875.0 / 199316789632.0,
+                               -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
+
+struct Workspace {
+    double* base = nullptr;
+    double* k[7];
+    double* ytmp;
+    double* unew;
+    double* pinned = nullptr;
+    ~Workspace() {
+        if (base) cudaFree(base);
+        if (pinned) cudaFreeHost(pinned);
+    }
+};
+
+// sum over sinks of the dense output at theta, from the tails gathered by k_rk_errnorm
+static double sink_dense_sum(const double* tails, int R, double h, double theta) {
+    double s = 0.0;
+    const double th = theta, th1 = 1.0 - theta;
+    for (int r = 0; r < R; ++r) {
+        const double u0 = tails[0 * R + r], u1 = tails[1 * R + r];
+        const double r2 = u1 - u0;
+        const double r3 = h * tails[2 * R + r] - r2;
+        const double r4 = r2 - h * tails[8 * R + r] - r3;
+        double r5 = 0.0;
+        for (int j = 0; j < 7; ++j) r5 += h * DP_D[j] * tails[(2 + j) * R + r];
+        s += u0 + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+    }
+    return s;
+}
+
+static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
+                     double* u, const ncme_solve_opts* o, ncme_solve_stats* st) {
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t s = ctx->stream;
+    const int64_t N = A->N, n = A->n;
+    const int R = A->nr;
+    const int64_t launches0 = ctx->launches;
+    Workspace ws;
+    const size_t Npad = round_up<size_t>((size_t)N, 32);
+    NCME_CUDA(cudaMalloc(&ws.base, Npad * 9 * sizeof(double)));
+    for (int j = 0; j < 7; ++j) ws.k[j] = ws.base + Npad * j;
+    ws.ytmp = ws.base + Npad * 7;
+    ws.unew = ws.base + Npad * 8;
+    if (save_fn) NCME_CUDA(cudaMallocHost(&ws.pinned, (size_t)N * sizeof(double)));
+
+    double coef[NCME_MAX_REACTIONS];
+    for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
+    auto rhs = [&](double t, const double* x, double* y) -> int {
+        if (coef_fn) coef_fn(t, coef, user);
+        st->rhs_evals++;
+        return ncme_matvec(A, coef, x, y, 0.0);
+    };
+    auto save = [&](double t, const double* v_dev) -> int {
+        if (!save_fn) return NCME_OK;
+        NCME_CUDA(cudaMemcpyAsync(ws.pinned, v_dev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        save_fn(t, ws.pinned, user);
+        st->nsaved++;
+        return NCME_OK;
+    };
+    auto lincomb = [&](int kterms, const double* cs, const double* const* xs, double* out) -> int {
+        // drop zero coefficients (a_72 = 0)
+        double c2[8];
+        const double* x2[8];
+        int m = 0;
+        for (int j = 0; j < kterms; ++j)
+            if (cs[j] != 0.0) {
+                c2[m] = cs[j];
+                x2[m] = xs[j];
+                ++m;
+            }
+        return ncme_vec_lincomb(ctx, N, m, c2, x2, out);
+    };
+
+    const double rtol = o->rtol > 0 ? o->rtol : 1e-4, atol = o->atol > 0 ? o->atol : 1e-6;
+    const int64_t max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
+    const double tspan = t1 - t0;
+    double t = t0;
+    int isave = 0;
+    while (isave < o->nsave && o->save_t[isave] < t0) ++isave;
+    if (o->save_every_step) NCME_TRY(save(t0, u));
+    while (isave < o->nsave && o->save_t[isave] == t0) {
+        NCME_TRY(save(t0, u));
+        ++isave;
+    }
+    st->t_final = t0;
+    st->event_hit = 0;
+    if (!(tspan > 0)) return NCME_OK;
+
+    NCME_TRY(rhs(t, u, ws.k[0]));  // u == ucur here
+    // initial step: h = 0.01 * ||u|| / ||f|| in the weighted norm (Hairer), clipped to the span
+    double h = o->h_init;
+    if (!(h > 0)) {
+        double d0 = 0, d1 = 0;
+        NCME_TRY(ncme_vec_wrms(ctx, N, u, u, u, atol, rtol, &d0));
+        NCME_TRY(ncme_vec_wrms(ctx, N, ws.k[0], u, u, atol, rtol, &d1));
+        h = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h = std::min(h, tspan);
+    }
+    double* ucur = u;          // current solution (caller's buffer or the workspace slot)
+    double* unext = ws.unew;   // target of the 7th stage
+    double g_prev = 0.0;
+    bool have_g = false;
+    bool last_rejected = false;
+    StepArgs ea;
+    ea.N = N;
+    ea.n = n;
+    ea.R = R;
+    for (int j = 0; j < 7; ++j) ea.k[j] = ws.k[j];
+    ea.atol = atol;
+    ea.rtol = rtol;
+    ea.partials = ctx->red_partials;
+    ea.counter = ctx->red_counter;
+    ea.result = ctx->red_result_dev;
+    int64_t nb = (N + (int64_t)ST * 8 - 1) / ((int64_t)ST * 8);
+    nb = std::max<int64_t>(1, std::min<int64_t>(nb, 4096));
+    const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+
+    while (t < t1) {
+        if (st->steps + st->rejected >= max_steps) {
+            set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)max_steps, t);
+            return NCME_ERR_SOLVER;
+        }
+        bool last = false;
+        if (t + h >= t1 || t1 - (t + h) < 1e-12 * tspan) {
+            h = t1 - t;
+            last = true;
+        }
+        // stages 2..7
+        for (int i = 1; i < 7; ++i) {
+            double cs[8];
+            const double* xs[8];
+            cs[0] = 1.0;
+            xs[0] = ucur;
+            for (int j = 0; j < i; ++j) {
+                cs[1 + j] = h * DP_A[i][j];
+                xs[1 + j] = ws.k[j];
+            }
+            double* dst = (i == 6) ? unext : ws.ytmp;
+            NCME_TRY(lincomb(1 + i, cs, xs, dst));
+            NCME_TRY(rhs(t + DP_C[i] * h, dst, ws.k[i]));
+        }
+        for (int j = 0; j < 7; ++j) ea.e[j] = h * DP_E[j];
+        ea.u = ucur;
+        ea.unew = unext;
+        k_rk_errnorm<<<(unsigned)nb, ST, 0, s>>>(ea);
+        ctx->launches++;
+        NCME_CUDA(cudaGetLastError());
+        NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * (1 + 9 * R),
+                                  cudaMemcpyDeviceToHost, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        const double err = sqrt(ctx->red_result_host[0] / (double)N);
+        if (!(err <= 1.0)) {  // reject (also catches NaN)
+            st->rejected++;
+            const double fac = isfinite(err) ? std::max(0.2, 0.9 * pow(err, -0.2)) : 0.1;
+            h *= fac;
+            last_rejected = true;
+            if (h < hmin) {
+                set_error("integrator: step size underflow at t = %g (err = %g)", t, err);
+                return NCME_ERR_SOLVER;
+            }
+            continue;
+        }
+        st->steps++;
+        const double* tails = ctx->red_result_host + 1;
+        double theta_end = 1.0;
+        bool event = false;
+        if (o->check_event) {
+            // g(theta) = sum_sinks(dense(theta)) - slope * (t + theta h), sampled like interp_points
+            if (!have_g) {
+                g_prev = sink_dense_sum(tails, R, h, 0.0) - o->event_slope * t;
+                have_g = true;
+            }
+            const int NS_ = 16;
+            double ga = g_prev, tha = 0.0;
+            for (int q = 1; q <= NS_; ++q) {
+                const double thb = (double)q / NS_;
+                const double gb = sink_dense_sum(tails, R, h, thb) - o->event_slope * (t + thb * h);
+                if (ga <= 0.0 && gb > 0.0) {
+                    double lo = tha, hi = thb;
+                    for (int it = 0; it < 60; ++it) {
+                        const double mid = 0.5 * (lo + hi);
+                        const double gm = sink_dense_sum(tails, R, h, mid) - o->event_slope * (t + mid * h);
+                        if (gm > 0.0)
+                            hi = mid;
+                        else
+                            lo = mid;
+                    }
+                    theta_end = hi;
+                    event = true;
+                    break;
+                }
+                ga = gb;
+                tha = thb;
+            }
+            if (!event) g_prev = ga;
+        }
+        // dense-output saves inside (t, t + theta_end*h]
+        DenseArgs da;
+        da.N = N;
+        da.u = ucur;
+        da.unew = unext;
+        for (int j = 0; j < 7; ++j) {
+            da.k[j] = ws.k[j];
+            da.d[j] = h * DP_D[j];
+        }
+        da.h = h;
+        da.out = ws.ytmp;
+        const double t_hi = t + theta_end * h;
+        while (isave < o->nsave && o->save_t[isave] <= t_hi + 1e-14 * fabs(t_hi)) {
+            const double ts = o->save_t[isave];
+            const double th = std::min(1.0, std::max(0.0, (ts - t) / h));
+            if (th >= 1.0 && !event) {
+                NCME_TRY(save(ts, unext));
+            } else {
+                da.theta = th;
+                k_rk_dense<<<(unsigned)((N + ST - 1) / ST), ST, 0, s>>>(da);
+                ctx->launches++;
+                NCME_TRY(save(ts, ws.ytmp));
+            }
+            ++isave;
+        }
+        if (event) {
+            da.theta = theta_end;
+            k_rk_dense<<<(unsigned)((N + ST - 1) / ST), ST, 0, s>>>(da);
+            ctx->launches++;
+            NCME_CUDA(cudaGetLastError());
+            NCME_CUDA(cudaMemcpyAsync(u, ws.ytmp, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            t = t_hi;
+            st->event_hit = 1;
+            st->h_last = h;
+            break;
+        }
+        // accept: u <-> unew and k1 <-> k7 (FSAL) by pointer swaps, no copies
+        std::swap(ucur, unext);
+        std::swap(ws.k[0], ws.k[6]);
+        ea.k[0] = ws.k[0];
+        ea.k[6] = ws.k[6];
+        t = last ? t1 : t + h;
+        if (o->save_every_step) NCME_TRY(save(t, ucur));
+        st->h_last = h;
+        double fac = (err > 0) ? 0.9 * pow(err, -0.2) : 5.0;
+        fac = std::min(last_rejected ? 1.0 : 5.0, std::max(0.2, fac));
+        last_rejected = false;
+        if (!last) h *= fac;
+    }
+    if (!st->event_hit && ucur != u)
+        NCME_CUDA(cudaMemcpyAsync(u, ucur, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    NCME_CUDA(cudaStreamSynchronize(s));
+    st->t_final = t;
+    st->launches = ctx->launches - launches0;
+    return NCME_OK;
+}
+
+}  // namespace ncme
+
+using namespace ncme;
+
+extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0,
+                                  double t1, double* u_dev, const ncme_solve_opts* opts, ncme_solve_stats* stats) {
+    NCME_REQUIRE(A && u_dev && opts && stats, "null argument");
+    NCME_REQUIRE(t1 >= t0, "solve_segment: t1 < t0");
+    NCME_REQUIRE(opts->nsave == 0 || opts->save_t, "save_t is null");
+    bool need_coef = false;
+    for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] != NCME_TIME_INVARIANT);
+    NCME_REQUIRE(coef_fn || !need_coef, "the matrix has time-varying reactions: a coefficient callback is required");
+    memset(stats, 0, sizeof(*stats));
+    if (opts->method == 0) return solve_dp5(A, coef_fn, save_fn, user, t0, t1, u_dev, opts, stats);
+    set_error("unknown integrator method %d", opts->method);
+    return NCME_ERR_ARG;
+}

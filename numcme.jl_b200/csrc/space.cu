@@ -277,6 +277,7 @@ static int ensure_scratch(ncme_space* sp, int64_t m) {
 int space_addstates(ncme_space* sp, int64_t ncand, int64_t* added) {
     ncme_ctx* ctx = sp->ctx;
     *added = 0;
+    sp->last_delete_nold = -1;  // the flags/pos scratch is about to be reused
     if (ncand <= 0) return NCME_OK;
     NCME_REQUIRE((uint64_t)sp->n + (uint64_t)ncand < 0xFFFFFFF0ull, "state space exceeds the 32-bit index range");
     NCME_TRY(ensure_scratch(sp, ncand));
@@ -297,6 +298,55 @@ int space_addstates(ncme_space* sp, int64_t ncand, int64_t* added) {
     sp->version++;
     *added = (int64_t)m;
     return NCME_OK;
+}
+
+// deleteat! with the keep flags already in sp->flags[0..n): compaction through the old->new map
+// (:283-317), hash-table rebuild, sink re-derivation (:318-329).  sp->flags / sp->pos stay valid
+// afterwards (last_delete_nold) so that vectors can be compacted with the same map.
+int space_delete_flagged(ncme_space* sp) {
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t s = ctx->stream;
+    const int64_t n = sp->n;
+    NCME_TRY(sp->pos.reserve((size_t)n, s, false));
+    NCME_TRY(sp->scan_scratch.reserve(scan_scratch_elems(n), s, false));
+    uint64_t m = 0;
+    NCME_TRY(exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, n, sp->scan_scratch.p, sp->scan_scratch.cap, &m));
+    sp->last_delete_nold = n;
+    sp->last_delete_nnew = (int64_t)m;
+    if ((int64_t)m == n) return NCME_OK;
+    DevArray<uint64_t> k2;
+    DevArray<uint32_t> p2, m2;
+    const int64_t ld2 = round_up<int64_t>((int64_t)m > 1024 ? (int64_t)m : 1024, 64);
+    NCME_TRY(k2.reserve((size_t)ld2, s, false));
+    NCME_TRY(m2.reserve((size_t)ld2, s, false));
+    NCME_TRY(p2.reserve((size_t)ld2 * sp->nr, s, false));
+    LAUNCH(ctx, k_compact_space, n, sp->flags.p, sp->pos.p, n, sp->keys.p, sp->pred.p, sp->ld, sp->sinkmask.p, sp->nr, k2.p,
+           p2.p, ld2, m2.p);
+    NCME_CUDA(cudaStreamSynchronize(s));
+    sp->keys.release();
+    sp->pred.release();
+    sp->sinkmask.release();
+    sp->keys = k2;
+    sp->pred = p2;
+    sp->sinkmask = m2;
+    sp->ld = ld2;
+    sp->n = (int64_t)m;
+    sp->version++;
+    if (sp->n == 0) {
+        NCME_CUDA(cudaMemsetAsync(sp->tkeys.p, 0xFF, sp->tcap * sizeof(uint64_t), s));
+        NCME_CUDA(cudaMemsetAsync(sp->tvals.p, 0xFF, sp->tcap * sizeof(uint32_t), s));
+        return NCME_OK;
+    }
+    NCME_TRY(space_rebuild_table(sp, 4 * (uint64_t)(sp->n + 256)));
+    LAUNCH(ctx, k_rederive_sinks, sp->n * sp->nr, sp->hview(), sp->layout, sp->sdev, sp->keys.p, sp->n, sp->sinkmask.p);
+    NCME_CUDA(cudaStreamSynchronize(s));
+    return NCME_OK;
+}
+
+__global__ void k_compact_vector(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, int64_t n,
+                                 const double* __restrict__ in, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) out[pos[i]] = in[i];
 }
 
 static int space_alloc(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, ncme_space** out) {
@@ -470,6 +520,7 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
     NCME_REQUIRE(sp, "null space");
     if (expansionlevel <= 0 || sp->n == 0) return NCME_OK;
     ncme_ctx* ctx = sp->ctx;
+    sp->last_delete_nold = -1;
     int reacts[NCME_MAX_REACTIONS];
     int nreact = 0;
     uint32_t reactmask = 0;
@@ -546,41 +597,18 @@ int ncme_space_delete(ncme_space* sp, int64_t nids, const int64_t* ids) {
         ids0[(size_t)k] = (uint32_t)(ids[k] - 1);
     }
     NCME_TRY(sp->flags.reserve((size_t)n, s, false));
-    NCME_TRY(sp->pos.reserve((size_t)n, s, false));
-    NCME_TRY(sp->scan_scratch.reserve(scan_scratch_elems(n), s, false));
     NCME_TRY(sp->cand_slot.reserve((size_t)nids, s, false));
     NCME_CUDA(cudaMemcpyAsync(sp->cand_slot.p, ids0.data(), (size_t)nids * 4, cudaMemcpyHostToDevice, s));
     LAUNCH(ctx, k_fill_u32, n, sp->flags.p, n, 1u);
     LAUNCH(ctx, k_clear_flags_at, nids, sp->cand_slot.p, nids, sp->flags.p);
-    uint64_t m = 0;
-    NCME_TRY(exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, n, sp->scan_scratch.p, sp->scan_scratch.cap, &m));
-    // compact into fresh arrays
-    DevArray<uint64_t> k2;
-    DevArray<uint32_t> p2, m2;
-    const int64_t ld2 = round_up<int64_t>((int64_t)m > 1024 ? (int64_t)m : 1024, 64);
-    NCME_TRY(k2.reserve((size_t)ld2, s, false));
-    NCME_TRY(m2.reserve((size_t)ld2, s, false));
-    NCME_TRY(p2.reserve((size_t)ld2 * sp->nr, s, false));
-    LAUNCH(ctx, k_compact_space, n, sp->flags.p, sp->pos.p, n, sp->keys.p, sp->pred.p, sp->ld, sp->sinkmask.p, sp->nr, k2.p,
-           p2.p, ld2, m2.p);
-    NCME_CUDA(cudaStreamSynchronize(s));
-    sp->keys.release();
-    sp->pred.release();
-    sp->sinkmask.release();
-    sp->keys = k2;
-    sp->pred = p2;
-    sp->sinkmask = m2;
-    sp->ld = ld2;
-    sp->n = (int64_t)m;
-    sp->version++;
-    if (sp->n == 0) {
-        NCME_CUDA(cudaMemsetAsync(sp->tkeys.p, 0xFF, sp->tcap * sizeof(uint64_t), s));
-        NCME_CUDA(cudaMemsetAsync(sp->tvals.p, 0xFF, sp->tcap * sizeof(uint32_t), s));
-        return NCME_OK;
-    }
-    NCME_TRY(space_rebuild_table(sp, 4 * (uint64_t)(sp->n + 256)));
-    LAUNCH(ctx, k_rederive_sinks, sp->n * sp->nr, sp->hview(), sp->layout, sp->sdev, sp->keys.p, sp->n, sp->sinkmask.p);
-    NCME_CUDA(cudaStreamSynchronize(s));
+    NCME_CUDA(cudaStreamSynchronize(s));  // ids0 is a host temporary
+    return space_delete_flagged(sp);
+}
+
+int ncme_space_compact_vector(ncme_space* sp, const double* in_dev, double* out_dev) {
+    NCME_REQUIRE(sp && in_dev && out_dev && in_dev != out_dev, "bad arguments");
+    NCME_REQUIRE(sp->last_delete_nold >= 0, "no deletion to apply (the space was mutated since the last delete/prune)");
+    LAUNCH(sp->ctx, k_compact_vector, sp->last_delete_nold, sp->flags.p, sp->pos.p, sp->last_delete_nold, in_dev, out_dev);
     return NCME_OK;
 }
 

@@ -127,6 +127,20 @@ class StateSpaceSparse:
         if ids.size:
             L.check(L.load().ncme_space_delete(self._h, ids.size, L.ptr(ids, C.c_int64)))
 
+    def prune_by_mass_(self, p_dev, threshold: float, strict: bool) -> int:
+        """The dropstates branch of adapt! on the device (rstepadapters.jl:40-46 / :93-99): deletes the
+        ``dropcount`` least probable states; returns dropcount.  Follow with ``compact_vector``."""
+        from .device import device_ptr
+        dc = C.c_int64()
+        L.check(L.load().ncme_space_prune_by_mass(self._h, C.c_void_p(device_ptr(p_dev)), float(threshold),
+                                                  1 if strict else 0, C.byref(dc)))
+        return dc.value
+
+    def compact_vector(self, vin, vout):
+        """deleteat!(p, dropids) for a device vector, using the map of the last delete/prune."""
+        from .device import device_ptr
+        L.check(L.load().ncme_space_compact_vector(self._h, C.c_void_p(device_ptr(vin)), C.c_void_p(device_ptr(vout))))
+
     def close(self):
         if getattr(self, "_h", None):
             L.load().ncme_space_destroy(self._h)

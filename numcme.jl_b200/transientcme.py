@@ -1,0 +1,263 @@
+"""Transient FSP solves behind the reference's API, with the FSP vector resident in HBM.
+
+Reference: src/transientcme/sparse/fspsolve.jl (fixed-space ``solve`` :10-41, ``AdaptiveFspSparse``
+:59-62, adaptive ``solve`` :105-197) and src/transientcme/sparse/rstepadapters.jl (``RStepAdapter``
+:12-52, ``SelectiveRStepAdapter`` :61-110).
+
+The reference hands the right-hand side to DifferentialEquations.jl / Sundials (host vectors).  Here
+``ode_method=None`` (a legal value of the reference's ``Union{Nothing,AbstractODEAlgorithm}`` field)
+selects the native device-resident integrator of libncme (``ncme_solve_segment``): u, the stage
+vectors, the error norm and the sink event all stay on the GPU; per step only a norm and R sink
+entries cross PCIe.  Space adaptation (prune by mass, expand) runs on the device as well.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib as L
+from .cmemodel import CmeModel
+from .device import DeviceVector
+from .fspmatrix import FspMatrixSparse, matvec_
+from .fspvector import FspOutputSparse, FspVectorSparse
+from .statespace import StateSpaceSparse
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+class NativeRK45:
+    """Device-resident Dormand-Prince 5(4) (libncme method 0).  The value ``None`` means the same."""
+    method = 0
+
+
+class RStepAdapter:
+    """rstepadapters.jl:12-16"""
+    selective = False
+
+    def __init__(self, initial_step_count: int, max_step_count: int, dropstates: bool):
+        self.initial_step_count = int(initial_step_count)
+        self.max_step_count = int(max_step_count)
+        self.dropstates = bool(dropstates)
+
+
+class SelectiveRStepAdapter(RStepAdapter):
+    """rstepadapters.jl:61-65: only explores through reactions whose sink is still gaining mass."""
+    selective = True
+
+
+class AdaptiveFspSparse:
+    """fspsolve.jl:59-62"""
+
+    def __init__(self, ode_method=None, space_adapter=None):
+        if space_adapter is None:
+            raise L.ArgumentError("space_adapter is required")
+        self.ode_method = ode_method
+        self.space_adapter = space_adapter
+
+
+def _grow(ctx, p: DeviceVector, n_new: int) -> DeviceVector:
+    """append!(p, zeros(n_new - length(p)))"""
+    if n_new == p.n:
+        return p
+    q = DeviceVector.zeros(ctx, n_new)
+    if p.n:
+        q.view(0, p.n).copy_from(p)
+    return q
+
+
+def init_(space: StateSpaceSparse, adapter: RStepAdapter, p: DeviceVector, t: float, fsptol: float) -> DeviceVector:
+    """init!(statespace, adapter, p, t, fsptol)   rstepadapters.jl:23-28 / :74-79"""
+    space.expand_(adapter.initial_step_count)
+    return _grow(space.ctx, p, space.get_state_count())
+
+
+def adapt_(space: StateSpaceSparse, adapter: RStepAdapter, p: DeviceVector, sinks: np.ndarray, t: float, tend: float,
+           fsptol: float, dsinks: np.ndarray | None = None) -> DeviceVector:
+    """adapt!(statespace, adapter, p, sinks, t, tend, fsptol; integrator)   rstepadapters.jl:35-52 / :86-110.
+    ``dsinks`` (d sinks / dt at t, what the reference reads through get_du!) is required by the selective adapter."""
+    ctx = space.ctx
+    if adapter.selective and p.n == 0:
+        raise L.ArgumentError("Empty `p` input in `adapt!`.")
+    if adapter.dropstates and p.n:
+        thr = 1.0 - t * fsptol / tend
+        dropped = space.prune_by_mass_(p, thr, strict=adapter.selective)
+        if dropped:
+            q = DeviceVector(ctx, space.get_state_count())
+            space.compact_vector(p, q)
+            p = q
+    if adapter.selective:
+        if dsinks is None:
+            raise L.ArgumentError("SelectiveRStepAdapter needs the sink derivatives")
+        only = [int(r) + 1 for r in np.nonzero(np.asarray(dsinks) > 0)[0]]
+        space.expand_(adapter.max_step_count, onlyreactions=only)   # empty => all, like the reference (:163)
+    else:
+        space.expand_(adapter.max_step_count)
+    return _grow(ctx, p, space.get_state_count())
+
+
+class _Segment:
+    """One call of ncme_solve_segment with host callbacks for time factors and output slices."""
+
+    def __init__(self, A: FspMatrixSparse, rtol, atol, method=0):
+        self.A = A
+        self.rtol, self.atol, self.method = rtol, atol, method
+        self.saved_t, self.saved_u = [], []
+        N = A.rowcount
+
+        def coef_cb(t, coef_ptr, _user):
+            c = A.coefficients(t)
+            A._refresh_joint(t)
+            for r in A.separabletv_propensity_ids:
+                coef_ptr[r - 1] = c[r - 1]
+
+        def save_cb(t, u_ptr, _user):
+            self.saved_t.append(float(t))
+            self.saved_u.append(np.ctypeslib.as_array(u_ptr, shape=(N,)).copy())
+
+        self._coef_cb = L.COEF_FN(coef_cb)
+        self._save_cb = L.SAVE_FN(save_cb)
+        self.needs_coef = bool(A.separabletv_propensity_ids or A.jointtv_propensity_ids)
+
+    def run(self, u: DeviceVector, t0, t1, saveat=None, save_every_step=False, event_slope=None):
+        opts = L.SolveOpts()
+        opts.rtol, opts.atol = float(self.rtol), float(self.atol)
+        opts.check_event = 0 if event_slope is None else 1
+        opts.event_slope = 0.0 if event_slope is None else float(event_slope)
+        opts.save_every_step = 1 if save_every_step else 0
+        sv = np.ascontiguousarray(saveat if saveat is not None else [], dtype=np.float64)
+        opts.nsave = int(sv.size)
+        opts.save_t = sv.ctypes.data_as(C.POINTER(C.c_double))
+        opts.h_init = 0.0
+        opts.max_steps = 0
+        opts.method = int(self.method)
+        stats = L.SolveStats()
+        self.saved_t, self.saved_u = [], []
+        cb = C.cast(self._coef_cb, C.c_void_p) if self.needs_coef else None
+        L.check(L.load().ncme_solve_segment(self.A.handle, cb, C.cast(self._save_cb, C.c_void_p), None, float(t0),
+                                            float(t1), C.c_void_p(u.ptr), C.byref(opts), C.byref(stats)))
+        return stats
+
+
+def _method_code(ode_method):
+    if ode_method is None:
+        return 0
+    if hasattr(ode_method, "method"):
+        return int(ode_method.method)
+    raise L.ArgumentError("ode_method must be None (native device integrator) or a Native* method object; "
+                          "DifferentialEquations.jl algorithms only exist on the Julia side")
+
+
+def _saveat_array(saveat, tspan):
+    if saveat is None:
+        return None
+    if np.isscalar(saveat):
+        return np.arange(tspan[0], tspan[1] + 0.5 * saveat, saveat, dtype=np.float64)
+    sv = np.asarray(list(saveat), dtype=np.float64)
+    return sv if sv.size else None
+
+
+def _initial(model, initial_distribution):
+    if not isinstance(initial_distribution, FspVectorSparse):
+        raise L.ArgumentError("initial_distribution must be a FspVectorSparse")
+    return initial_distribution.states, np.array(initial_distribution.values, dtype=np.float64)
+
+
+def solve(model: CmeModel, initial_distribution: FspVectorSparse, tspan, algorithm=None, saveat=None, fsptol=1.0e-6,
+          odeatol=1.0e-6, odertol=1.0e-4, verbose=False, ctx=None) -> FspOutputSparse:
+    """``solve(model, p0, tspan, ode_method; saveat, odeatol, odertol)``   (fixed space, fspsolve.jl:10-41) when
+    ``algorithm`` is None or an ODE method, and
+    ``solve(model, p0, tspan, fspalgorithm::AdaptiveFspSparse; saveat, fsptol, odeatol, odertol, verbose)``
+    (adaptive, fspsolve.jl:105-197) when it is an ``AdaptiveFspSparse``."""
+    if isinstance(algorithm, AdaptiveFspSparse):
+        return _solve_adaptive(model, initial_distribution, tspan, algorithm, saveat, fsptol, odeatol, odertol, verbose, ctx)
+    return _solve_fixed(model, initial_distribution, tspan, algorithm, saveat, odeatol, odertol, ctx)
+
+
+def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx):
+    states0, vals0 = _initial(model, p0)
+    space = StateSpaceSparse(model.stoich_matrix, states0, ctx=ctx)
+    R = space.get_sink_count()
+    # duplicates/negatives are dropped by the space; place p0 by lookup
+    idx = space.lookup(states0)
+    n = space.get_state_count()
+    u0 = np.zeros(n + R)
+    u0[idx[idx > 0] - 1] = vals0[idx > 0]
+    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+    u = DeviceVector.from_host(space.ctx, u0)
+    sv = _saveat_array(saveat, tspan)
+    seg = _Segment(A, odertol, odeatol, _method_code(ode_method))
+    t_wall = time.perf_counter()
+    stats = seg.run(u, tspan[0], tspan[1], saveat=sv, save_every_step=sv is None)
+    out = FspOutputSparse()
+    states = space.get_states()
+    for t, uu in zip(seg.saved_t, seg.saved_u):
+        out.t.append(t)
+        out.p.append(FspVectorSparse(states, uu[:n]))
+        out.sinks.append(uu[n:].copy())
+    out.stats = {"steps": stats.steps, "rejected": stats.rejected, "rhs_evals": stats.rhs_evals,
+                 "launches": stats.launches, "adapts": 0, "wall_s": time.perf_counter() - t_wall, "final_states": n}
+    return out
+
+
+def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, verbose, ctx):
+    tstart, tend = min(tspan), max(tspan)
+    sv = _saveat_array(saveat, tspan)
+    adapter = alg.space_adapter
+    method = _method_code(alg.ode_method)
+    states0, vals0 = _initial(model, p0)
+    space = StateSpaceSparse(model.stoich_matrix, states0, ctx=ctx)
+    ctx = space.ctx
+    R = space.get_sink_count()
+    idx = space.lookup(states0)
+    pv = np.zeros(space.get_state_count())
+    pv[idx[idx > 0] - 1] = vals0[idx > 0]
+    t_wall = time.perf_counter()
+    p = init_(space, adapter, DeviceVector.from_host(ctx, pv), tstart, fsptol)
+    tnow = tstart
+    sinks = np.zeros(R)
+    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+    out = FspOutputSparse()
+    tot = {"steps": 0, "rejected": 0, "rhs_evals": 0, "launches": 0, "adapts": 0, "matrix_builds": 1}
+    while tnow < tend:
+        n = space.get_state_count()
+        u = DeviceVector(ctx, n + R)
+        u.view(0, n).copy_from(p)
+        u.view(n, R).upload(sinks)
+        seg = _Segment(A, odertol, odeatol, method)
+        stats = seg.run(u, tnow, tend, saveat=sv, save_every_step=sv is None, event_slope=fsptol / tend)
+        for k in ("steps", "rejected", "rhs_evals", "launches"):
+            tot[k] += getattr(stats, k)
+        states = space.get_states() if seg.saved_t else None
+        for t, uu in zip(seg.saved_t, seg.saved_u):
+            out.t.append(t)
+            out.p.append(FspVectorSparse(states, uu[:n]))
+            out.sinks.append(uu[n:].copy())
+        tnow = stats.t_final
+        if stats.event_hit and tnow < tend:
+            sinks = u.to_host(n, R)
+            dsinks = None
+            if adapter.selective:                        # get_du!(du, integrator) (rstepadapters.jl:100-103)
+                du = DeviceVector(ctx, n + R)
+                matvec_(du, tnow, A, u)
+                dsinks = du.to_host(n, R)
+            p = adapt_(space, adapter, u.view(0, n).clone(), sinks, tnow, tend, fsptol, dsinks=dsinks)
+            A.close()
+            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+            tot["adapts"] += 1
+            tot["matrix_builds"] += 1
+            if sinks.sum() >= tnow * fsptol / tend:      # re-arm the event (fspsolve.jl:179-181)
+                sinks = sinks - EPS
+            if verbose:
+                print(f"t = {tnow:.2f}. Update state space. New size: {space.get_state_count()}.")
+        else:
+            uu = u.to_host()
+            out.t.append(tnow)                           # final slice (duplicates the last saveat point when
+            out.p.append(FspVectorSparse(space.get_states(), uu[:n]))   # tend is in saveat, as the reference, Q3)
+            out.sinks.append(uu[n:].copy())
+            tnow = tend
+    tot["wall_s"] = time.perf_counter() - t_wall
+    tot["final_states"] = space.get_state_count()
+    out.stats = tot
+    return out

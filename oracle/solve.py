@@ -104,7 +104,7 @@ def solve_adaptive(stoich, propensities, parameters, states0, p0, tspan, adapter
         def event(t, u, n=n):
             return u[n:].sum() - fsptol * t / tend
         event.terminal = True
-        event.direction = 0
+        event.direction = 1     # rising crossings only (g(t0) = 0 at the very start must not fire)
 
         te = None
         if saveat is not None:
@@ -112,6 +112,8 @@ def solve_adaptive(stoich, propensities, parameters, states0, p0, tspan, adapter
         sol = solve_ivp(rhs, (tnow, tend), unow, method=method, atol=odeatol, rtol=odertol,
                         events=event, t_eval=te, dense_output=False)
         hit = sol.status == 1
+        sol.t = np.asarray(sol.t, dtype=np.float64)
+        sol.y = np.asarray(sol.y, dtype=np.float64).reshape(unow.size, -1)
         t_stop = float(sol.t_events[0][0]) if hit else tend
         u_stop = sol.y_events[0][0] if hit else (sol.y[:, -1] if te is None else None)
         st = space.states_array().copy()

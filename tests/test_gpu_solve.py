@@ -1,0 +1,177 @@
+"""GPU parity for the transient solve path: native device integrator, sink event, prune/expand adapters,
+saveat -- against the oracle loop (scipy, tight tolerances), analytic solutions, and the reference's own
+solver tests (test/test_solver.jl)."""
+import math
+
+import numpy as np
+import pytest
+from scipy.stats import poisson
+
+from fixtures import FSPMAT_THETA, TELEGRAPH_S, TOGGLE_S, fspmat_propensities
+from oracle.solve import RStepAdapterOracle, SelectiveRStepAdapterOracle, solve_adaptive, solve_fixed
+from oracle.statespace import StateSpaceOracleFast
+from test_gpu_matvec import _to_pkg_props
+
+pytestmark = pytest.mark.gpu
+
+
+def _align(states_a, vals_a, states_b, vals_b):
+    """values of two sparse vectors on the union of their supports"""
+    d = {}
+    for s, v in zip(map(tuple, states_a.tolist()), vals_a):
+        d[s] = [v, 0.0]
+    for s, v in zip(map(tuple, states_b.tolist()), vals_b):
+        d.setdefault(s, [0.0, 0.0])[1] = v
+    arr = np.array(list(d.values()))
+    return arr[:, 0], arr[:, 1]
+
+
+def test_fixed_space_solve(pkg):  # test/test_solver.jl:55-77
+    model = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, fspmat_propensities("tv")), FSPMAT_THETA)
+    sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])
+    sp.expand_(20)
+    p0 = pkg.FspVectorSparse.from_pairs(sp, [([1, 0, 0], 1.0)])
+    touts = np.arange(0.0, 121.0, 20.0)
+    sol = pkg.solve(model, p0, (0.0, 120.0), None, odertol=1e-4, odeatol=1e-14, saveat=touts)
+    assert len(sol) == len(touts)
+    assert isinstance(sol[0], pkg.FspOutputSliceSparse)
+    for p, s in zip(sol.p, sol.sinks):
+        assert p.sum() + s.sum() == pytest.approx(1.0, abs=1e-12)
+    dense = pkg.solve(model, p0, (0.0, 120.0), None, odertol=1e-4, odeatol=1e-14)   # saveat = []: every step
+    assert len(dense) == dense.stats["steps"] + 1
+    # values vs the oracle at tight tolerance
+    tight = pkg.solve(model, p0, (0.0, 120.0), None, odertol=1e-9, odeatol=1e-13, saveat=touts)
+    ref = solve_fixed(TELEGRAPH_S, fspmat_propensities("tv"), FSPMAT_THETA, sp.get_states(), p0.values, (0.0, 120.0),
+                      saveat=touts, odeatol=1e-13, odertol=1e-10, method="LSODA")
+    for k in range(len(touts)):
+        assert np.abs(tight.p[k].values - ref["p"][k]).max() < 1e-8
+        assert np.abs(tight.sinks[k] - ref["sinks"][k]).max() < 1e-8
+
+
+@pytest.mark.parametrize("selective", [False, True])
+def test_adaptive_solve_reference_tests(pkg, selective):  # test/test_solver.jl:80-99
+    ada = (pkg.SelectiveRStepAdapter if selective else pkg.RStepAdapter)(10, 10, True)
+    alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=ada)
+    k01, k10, lam, gam = FSPMAT_THETA
+    tv = lambda t, p: max(0.0, 1.0 - math.sin(math.pi * t / 2))
+    m1 = pkg.CmeModel(TELEGRAPH_S, [pkg.propensity(lambda x, p: k01 * x[0]), pkg.propensity(lambda x, p: k10 * x[1], tv),
+                                    pkg.propensity(lambda x, p: lam * x[1]), pkg.propensity(lambda x, p: gam * x[2])], [])
+    m2 = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, fspmat_propensities("tv")), FSPMAT_THETA)
+    p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
+    touts = np.arange(0.0, 121.0, 20.0)
+    s1 = pkg.solve(m1, p0, (0.0, 120.0), alg, odertol=1e-4, odeatol=1e-14, saveat=touts)
+    s2 = pkg.solve(m2, p0, (0.0, 120.0), alg, odertol=1e-4, odeatol=1e-14, saveat=touts)
+    assert s1.stats["adapts"] >= 1
+    for sol in (s1, s2):
+        for p, s in zip(sol.p, sol.sinks):
+            assert p.sum() + s.sum() == pytest.approx(1.0, abs=1e-9)
+        assert sol.sinks[-1].sum() <= 1e-6 * 1.001
+    assert len(s1) == len(s2)
+    for a, b in zip(s1.p, s2.p):
+        assert np.array_equal(a.states, b.states)
+        assert np.abs(a.values - b.values).sum() <= 1e-14
+
+
+def test_adaptive_values_vs_oracle(pkg):
+    """Knife-edge pruning may give different fringe sets: compare values on the union."""
+    alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=pkg.RStepAdapter(5, 10, True))
+    model = pkg.workloads.telegraph_model()
+    p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
+    touts = [50.0, 150.0, 300.0]
+    sol = pkg.solve(model, p0, (0.0, 300.0), alg, saveat=touts, fsptol=1e-6, odeatol=1e-12, odertol=1e-8)
+    ref = solve_adaptive(TELEGRAPH_S, model.propensities, model.parameters, [[1, 0, 0]], [1.0], (0.0, 300.0),
+                         RStepAdapterOracle(5, 10, True), saveat=touts, fsptol=1e-6, odeatol=1e-13, odertol=1e-10,
+                         method="LSODA")
+    for k in range(len(touts)):
+        assert sol.t[k] == pytest.approx(touts[k])
+        a, b = _align(sol.p[k].states, sol.p[k].values, ref["states"][k], ref["p"][k])
+        assert np.abs(a - b).max() < 2e-6          # both are within fsptol of the exact CME solution
+        assert sol.p[k].sum() + sol.sinks[k].sum() == pytest.approx(1.0, abs=1e-9)
+
+
+def test_birth_death_poisson(pkg):
+    S = np.array([[1], [-1]]).T
+    lam, gam = 10.0, 0.5
+    model = pkg.CmeModel(S, [pkg.propensity(lambda x, p: p[0] + 0.0 * x[0]), pkg.propensity(lambda x, p: p[1] * x[0])],
+                         [lam, gam])
+    alg = pkg.AdaptiveFspSparse(ode_method=pkg.NativeRK45(), space_adapter=pkg.RStepAdapter(10, 10, False))
+    sol = pkg.solve(model, pkg.FspVectorSparse([[0]], [1.0]), (0.0, 4.0), alg, saveat=[1.0, 4.0], fsptol=1e-8,
+                    odeatol=1e-13, odertol=1e-9)
+    for k, t in enumerate([1.0, 4.0]):
+        mu = lam / gam * (1 - math.exp(-gam * t))
+        assert np.abs(sol.p[k].values - poisson.pmf(sol.p[k].states[:, 0], mu)).max() < 1e-7
+
+
+def test_toggle_variants_agree(pkg):  # examples/toggleswitch_fsp_variants.jl (shortened horizon)
+    touts = np.arange(0.0, 7201.0, 600.0)
+    p0 = pkg.FspVectorSparse([[0, 0]], [1.0])
+    res = {}
+    for name, sep, ada in [("full_sep", True, pkg.RStepAdapter(20, 5, True)), ("sel_sep", True, pkg.SelectiveRStepAdapter(20, 5, True)),
+                           ("full_joint", False, pkg.RStepAdapter(20, 5, True))]:
+        model = pkg.workloads.toggle_model(separable=sep)
+        res[name] = pkg.solve(model, p0, (0.0, 7200.0), pkg.AdaptiveFspSparse(None, ada), saveat=touts, odertol=1e-6,
+                              odeatol=1e-14)
+    for name, sol in res.items():
+        assert len(sol) == len(touts) + 1                      # + the final slice (duplicate of tend, as the reference)
+        for p, s in zip(sol.p, sol.sinks):
+            assert p.sum() + s.sum() == pytest.approx(1.0, abs=1e-9)
+    for k in range(len(touts)):
+        a, b = _align(res["full_sep"].p[k].states, res["full_sep"].p[k].values, res["full_joint"].p[k].states,
+                      res["full_joint"].p[k].values)
+        assert np.abs(a - b).max() < 1e-7
+        a, b = _align(res["full_sep"].p[k].states, res["full_sep"].p[k].values, res["sel_sep"].p[k].states,
+                      res["sel_sep"].p[k].values)
+        assert np.abs(a - b).max() < 5e-6
+
+
+def test_prune_by_mass_matches_oracle(pkg, ctx):
+    rng = np.random.default_rng(11)
+    for n, strict in [(10, False), (1000, False), (5000, True), (70001, False)]:
+        osp = StateSpaceOracleFast(TOGGLE_S, [0, 0])
+        L = int(math.sqrt(2 * n)) + 2
+        osp.expand(L)
+        m = osp.get_state_count()
+        p = rng.random(m) ** 8
+        p[rng.integers(0, m, size=m // 10)] = 0.0               # ties
+        p[rng.integers(0, m, size=3)] = -1e-18                  # tiny negatives, as an integrator leaves them
+        p /= p.sum() / (1 - 3e-7)
+        ada = (SelectiveRStepAdapterOracle if strict else RStepAdapterOracle)(1, 1, True)
+        ids = ada.drop_ids(p, 0.5, 1.0, 1e-6)
+        sp = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
+        sp.expand_(L)
+        dp = pkg.DeviceVector.from_host(ctx, p)
+        dropped = sp.prune_by_mass_(dp, 1.0 - 0.5 * 1e-6, strict)
+        assert abs(dropped - len(ids)) <= 2                     # knife-edge: cumulative rounding may shift the count
+        if dropped == len(ids):
+            osp.deleteat(ids)
+            assert np.array_equal(sp.get_states(), osp.states_array())
+            assert np.array_equal(sp.get_sink_connectivity().astype(np.int64), osp.sink_connectivity_array())
+            q = pkg.DeviceVector(ctx, sp.get_state_count())
+            sp.compact_vector(dp, q)
+            assert np.array_equal(q.to_host(), np.delete(p, ids - 1))
+        assert p.sum() - np.sort(p)[:dropped].sum() >= 1.0 - 0.5e-6 - 1e-12
+
+
+def test_vector_ops(pkg, ctx):
+    rng = np.random.default_rng(0)
+    n = 100003
+    a, b, c = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    da, db, dc = (pkg.DeviceVector.from_host(ctx, v) for v in (a, b, c))
+    assert da.sum() == pytest.approx(a.sum(), rel=1e-12, abs=1e-9)
+    assert da.dot(db) == pytest.approx(a @ b, rel=1e-12, abs=1e-9)
+    assert da.sum(7, 1000) == pytest.approx(a[7:1007].sum(), rel=1e-12, abs=1e-12)
+    out = pkg.DeviceVector(ctx, n)
+    out.lincomb([2.0, -1.0, 0.5], [da, db, dc])
+    assert np.allclose(out.to_host(), 2 * a - b + 0.5 * c, rtol=1e-15, atol=1e-15)
+    out.axpy(3.0, da)
+    assert np.allclose(out.to_host(), 5 * a - b + 0.5 * c, rtol=1e-14, atol=1e-14)
+    out.scale(0.5)
+    assert np.allclose(out.to_host(), 0.5 * (5 * a - b + 0.5 * c), rtol=1e-14, atol=1e-14)
+    w = da.wrms(db, dc, 1e-6, 1e-3)
+    assert w == pytest.approx(np.sqrt(np.mean((a / (1e-6 + 1e-3 * np.maximum(np.abs(b), np.abs(c)))) ** 2)), rel=1e-12)
+    assert not da.any_nonfinite()
+    a2 = a.copy()
+    a2[5] = np.nan
+    assert pkg.DeviceVector.from_host(ctx, a2).any_nonfinite()
+    assert np.array_equal(da.view(10, 20).to_host(), a[10:30])
+    assert da.sum() == da.sum()                                  # deterministic
