@@ -172,6 +172,30 @@ int ncme_vec_wrms(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* u
                   double atol, double rtol, double* out);
 int ncme_vec_any_nonfinite(ncme_ctx* ctx, int64_t n, const double* x_dev, int* out);
 
+/* ---------------------------------------------------------------- multi-GPU (K8) --------------- */
+/* One process per GPU.  The reference is single-process (no collective call site exists in it); large state
+ * spaces are row-sharded here: rank r owns a contiguous block of state rows of A and the matching slices of every
+ * FSP vector; a matvec exchanges the halo of x with the neighbouring shards (grouped ncclSend/ncclRecv, overlapped
+ * with the rows that touch no halo entry) and the nr sink rows are partial sums that are all-reduced.
+ * The state space itself is replicated (every rank runs the same expand!/prune; they are rare next to matvecs). */
+typedef struct ncme_comm ncme_comm;
+/* rank 0 creates the id and the host language broadcasts the 128 bytes (torch.distributed / MPI / Distributed.jl) */
+int ncme_comm_unique_id(char* out128);
+int ncme_comm_create(ncme_ctx* ctx, int rank, int nranks, const char* uid128, ncme_comm** out);
+int ncme_comm_destroy(ncme_comm* comm);
+int ncme_comm_rank(ncme_comm* comm, int* rank, int* nranks);
+int ncme_comm_allreduce_sum(ncme_comm* comm, double* buf_dev, int64_t count);
+int ncme_comm_allgatherv(ncme_comm* comm, const double* send_dev, double* recv_dev, const int64_t* counts,
+                         const int64_t* displs);
+/* FspMatrixSparse restricted to this rank's rows.  propvals covers ALL states (n_global x nr, as ncme_matrix_create).
+ * Vectors used with a sharded matrix hold [local rows | nr sink entries]; a matvec INPUT must be allocated with
+ * info[2] doubles of margin before it and info[3] after it (the halo is received in place).
+ * ncme_matvec on a sharded matrix returns globally reduced sink entries on every rank. */
+int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
+                               ncme_matrix** out);
+/* info = {row_lo, row_hi, halo_lo, halo_hi, n_global, interior_begin, interior_end, nranks} */
+int ncme_matrix_shard_info(ncme_matrix* mat, int64_t info[8]);
+
 /* ---------------------------------------------------------------- prune (adapt!) --------------- */
 /* The dropstates branch of adapt!           src/transientcme/sparse/rstepadapters.jl:40-46 (RStepAdapter, strict=0:
  * `>=`) and :93-99 (SelectiveRStepAdapter, strict=1: `>`):

@@ -16,4 +16,5 @@ from .fspmatrix import FspMatrixSparse, matvec_, matvecadd_, matvec, get_rowcoun
 from .sensmatrix import ForwardSensFspMatrixSparse, sens_matvec_
 from .fspvector import FspVectorSparse, FspOutputSparse, FspOutputSliceSparse
 from .transientcme import (solve, AdaptiveFspSparse, RStepAdapter, SelectiveRStepAdapter, NativeRK45, init_, adapt_)
+from .parallel import Comm, ShardedVector, shard_bounds
 from . import workloads

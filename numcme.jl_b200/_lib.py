@@ -69,6 +69,14 @@ SIGNATURES = {
     "ncme_sensmatrix_destroy": (cint, [p_void]),
     "ncme_sensmatrix_set_joint_values": (cint, [p_void, cint, p_f64]),
     "ncme_sens_matvec": (cint, [p_void, p_f64, p_f64, p_void, p_void]),
+    "ncme_comm_unique_id": (cint, [C.c_char_p]),
+    "ncme_comm_create": (cint, [p_void, cint, cint, C.c_char_p, C.POINTER(p_void)]),
+    "ncme_comm_destroy": (cint, [p_void]),
+    "ncme_comm_rank": (cint, [p_void, C.POINTER(cint), C.POINTER(cint)]),
+    "ncme_comm_allreduce_sum": (cint, [p_void, p_void, i64]),
+    "ncme_comm_allgatherv": (cint, [p_void, p_void, p_void, p_i64, p_i64]),
+    "ncme_matrix_create_sharded": (cint, [p_void, p_void, p_i32, p_f64, C.POINTER(p_void)]),
+    "ncme_matrix_shard_info": (cint, [p_void, p_i64]),
     "ncme_space_prune_by_mass": (cint, [p_void, p_void, f64, cint, p_i64]),
     "ncme_space_compact_vector": (cint, [p_void, p_void, p_void]),
     "ncme_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),

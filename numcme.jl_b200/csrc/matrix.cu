@@ -3,6 +3,10 @@
 // joint refresh :154-166, matvec!/matvecadd! :196-247).
 #include "matrix.cuh"
 
+#include <algorithm>
+
+#include "comm.cuh"
+
 namespace ncme {
 
 constexpr int SINK_CHUNK = 2048;
@@ -63,7 +67,7 @@ __device__ __forceinline__ void sink_task(const MatvecArgs& a) {
     __shared__ bool is_last;
     const int4 t = a.tasks[blockIdx.x];
     double s = 0.0;
-    for (int k = t.y + (int)threadIdx.x; k < t.z; k += MV_THREADS) s += __ldcs(a.sink_val + k) * __ldg(a.x + __ldcs(a.sink_row + k));
+    for (int k = t.y + (int)threadIdx.x; k < t.z; k += MV_THREADS) s += __ldcs(a.sink_val + k) * __ldg(a.xd + __ldcs(a.sink_row + k));
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -98,12 +102,13 @@ __device__ __forceinline__ void sink_task(const MatvecArgs& a) {
 // time-dependent coefficients that arrive by value in the launch parameters.
 template <int S, int ROWS>
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
-    if ((int)blockIdx.x < a.ntasks) {
+    const int nt = a.do_sinks ? a.ntasks : 0;
+    if ((int)blockIdx.x < nt) {
         sink_task(a);
         return;
     }
-    const int64_t i0 = ((int64_t)(blockIdx.x - a.ntasks) * MV_THREADS + threadIdx.x) * ROWS;
-    if (i0 >= a.n) return;
+    const int64_t i0 = a.row_begin + ((int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x) * ROWS;
+    if (i0 >= a.row_end) return;
 
     uint32_t c[S][ROWS];
     double v[S][ROWS];
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
     }
     double acc[ROWS];
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) acc[j] = (i0 + j < a.n) ? d[j] * __ldg(a.x + i0 + j) : 0.0;
+    for (int j = 0; j < ROWS; ++j) acc[j] = (i0 + j < a.row_end) ? d[j] * __ldg(a.xd + i0 + j) : 0.0;
     double g[S][ROWS];
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
     }
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
-        if (i0 + j < a.n) {
+        if (i0 + j < a.row_end) {
             double out = acc[j];
             if (a.beta != 0.0) out += a.beta * a.y[i0 + j];
             a.y[i0 + j] = out;
@@ -147,15 +152,16 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
 
 // Generic slot count (> 16 slots): same data flow without the register tile.
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_constant__ MatvecArgs a) {
-    if ((int)blockIdx.x < a.ntasks) {
+    const int nt = a.do_sinks ? a.ntasks : 0;
+    if ((int)blockIdx.x < nt) {
         sink_task(a);
         return;
     }
-    const int64_t i = (int64_t)(blockIdx.x - a.ntasks) * MV_THREADS + threadIdx.x;
-    if (i >= a.n) return;
+    const int64_t i = a.row_begin + (int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x;
+    if (i >= a.row_end) return;
     double d = 0.0;
     for (int k = 0; k < a.ndiag; ++k) d = fma(a.diag_coef[k], __ldcs(a.diag + (int64_t)k * a.ld + i), d);
-    double acc = d * __ldg(a.x + i);
+    double acc = d * __ldg(a.xd + i);
 #pragma unroll 4
     for (int s = 0; s < a.nslots; ++s) {
         const uint32_t c = __ldcs(a.col + (int64_t)s * a.ld + i);
@@ -169,7 +175,9 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_
 template <int ROWS>
 static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
     const int64_t rows_per_block = (int64_t)MV_THREADS * ROWS;
-    const unsigned grid = (unsigned)(a.ntasks + (a.n + rows_per_block - 1) / rows_per_block);
+    const int64_t nrows = a.row_end - a.row_begin;
+    const unsigned grid = (unsigned)((a.do_sinks ? a.ntasks : 0) + (nrows + rows_per_block - 1) / rows_per_block);
+    if (grid == 0) return 0;
     cudaStream_t st = A->ctx->stream;
     switch (a.nslots) {
 #define NCME_CASE(SS)                                              \
@@ -200,8 +208,8 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
             rc = launch_rows<1>(A, a);
     }
     if (rc != 0) {
-        const unsigned grid = (unsigned)(a.ntasks + (a.n + MV_THREADS - 1) / MV_THREADS);
-        k_fsp_matvec_generic<<<grid, MV_THREADS, 0, ctx->stream>>>(a);
+        const unsigned grid = (unsigned)((a.do_sinks ? a.ntasks : 0) + (a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS);
+        if (grid) k_fsp_matvec_generic<<<grid, MV_THREADS, 0, ctx->stream>>>(a);
     }
     ctx->launches++;
     NCME_CUDA(cudaGetLastError());
@@ -233,6 +241,82 @@ int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a) {
     for (int r = 0; r <= A->nr; ++r) a->task_ptr[r] = A->task_ptr[r];
     a->sink_partial = A->sink_partial.p;
     a->sink_counter = A->sink_counter;
+    a->row_begin = 0;
+    a->row_end = A->n;
+    a->do_sinks = 1;
+    return NCME_OK;
+}
+
+// Halo of x between row shards: one grouped ncclSend/ncclRecv round with the ranks whose rows this rank's
+// predecessor window touches (rank +-1 for level-ordered state spaces).
+int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st) {
+    if (!A->comm || A->comm->nranks == 1 || (A->halo_send.empty() && A->halo_recv.empty())) return NCME_OK;
+    const NcclApi* api = nccl_api();
+    double* x = const_cast<double*>(x_local);
+    NCME_NCCL(api->GroupStart());
+    for (const auto& sg : A->halo_send) {
+        ncclResult_t r = api->Send(x + sg.offset, (size_t)sg.count, ncclDouble, sg.peer, A->comm->nccl, st);
+        if (r != ncclSuccess) {
+            api->GroupEnd();
+            set_error("ncclSend failed: %s", api->GetErrorString(r));
+            return NCME_ERR_COMM;
+        }
+        A->comm->bytes_sent += 8 * sg.count;
+    }
+    for (const auto& sg : A->halo_recv) {
+        ncclResult_t r = api->Recv(x + sg.offset, (size_t)sg.count, ncclDouble, sg.peer, A->comm->nccl, st);
+        if (r != ncclSuccess) {
+            api->GroupEnd();
+            set_error("ncclRecv failed: %s", api->GetErrorString(r));
+            return NCME_ERR_COMM;
+        }
+    }
+    NCME_NCCL(api->GroupEnd());
+    return NCME_OK;
+}
+
+int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, double* y_local, double beta, int reduce_sinks) {
+    MatvecArgs a;
+    matvec_fill_args(A, coef, &a);
+    a.xd = x_local;
+    a.x = x_local - A->hl;
+    a.y = y_local;
+    a.beta = beta;
+    ncme_comm* c = A->comm;
+    if (!c || c->nranks == 1) return matvec_launch(A, a);
+    cudaStream_t st = A->ctx->stream;
+    const bool overlap = A->b1 > A->b0;
+    if (!overlap) {
+        NCME_TRY(halo_exchange(A, x_local, st));
+        NCME_TRY(matvec_launch(A, a));
+    } else {
+        // halo on the communication stream while the rows that touch no halo entry are computed
+        NCME_CUDA(cudaEventRecord(c->ev_ready, st));
+        NCME_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+        NCME_TRY(halo_exchange(A, x_local, c->comm_stream));
+        NCME_CUDA(cudaEventRecord(c->ev_done, c->comm_stream));
+        MatvecArgs in = a;
+        in.row_begin = A->b0;
+        in.row_end = A->b1;
+        in.do_sinks = 1;     // sink rows read local x only
+        NCME_TRY(matvec_launch(A, in));
+        NCME_CUDA(cudaStreamWaitEvent(st, c->ev_done, 0));
+        if (A->b0 > 0) {
+            MatvecArgs lo = a;
+            lo.row_begin = 0;
+            lo.row_end = A->b0;
+            lo.do_sinks = 0;
+            NCME_TRY(matvec_launch(A, lo));
+        }
+        if (A->b1 < A->n) {
+            MatvecArgs hi = a;
+            hi.row_begin = A->b1;
+            hi.row_end = A->n;
+            hi.do_sinks = 0;
+            NCME_TRY(matvec_launch(A, hi));
+        }
+    }
+    if (reduce_sinks) NCME_TRY(comm_allreduce_sum(c, y_local + A->n, (size_t)A->nr, st));
     return NCME_OK;
 }
 
@@ -243,30 +327,58 @@ struct SlotReactions {
 };
 
 // col/val of one slot from the predecessor table and the uploaded state factors G[r][i].
-__global__ void k_assemble_slot(const uint32_t* __restrict__ pred_r0, const double* __restrict__ G, int64_t n,
-                                SlotReactions sr, uint32_t* __restrict__ col, double* __restrict__ val, int64_t ld) {
+struct ShardGeom {
+    int64_t n_global, row_lo, row_hi, ext_lo, nloc;
+    int nr;
+};
+
+// position of global state j inside the halo-padded x buffer [halo_lo | local | sinks | halo_hi]
+__device__ __forceinline__ uint32_t padded_pos(const ShardGeom& g, int64_t j) {
+    return (uint32_t)(j - g.ext_lo + (j >= g.row_hi ? g.nr : 0));
+}
+
+__global__ void k_assemble_slot(const uint32_t* __restrict__ pred_r0 /*global rows*/, const double* __restrict__ G,
+                                ShardGeom g, SlotReactions sr, uint32_t* __restrict__ col, double* __restrict__ val,
+                                int64_t ld) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ld) return;
-    uint32_t c = 0;
+    uint32_t c = padded_pos(g, g.row_lo);
     double v = 0.0;
-    if (i < n) {
-        const uint32_t p = pred_r0[i];
-        c = (p == NONE32) ? (uint32_t)i : p;
+    if (i < g.nloc) {
+        const int64_t gi = g.row_lo + i;
+        const uint32_t p = pred_r0[gi];
+        c = padded_pos(g, p == NONE32 ? gi : (int64_t)p);
         if (p != NONE32)
-            for (int k = 0; k < sr.count; ++k) v += G[(int64_t)sr.r[k] * n + p];
+            for (int k = 0; k < sr.count; ++k) v += G[(int64_t)sr.r[k] * g.n_global + p];
     }
     col[i] = c;
     val[i] = v;
 }
 
-__global__ void k_assemble_diag(const double* __restrict__ G, int64_t n, SlotReactions sr, double* __restrict__ diag,
+__global__ void k_assemble_diag(const double* __restrict__ G, ShardGeom g, SlotReactions sr, double* __restrict__ diag,
                                 int64_t ld) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ld) return;
     double v = 0.0;
-    if (i < n)
-        for (int k = 0; k < sr.count; ++k) v -= G[(int64_t)sr.r[k] * n + i];
+    if (i < g.nloc)
+        for (int k = 0; k < sr.count; ++k) v -= G[(int64_t)sr.r[k] * g.n_global + g.row_lo + i];
     diag[i] = v;
+}
+
+// predecessor window of the local rows (min / max global predecessor index) and the interior row range
+__global__ void k_pred_window(const uint32_t* __restrict__ pred_r /*global rows*/, ShardGeom g, unsigned int* mnmx /*[4]*/) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.nloc) return;
+    const uint32_t p = pred_r[g.row_lo + i];
+    if (p == NONE32) return;
+    if ((int64_t)p < g.row_lo) {
+        atomicMin(&mnmx[0], p);
+        atomicMax(&mnmx[2], (unsigned int)(i + 1));   // rows [0, b0) touch the low halo
+    }
+    if ((int64_t)p >= g.row_hi) {
+        atomicMax(&mnmx[1], p);
+        atomicMin(&mnmx[3], (unsigned int)i);         // rows [b1, nloc) touch the high halo
+    }
 }
 
 __global__ void k_bit_flags(const uint32_t* __restrict__ mask, int64_t n, int r, uint32_t* __restrict__ flags) {
@@ -293,7 +405,7 @@ __global__ void k_set_joint(const double* __restrict__ vals, int64_t n, const ui
                             double* __restrict__ val, double* __restrict__ diag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t c = col[i];
+    const uint32_t c = col[i];   // single-GPU matrices only: padded position == global index
     val[i] = (c == (uint32_t)i) ? 0.0 : vals[c];
     diag[i] = -vals[i];
 }
@@ -317,16 +429,29 @@ static bool zero_stoich(const ncme_space* sp, int r) {
     return true;
 }
 
-static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A) {
+static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A, ncme_comm* comm) {
     ncme_ctx* ctx = sp->ctx;
     cudaStream_t st = ctx->stream;
     const int nr = sp->nr;
-    const int64_t n = sp->n;
+    const int64_t ng = sp->n;             // global number of states
+    // contiguous row blocks, boundaries on multiples of 64 rows (vector-load alignment of the row ranges)
+    const int P = comm ? comm->nranks : 1, me = comm ? comm->rank : 0;
+    auto cut = [&](int r) -> int64_t {
+        if (r <= 0) return 0;
+        if (r >= P) return ng;
+        return std::min<int64_t>(ng, round_up<int64_t>((int64_t)((__int128)ng * r / P), 64));
+    };
+    const int64_t row_lo = cut(me), row_hi = cut(me + 1);
+    const int64_t n = row_hi - row_lo;    // local rows
     A->ctx = ctx;
+    A->comm = (comm && comm->nranks > 1) ? comm : nullptr;
     A->ns = sp->ns;
     A->nr = nr;
     A->n = n;
     A->N = n + nr;
+    A->n_global = ng;
+    A->row_lo = row_lo;
+    A->row_hi = row_hi;
     A->ld = round_up<int64_t>(n > 0 ? n : 1, 64);
     for (int r = 0; r < nr; ++r) {
         NCME_REQUIRE(kind[r] >= 0 && kind[r] <= 2, "bad reaction kind");
@@ -376,28 +501,86 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     A->nslots = nslots;
     A->ndiag = ndiag;
 
-    // ---- upload the state factors (joint reactions start at zero, :87,129)
+    // ---- upload the state factors of ALL states (the values at predecessors outside the shard are needed;
+    //      joint reactions start at zero, :87,129)
     DevArray<double> G;
-    NCME_TRY(G.reserve((size_t)(n > 0 ? n : 1) * nr, st, false));
-    for (int r = 0; r < nr && n > 0; ++r) {
+    NCME_TRY(G.reserve((size_t)(ng > 0 ? ng : 1) * nr, st, false));
+    for (int r = 0; r < nr && ng > 0; ++r) {
         if (kind[r] == NCME_JOINT_TV || !propvals)
-            NCME_CUDA(cudaMemsetAsync(G.p + (size_t)r * n, 0, (size_t)n * 8, st));
+            NCME_CUDA(cudaMemsetAsync(G.p + (size_t)r * ng, 0, (size_t)ng * 8, st));
         else
-            NCME_CUDA(cudaMemcpyAsync(G.p + (size_t)r * n, propvals + (size_t)r * n, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            NCME_CUDA(cudaMemcpyAsync(G.p + (size_t)r * ng, propvals + (size_t)r * ng, (size_t)ng * 8, cudaMemcpyHostToDevice, st));
     }
+    // ---- predecessor window of the local rows -> halo extents and the halo-free interior row range
+    ShardGeom geom{ng, row_lo, row_hi, row_lo, n, nr};
+    A->ext_lo = row_lo;
+    A->ext_hi = row_hi;
+    A->b0 = 0;
+    A->b1 = n;
+    if (A->comm && n > 0) {
+        unsigned int h_mm[4] = {0xFFFFFFFFu, 0u, 0u, (unsigned int)n};
+        unsigned int* d_mm = nullptr;
+        NCME_CUDA(cudaMalloc(&d_mm, sizeof(h_mm)));
+        NCME_CUDA(cudaMemcpyAsync(d_mm, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, st));
+        for (int s = 0; s < nslots; ++s) {
+            k_pred_window<<<nblk(n), 256, 0, st>>>(sp->pred.p + (size_t)slots[s].r[0] * sp->ld, geom, d_mm);
+            ctx->launches++;
+        }
+        NCME_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_mm);
+        if (h_mm[0] != 0xFFFFFFFFu) A->ext_lo = std::min<int64_t>(row_lo, (int64_t)h_mm[0]);
+        if (h_mm[1] != 0u) A->ext_hi = std::max<int64_t>(row_hi, (int64_t)h_mm[1] + 1);
+        A->b0 = round_up<int64_t>((int64_t)h_mm[2], 64);
+        A->b1 = (int64_t)h_mm[3] / 64 * 64;
+        if (A->b0 >= A->b1) A->b0 = A->b1 = 0;   // no halo-free interior: everything waits for the halo
+    }
+    A->hl = row_lo - A->ext_lo;
+    A->hh = A->ext_hi - row_hi;
+    geom.ext_lo = A->ext_lo;
+    NCME_REQUIRE(A->ext_hi - A->ext_lo + nr < 0xFFFFFFF0ll, "padded window exceeds the 32-bit index range");
     NCME_TRY(A->col.reserve((size_t)A->ld * (nslots > 0 ? nslots : 1), st, false));
     NCME_TRY(A->val.reserve((size_t)A->ld * (nslots > 0 ? nslots : 1), st, false));
     NCME_TRY(A->diag.reserve((size_t)A->ld * (ndiag > 0 ? ndiag : 1), st, false));
     for (int s = 0; s < nslots; ++s) {
-        k_assemble_slot<<<nblk(A->ld), 256, 0, st>>>(sp->pred.p + (size_t)slots[s].r[0] * sp->ld, G.p, n, slots[s],
+        k_assemble_slot<<<nblk(A->ld), 256, 0, st>>>(sp->pred.p + (size_t)slots[s].r[0] * sp->ld, G.p, geom, slots[s],
                                                      A->col.p + (size_t)s * A->ld, A->val.p + (size_t)s * A->ld, A->ld);
         ctx->launches++;
     }
     for (int d = 0; d < ndiag; ++d) {
-        k_assemble_diag<<<nblk(A->ld), 256, 0, st>>>(G.p, n, diags[d], A->diag.p + (size_t)d * A->ld, A->ld);
+        k_assemble_diag<<<nblk(A->ld), 256, 0, st>>>(G.p, geom, diags[d], A->diag.p + (size_t)d * A->ld, A->ld);
         ctx->launches++;
     }
     NCME_CUDA(cudaGetLastError());
+    // ---- halo plan: who owns what I need, who needs what I own
+    if (A->comm) {
+        double mine[4] = {(double)row_lo, (double)row_hi, (double)A->ext_lo, (double)A->ext_hi};
+        double* all = A->comm->scratch;
+        NCME_CUDA(cudaMemcpyAsync(all + 4 * me, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+        NCME_NCCL(nccl_api()->AllGather(all + 4 * me, all, 4, ncclDouble, A->comm->nccl, st));
+        std::vector<double> h((size_t)4 * P);
+        NCME_CUDA(cudaMemcpyAsync(h.data(), all, sizeof(double) * 4 * P, cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        auto isect = [](int64_t a0, int64_t a1, int64_t b0, int64_t b1, int64_t* s0, int64_t* s1) {
+            *s0 = std::max(a0, b0);
+            *s1 = std::min(a1, b1);
+            return *s1 > *s0;
+        };
+        A->halo_send.clear();
+        A->halo_recv.clear();
+        for (int q = 0; q < P; ++q) {
+            if (q == me) continue;
+            const int64_t qlo = (int64_t)h[4 * q], qhi = (int64_t)h[4 * q + 1], qelo = (int64_t)h[4 * q + 2],
+                          qehi = (int64_t)h[4 * q + 3];
+            int64_t s0, s1;
+            // what q needs from my rows: its low halo [qelo, qlo) and its high halo [qhi, qehi)
+            if (isect(qelo, qlo, row_lo, row_hi, &s0, &s1)) A->halo_send.push_back({q, s0 - row_lo, s1 - s0});
+            if (isect(qhi, qehi, row_lo, row_hi, &s0, &s1)) A->halo_send.push_back({q, s0 - row_lo, s1 - s0});
+            // what I need from q's rows
+            if (isect(A->ext_lo, row_lo, qlo, qhi, &s0, &s1)) A->halo_recv.push_back({q, s0 - row_lo, s1 - s0});
+            if (isect(row_hi, A->ext_hi, qlo, qhi, &s0, &s1)) A->halo_recv.push_back({q, s0 - row_lo + nr, s1 - s0});
+        }
+    }
 
     // ---- sink lists (rows ascending inside each reaction) and structural counts
     DevArray<uint32_t> flags, pos, scratch;
@@ -408,7 +591,7 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     std::vector<uint64_t> nsink_r((size_t)nr, 0);
     int rc = NCME_OK;
     for (int r = 0; r < nr && n > 0 && rc == NCME_OK; ++r) {
-        k_pred_flags<<<nblk(n), 256, 0, st>>>(sp->pred.p + (size_t)r * sp->ld, n, flags.p);
+        k_pred_flags<<<nblk(n), 256, 0, st>>>(sp->pred.p + (size_t)r * sp->ld + row_lo, n, flags.p);
         ctx->launches++;
         uint64_t tot = 0;
         rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, &tot);
@@ -419,7 +602,7 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     for (int r = 0; r < nr && rc == NCME_OK; ++r) {
         uint64_t tot = 0;
         if (n > 0) {
-            k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p, n, r, flags.p);
+            k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p + row_lo, n, r, flags.p);
             ctx->launches++;
             rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, &tot);
         }
@@ -433,10 +616,10 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     }
     for (int r = 0; r < nr && rc == NCME_OK && n > 0; ++r) {
         if (nsink_r[(size_t)r] == 0) continue;
-        k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p, n, r, flags.p);
+        k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p + row_lo, n, r, flags.p);
         ctx->launches++;
         rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, nullptr);
-        k_fill_sinks<<<nblk(n), 256, 0, st>>>(flags.p, pos.p, n, G.p + (size_t)r * n, A->sink_row.p + A->sink_ptr[r],
+        k_fill_sinks<<<nblk(n), 256, 0, st>>>(flags.p, pos.p, n, G.p + (size_t)r * ng + row_lo, A->sink_row.p + A->sink_ptr[r],
                                               A->sink_val.p + A->sink_ptr[r]);
         ctx->launches++;
     }
@@ -497,15 +680,36 @@ using namespace ncme;
 extern "C" {
 
 int ncme_matrix_create(ncme_space* space, const int32_t* kind, const double* propvals, ncme_matrix** out) {
+    return ncme_matrix_create_sharded(space, nullptr, kind, propvals, out);
+}
+
+int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
+                               ncme_matrix** out) {
     NCME_REQUIRE(space && kind && out, "null argument");
     NCME_REQUIRE(propvals || space->n == 0, "propvals is null");
+    if (comm && comm->nranks > 1)
+        for (int r = 0; r < space->nr; ++r)
+            NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
     ncme_matrix* A = new ncme_matrix();
-    int st = matrix_build(space, kind, propvals, A);
+    int st = matrix_build(space, kind, propvals, A, comm);
     if (st != NCME_OK) {
         ncme_matrix_destroy(A);
         return st;
     }
     *out = A;
+    return NCME_OK;
+}
+
+int ncme_matrix_shard_info(ncme_matrix* A, int64_t info[8]) {
+    NCME_REQUIRE(A && info, "null argument");
+    info[0] = A->row_lo;
+    info[1] = A->row_hi;
+    info[2] = A->hl;
+    info[3] = A->hh;
+    info[4] = A->n_global;
+    info[5] = A->b0;
+    info[6] = A->b1;
+    info[7] = A->comm ? A->comm->nranks : 1;
     return NCME_OK;
 }
 
@@ -544,6 +748,7 @@ int ncme_matrix_set_joint_values(ncme_matrix* A, int reaction, const double* val
                  "reaction %d is not a joint time-varying reaction", reaction);
     const int r = reaction - 1;
     const int s = A->reaction_slot[r], d = A->reaction_diag[r];
+    NCME_REQUIRE(!A->comm, "joint reactions are single-GPU only");
     if (s < 0 || A->n == 0) return NCME_OK;
     ncme_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
@@ -570,16 +775,13 @@ int ncme_matvec(ncme_matrix* A, const double* coef, const double* x_dev, double*
     bool need_coef = false;
     for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] == NCME_SEPARABLE_TV);
     NCME_REQUIRE(coef || !need_coef, "coef is null but the matrix has separable time-varying reactions");
-    MatvecArgs a;
-    matvec_fill_args(A, coef, &a);
-    a.x = x_dev;
-    a.y = y_dev;
-    a.beta = beta;
-    return matvec_launch(A, a);
+    NCME_REQUIRE(!(A->comm && beta != 0.0), "matvecadd! is not supported on row-sharded matrices");
+    return matvec_dist(A, coef, x_dev, y_dev, beta, 1);
 }
 
 int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, double* y_host, double beta) {
     NCME_REQUIRE(A && x_host && y_host, "null argument");
+    NCME_REQUIRE(!A->comm, "the host-buffer matvec is single-GPU only");
     ncme_ctx* ctx = A->ctx;
     const size_t bytes = (size_t)A->N * sizeof(double);
     if (ctx->stage_dev_bytes < bytes) {

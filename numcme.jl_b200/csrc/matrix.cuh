@@ -18,11 +18,25 @@
 #pragma once
 #include "space.cuh"
 
+struct ncme_comm;
+
 struct ncme_matrix {
     ncme_ctx* ctx = nullptr;
     int ns = 0, nr = 0;
-    int64_t n = 0, N = 0, ld = 0;
+    int64_t n = 0, N = 0, ld = 0;   // n = rows held by this rank, N = n + nr (local vector length)
     int kind[NCME_MAX_REACTIONS] = {0};
+
+    // row sharding (K8).  Single GPU: comm == nullptr, row_lo = 0, row_hi = n_global = n, no halo.
+    // x vectors are addressed through xb = x_local - hl: [halo_lo (hl) | local rows (n) | sinks (nr) | halo_hi (hh)]
+    ncme_comm* comm = nullptr;
+    int64_t n_global = 0, row_lo = 0, row_hi = 0, ext_lo = 0, ext_hi = 0, hl = 0, hh = 0;
+    int64_t b0 = 0, b1 = 0;         // rows [b0, b1) touch no halo entry (computed while the halo is in flight)
+    struct HaloSeg {
+        int peer;
+        int64_t offset;  // doubles, relative to x_local (may be negative for the low halo)
+        int64_t count;
+    };
+    std::vector<HaloSeg> halo_send, halo_recv;
 
     int nslots = 0;
     int slot_coef_src[NCME_MAX_REACTIONS] = {0};   // reaction whose time factor scales the slot, -1 => 1.0
@@ -76,12 +90,20 @@ struct MatvecArgs {
     int task_ptr[NCME_MAX_REACTIONS + 1];
     double* sink_partial;
     unsigned int* sink_counter;
-    const double* x;
+    const double* x;    // xb: base of the halo-padded input (== xd on a single GPU)
+    const double* xd;   // x_local: entry of row i is xd[i]
     double* y;
     double beta;
+    int64_t row_begin, row_end;  // rows handled by this launch
+    int do_sinks;                // 1: the sink-task CTAs run in this launch
 };
 
 int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a);
 int matvec_launch(ncme_matrix* A, const MatvecArgs& a);
+// y_local = A(t) x_local for a (possibly sharded) matrix.  Sharded: exchanges the halo of x in place (x_local must
+// have hl doubles of margin before it and hh after its nr sink entries); the nr sink entries of y hold this rank's
+// partial sums unless reduce_sinks != 0.
+int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, double* y_local, double beta, int reduce_sinks);
+int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st);
 
 }  // namespace ncme

@@ -257,6 +257,7 @@ int ncme_sensmatrix_destroy(ncme_sensmatrix* SA) {
 int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t* ent_reaction, const int32_t* ent_param,
                            const double* dpropvals, ncme_sensmatrix** out) {
     NCME_REQUIRE(A && out && npar >= 0 && nentries >= 0, "bad arguments");
+    NCME_REQUIRE(!A->comm, "the sensitivity matrix is single-GPU only");
     NCME_REQUIRE(nentries <= SMAX_ENT, "too many (reaction, parameter) entries (max %d)", SMAX_ENT);
     NCME_REQUIRE(npar <= SMAX_ENT, "too many parameters (max %d)", SMAX_ENT);
     NCME_REQUIRE(nentries == 0 || (ent_reaction && ent_param && dpropvals), "null entry arrays");
@@ -360,6 +361,7 @@ int ncme_sens_matvec(ncme_sensmatrix* SA, const double* coef, const double* dcoe
     SensArgs a;
     matvec_fill_args(A, coef, &a.m);
     a.m.x = X;
+    a.m.xd = X;
     a.m.y = Y;
     a.m.beta = 0.0;
     a.npar = SA->npar;

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 
+#include "comm.cuh"
 #include "matrix.cuh"
 #include "vec.cuh"
 
@@ -35,7 +36,8 @@ __global__ void __launch_bounds__(ST) k_rk_errnorm(const __grid_constant__ StepA
     __shared__ double wsum[ST / 32];
     __shared__ bool is_last;
     double s = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x; i < a.N; i += (int64_t)gridDim.x * ST) {
+    // state rows only: the sink entries are per-rank partial sums, their contribution is added by the host
+    for (int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * ST) {
         double err = 0.0;
 #pragma unroll
         for (int j = 0; j < 7; ++j)
@@ -123,15 +125,18 @@ struct Workspace {
     double* base = nullptr;
     double* k[7];
     double* ytmp;
-    double* unew;
+    double* ua;
+    double* ub;
+    double* full = nullptr;     // n_global + R, for gathered output slices (sharded runs)
     double* pinned = nullptr;
     ~Workspace() {
         if (base) cudaFree(base);
+        if (full) cudaFree(full);
         if (pinned) cudaFreeHost(pinned);
     }
 };
 
-// sum over sinks of the dense output at theta, from the tails gathered by k_rk_errnorm
+// sum over sinks of the dense output at theta, from the (globally reduced) tails gathered by k_rk_errnorm
 static double sink_dense_sum(const double* tails, int R, double h, double theta) {
     double s = 0.0;
     const double th = theta, th1 = 1.0 - theta;
@@ -147,43 +152,78 @@ static double sink_dense_sum(const double* tails, int R, double h, double theta)
     return s;
 }
 
+__global__ void k_zero_tail(double* p, int R) {
+    if ((int)threadIdx.x < R) p[threadIdx.x] = 0.0;
+}
+
 static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
                      double* u, const ncme_solve_opts* o, ncme_solve_stats* st) {
     ncme_ctx* ctx = A->ctx;
+    ncme_comm* comm = A->comm;          // nullptr on a single GPU
     cudaStream_t s = ctx->stream;
-    const int64_t N = A->N, n = A->n;
+    const int64_t N = A->N, n = A->n;   // local vector length / local rows
     const int R = A->nr;
+    const int64_t Nglob = A->n_global + R;
     const int64_t launches0 = ctx->launches;
     Workspace ws;
-    const size_t Npad = round_up<size_t>((size_t)N, 32);
-    NCME_CUDA(cudaMalloc(&ws.base, Npad * 9 * sizeof(double)));
-    for (int j = 0; j < 7; ++j) ws.k[j] = ws.base + Npad * j;
-    ws.ytmp = ws.base + Npad * 7;
-    ws.unew = ws.base + Npad * 8;
-    if (save_fn) NCME_CUDA(cudaMallocHost(&ws.pinned, (size_t)N * sizeof(double)));
+    // every vector that can be a matvec input carries the halo margins: [hl | n rows | R sinks | hh]
+    const size_t hl = round_up<size_t>((size_t)A->hl, 32), hh = round_up<size_t>((size_t)A->hh, 32);
+    const size_t Npad = hl + round_up<size_t>((size_t)N, 32) + hh;
+    NCME_CUDA(cudaMalloc(&ws.base, Npad * 10 * sizeof(double)));
+    for (int j = 0; j < 7; ++j) ws.k[j] = ws.base + Npad * j + hl;
+    ws.ytmp = ws.base + Npad * 7 + hl;
+    ws.ua = ws.base + Npad * 8 + hl;
+    ws.ub = ws.base + Npad * 9 + hl;
+    if (save_fn) NCME_CUDA(cudaMallocHost(&ws.pinned, (size_t)Nglob * sizeof(double)));
+    if (save_fn && comm) NCME_CUDA(cudaMalloc(&ws.full, (size_t)Nglob * sizeof(double)));
 
     double coef[NCME_MAX_REACTIONS];
     for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
     auto rhs = [&](double t, const double* x, double* y) -> int {
         if (coef_fn) coef_fn(t, coef, user);
         st->rhs_evals++;
-        return ncme_matvec(A, coef, x, y, 0.0);
+        return matvec_dist(A, coef, x, y, 0.0, /*reduce_sinks=*/0);
     };
+    // hand a slice to the host: sharded runs gather [all state rows | reduced sinks] on every rank first.
+    // `v_dev` holds per-rank partial sink entries (see below).
+    std::vector<int64_t> counts, displs;
+    if (comm) {
+        counts.resize(comm->nranks);
+        displs.resize(comm->nranks);
+        double mine = (double)n;
+        NCME_CUDA(cudaMemcpyAsync(comm->scratch + comm->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
+        NCME_NCCL(nccl_api()->AllGather(comm->scratch + comm->rank, comm->scratch, 1, ncclDouble, comm->nccl, s));
+        std::vector<double> hc(comm->nranks);
+        NCME_CUDA(cudaMemcpyAsync(hc.data(), comm->scratch, sizeof(double) * comm->nranks, cudaMemcpyDeviceToHost, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        int64_t off = 0;
+        for (int r = 0; r < comm->nranks; ++r) {
+            counts[r] = (int64_t)hc[r];
+            displs[r] = off;
+            off += counts[r];
+        }
+    }
     auto save = [&](double t, const double* v_dev) -> int {
         if (!save_fn) return NCME_OK;
-        NCME_CUDA(cudaMemcpyAsync(ws.pinned, v_dev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+        const double* src = v_dev;
+        if (comm) {
+            NCME_TRY(comm_allgatherv(comm, v_dev, ws.full, counts.data(), displs.data(), s));
+            NCME_CUDA(cudaMemcpyAsync(ws.full + A->n_global, v_dev + n, (size_t)R * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            NCME_TRY(comm_allreduce_sum(comm, ws.full + A->n_global, (size_t)R, s));
+            src = ws.full;
+        }
+        NCME_CUDA(cudaMemcpyAsync(ws.pinned, src, (size_t)Nglob * sizeof(double), cudaMemcpyDeviceToHost, s));
         NCME_CUDA(cudaStreamSynchronize(s));
         save_fn(t, ws.pinned, user);
         st->nsaved++;
         return NCME_OK;
     };
     auto lincomb = [&](int kterms, const double* cs, const double* const* xs, double* out) -> int {
-        // drop zero coefficients (a_72 = 0)
         double c2[8];
         const double* x2[8];
         int m = 0;
         for (int j = 0; j < kterms; ++j)
-            if (cs[j] != 0.0) {
+            if (cs[j] != 0.0) {   // a_72 = 0
                 c2[m] = cs[j];
                 x2[m] = xs[j];
                 ++m;
@@ -195,29 +235,55 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
     const int64_t max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
     const double tspan = t1 - t0;
     double t = t0;
-    int isave = 0;
-    while (isave < o->nsave && o->save_t[isave] < t0) ++isave;
-    if (o->save_every_step) NCME_TRY(save(t0, u));
-    while (isave < o->nsave && o->save_t[isave] == t0) {
-        NCME_TRY(save(t0, u));
-        ++isave;
-    }
     st->t_final = t0;
     st->event_hit = 0;
-    if (!(tspan > 0)) return NCME_OK;
 
-    NCME_TRY(rhs(t, u, ws.k[0]));  // u == ucur here
+    // Inside the integrator the R sink entries of every vector are PER-RANK PARTIAL SUMS (their sum over ranks is
+    // the true value): every operation on them is linear and they never feed back into A x, so no per-matvec
+    // all-reduce is needed.  Rank 0 carries the incoming (replicated) sink values.
+    double* ucur = ws.ua;
+    double* unext = ws.ub;
+    NCME_CUDA(cudaMemcpyAsync(ucur, u, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (comm && comm->rank != 0) {
+        k_zero_tail<<<1, 32, 0, s>>>(ucur + n, R);
+        ctx->launches++;
+    }
+    auto finish = [&](const double* src) -> int {   // hand the local slice back with reduced sinks
+        if (src != u) NCME_CUDA(cudaMemcpyAsync(u, src, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        NCME_TRY(comm_allreduce_sum(comm, u + n, (size_t)R, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        st->launches = ctx->launches - launches0;
+        return NCME_OK;
+    };
+
+    int isave = 0;
+    while (isave < o->nsave && o->save_t[isave] < t0) ++isave;
+    if (o->save_every_step) NCME_TRY(save(t0, ucur));
+    while (isave < o->nsave && o->save_t[isave] == t0) {
+        NCME_TRY(save(t0, ucur));
+        ++isave;
+    }
+    if (!(tspan > 0)) return finish(ucur);
+
+    NCME_TRY(rhs(t, ucur, ws.k[0]));
     // initial step: h = 0.01 * ||u|| / ||f|| in the weighted norm (Hairer), clipped to the span
     double h = o->h_init;
     if (!(h > 0)) {
         double d0 = 0, d1 = 0;
-        NCME_TRY(ncme_vec_wrms(ctx, N, u, u, u, atol, rtol, &d0));
-        NCME_TRY(ncme_vec_wrms(ctx, N, ws.k[0], u, u, atol, rtol, &d1));
+        NCME_TRY(ncme_vec_wrms(ctx, n > 0 ? n : 1, ucur, ucur, ucur, atol, rtol, &d0));
+        NCME_TRY(ncme_vec_wrms(ctx, n > 0 ? n : 1, ws.k[0], ucur, ucur, atol, rtol, &d1));
+        double ss[2] = {d0 * d0 * (double)n, d1 * d1 * (double)n};
+        if (comm) {
+            NCME_CUDA(cudaMemcpyAsync(comm->scratch, ss, sizeof(ss), cudaMemcpyHostToDevice, s));
+            NCME_TRY(comm_allreduce_sum(comm, comm->scratch, 2, s));
+            NCME_CUDA(cudaMemcpyAsync(ss, comm->scratch, sizeof(ss), cudaMemcpyDeviceToHost, s));
+            NCME_CUDA(cudaStreamSynchronize(s));
+        }
+        d0 = sqrt(ss[0] / (double)A->n_global);
+        d1 = sqrt(ss[1] / (double)A->n_global);
         h = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h = std::min(h, tspan);
     }
-    double* ucur = u;          // current solution (caller's buffer or the workspace slot)
-    double* unext = ws.unew;   // target of the 7th stage
     double g_prev = 0.0;
     bool have_g = false;
     bool last_rejected = false;
@@ -231,9 +297,10 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
     ea.partials = ctx->red_partials;
     ea.counter = ctx->red_counter;
     ea.result = ctx->red_result_dev;
-    int64_t nb = (N + (int64_t)ST * 8 - 1) / ((int64_t)ST * 8);
+    int64_t nb = (n + (int64_t)ST * 8 - 1) / ((int64_t)ST * 8);
     nb = std::max<int64_t>(1, std::min<int64_t>(nb, 4096));
     const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+    const size_t nres = (size_t)(1 + 9 * R);
 
     while (t < t1) {
         if (st->steps + st->rejected >= max_steps) {
@@ -245,8 +312,7 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
             h = t1 - t;
             last = true;
         }
-        // stages 2..7
-        for (int i = 1; i < 7; ++i) {
+        for (int i = 1; i < 7; ++i) {   // stages 2..7
             double cs[8];
             const double* xs[8];
             cs[0] = 1.0;
@@ -265,10 +331,18 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
         k_rk_errnorm<<<(unsigned)nb, ST, 0, s>>>(ea);
         ctx->launches++;
         NCME_CUDA(cudaGetLastError());
-        NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * (1 + 9 * R),
-                                  cudaMemcpyDeviceToHost, s));
+        NCME_TRY(comm_allreduce_sum(comm, ctx->red_result_dev, nres, s));   // one small all-reduce per step
+        NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * nres, cudaMemcpyDeviceToHost, s));
         NCME_CUDA(cudaStreamSynchronize(s));
-        const double err = sqrt(ctx->red_result_host[0] / (double)N);
+        const double* tails = ctx->red_result_host + 1;
+        double sumsq = ctx->red_result_host[0];
+        for (int r = 0; r < R; ++r) {   // sink rows, from the reduced tails
+            double e = 0.0;
+            for (int j = 0; j < 7; ++j) e += h * DP_E[j] * tails[(2 + j) * R + r];
+            const double w = atol + rtol * std::max(fabs(tails[r]), fabs(tails[R + r]));
+            sumsq += (e / w) * (e / w);
+        }
+        const double err = sqrt(sumsq / (double)Nglob);
         if (!(err <= 1.0)) {  // reject (also catches NaN)
             st->rejected++;
             const double fac = isfinite(err) ? std::max(0.2, 0.9 * pow(err, -0.2)) : 0.1;
@@ -281,7 +355,6 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
             continue;
         }
         st->steps++;
-        const double* tails = ctx->red_result_host + 1;
         double theta_end = 1.0;
         bool event = false;
         if (o->check_event) {
@@ -344,11 +417,10 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
             k_rk_dense<<<(unsigned)((N + ST - 1) / ST), ST, 0, s>>>(da);
             ctx->launches++;
             NCME_CUDA(cudaGetLastError());
-            NCME_CUDA(cudaMemcpyAsync(u, ws.ytmp, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            t = t_hi;
+            st->t_final = t_hi;
             st->event_hit = 1;
             st->h_last = h;
-            break;
+            return finish(ws.ytmp);
         }
         // accept: u <-> unew and k1 <-> k7 (FSAL) by pointer swaps, no copies
         std::swap(ucur, unext);
@@ -363,12 +435,8 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
         last_rejected = false;
         if (!last) h *= fac;
     }
-    if (!st->event_hit && ucur != u)
-        NCME_CUDA(cudaMemcpyAsync(u, ucur, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    NCME_CUDA(cudaStreamSynchronize(s));
     st->t_final = t;
-    st->launches = ctx->launches - launches0;
-    return NCME_OK;
+    return finish(ucur);
 }
 
 }  // namespace ncme

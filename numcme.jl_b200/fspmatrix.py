@@ -21,8 +21,11 @@ from .statespace import StateSpaceSparse
 
 
 class FspMatrixSparse:
-    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=()):
+    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=(), comm=None):
+        """``comm`` (a parallel.Comm) restricts the matrix to this rank's row block (K8); vectors are then the
+        local slices ``[rows | R sinks]`` and matvec inputs need halo margins (see parallel.ShardedVector)."""
         self.ctx = space.ctx
+        self.comm = comm
         self.parameters = parameters
         self.propensities = list(propensity_functions)
         if len(self.propensities) != space.nr:
@@ -34,7 +37,7 @@ class FspMatrixSparse:
         n = self.states.shape[0]
         self.n = n
         self.nr = space.nr
-        self.rowcount = self.colcount = n + space.get_sink_count()
+        self.rowcount = self.colcount = n + space.get_sink_count()   # global size, as size(A) in the reference
         self.kinds = np.array([a.kind_code for a in self.propensities], dtype=np.int32)
         self.timeinvariant_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "ti"]
         self.separabletv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "sep"]
@@ -47,9 +50,11 @@ class FspMatrixSparse:
                 propvals[r, :n] = eval_over_states(a.statefactor, self.states, parameters)
         propvals = np.ascontiguousarray(propvals[:, :n]) if n else propvals
         h = L.p_void()
-        L.check(L.load().ncme_matrix_create(space.handle, L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double),
-                                            C.byref(h)))
+        L.check(L.load().ncme_matrix_create_sharded(space.handle, comm.handle if comm is not None else None,
+                                                    L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double), C.byref(h)))
         self._h = h
+        info = self.shard_info()
+        self.local_len = info["row_hi"] - info["row_lo"] + self.nr
         self.t_cache = -np.inf
         self._coef = np.ones(self.nr, dtype=np.float64)
 
@@ -74,6 +79,12 @@ class FspMatrixSparse:
         return {"nterms": nt.value, "nnz_per_term": [nnz[k] for k in range(nt.value)],
                 "algorithmic_bytes": ab.value, "device_bytes": db.value}
 
+    def shard_info(self) -> dict:
+        info = (C.c_int64 * 8)()
+        L.check(L.load().ncme_matrix_shard_info(self._h, info))
+        keys = ["row_lo", "row_hi", "halo_lo", "halo_hi", "n_global", "interior_begin", "interior_end", "nranks"]
+        return dict(zip(keys, [int(v) for v in info]))
+
     def set_tuning(self, rows_per_thread: int):
         L.check(L.load().ncme_matrix_set_tuning(self._h, int(rows_per_thread)))
 
@@ -93,7 +104,7 @@ class FspMatrixSparse:
             L.check(L.load().ncme_matrix_set_joint_values(self._h, r, L.ptr(vals, C.c_double)))
 
     def _apply(self, out, t, v, beta: float):
-        N = self.rowcount
+        N = self.local_len
         if vec_len(out) != N or vec_len(v) != N:
             raise L.ArgumentError(f"DimensionMismatch: matrix is {N}x{N}, got vectors of length {vec_len(v)} and {vec_len(out)}")
         coef = self.coefficients(float(t))

@@ -165,31 +165,72 @@ def _initial(model, initial_distribution):
 
 
 def solve(model: CmeModel, initial_distribution: FspVectorSparse, tspan, algorithm=None, saveat=None, fsptol=1.0e-6,
-          odeatol=1.0e-6, odertol=1.0e-4, verbose=False, ctx=None) -> FspOutputSparse:
+          odeatol=1.0e-6, odertol=1.0e-4, verbose=False, ctx=None, comm=None) -> FspOutputSparse:
     """``solve(model, p0, tspan, ode_method; saveat, odeatol, odertol)``   (fixed space, fspsolve.jl:10-41) when
     ``algorithm`` is None or an ODE method, and
     ``solve(model, p0, tspan, fspalgorithm::AdaptiveFspSparse; saveat, fsptol, odeatol, odertol, verbose)``
-    (adaptive, fspsolve.jl:105-197) when it is an ``AdaptiveFspSparse``."""
+    (adaptive, fspsolve.jl:105-197) when it is an ``AdaptiveFspSparse``.
+
+    ``comm`` (parallel.Comm, one process per GPU) row-shards the matrix and every FSP vector over the ranks; the
+    state space and the adaptation decisions are replicated, every rank returns the same (gathered) output."""
+    if comm is not None and ctx is None:
+        ctx = comm.ctx
     if isinstance(algorithm, AdaptiveFspSparse):
-        return _solve_adaptive(model, initial_distribution, tspan, algorithm, saveat, fsptol, odeatol, odertol, verbose, ctx)
-    return _solve_fixed(model, initial_distribution, tspan, algorithm, saveat, odeatol, odertol, ctx)
+        return _solve_adaptive(model, initial_distribution, tspan, algorithm, saveat, fsptol, odeatol, odertol, verbose,
+                               ctx, comm)
+    return _solve_fixed(model, initial_distribution, tspan, algorithm, saveat, odeatol, odertol, ctx, comm)
 
 
-def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx):
+class _Dist:
+    """Distribution of one FSP vector over the ranks for a given (sharded or not) matrix."""
+
+    def __init__(self, A: FspMatrixSparse, comm):
+        from .parallel import ShardedVector, shard_bounds
+        self.A, self.comm = A, comm
+        info = A.shard_info()
+        self.lo, self.hi, self.ng = info["row_lo"], info["row_hi"], info["n_global"]
+        self.nloc = self.hi - self.lo
+        self.R = A.nr
+        self.u = ShardedVector(A)
+        P = comm.nranks if comm is not None else 1
+        cuts = shard_bounds(self.ng, P)
+        self.counts = [cuts[r + 1] - cuts[r] for r in range(P)]
+        self.displs = cuts[:-1]
+
+    def load(self, p_full: DeviceVector, sinks: np.ndarray):
+        if self.nloc:
+            self.u.v.view(0, self.nloc).copy_from(p_full.view(self.lo, self.nloc))
+        self.u.v.view(self.nloc, self.R).upload(sinks)
+
+    def gather(self) -> DeviceVector:
+        """p (all states) on every rank"""
+        full = DeviceVector(self.A.ctx, self.ng)
+        if self.comm is not None and self.comm.nranks > 1:
+            self.comm.allgatherv(self.u.v, full, self.counts, self.displs)
+        elif self.ng:
+            full.copy_from(self.u.v.view(0, self.ng))
+        return full
+
+    def sinks(self) -> np.ndarray:
+        return self.u.v.to_host(self.nloc, self.R)
+
+
+def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx, comm=None):
     states0, vals0 = _initial(model, p0)
     space = StateSpaceSparse(model.stoich_matrix, states0, ctx=ctx)
     R = space.get_sink_count()
     # duplicates/negatives are dropped by the space; place p0 by lookup
     idx = space.lookup(states0)
     n = space.get_state_count()
-    u0 = np.zeros(n + R)
-    u0[idx[idx > 0] - 1] = vals0[idx > 0]
-    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters)
-    u = DeviceVector.from_host(space.ctx, u0)
+    pv = np.zeros(n)
+    pv[idx[idx > 0] - 1] = vals0[idx > 0]
+    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
+    dist = _Dist(A, comm)
+    dist.load(DeviceVector.from_host(space.ctx, pv), np.zeros(R))
     sv = _saveat_array(saveat, tspan)
     seg = _Segment(A, odertol, odeatol, _method_code(ode_method))
     t_wall = time.perf_counter()
-    stats = seg.run(u, tspan[0], tspan[1], saveat=sv, save_every_step=sv is None)
+    stats = seg.run(dist.u.v, tspan[0], tspan[1], saveat=sv, save_every_step=sv is None)
     out = FspOutputSparse()
     states = space.get_states()
     for t, uu in zip(seg.saved_t, seg.saved_u):
@@ -201,7 +242,7 @@ def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx):
     return out
 
 
-def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, verbose, ctx):
+def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, verbose, ctx, comm=None):
     tstart, tend = min(tspan), max(tspan)
     sv = _saveat_array(saveat, tspan)
     adapter = alg.space_adapter
@@ -214,19 +255,18 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
     pv = np.zeros(space.get_state_count())
     pv[idx[idx > 0] - 1] = vals0[idx > 0]
     t_wall = time.perf_counter()
-    p = init_(space, adapter, DeviceVector.from_host(ctx, pv), tstart, fsptol)
+    p = init_(space, adapter, DeviceVector.from_host(ctx, pv), tstart, fsptol)   # all states, replicated
     tnow = tstart
     sinks = np.zeros(R)
-    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
     out = FspOutputSparse()
     tot = {"steps": 0, "rejected": 0, "rhs_evals": 0, "launches": 0, "adapts": 0, "matrix_builds": 1}
     while tnow < tend:
         n = space.get_state_count()
-        u = DeviceVector(ctx, n + R)
-        u.view(0, n).copy_from(p)
-        u.view(n, R).upload(sinks)
+        dist = _Dist(A, comm)
+        dist.load(p, sinks)
         seg = _Segment(A, odertol, odeatol, method)
-        stats = seg.run(u, tnow, tend, saveat=sv, save_every_step=sv is None, event_slope=fsptol / tend)
+        stats = seg.run(dist.u.v, tnow, tend, saveat=sv, save_every_step=sv is None, event_slope=fsptol / tend)
         for k in ("steps", "rejected", "rhs_evals", "launches"):
             tot[k] += getattr(stats, k)
         states = space.get_states() if seg.saved_t else None
@@ -235,16 +275,16 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
             out.p.append(FspVectorSparse(states, uu[:n]))
             out.sinks.append(uu[n:].copy())
         tnow = stats.t_final
+        sinks = dist.sinks()
         if stats.event_hit and tnow < tend:
-            sinks = u.to_host(n, R)
             dsinks = None
             if adapter.selective:                        # get_du!(du, integrator) (rstepadapters.jl:100-103)
-                du = DeviceVector(ctx, n + R)
-                matvec_(du, tnow, A, u)
-                dsinks = du.to_host(n, R)
-            p = adapt_(space, adapter, u.view(0, n).clone(), sinks, tnow, tend, fsptol, dsinks=dsinks)
+                du = DeviceVector(ctx, dist.nloc + R)
+                matvec_(du, tnow, A, dist.u.v)
+                dsinks = du.to_host(dist.nloc, R)
+            p = adapt_(space, adapter, dist.gather(), sinks, tnow, tend, fsptol, dsinks=dsinks)
             A.close()
-            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
             tot["adapts"] += 1
             tot["matrix_builds"] += 1
             if sinks.sum() >= tnow * fsptol / tend:      # re-arm the event (fspsolve.jl:179-181)
@@ -252,10 +292,9 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
             if verbose:
                 print(f"t = {tnow:.2f}. Update state space. New size: {space.get_state_count()}.")
         else:
-            uu = u.to_host()
             out.t.append(tnow)                           # final slice (duplicates the last saveat point when
-            out.p.append(FspVectorSparse(space.get_states(), uu[:n]))   # tend is in saveat, as the reference, Q3)
-            out.sinks.append(uu[n:].copy())
+            out.p.append(FspVectorSparse(space.get_states(), dist.gather().to_host()))   # tend is in saveat, Q3)
+            out.sinks.append(sinks.copy())
             tnow = tend
     tot["wall_s"] = time.perf_counter() - t_wall
     tot["final_states"] = space.get_state_count()

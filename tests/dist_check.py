@@ -1,0 +1,88 @@
+"""Multi-rank parity check, launched by tests/test_gpu_multi.py through torchrun (one rank per GPU):
+row-sharded matvec / solve against the single-GPU path computed on the same rank."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    rank = int(os.environ["RANK"])
+    local = int(os.environ["LOCAL_RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ctx = pkg.Context(local)
+    comm = pkg.Comm.from_torch(ctx)
+    levels = int(os.environ.get("NCME_DIST_LEVELS", "60"))
+
+    # ---- matvec: M-3D TV variant, sharded vs full
+    model = pkg.workloads.m3d_model(time_varying=True)
+    space = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0, 0], ctx=ctx)
+    space.expand_(levels)
+    n = space.get_state_count()
+    A_full = pkg.FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+    A_sh = pkg.FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
+    info = A_sh.shard_info()
+    lo, hi = info["row_lo"], info["row_hi"]
+    assert info["nranks"] == world and info["n_global"] == n
+    cuts = pkg.shard_bounds(n, world)
+    assert (lo, hi) == (cuts[rank], cuts[rank + 1]), (lo, hi, cuts)
+    rng = np.random.default_rng(0)
+    x = rng.random(n + 6)
+    y_ref = pkg.matvec(2.5, A_full, x)
+    xs = pkg.ShardedVector(A_sh, fill=np.concatenate([x[lo:hi], x[n:]]))
+    ys = pkg.DeviceVector(ctx, hi - lo + 6)
+    for _ in range(3):
+        pkg.matvec_(ys, 2.5, A_sh, xs.v)
+    y = ys.to_host()
+    assert np.array_equal(y[:hi - lo], y_ref[lo:hi]), "state rows differ from the single-GPU result"
+    assert np.abs(y[hi - lo:] - y_ref[n:]).max() <= 1e-12 * np.abs(y_ref[n:]).max(), "sink rows differ"
+    gsum = torch.tensor([y[:hi - lo].sum()], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(gsum)
+    ones = pkg.ShardedVector(A_sh, fill=np.ones(hi - lo + 6))
+    pkg.matvec_(ys, 2.5, A_sh, ones.v)
+    yo = ys.to_host()
+    tot = torch.tensor([yo[:hi - lo].sum()], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(tot)
+    assert abs(float(tot) + yo[hi - lo:].sum()) <= 1e-9, "column sums of the sharded operator are not zero"
+
+    # ---- adaptive solve: telegraph, sharded vs single GPU (same adaptation decisions expected)
+    tm = pkg.workloads.telegraph_model()
+    p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
+    alg = pkg.AdaptiveFspSparse(None, pkg.RStepAdapter(5, 10, True))
+    touts = [50.0, 150.0, 300.0]
+    s1 = pkg.solve(tm, p0, (0.0, 300.0), alg, saveat=touts, odeatol=1e-12, odertol=1e-8, ctx=ctx)
+    s2 = pkg.solve(tm, p0, (0.0, 300.0), alg, saveat=touts, odeatol=1e-12, odertol=1e-8, comm=comm)
+    assert len(s1) == len(s2)
+    for a, b, sa, sb in zip(s1.p, s2.p, s1.sinks, s2.sinks):
+        assert np.array_equal(a.states, b.states)
+        assert np.abs(a.values - b.values).max() < 1e-10
+        assert np.abs(sa - sb).max() < 1e-12
+    assert s2.stats["adapts"] == s1.stats["adapts"] >= 1
+
+    # ---- fixed-space solve on the 3-species model, sharded vs single
+    sp0 = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0, 0], ctx=ctx)
+    sp0.expand_(40)
+    pfull = pkg.FspVectorSparse.from_pairs(sp0, [([0, 0, 0], 1.0)])
+    f1 = pkg.solve(model, pfull, (0.0, 0.5), None, saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-8, ctx=ctx)
+    f2 = pkg.solve(model, pfull, (0.0, 0.5), None, saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-8, comm=comm)
+    for a, b in zip(f1.p, f2.p):
+        assert np.abs(a.values - b.values).max() < 1e-12
+    assert f1.stats["steps"] == f2.stats["steps"]
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST_CHECK_OK world={world} n={n} halo=({info['halo_lo']},{info['halo_hi']}) "
+              f"interior=[{info['interior_begin']},{info['interior_end']})")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
