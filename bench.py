@@ -7,7 +7,10 @@ A "step" is one fused FSP matvec y = A(t) x over the whole state space (n = 10 0
 R = 6, time-varying variant: 1 041 MB algorithmic bytes per step, far larger than the 126 MB L2).
 `value` = algorithmic GB/s with x, y and A resident in HBM; `e2e` = the same metric through the
 host-buffer C-ABI entry point (pinned host x -> H2D -> kernel -> D2H y inside the timed region).
-At N > 1 (torchrun) every rank runs the same workload on its own GPU (weak scaling, replicas).
+At N > 1 (torchrun, one rank per GPU) the SAME global operator is row-sharded over the ranks (strong scaling):
+halo of x by grouped ncclSend/ncclRecv overlapped with the halo-free rows, value = global bytes / max-over-ranks
+time.  The JSON line also carries `solve`: wall time of a fixed-space FSP solve on the same operator with the
+native device-resident integrator (the second half of BASELINE.json's metric).
 """
 from __future__ import annotations
 
@@ -23,6 +26,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/INFO; the contract is ONE JSON line on stdout
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 METRIC = "fsp_matvec_hbm_gbs"
 UNIT = "GB/s"
@@ -125,6 +131,8 @@ def main():
     ap.add_argument("--levels", type=int, default=None, help="expansion depth of the M-3D simplex (default 390)")
     ap.add_argument("--rows", type=int, default=0, help="matvec kernel variant: rows per thread (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-solve", action="store_true", help="skip the fixed-space solve leg")
+    ap.add_argument("--solve-t", type=float, default=2.0, help="horizon of the solve leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -138,7 +146,7 @@ def main():
     levels = args.levels or pkg.workloads.M3D_LEVELS
     config = {"workload": f"M-3D three-species birth-death FSP, time-varying variant, simplex L={levels}",
               "levels": levels, "reactions": 6, "l2_policy": "inputs (matrix ~1 GB) larger than the 126 MB L2",
-              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak scaling)"}
+              "parallelism": "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -146,8 +154,8 @@ def main():
         gbs, dt, info, _ = cpu_reference_arm(CPU_SAMPLE_LEVELS, max(1, min(K, 40)), min(W, 3))
         line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": max(1, min(K, 40)), "warmup": min(W, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": info,
+                "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "cpu_baseline": info,
                 "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -155,11 +163,15 @@ def main():
     import torch
     import torch.distributed as dist
 
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    torch.cuda.set_device(local_rank)
     ctx = pkg.Context(local_rank)
     ctx.use_torch_stream()
+    comm = pkg.Comm.from_torch(ctx) if world > 1 else None
+    config["parallelism"] = "single GPU" if world == 1 else (
+        f"row-sharded over {world} GPUs (contiguous state blocks, halo of x by grouped ncclSend/ncclRecv overlapped "
+        f"with the halo-free rows; state space replicated)")
 
     # ---- build the workload through the product path: GPU expand, host propensities, GPU assembly
     model = pkg.workloads.m3d_model(time_varying=True)
@@ -167,21 +179,28 @@ def main():
     space = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0, 0], ctx=ctx)
     space.expand_(levels)
     t_expand = time.perf_counter() - t_build
-    A = pkg.FspMatrixSparse(space, model.propensities, parameters=model.parameters)
+    A = pkg.FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
     t_assemble = time.perf_counter() - t_build - t_expand
     if args.rows:
         A.set_tuning(args.rows)
-    st = A.stats()
-    nbytes = st["algorithmic_bytes"]
-    N = A.size(1)
     n = space.get_state_count()
-    config.update({"states": n, "algorithmic_bytes_per_step": nbytes, "nnz_per_term": st["nnz_per_term"],
-                   "expand_s": round(t_expand, 3), "assemble_s": round(t_assemble, 3)})
+    R = 6
+    info = A.shard_info()
+    nloc = info["row_hi"] - info["row_lo"]
+    st = A.stats()
+    # algorithmic bytes of the GLOBAL operator; per-rank stats cover the local rows only
+    nb_t = torch.tensor([st["algorithmic_bytes"] - 16 * R], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(nb_t)
+    nbytes = int(nb_t.item()) + 16 * R
+    config.update({"states": n, "algorithmic_bytes_per_step": nbytes, "expand_s": round(t_expand, 3),
+                   "assemble_s": round(t_assemble, 3), "halo_doubles": [info["halo_lo"], info["halo_hi"]]})
     rng = np.random.default_rng(0)
-    xh = rng.random(N)
-    xh /= xh.sum()
-    x = pkg.DeviceVector.from_host(ctx, xh)
-    y = pkg.DeviceVector(ctx, N)
+    xg = rng.random(n + R)
+    xg /= xg.sum()
+    xh = np.concatenate([xg[info["row_lo"]:info["row_hi"]], xg[n:]])
+    x = pkg.ShardedVector(A, fill=xh)
+    y = pkg.DeviceVector(ctx, nloc + R)
     tt = 2.5
 
     def barrier():
@@ -189,9 +208,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    # ---- device-resident timing: one step = one fused matvec over the whole (sharded) state space
     for _ in range(W):
-        pkg.matvec_(y, tt, A, x)
+        A.matvec_local_(y, tt, x.v)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -199,58 +218,99 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        pkg.matvec_(y, tt, A, x)
+        A.matvec_local_(y, tt, x.v)
     e1.record()
     barrier()
     launches = ctx.launch_count() - l0
     ms = e0.elapsed_time(e1) / K
     clocks = sampler.stop()
 
-    # ---- end to end through host buffers (pinned), H2D + kernel + D2H per step
-    xp = torch.empty(N, dtype=torch.float64).pin_memory()
-    yp = torch.empty(N, dtype=torch.float64).pin_memory()
+    # ---- end to end through host buffers (pinned): H2D of x, kernel, D2H of y inside the timed region
+    xp = torch.empty(nloc + R, dtype=torch.float64).pin_memory()
+    yp = torch.empty(nloc + R, dtype=torch.float64).pin_memory()
     xp.numpy()[:] = xh
     Ke = max(3, min(K, 20))
+
+    def e2e_step():
+        if world == 1:
+            pkg.matvec_(yp.numpy(), tt, A, xp.numpy())        # ncme_matvec_host: H2D + kernel + D2H
+        else:
+            x.v.upload(xp.numpy())
+            pkg.matvec_(y, tt, A, x.v)
+            yp.numpy()[:] = y.to_host()
     for _ in range(3):
-        pkg.matvec_(yp.numpy(), tt, A, xp.numpy())
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e0.record()
     for _ in range(Ke):
-        pkg.matvec_(yp.numpy(), tt, A, xp.numpy())
-    e1.record()
+        e2e_step()
     barrier()
-    ms_e2e = e0.elapsed_time(e1) / Ke
-    wall_e2e = (time.perf_counter() - t0) / Ke * 1e3
-    ms_e2e = max(ms_e2e, wall_e2e)
-    checksum = float(yp.numpy().sum())
+    ms_e2e = (time.perf_counter() - t0) / Ke * 1e3
+    checksum = float(yp.numpy()[:nloc].sum())
+
+    # ---- second half of the metric: full FSP solve wall time (fixed M-3D space, p0 = delta at the origin)
+    solve_info = None
+    if not args.no_solve:
+        from numcme_jl_b200.transientcme import _Dist, _Segment
+        pfull = pkg.DeviceVector.zeros(ctx, n)
+        pfull.view(0, 1).upload(np.ones(1))
+        d = _Dist(A, comm)
+        d.load(pfull, np.zeros(R))
+        seg = _Segment(A, 1e-4, 1e-8, 0)
+        barrier()
+        tw = time.perf_counter()
+        sstats = seg.run(d.u.v, 0.0, args.solve_t, saveat=[args.solve_t])
+        barrier()
+        wall = time.perf_counter() - tw
+        uu = seg.saved_u[-1]
+        solve_info = {"wall_s": wall, "tspan": [0.0, args.solve_t], "method": "native DP5(4), device-resident",
+                      "odertol": 1e-4, "odeatol": 1e-8, "steps": int(sstats.steps), "rejected": int(sstats.rejected),
+                      "rhs_evals": int(sstats.rhs_evals), "launches": int(sstats.launches),
+                      "ms_per_rhs_incl_vector_ops": wall * 1e3 / max(int(sstats.rhs_evals), 1),
+                      "mass": float(uu.sum()), "sinks": float(uu[n:].sum()), "mean_x": [float((uu[:n] * space.get_states()[:, k]).sum()) for k in range(3)] if rank == 0 else None}
 
     if world > 1:
-        tms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
+        tms = torch.tensor([ms, ms_e2e, solve_info["wall_s"] if solve_info else 0.0], dtype=torch.float64,
+                           device=f"cuda:{local_rank}")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(tms[0]), float(tms[1])
+        if solve_info:
+            solve_info["wall_s"] = float(tms[2])
+        cs = torch.tensor([checksum], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(cs)
+        checksum = float(cs)
 
-    value = world * nbytes / (ms * 1e-3) / 1e9
-    e2e_value = world * nbytes / (ms_e2e * 1e-3) / 1e9
+    value = nbytes / (ms * 1e-3) / 1e9                      # whole job: global operator bytes / max-over-ranks time
+    e2e_value = nbytes / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    per_gpu = nbytes / (ms * 1e-3) / 1e9
+    per_gpu = value / world
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
-                    "ms_per_step": ms_e2e, "checksum_sum_y": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (nloc + R) * world,
+                    "d2h_bytes_per_step": 8 * (nloc + R) * world, "ms_per_step": ms_e2e, "checksum_sum_y_states": checksum},
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": UNIT, "frac": per_gpu / peak,
                          "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu / 8000.0,
-                         "kernel": "k_fsp_matvec", "launch_us": ms * 1e3 / max(launches / K, 1)}}
+                         "kernel": "k_fsp_matvec", "launch_us": ms * 1e3 / max(launches / K, 1),
+                         "note": "achieved = algorithmic bytes (SURVEY 8(d)) / CUDA-event time per launch, per GPU"}}
+    if abs(per_gpu / peak) > 1.5:
+        line["roofline"]["timing_suspect"] = True
+    if solve_info:
+        line["solve"] = solve_info
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and world == 1:
         try:
             line["roofline"]["traffic"] = json.load(open(tr)).get("k_fsp_matvec_dram_bytes_per_launch")
         except Exception:
             pass
     if rank == 0 and world == 1 and not args.no_cpu:
-        gbs, dt, info, (OA, v, out) = cpu_reference_arm(CPU_SAMPLE_LEVELS, 20, 2)
-        line["cpu_baseline"] = info
+        gbs, dt, info_cpu, _ = cpu_reference_arm(CPU_SAMPLE_LEVELS, 20, 2)
+        line["cpu_baseline"] = info_cpu
+        if solve_info:
+            # estimate: the reference spends (at least) one serial CPU matvec per RHS evaluation
+            line["solve"]["cpu_est_s"] = solve_info["rhs_evals"] * (nbytes / (gbs * 1e9))
+            line["solve"]["cpu_est_note"] = "rhs_evals x full-size matvec time at the measured 1-core CPU GB/s (lower bound: no integrator vector ops)"
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -193,6 +193,9 @@ int ncme_comm_allgatherv(ncme_comm* comm, const double* send_dev, double* recv_d
  * ncme_matvec on a sharded matrix returns globally reduced sink entries on every rank. */
 int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
                                ncme_matrix** out);
+/* As ncme_matvec, but the nr sink entries of y_dev are left as this rank's partial sums (their sum over the ranks
+ * is the result): what the native integrator does per stage, deferring the reduction to one all-reduce per step. */
+int ncme_matvec_local(ncme_matrix* mat, const double* coef, const double* x_dev, double* y_dev);
 /* info = {row_lo, row_hi, halo_lo, halo_hi, n_global, interior_begin, interior_end, nranks} */
 int ncme_matrix_shard_info(ncme_matrix* mat, int64_t info[8]);
 

@@ -104,7 +104,10 @@ int ncme_comm_create(ncme_ctx* ctx, int rank, int nranks, const char* uid128, nc
     c->rank = rank;
     c->nranks = nranks;
     NCME_CUDA(cudaSetDevice(ctx->device));
-    if (cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: the halo transfer must get SM slots ahead of the (much larger) interior-rows kernel
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&c->scratch, 4096 * sizeof(double)) != cudaSuccess) {

@@ -67,6 +67,13 @@ struct ncme_ctx {
     double* stage_dev_x = nullptr;
     double* stage_dev_y = nullptr;
     size_t stage_dev_bytes = 0;
+    // grow-only caches of the native integrator (re-used by every segment of a solve)
+    double* solve_ws = nullptr;
+    size_t solve_ws_bytes = 0;
+    double* solve_pinned = nullptr;
+    size_t solve_pinned_bytes = 0;
+    double* solve_full = nullptr;
+    size_t solve_full_bytes = 0;
 };
 
 namespace ncme {

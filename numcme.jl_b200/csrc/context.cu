@@ -67,6 +67,9 @@ int ncme_ctx_destroy(ncme_ctx* ctx) {
     if (ctx->red_result_host) cudaFreeHost(ctx->red_result_host);
     if (ctx->stage_dev_x) cudaFree(ctx->stage_dev_x);
     if (ctx->stage_dev_y) cudaFree(ctx->stage_dev_y);
+    if (ctx->solve_ws) cudaFree(ctx->solve_ws);
+    if (ctx->solve_full) cudaFree(ctx->solve_full);
+    if (ctx->solve_pinned) cudaFreeHost(ctx->solve_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return NCME_OK;

@@ -4,6 +4,7 @@
 #include "matrix.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 #include "comm.cuh"
 
@@ -285,7 +286,8 @@ int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, doubl
     ncme_comm* c = A->comm;
     if (!c || c->nranks == 1) return matvec_launch(A, a);
     cudaStream_t st = A->ctx->stream;
-    const bool overlap = A->b1 > A->b0;
+    static const bool no_overlap_env = getenv("NCME_NO_OVERLAP") != nullptr;   // experiments only
+    const bool overlap = A->b1 > A->b0 && !no_overlap_env;
     if (!overlap) {
         NCME_TRY(halo_exchange(A, x_local, st));
         NCME_TRY(matvec_launch(A, a));
@@ -777,6 +779,14 @@ int ncme_matvec(ncme_matrix* A, const double* coef, const double* x_dev, double*
     NCME_REQUIRE(coef || !need_coef, "coef is null but the matrix has separable time-varying reactions");
     NCME_REQUIRE(!(A->comm && beta != 0.0), "matvecadd! is not supported on row-sharded matrices");
     return matvec_dist(A, coef, x_dev, y_dev, beta, 1);
+}
+
+int ncme_matvec_local(ncme_matrix* A, const double* coef, const double* x_dev, double* y_dev) {
+    NCME_REQUIRE(A && x_dev && y_dev && x_dev != y_dev, "bad arguments");
+    bool need_coef = false;
+    for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] == NCME_SEPARABLE_TV);
+    NCME_REQUIRE(coef || !need_coef, "coef is null but the matrix has separable time-varying reactions");
+    return matvec_dist(A, coef, x_dev, y_dev, 0.0, 0);
 }
 
 int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, double* y_host, double beta) {

@@ -121,7 +121,7 @@ static const double DP_D[7] = {-12715105075.0 / 11282082432.0, 0, 87487479700.0 
                                -10690763975.0 / 1880347072.0, 701980252875.0 / 199316789632.0,
                                -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
 
-struct Workspace {
+struct Workspace {       // views into the context's grow-only caches
     double* base = nullptr;
     double* k[7];
     double* ytmp;
@@ -129,12 +129,26 @@ struct Workspace {
     double* ub;
     double* full = nullptr;     // n_global + R, for gathered output slices (sharded runs)
     double* pinned = nullptr;
-    ~Workspace() {
-        if (base) cudaFree(base);
-        if (full) cudaFree(full);
-        if (pinned) cudaFreeHost(pinned);
-    }
 };
+
+static int cache_reserve(double** p, size_t* have, size_t want, bool pinned) {
+    if (*have >= want) return NCME_OK;
+    if (*p) {
+        if (pinned)
+            cudaFreeHost(*p);
+        else
+            cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    cudaError_t e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        set_error("integrator workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return NCME_ERR_NOMEM;
+    }
+    *have = want;
+    return NCME_OK;
+}
 
 // sum over sinks of the dense output at theta, from the (globally reduced) tails gathered by k_rk_errnorm
 static double sink_dense_sum(const double* tails, int R, double h, double theta) {
@@ -169,13 +183,20 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
     // every vector that can be a matvec input carries the halo margins: [hl | n rows | R sinks | hh]
     const size_t hl = round_up<size_t>((size_t)A->hl, 32), hh = round_up<size_t>((size_t)A->hh, 32);
     const size_t Npad = hl + round_up<size_t>((size_t)N, 32) + hh;
-    NCME_CUDA(cudaMalloc(&ws.base, Npad * 10 * sizeof(double)));
+    NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 10 * sizeof(double), false));
+    ws.base = ctx->solve_ws;
     for (int j = 0; j < 7; ++j) ws.k[j] = ws.base + Npad * j + hl;
     ws.ytmp = ws.base + Npad * 7 + hl;
     ws.ua = ws.base + Npad * 8 + hl;
     ws.ub = ws.base + Npad * 9 + hl;
-    if (save_fn) NCME_CUDA(cudaMallocHost(&ws.pinned, (size_t)Nglob * sizeof(double)));
-    if (save_fn && comm) NCME_CUDA(cudaMalloc(&ws.full, (size_t)Nglob * sizeof(double)));
+    if (save_fn) {
+        NCME_TRY(cache_reserve(&ctx->solve_pinned, &ctx->solve_pinned_bytes, (size_t)Nglob * sizeof(double), true));
+        ws.pinned = ctx->solve_pinned;
+    }
+    if (save_fn && comm) {
+        NCME_TRY(cache_reserve(&ctx->solve_full, &ctx->solve_full_bytes, (size_t)Nglob * sizeof(double), false));
+        ws.full = ctx->solve_full;
+    }
 
     double coef[NCME_MAX_REACTIONS];
     for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;

@@ -121,6 +121,12 @@ class FspMatrixSparse:
             return
         raise L.ArgumentError("out/v must both be device vectors or `out` a contiguous float64 numpy array")
 
+    def matvec_local_(self, out, t, v):
+        """Sharded matvec that leaves the sink entries as per-rank partial sums (see ncme_matvec_local)."""
+        coef = self.coefficients(float(t))
+        L.check(L.load().ncme_matvec_local(self._h, L.ptr(coef, C.c_double), C.c_void_p(device_ptr(v)),
+                                           C.c_void_p(device_ptr(out))))
+
     def close(self):
         if getattr(self, "_h", None):
             L.load().ncme_matrix_destroy(self._h)
