@@ -132,8 +132,13 @@ int ncme_matvec_host(ncme_matrix* mat, const double* coef, const double* x_host,
 int ncme_matrix_stats(ncme_matrix* mat, int* nterms, int64_t* nnz_per_term, int64_t* algorithmic_bytes,
                       int64_t* device_bytes);
 
-/* Launch tuning for experiments: rows each thread owns in the matvec kernel (0 = auto, 1, 2 or 4). */
+/* Launch tuning for experiments: rows each thread owns in the matvec kernel (0 = auto, 1, 2 or 4);
+ * +16 selects the experimental byte-compressed column indices (1 byte per index + per-chunk descriptor; 15 % less
+ * DRAM traffic but latency-bound in its current form, so off by default). */
 int ncme_matrix_set_tuning(ncme_matrix* mat, int rows_per_thread);
+
+/* info = {#(64-row chunk, slot) pairs, #pairs that fell back to 32-bit indices, compression enabled, #slots} */
+int ncme_matrix_compression_info(ncme_matrix* mat, int64_t info[4]);
 
 /* ---------------------------------------------------------------- ForwardSensFspMatrixSparse -- */
 /* ForwardSensFspMatrixSparse{Float64}(model, space)

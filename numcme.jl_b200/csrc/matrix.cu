@@ -101,7 +101,50 @@ __device__ __forceinline__ void sink_task(const MatvecArgs& a) {
 // (vector loads), gathers x through the read-only path (neighbouring rows have neighbouring
 // predecessors, so the gathers of a warp coalesce into a few L1 lines), and finally applies the
 // time-dependent coefficients that arrive by value in the launch parameters.
-template <int S, int ROWS>
+template <int ROWS>
+__device__ __forceinline__ void ld_stream(const uint8_t* __restrict__ p, uint32_t (&v)[ROWS]);
+template <>
+__device__ __forceinline__ void ld_stream<1>(const uint8_t* __restrict__ p, uint32_t (&v)[1]) {
+    v[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void ld_stream<2>(const uint8_t* __restrict__ p, uint32_t (&v)[2]) {
+    uchar2 t = __ldcs(reinterpret_cast<const uchar2*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+}
+template <>
+__device__ __forceinline__ void ld_stream<4>(const uint8_t* __restrict__ p, uint32_t (&v)[4]) {
+    uchar4 t = __ldcs(reinterpret_cast<const uchar4*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+    v[2] = t.z;
+    v[3] = t.w;
+}
+
+// Compressed column indices.  C8: one byte per entry + a per-(64-row chunk, slot) descriptor {base, mode}:
+// mode 1: col = base + d;  2: col = base + d + k;  3: col = base + d + (63 - k)  (k = row within the chunk; the
+// reference's LIFO level order makes predecessor indices run against the row index);  d == 255: no predecessor
+// (col = the row itself, val = 0);  mode 0: the chunk's range does not fit => 32-bit indices (rare, loaded late).
+// The byte and descriptor loads are issued unconditionally and up front, so they add no level to the dependent
+// load chain (descriptor -> index -> gather would otherwise be three serialized DRAM latencies).
+template <int ROWS>
+__device__ __forceinline__ void decode_cols(const MatvecArgs& a, int s, int64_t i0, const int2 desc, const uint32_t (&d)[ROWS],
+                                            uint32_t (&c)[ROWS]) {
+    if (desc.y == 0) {
+        ld_stream<ROWS>(a.col + (int64_t)s * a.ld + i0, c);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const int k = (int)((i0 + j) & 63);
+        const int shift = desc.y == 2 ? k : (desc.y == 3 ? 63 - k : 0);
+        // d == 255: no predecessor -> the row itself (padding rows past n are clamped into the buffer)
+        c[j] = (d[j] == 255u) ? (a.self_off + (uint32_t)min(i0 + j, a.n - 1)) : (uint32_t)(desc.x + (int)d[j] + shift);
+    }
+}
+
+template <int S, int ROWS, bool C8>
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
     const int nt = a.do_sinks ? a.ntasks : 0;
     if ((int)blockIdx.x < nt) {
@@ -111,17 +154,60 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
     const int64_t i0 = a.row_begin + ((int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x) * ROWS;
     if (i0 >= a.row_end) return;
 
+    // ---- first-level loads: all independent, all issued before the first use (one exposed DRAM latency)
+    double xi[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) xi[j] = (i0 + j < a.row_end) ? __ldg(a.xd + i0 + j) : 0.0;
     uint32_t c[S][ROWS];
     double v[S][ROWS];
+    int2 desc[C8 ? S : 1];
+    if (C8) {
+        const int2* dp = a.cdesc + (i0 >> 6) * S;   // descriptors of one chunk are contiguous: [chunk][slot]
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        ld_stream<ROWS>(a.col + (int64_t)s * a.ld + i0, c[s]);
-        ld_stream<ROWS>(a.val + (int64_t)s * a.ld + i0, v[s]);
+        for (int s = 0; s < S; ++s) desc[s] = __ldg(dp + s);
+#pragma unroll
+        for (int s = 0; s < S; ++s) ld_stream<ROWS>(a.col8 + (int64_t)s * a.ld + i0, c[s]);   // raw bytes for now
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) ld_stream<ROWS>(a.col + (int64_t)s * a.ld + i0, c[s]);
     }
+#pragma unroll
+    for (int s = 0; s < S; ++s) ld_stream<ROWS>(a.val + (int64_t)s * a.ld + i0, v[s]);
+    constexpr int MAXD = 3;   // diagonal arrays loaded up front (time-invariant sum + two time-varying reactions)
+    double dg[MAXD][ROWS];
+#pragma unroll
+    for (int k = 0; k < MAXD; ++k) {
+        if (k < a.ndiag) {
+            ld_stream<ROWS>(a.diag + (int64_t)k * a.ld + i0, dg[k]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) dg[k][j] = 0.0;
+        }
+    }
+    // ---- second level: the gathers of x
+    if (C8) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            uint32_t d8[ROWS];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) d8[j] = c[s][j];
+            decode_cols<ROWS>(a, s, i0, desc[s], d8, c[s]);
+        }
+    }
+    double g[S][ROWS];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) g[s][j] = __ldg(a.x + c[s][j]);
+    // ---- arithmetic
     double d[ROWS];
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) d[j] = 0.0;
-    for (int k = 0; k < a.ndiag; ++k) {
+#pragma unroll
+    for (int k = 0; k < MAXD; ++k)
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) d[j] = fma(k < a.ndiag ? a.diag_coef[k] : 0.0, dg[k][j], d[j]);
+    for (int k = MAXD; k < a.ndiag; ++k) {   // rare: more than two time-varying reactions
         double t[ROWS];
         ld_stream<ROWS>(a.diag + (int64_t)k * a.ld + i0, t);
 #pragma unroll
@@ -129,12 +215,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
     }
     double acc[ROWS];
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) acc[j] = (i0 + j < a.row_end) ? d[j] * __ldg(a.xd + i0 + j) : 0.0;
-    double g[S][ROWS];
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) g[s][j] = __ldg(a.x + c[s][j]);
+    for (int j = 0; j < ROWS; ++j) acc[j] = d[j] * xi[j];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const double cs = a.slot_coef[s];
@@ -173,7 +254,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_
     a.y[i] = acc;
 }
 
-template <int ROWS>
+template <int ROWS, bool C8>
 static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
     const int64_t rows_per_block = (int64_t)MV_THREADS * ROWS;
     const int64_t nrows = a.row_end - a.row_begin;
@@ -183,7 +264,7 @@ static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
     switch (a.nslots) {
 #define NCME_CASE(SS)                                              \
     case SS:                                                       \
-        k_fsp_matvec<SS, ROWS><<<grid, MV_THREADS, 0, st>>>(a);    \
+        k_fsp_matvec<SS, ROWS, C8><<<grid, MV_THREADS, 0, st>>>(a); \
         break;
         NCME_CASE(1) NCME_CASE(2) NCME_CASE(3) NCME_CASE(4) NCME_CASE(5) NCME_CASE(6) NCME_CASE(7) NCME_CASE(8)
         NCME_CASE(9) NCME_CASE(10) NCME_CASE(11) NCME_CASE(12) NCME_CASE(13) NCME_CASE(14) NCME_CASE(15) NCME_CASE(16)
@@ -200,13 +281,14 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
     if (rows == 0) rows = (a.nslots <= 8) ? 2 : 1;
     // vector loads of x[i0..] / y are not used (scalar), but the matrix streams need i0 % ROWS == 0 only.
     int rc = -1;
+    const bool c8 = A->use_c8 && A->col8.p != nullptr;
     if (a.nslots >= 1 && a.nslots <= 16) {
         if (rows == 4 && a.nslots <= 8)
-            rc = launch_rows<4>(A, a);
+            rc = c8 ? launch_rows<4, true>(A, a) : launch_rows<4, false>(A, a);
         else if (rows >= 2)
-            rc = launch_rows<2>(A, a);
+            rc = c8 ? launch_rows<2, true>(A, a) : launch_rows<2, false>(A, a);
         else
-            rc = launch_rows<1>(A, a);
+            rc = c8 ? launch_rows<1, true>(A, a) : launch_rows<1, false>(A, a);
     }
     if (rc != 0) {
         const unsigned grid = (unsigned)((a.do_sinks ? a.ntasks : 0) + (a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS);
@@ -219,6 +301,10 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
 
 int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a) {
     a->col = A->col.p;
+    a->col8 = A->col8.p;
+    a->cdesc = A->cdesc.p;
+    a->nchunks = A->nchunks;
+    a->self_off = (uint32_t)A->hl;
     a->val = A->val.p;
     a->diag = A->diag.p;
     a->n = A->n;
@@ -380,6 +466,70 @@ __global__ void k_pred_window(const uint32_t* __restrict__ pred_r /*global rows*
     if ((int64_t)p >= g.row_hi) {
         atomicMax(&mnmx[1], p);
         atomicMin(&mnmx[3], (unsigned int)i);         // rows [b1, nloc) touch the high halo
+    }
+}
+
+// One warp per (slot, 64-row chunk): pick the addressing mode whose residual range fits one byte.
+__global__ void k_compress_cols(const uint32_t* __restrict__ col, int64_t ld, int64_t n, int64_t nchunks, int nslots,
+                                uint32_t self_off, uint8_t* __restrict__ col8, int2* __restrict__ cdesc,
+                                unsigned long long* wide_count) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nchunks * nslots) return;
+    const int s = (int)(w / nchunks);
+    const int64_t chunk = w % nchunks;
+    const int64_t r0 = chunk * 64;
+    long long mn[3] = {(1ll << 40), (1ll << 40), (1ll << 40)}, mx[3] = {-(1ll << 40), -(1ll << 40), -(1ll << 40)};
+    long long cv[2];
+    bool has[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        const int64_t i = r0 + k;
+        const uint32_t c = col[(int64_t)s * ld + i];
+        has[h] = (i < n) && c != self_off + (uint32_t)i;
+        cv[h] = (long long)c;
+        if (has[h]) {
+            const long long r[3] = {cv[h], cv[h] - k, cv[h] - (63 - k)};
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                mn[m] = min(mn[m], r[m]);
+                mx[m] = max(mx[m], r[m]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn[m] = min(mn[m], __shfl_xor_sync(0xffffffffu, mn[m], d));
+            mx[m] = max(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], d));
+        }
+    int mode = 0;
+    long long base = 0;
+    if (mx[0] < mn[0]) {          // no predecessor in the whole chunk
+        mode = 1;
+        base = 0;
+    } else {
+        for (int m = 2; m >= 0; --m)   // prefer the plain mode when several fit
+            if (mx[m] - mn[m] <= 254 && mn[m] > -(1ll << 31) && mx[m] < (1ll << 31)) {
+                mode = m + 1;
+                base = mn[m];
+            }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        uint8_t d = 255;
+        if (mode != 0 && has[h]) {
+            const long long shift = mode == 2 ? k : (mode == 3 ? 63 - k : 0);
+            d = (uint8_t)(cv[h] - shift - base);
+        }
+        col8[(int64_t)s * ld + r0 + k] = d;
+    }
+    if (lane == 0) {
+        cdesc[chunk * nslots + s] = make_int2((int)base, mode);
+        if (mode == 0) atomicAdd(wide_count, 1ull);
     }
 }
 
@@ -554,6 +704,24 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         ctx->launches++;
     }
     NCME_CUDA(cudaGetLastError());
+    // ---- byte-compressed column indices for the matvec fast path
+    A->nchunks = A->ld / 64;
+    if (nslots > 0) {
+        NCME_TRY(A->col8.reserve((size_t)A->ld * nslots, st, false));
+        NCME_TRY(A->cdesc.reserve((size_t)A->nchunks * nslots, st, false));
+        unsigned long long* d_wide = nullptr;
+        NCME_CUDA(cudaMalloc(&d_wide, sizeof(unsigned long long)));
+        NCME_CUDA(cudaMemsetAsync(d_wide, 0, sizeof(unsigned long long), st));
+        const int64_t nwarps = A->nchunks * nslots;
+        k_compress_cols<<<nblk(nwarps * 32), 256, 0, st>>>(A->col.p, A->ld, n, A->nchunks, nslots, (uint32_t)A->hl,
+                                                           A->col8.p, A->cdesc.p, d_wide);
+        ctx->launches++;
+        unsigned long long hw = 0;
+        NCME_CUDA(cudaMemcpyAsync(&hw, d_wide, sizeof(hw), cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_wide);
+        A->wide_chunks = (int64_t)hw;
+    }
     // ---- halo plan: who owns what I need, who needs what I own
     if (A->comm) {
         double mine[4] = {(double)row_lo, (double)row_hi, (double)A->ext_lo, (double)A->ext_hi};
@@ -719,6 +887,8 @@ int ncme_matrix_destroy(ncme_matrix* A) {
     if (!A) return NCME_OK;
     if (A->ctx) cudaStreamSynchronize(A->ctx->stream);
     A->col.release();
+    A->col8.release();
+    A->cdesc.release();
     A->val.release();
     A->diag.release();
     A->sink_row.release();
@@ -738,9 +908,12 @@ int ncme_matrix_size(ncme_matrix* A, int64_t* rows, int64_t* cols) {
 }
 
 int ncme_matrix_set_tuning(ncme_matrix* A, int rows_per_thread) {
-    NCME_REQUIRE(A && (rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4),
-                 "rows_per_thread must be 0, 1, 2 or 4");
-    A->tune_rows = rows_per_thread;
+    // rows_per_thread: 0 (auto), 1, 2, 4; add 16 to use the byte-compressed column indices (experimental)
+    const int rows = rows_per_thread & 15;
+    NCME_REQUIRE(A && (rows == 0 || rows == 1 || rows == 2 || rows == 4) && (rows_per_thread & ~31) == 0,
+                 "rows_per_thread must be 0, 1, 2 or 4 (+16: byte-compressed column indices)");
+    A->tune_rows = rows;
+    A->use_c8 = (rows_per_thread & 16) ? 1 : 0;
     return NCME_OK;
 }
 
@@ -812,14 +985,24 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
     return NCME_OK;
 }
 
+int ncme_matrix_compression_info(ncme_matrix* A, int64_t info[4]) {
+    NCME_REQUIRE(A && info, "null argument");
+    info[0] = A->nchunks * A->nslots;   // (64-row chunk, slot) pairs
+    info[1] = A->wide_chunks;           // of which kept on 32-bit column indices
+    info[2] = A->use_c8;
+    info[3] = A->nslots;
+    return NCME_OK;
+}
+
 int ncme_matrix_stats(ncme_matrix* A, int* nterms, int64_t* nnz_per_term, int64_t* algorithmic_bytes, int64_t* device_bytes) {
     NCME_REQUIRE(A, "null matrix");
     if (nterms) *nterms = A->nterms;
     if (nnz_per_term)
         for (int k = 0; k < A->nterms; ++k) nnz_per_term[k] = A->nnz_term[k];
     if (algorithmic_bytes) *algorithmic_bytes = A->algorithmic_bytes;
-    if (device_bytes)
-        *device_bytes = (int64_t)A->ld * (12 * A->nslots + 8 * A->ndiag) + 12 * A->nsink + 16 * A->N;
+    if (device_bytes)   // bytes one matvec actually streams with the compressed indices
+        *device_bytes = (int64_t)A->ld * (9 * A->nslots + 8 * A->ndiag) + A->wide_chunks * 256 + 8 * A->nchunks * A->nslots +
+                        12 * A->nsink + 16 * A->N;
     return NCME_OK;
 }
 

@@ -49,7 +49,13 @@ struct ncme_matrix {
     ncme::DevArray<uint32_t> col;   // [nslots][ld]
     ncme::DevArray<double> val;     // [nslots][ld]
     ncme::DevArray<double> diag;    // [ndiag][ld]
-    ncme::DevArray<uint32_t> pred_copy;  // [nr][ld] snapshot of the space's predecessor table (NONE32 kept)
+    // compressed column indices (K1 fast path): one byte per (slot,row) relative to a per-(slot, 64-row chunk)
+    // descriptor {base:i32, mode:u32}; mode 0 = chunk stays on the 32-bit array (range does not fit)
+    ncme::DevArray<uint8_t> col8;     // [nslots][ld]
+    ncme::DevArray<int2> cdesc;       // [nslots][ld/64]
+    int64_t nchunks = 0;
+    int64_t wide_chunks = 0;          // chunk-slots that fell back to 32-bit indices
+    int use_c8 = 0;                   // off by default: measured slower than 32-bit indices (profiles/README.md)
 
     // sink rows: entries grouped by reaction, rows ascending inside a reaction
     int64_t nsink = 0;
@@ -90,6 +96,10 @@ struct MatvecArgs {
     int task_ptr[NCME_MAX_REACTIONS + 1];
     double* sink_partial;
     unsigned int* sink_counter;
+    const uint8_t* col8;
+    const int2* cdesc;
+    int64_t nchunks;
+    uint32_t self_off;  // padded position of row i is self_off + i
     const double* x;    // xb: base of the halo-padded input (== xd on a single GPU)
     const double* xd;   // x_local: entry of row i is xd[i]
     double* y;

@@ -79,6 +79,11 @@ class FspMatrixSparse:
         return {"nterms": nt.value, "nnz_per_term": [nnz[k] for k in range(nt.value)],
                 "algorithmic_bytes": ab.value, "device_bytes": db.value}
 
+    def compression_info(self) -> dict:
+        info = (C.c_int64 * 4)()
+        L.check(L.load().ncme_matrix_compression_info(self._h, info))
+        return {"chunk_slots": int(info[0]), "wide_chunk_slots": int(info[1]), "enabled": bool(info[2]), "slots": int(info[3])}
+
     def shard_info(self) -> dict:
         info = (C.c_int64 * 8)()
         L.check(L.load().ncme_matrix_shard_info(self._h, info))

@@ -59,7 +59,7 @@ def test_separable_equals_joint(pkg):  # test/test_fspmat.jl:68
         assert np.linalg.norm(pkg.matvec(t, A1, v) - pkg.matvec(t, A2, v)) <= 1e-15
 
 
-@pytest.mark.parametrize("rows", [0, 1, 2, 4])
+@pytest.mark.parametrize("rows", [0, 1, 2, 4, 16, 17, 18, 20])   # +16: byte-compressed column indices
 def test_rectangular_telegraph_all_kernel_variants(pkg, rows):
     props, grads, pattern, states = sens_telegraph()
     sp = pkg.StateSpaceSparse(TELEGRAPH_S, states)
@@ -125,9 +125,13 @@ def test_m2d_100k_vs_oracle(pkg):
     rng = np.random.default_rng(0)
     v = rng.random(A.size(1))
     v /= v.sum()
-    for rows in (1, 2, 4):
+    ref = OA.matvec(0.0, v)
+    outs = []
+    for rows in (1, 2, 4, 17, 18, 20):
         A.set_tuning(rows)
-        assert _relerr(pkg.matvec(0.0, A, v), OA.matvec(0.0, v)) <= RTOL
+        outs.append(pkg.matvec(0.0, A, v))
+        assert _relerr(outs[-1], ref) <= RTOL
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])      # all variants are bitwise identical
     assert abs(pkg.matvec(0.0, A, np.ones(A.size(1))).sum()) <= 1e-9
 
 
