@@ -254,6 +254,13 @@ typedef struct ncme_solve_stats {
 int ncme_solve_segment(ncme_matrix* mat, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
                        double* u_dev, const ncme_solve_opts* opts, ncme_solve_stats* stats);
 
+/* Forward-sensitivity segment (src/forwardsenscme/sparse/forwardsenscmesparse.jl:142-166): the same integrator on
+ * the block vector U = [p; s_1; ...; s_P] ((P+1)*(n+nr) doubles) with ncme_sens_matvec as right-hand side; the event
+ * watches the sinks of the probability block.  coef_fn fills nr + nentries doubles: coef[r] as for ncme_matvec, then
+ * dcoef[e] as for ncme_sens_matvec.  Single GPU. */
+int ncme_sens_solve_segment(ncme_sensmatrix* smat, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0,
+                            double t1, double* U_dev, const ncme_solve_opts* opts, ncme_solve_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,5 +16,7 @@ from .fspmatrix import FspMatrixSparse, matvec_, matvecadd_, matvec, get_rowcoun
 from .sensmatrix import ForwardSensFspMatrixSparse, sens_matvec_
 from .fspvector import FspVectorSparse, FspOutputSparse, FspOutputSliceSparse
 from .transientcme import (solve, AdaptiveFspSparse, RStepAdapter, SelectiveRStepAdapter, NativeRK45, init_, adapt_)
+from .forwardsenscme import (ForwardSensFspInitialConditionSparse, forwardsens_initial_condition, ForwardSensRStepAdapter,
+                             AdaptiveForwardSensFspSparse, ForwardSensFspOutputSparse, ForwardSensFspOutputSliceSparse)
 from .parallel import Comm, ShardedVector, shard_bounds
 from . import workloads

@@ -82,6 +82,7 @@ SIGNATURES = {
     "ncme_space_prune_by_mass": (cint, [p_void, p_void, f64, cint, p_i64]),
     "ncme_space_compact_vector": (cint, [p_void, p_void, p_void]),
     "ncme_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),
+    "ncme_sens_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),
     "ncme_vec_fill": (cint, [p_void, i64, f64, p_void]),
     "ncme_vec_copy": (cint, [p_void, i64, p_void, p_void]),
     "ncme_vec_scale": (cint, [p_void, i64, f64, p_void]),

@@ -115,5 +115,6 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a);
 // partial sums unless reduce_sinks != 0.
 int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, double* y_local, double beta, int reduce_sinks);
 int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st);
+int sens_describe(ncme_sensmatrix* SA, ncme_matrix** A, int* npar, int* nent);
 
 }  // namespace ncme

@@ -234,6 +234,14 @@ static int sens_fill_entry(ncme_sensmatrix* SA, int e, const double* dG_host) {
     return NCME_OK;
 }
 
+int sens_describe(ncme_sensmatrix* SA, ncme_matrix** A, int* npar, int* nent) {
+    NCME_REQUIRE(SA, "null sensitivity matrix");
+    *A = SA->A;
+    *npar = SA->npar;
+    *nent = SA->nent;
+    return NCME_OK;
+}
+
 }  // namespace ncme
 
 using namespace ncme;

@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <functional>
 
 #include "comm.cuh"
 #include "matrix.cuh"
@@ -19,8 +20,8 @@ namespace ncme {
 constexpr int ST = 256;
 
 struct StepArgs {
-    int64_t N;        // vector length n + R
-    int64_t n;        // states
+    int64_t N;        // local vector length
+    int64_t n;        // offset of the R event-sink entries ([n, n+R) is excluded from the kernel's sum)
     int R;
     const double* u;
     const double* unew;
@@ -36,8 +37,9 @@ __global__ void __launch_bounds__(ST) k_rk_errnorm(const __grid_constant__ StepA
     __shared__ double wsum[ST / 32];
     __shared__ bool is_last;
     double s = 0.0;
-    // state rows only: the sink entries are per-rank partial sums, their contribution is added by the host
-    for (int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * ST) {
+    // all entries but the R event sinks: those may be per-rank partial sums, the host adds their contribution
+    for (int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x; i < a.N; i += (int64_t)gridDim.x * ST) {
+        if (i >= a.n && i < a.n + a.R) continue;
         double err = 0.0;
 #pragma unroll
         for (int j = 0; j < 7; ++j)
@@ -166,22 +168,35 @@ static double sink_dense_sum(const double* tails, int R, double h, double theta)
     return s;
 }
 
+// What the integrator needs to know about du/dt = F(t) u.
+struct OdeSystem {
+    ncme_ctx* ctx = nullptr;
+    ncme_comm* comm = nullptr;   // row-sharded FSP vectors only
+    int64_t len = 0;             // local vector length
+    int64_t sink_off = 0;        // the R event-sink entries are [sink_off, sink_off + R)
+    int R = 0;
+    int64_t hl = 0, hh = 0;      // halo margins every RHS input must carry
+    int64_t len_global = 0;      // number of entries of the global vector (error norm)
+    int64_t n_global = 0;        // sharded: global number of state rows (output gather)
+    std::function<int(double, const double*, double*)> rhs;
+};
+
 __global__ void k_zero_tail(double* p, int R) {
     if ((int)threadIdx.x < R) p[threadIdx.x] = 0.0;
 }
 
-static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
-                     double* u, const ncme_solve_opts* o, ncme_solve_stats* st) {
-    ncme_ctx* ctx = A->ctx;
-    ncme_comm* comm = A->comm;          // nullptr on a single GPU
+static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0, double t1, double* u,
+                     const ncme_solve_opts* o, ncme_solve_stats* st) {
+    ncme_ctx* ctx = sys.ctx;
+    ncme_comm* comm = sys.comm;          // nullptr on a single GPU
     cudaStream_t s = ctx->stream;
-    const int64_t N = A->N, n = A->n;   // local vector length / local rows
-    const int R = A->nr;
-    const int64_t Nglob = A->n_global + R;
+    const int64_t N = sys.len, n = sys.sink_off;   // local vector length / offset of the event sinks
+    const int R = sys.R;
+    const int64_t Nglob = sys.len_global;
     const int64_t launches0 = ctx->launches;
     Workspace ws;
     // every vector that can be a matvec input carries the halo margins: [hl | n rows | R sinks | hh]
-    const size_t hl = round_up<size_t>((size_t)A->hl, 32), hh = round_up<size_t>((size_t)A->hh, 32);
+    const size_t hl = round_up<size_t>((size_t)sys.hl, 32), hh = round_up<size_t>((size_t)sys.hh, 32);
     const size_t Npad = hl + round_up<size_t>((size_t)N, 32) + hh;
     NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 10 * sizeof(double), false));
     ws.base = ctx->solve_ws;
@@ -198,12 +213,9 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
         ws.full = ctx->solve_full;
     }
 
-    double coef[NCME_MAX_REACTIONS];
-    for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
     auto rhs = [&](double t, const double* x, double* y) -> int {
-        if (coef_fn) coef_fn(t, coef, user);
         st->rhs_evals++;
-        return matvec_dist(A, coef, x, y, 0.0, /*reduce_sinks=*/0);
+        return sys.rhs(t, x, y);
     };
     // hand a slice to the host: sharded runs gather [all state rows | reduced sinks] on every rank first.
     // `v_dev` holds per-rank partial sink entries (see below).
@@ -229,8 +241,8 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
         const double* src = v_dev;
         if (comm) {
             NCME_TRY(comm_allgatherv(comm, v_dev, ws.full, counts.data(), displs.data(), s));
-            NCME_CUDA(cudaMemcpyAsync(ws.full + A->n_global, v_dev + n, (size_t)R * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            NCME_TRY(comm_allreduce_sum(comm, ws.full + A->n_global, (size_t)R, s));
+            NCME_CUDA(cudaMemcpyAsync(ws.full + sys.n_global, v_dev + n, (size_t)R * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            NCME_TRY(comm_allreduce_sum(comm, ws.full + sys.n_global, (size_t)R, s));
             src = ws.full;
         }
         NCME_CUDA(cudaMemcpyAsync(ws.pinned, src, (size_t)Nglob * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -291,17 +303,18 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
     double h = o->h_init;
     if (!(h > 0)) {
         double d0 = 0, d1 = 0;
-        NCME_TRY(ncme_vec_wrms(ctx, n > 0 ? n : 1, ucur, ucur, ucur, atol, rtol, &d0));
-        NCME_TRY(ncme_vec_wrms(ctx, n > 0 ? n : 1, ws.k[0], ucur, ucur, atol, rtol, &d1));
-        double ss[2] = {d0 * d0 * (double)n, d1 * d1 * (double)n};
+        const int64_t nn = comm ? n : N;   // sharded: state rows only (the sink entries are partial sums)
+        NCME_TRY(ncme_vec_wrms(ctx, nn > 0 ? nn : 1, ucur, ucur, ucur, atol, rtol, &d0));
+        NCME_TRY(ncme_vec_wrms(ctx, nn > 0 ? nn : 1, ws.k[0], ucur, ucur, atol, rtol, &d1));
+        double ss[2] = {d0 * d0 * (double)nn, d1 * d1 * (double)nn};
         if (comm) {
             NCME_CUDA(cudaMemcpyAsync(comm->scratch, ss, sizeof(ss), cudaMemcpyHostToDevice, s));
             NCME_TRY(comm_allreduce_sum(comm, comm->scratch, 2, s));
             NCME_CUDA(cudaMemcpyAsync(ss, comm->scratch, sizeof(ss), cudaMemcpyDeviceToHost, s));
             NCME_CUDA(cudaStreamSynchronize(s));
         }
-        d0 = sqrt(ss[0] / (double)A->n_global);
-        d1 = sqrt(ss[1] / (double)A->n_global);
+        d0 = sqrt(ss[0] / (double)Nglob);
+        d1 = sqrt(ss[1] / (double)Nglob);
         h = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h = std::min(h, tspan);
     }
@@ -318,7 +331,7 @@ static int solve_dp5(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn,
     ea.partials = ctx->red_partials;
     ea.counter = ctx->red_counter;
     ea.result = ctx->red_result_dev;
-    int64_t nb = (n + (int64_t)ST * 8 - 1) / ((int64_t)ST * 8);
+    int64_t nb = (N + (int64_t)ST * 8 - 1) / ((int64_t)ST * 8);
     nb = std::max<int64_t>(1, std::min<int64_t>(nb, 4096));
     const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
     const size_t nres = (size_t)(1 + 9 * R);
@@ -473,7 +486,55 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] != NCME_TIME_INVARIANT);
     NCME_REQUIRE(coef_fn || !need_coef, "the matrix has time-varying reactions: a coefficient callback is required");
     memset(stats, 0, sizeof(*stats));
-    if (opts->method == 0) return solve_dp5(A, coef_fn, save_fn, user, t0, t1, u_dev, opts, stats);
+    double coef[NCME_MAX_REACTIONS];
+    for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
+    OdeSystem sys;
+    sys.ctx = A->ctx;
+    sys.comm = A->comm;
+    sys.len = A->N;
+    sys.sink_off = A->n;
+    sys.R = A->nr;
+    sys.hl = A->hl;
+    sys.hh = A->hh;
+    sys.len_global = A->n_global + A->nr;
+    sys.n_global = A->n_global;
+    sys.rhs = [&](double t, const double* x, double* y) -> int {
+        if (coef_fn) coef_fn(t, coef, user);
+        return matvec_dist(A, coef, x, y, 0.0, /*reduce_sinks=*/0);
+    };
+    if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, u_dev, opts, stats);
+    set_error("unknown integrator method %d", opts->method);
+    return NCME_ERR_ARG;
+}
+
+// Forward-sensitivity segment: the same integrator on the block vector [p; s_1; ...; s_P] with the fused block
+// matvec as right-hand side (reference: src/forwardsenscme/sparse/forwardsenscmesparse.jl:142-166).  The event
+// watches the sinks of the probability block only (:153-155).  coef_fn fills coef[nr] then dcoef[nentries]
+// (contiguous: coef at [0, nr), dcoef at [nr, nr + nentries)).
+extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user,
+                                       double t0, double t1, double* U_dev, const ncme_solve_opts* opts,
+                                       ncme_solve_stats* stats) {
+    NCME_REQUIRE(SA && U_dev && opts && stats && coef_fn, "null argument");
+    NCME_REQUIRE(t1 >= t0, "solve_segment: t1 < t0");
+    NCME_REQUIRE(opts->nsave == 0 || opts->save_t, "save_t is null");
+    memset(stats, 0, sizeof(*stats));
+    ncme_matrix* A = nullptr;
+    int npar = 0, nent = 0;
+    NCME_TRY(sens_describe(SA, &A, &npar, &nent));
+    std::vector<double> cf((size_t)A->nr + (size_t)nent + 1, 1.0);
+    OdeSystem sys;
+    sys.ctx = A->ctx;
+    sys.comm = nullptr;
+    sys.len = (int64_t)(npar + 1) * A->N;
+    sys.sink_off = A->n;
+    sys.R = A->nr;
+    sys.len_global = sys.len;
+    sys.n_global = A->n;
+    sys.rhs = [&](double t, const double* x, double* y) -> int {
+        coef_fn(t, cf.data(), user);
+        return ncme_sens_matvec(SA, cf.data(), cf.data() + A->nr, x, y);
+    };
+    if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, U_dev, opts, stats);
     set_error("unknown integrator method %d", opts->method);
     return NCME_ERR_ARG;
 }

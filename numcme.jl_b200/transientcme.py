@@ -165,7 +165,7 @@ def _initial(model, initial_distribution):
 
 
 def solve(model: CmeModel, initial_distribution: FspVectorSparse, tspan, algorithm=None, saveat=None, fsptol=1.0e-6,
-          odeatol=1.0e-6, odertol=1.0e-4, verbose=False, ctx=None, comm=None) -> FspOutputSparse:
+          odeatol=None, odertol=1.0e-4, verbose=False, ctx=None, comm=None) -> FspOutputSparse:
     """``solve(model, p0, tspan, ode_method; saveat, odeatol, odertol)``   (fixed space, fspsolve.jl:10-41) when
     ``algorithm`` is None or an ODE method, and
     ``solve(model, p0, tspan, fspalgorithm::AdaptiveFspSparse; saveat, fsptol, odeatol, odertol, verbose)``
@@ -175,6 +175,14 @@ def solve(model: CmeModel, initial_distribution: FspVectorSparse, tspan, algorit
     state space and the adaptation decisions are replicated, every rank returns the same (gathered) output."""
     if comm is not None and ctx is None:
         ctx = comm.ctx
+    from .cmemodel import CmeModelWithSensitivity
+    sens = isinstance(model, CmeModelWithSensitivity)
+    if odeatol is None:                                   # code defaults: fspsolve.jl:109 / forwardsenscmesparse.jl:106
+        odeatol = 1.0e-10 if sens else 1.0e-6
+    if sens:                                              # forwardsenscmesparse.jl:99
+        from .forwardsenscme import solve_sens
+        return solve_sens(model, initial_distribution, tspan, algorithm, saveat=saveat, fsptol=fsptol, odeatol=odeatol,
+                          odertol=odertol, verbose=verbose, ctx=ctx)
     if isinstance(algorithm, AdaptiveFspSparse):
         return _solve_adaptive(model, initial_distribution, tspan, algorithm, saveat, fsptol, odeatol, odertol, verbose,
                                ctx, comm)

@@ -94,3 +94,42 @@ def test_sens_joint(pkg):
     for t in (0.3, 1.7):
         pkg.matvec_(out, t, SA, v)
         assert _relerr(out, OS.matvec(t, v)) <= 1e-12
+
+
+def test_sens_solve(pkg):
+    """test/test_sensfsp.jl (a smoke test in the reference) + the checks the reference lacks: the probability block
+    equals the plain FSP solve, d/dtheta of total mass is zero, sensitivities match central finite differences."""
+    import math
+    props, grads, pattern, _ = sens_telegraph()
+    model = _sensmodel(pkg, TELEGRAPH_S, props, grads, pattern, SENS_THETA)
+    ic = pkg.forwardsens_initial_condition([[1, 0, 0]], [1.0], [[0.0] for _ in range(5)])
+    alg = pkg.AdaptiveForwardSensFspSparse(ode_method=None, space_adapter=pkg.ForwardSensRStepAdapter(10, 10, True))
+    touts = [10.0, 40.0]
+    sol = pkg.solve(model, ic, (0.0, 40.0), alg, saveat=touts, fsptol=1e-8, odeatol=1e-12, odertol=1e-8)
+    assert sol.stats["adapts"] >= 1
+    assert isinstance(sol[0], pkg.ForwardSensFspOutputSliceSparse) and len(sol[0].S) == 5
+    for k in range(2):
+        assert sol.p[k].sum() + sol.sinks[k].sum() == pytest.approx(1.0, abs=1e-9)
+        for ip in range(5):
+            assert abs(sol.S[k][ip].values.sum() + sol.dsinks[k][ip].sum()) <= 1e-8
+    # probability block == plain solve
+    plain_alg = pkg.AdaptiveFspSparse(None, pkg.RStepAdapter(10, 10, True))
+
+    def plain(theta):
+        m = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, props), theta)
+        return pkg.solve(m, pkg.FspVectorSparse([[1, 0, 0]], [1.0]), (0.0, 40.0), plain_alg, saveat=touts, fsptol=1e-8,
+                         odeatol=1e-12, odertol=1e-8)
+
+    def on_states(fv, states):
+        d = fv.state2idx
+        return np.array([fv.values[d[tuple(s)] - 1] if tuple(s) in d else 0.0 for s in states.tolist()])
+    base = plain(SENS_THETA)
+    st = sol.p[1].states
+    assert np.abs(on_states(base.p[1], st) - sol.p[1].values).max() < 1e-7
+    for ip, h in [(2, 1e-4), (3, 1e-5), (4, 1e-3)]:                  # lambda, gamma, L (time factor parameter)
+        tp, tm = list(SENS_THETA), list(SENS_THETA)
+        tp[ip] += h
+        tm[ip] -= h
+        fd = (on_states(plain(tp).p[1], st) - on_states(plain(tm).p[1], st)) / (2 * h)
+        s = sol.S[1][ip].values
+        assert np.abs(fd - s).max() <= 2e-4 * max(np.abs(s).max(), 1e-3), (ip, np.abs(fd - s).max(), np.abs(s).max())
