@@ -170,8 +170,8 @@ def main():
     ctx.use_torch_stream()
     comm = pkg.Comm.from_torch(ctx) if world > 1 else None
     config["parallelism"] = "single GPU" if world == 1 else (
-        f"row-sharded over {world} GPUs (contiguous state blocks, halo of x by grouped ncclSend/ncclRecv overlapped "
-        f"with the halo-free rows; state space replicated)")
+        f"row-sharded over {world} GPUs (contiguous state blocks; halo of x pulled from the neighbours' HBM over NVLink "
+        f"by the boundary rows (CUDA IPC + flag epochs), NCCL send/recv fallback; state space replicated)")
 
     # ---- build the workload through the product path: GPU expand, host propensities, GPU assembly
     model = pkg.workloads.m3d_model(time_varying=True)
@@ -199,7 +199,7 @@ def main():
     xg = rng.random(n + R)
     xg /= xg.sum()
     xh = np.concatenate([xg[info["row_lo"]:info["row_hi"]], xg[n:]])
-    x = pkg.ShardedVector(A, fill=xh)
+    x = pkg.ShardedVector(A, fill=xh, register=True)     # peer-memory halo when sharded (collective registration)
     y = pkg.DeviceVector(ctx, nloc + R)
     tt = 2.5
 
@@ -311,6 +311,9 @@ def main():
             # estimate: the reference spends (at least) one serial CPU matvec per RHS evaluation
             line["solve"]["cpu_est_s"] = solve_info["rhs_evals"] * (nbytes / (gbs * 1e9))
             line["solve"]["cpu_est_note"] = "rhs_evals x full-size matvec time at the measured 1-core CPU GB/s (lower bound: no integrator vector ops)"
+    if comm is not None:
+        line["config"]["halo_transport"] = comm.info()
+        x.unregister()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

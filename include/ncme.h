@@ -198,6 +198,15 @@ int ncme_comm_allgatherv(ncme_comm* comm, const double* send_dev, double* recv_d
  * ncme_matvec on a sharded matrix returns globally reduced sink entries on every rank. */
 int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
                                ncme_matrix** out);
+/* Peer-memory halo (CUDA IPC over NVLink).  COLLECTIVE: every rank registers the allocation that holds its matvec
+ * input (base_dev from ncme_dmalloc / cudaMalloc, local rows starting local0 doubles into it, i.e. the halo_lo
+ * margin).  Matvecs whose input lies in a registered allocation skip NCCL: the boundary rows read the neighbours'
+ * HBM directly and cross-GPU flags (ready / done epochs, bounded waits) replace the collective.  Unregister
+ * (collective) before freeing.  The native integrator registers its own workspace. */
+int ncme_matrix_register_buffer(ncme_matrix* mat, void* base_dev, size_t bytes, int64_t local0);
+int ncme_matrix_unregister_buffer(ncme_matrix* mat, void* base_dev);
+/* info = {peer-memory transport available, #matvecs through peer memory, #matvecs through NCCL, halo bytes sent by NCCL} */
+int ncme_comm_info(ncme_comm* comm, int64_t info[4]);
 /* As ncme_matvec, but the nr sink entries of y_dev are left as this rank's partial sums (their sum over the ranks
  * is the result): what the native integrator does per stage, deferring the reduction to one all-reduce per step. */
 int ncme_matvec_local(ncme_matrix* mat, const double* coef, const double* x_dev, double* y_dev);

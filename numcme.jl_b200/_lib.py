@@ -77,6 +77,9 @@ SIGNATURES = {
     "ncme_comm_rank": (cint, [p_void, C.POINTER(cint), C.POINTER(cint)]),
     "ncme_comm_allreduce_sum": (cint, [p_void, p_void, i64]),
     "ncme_comm_allgatherv": (cint, [p_void, p_void, p_void, p_i64, p_i64]),
+    "ncme_matrix_register_buffer": (cint, [p_void, p_void, C.c_size_t, i64]),
+    "ncme_matrix_unregister_buffer": (cint, [p_void, p_void]),
+    "ncme_comm_info": (cint, [p_void, p_i64]),
     "ncme_matrix_create_sharded": (cint, [p_void, p_void, p_i32, p_f64, C.POINTER(p_void)]),
     "ncme_matrix_shard_info": (cint, [p_void, p_i64]),
     "ncme_space_prune_by_mass": (cint, [p_void, p_void, f64, cint, p_i64]),

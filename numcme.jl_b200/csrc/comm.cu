@@ -3,6 +3,7 @@
 #include "comm.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 
 namespace ncme {
 
@@ -68,6 +69,152 @@ int comm_allgatherv(ncme_comm* c, const double* send, double* recv, const int64_
     return NCME_OK;
 }
 
+// byte all-gather through the device scratch (handles, layout descriptors)
+static int allgather_bytes(ncme_comm* c, const void* mine, size_t nbytes, std::vector<char>* all) {
+    all->resize(nbytes * c->nranks);
+    if (c->nranks == 1) {
+        memcpy(all->data(), mine, nbytes);
+        return NCME_OK;
+    }
+    NCME_REQUIRE(nbytes * c->nranks <= 4096 * sizeof(double), "allgather_bytes: message too large");
+    cudaStream_t st = c->ctx->stream;
+    char* dev = (char*)c->scratch;
+    NCME_CUDA(cudaMemcpyAsync(dev + nbytes * c->rank, mine, nbytes, cudaMemcpyHostToDevice, st));
+    NCME_NCCL(nccl_api()->AllGather(dev + nbytes * c->rank, dev, nbytes, ncclChar, c->nccl, st));
+    NCME_CUDA(cudaMemcpyAsync(all->data(), dev, nbytes * c->nranks, cudaMemcpyDeviceToHost, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    return NCME_OK;
+}
+
+struct RegMsg {
+    cudaIpcMemHandle_t handle;
+    int64_t local0, stride, nvec;
+    int64_t valid;
+};
+
+int comm_register(ncme_comm* c, void* base, size_t bytes, int64_t local0, int64_t stride, int64_t nvec, const int* peers,
+                  int npeers) {
+    if (!c || c->nranks == 1 || !c->p2p_ok) return NCME_OK;
+    for (auto& r : c->regs)
+        if (r.base == base) return NCME_OK;
+    RegMsg mine;
+    memset(&mine, 0, sizeof(mine));
+    cudaError_t e = cudaIpcGetMemHandle(&mine.handle, base);
+    mine.valid = (e == cudaSuccess) ? 1 : 0;
+    if (e != cudaSuccess) cudaGetLastError();
+    mine.local0 = local0;
+    mine.stride = stride;
+    mine.nvec = nvec;
+    std::vector<char> all;
+    NCME_TRY(allgather_bytes(c, &mine, sizeof(mine), &all));
+    const RegMsg* msgs = (const RegMsg*)all.data();
+    bool ok = true;
+    for (int q = 0; q < c->nranks; ++q) ok &= msgs[q].valid != 0;
+    if (!ok) return NCME_OK;   // some rank could not export: nobody registers, matvecs stay on NCCL
+    RegBuf rb;
+    rb.base = base;
+    rb.bytes = bytes;
+    rb.local0 = local0;
+    rb.stride = stride;
+    rb.nvec = nvec;
+    for (int k = 0; k < npeers; ++k) {
+        const int q = peers[k];
+        if (q < 0 || q >= c->nranks || q == c->rank || rb.peer_base[q]) continue;
+        void* pb = nullptr;
+        e = cudaIpcOpenMemHandle(&pb, msgs[q].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
+            cudaGetLastError();
+            return NCME_ERR_COMM;
+        }
+        rb.peer_base[q] = pb;
+        rb.peer_local0[q] = msgs[q].local0;
+        rb.peer_stride[q] = msgs[q].stride;
+    }
+    c->regs.push_back(rb);
+    return NCME_OK;
+}
+
+int comm_unregister(ncme_comm* c, void* base) {
+    if (!c || c->nranks == 1 || !c->p2p_ok) return NCME_OK;
+    for (size_t k = 0; k < c->regs.size(); ++k) {
+        if (c->regs[k].base != base) continue;
+        NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
+        for (int q = 0; q < c->nranks; ++q)
+            if (c->regs[k].peer_base[q]) cudaIpcCloseMemHandle(c->regs[k].peer_base[q]);
+        c->regs.erase(c->regs.begin() + k);
+        // nobody may free before every rank has unmapped: a tiny all-reduce is the barrier
+        NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, c->ctx->stream));
+        NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
+        return NCME_OK;
+    }
+    return NCME_OK;
+}
+
+const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q) {
+    for (const auto& r : c->regs) {
+        const char* b = (const char*)r.base;
+        const char* x = (const char*)x_local;
+        if (x < b || x >= b + r.bytes || !r.peer_base[q]) continue;
+        const int64_t off = (int64_t)((x - b) / 8) - r.local0;
+        if (off < 0) continue;
+        int64_t v = 0;
+        if (r.stride > 0) {
+            if (off % r.stride != 0) continue;
+            v = off / r.stride;
+        } else if (off != 0) {
+            continue;
+        }
+        if (v >= r.nvec) continue;
+        return (const double*)r.peer_base[q] + r.peer_local0[q] + v * r.peer_stride[q];
+    }
+    return nullptr;
+}
+
+// Flags: every rank exports its PeerFlags block and maps everybody else's.
+static int comm_setup_p2p(ncme_comm* c) {
+    c->p2p_ok = false;
+    if (c->nranks == 1 || c->nranks > NCME_MAX_RANKS || getenv("NCME_HALO_NCCL")) return NCME_OK;
+    NCME_CUDA(cudaMalloc(&c->my_flags, sizeof(PeerFlags)));
+    NCME_CUDA(cudaMemset(c->my_flags, 0, sizeof(PeerFlags)));
+    struct {
+        cudaIpcMemHandle_t h;
+        int64_t valid;
+    } mine;
+    memset(&mine, 0, sizeof(mine));
+    cudaError_t e = cudaIpcGetMemHandle(&mine.h, c->my_flags);
+    mine.valid = e == cudaSuccess;
+    if (e != cudaSuccess) cudaGetLastError();
+    std::vector<char> all;
+    NCME_TRY(allgather_bytes(c, &mine, sizeof(mine), &all));
+    bool ok = true;
+    for (int q = 0; q < c->nranks; ++q) ok &= ((const decltype(mine)*)all.data())[q].valid != 0;
+    int opened = 1;
+    if (ok) {
+        for (int q = 0; q < c->nranks && opened; ++q) {
+            if (q == c->rank) continue;
+            void* pb = nullptr;
+            e = cudaIpcOpenMemHandle(&pb, ((const decltype(mine)*)all.data())[q].h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                opened = 0;
+            } else {
+                c->peer_flags[q] = (PeerFlags*)pb;
+            }
+        }
+    } else {
+        opened = 0;
+    }
+    // everybody must agree
+    double v = opened ? 0.0 : 1.0;
+    NCME_CUDA(cudaMemcpyAsync(c->scratch, &v, sizeof(double), cudaMemcpyHostToDevice, c->ctx->stream));
+    NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, c->ctx->stream));
+    NCME_CUDA(cudaMemcpyAsync(&v, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    c->p2p_ok = (v == 0.0);
+    return NCME_OK;
+}
+
 }  // namespace ncme
 
 using namespace ncme;
@@ -88,6 +235,14 @@ int ncme_comm_destroy(ncme_comm* c) {
     if (!c) return NCME_OK;
     if (c->ctx) cudaStreamSynchronize(c->ctx->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    for (auto& r : c->regs)
+        for (int q = 0; q < c->nranks; ++q)
+            if (r.peer_base[q]) cudaIpcCloseMemHandle(r.peer_base[q]);
+    c->regs.clear();
+    for (int q = 0; q < NCME_MAX_RANKS; ++q)
+        if (c->peer_flags[q]) cudaIpcCloseMemHandle(c->peer_flags[q]);
+    if (c->my_flags) cudaFree(c->my_flags);
+    cudaGetLastError();
     if (c->nccl && nccl_api()) nccl_api()->CommDestroy(c->nccl);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
@@ -130,8 +285,22 @@ int ncme_comm_create(ncme_ctx* ctx, int rank, int nranks, const char* uid128, nc
             ncme_comm_destroy(c);
             return NCME_ERR_COMM;
         }
+        int st = comm_setup_p2p(c);
+        if (st != NCME_OK) {
+            ncme_comm_destroy(c);
+            return st;
+        }
     }
     *out = c;
+    return NCME_OK;
+}
+
+int ncme_comm_info(ncme_comm* c, int64_t info[4]) {
+    NCME_REQUIRE(c && info, "null argument");
+    info[0] = c->p2p_ok ? 1 : 0;
+    info[1] = c->p2p_matvecs;
+    info[2] = c->nccl_matvecs;
+    info[3] = c->bytes_sent;
     return NCME_OK;
 }
 

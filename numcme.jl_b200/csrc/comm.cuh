@@ -6,6 +6,26 @@
 
 #include "common.cuh"
 
+constexpr int NCME_MAX_RANKS = 64;
+
+// Flags each rank exposes to its peers through CUDA IPC (peer GPUs store into them over NVLink).
+struct PeerFlags {
+    unsigned int ready[NCME_MAX_RANKS];   // ready[q] = e: rank q's input vector of matvec #e is complete
+    unsigned int done[NCME_MAX_RANKS];    // done[q]  = e: rank q has finished reading my vector in matvec #e
+    unsigned int error;                   // a wait timed out
+};
+
+// A device allocation whose vectors the neighbouring ranks may read directly (halo pull over NVLink).
+// Vector v of rank q starts (its local rows) at base_q + (local0_q + v * stride_q) doubles.
+struct RegBuf {
+    void* base = nullptr;
+    size_t bytes = 0;
+    int64_t local0 = 0, stride = 0, nvec = 1;
+    void* peer_base[NCME_MAX_RANKS] = {nullptr};
+    int64_t peer_local0[NCME_MAX_RANKS] = {0};
+    int64_t peer_stride[NCME_MAX_RANKS] = {0};
+};
+
 struct ncme_comm {
     ncme_ctx* ctx = nullptr;
     int rank = 0, nranks = 1;
@@ -14,6 +34,13 @@ struct ncme_comm {
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     double* scratch = nullptr;            // device, small
     int64_t bytes_sent = 0;
+    // peer-memory transport (CUDA IPC): flags + registered buffers
+    bool p2p_ok = false;
+    PeerFlags* my_flags = nullptr;
+    PeerFlags* peer_flags[NCME_MAX_RANKS] = {nullptr};
+    unsigned int epoch = 0;
+    std::vector<RegBuf> regs;
+    int64_t p2p_matvecs = 0, nccl_matvecs = 0;
 };
 
 namespace ncme {
@@ -41,6 +68,15 @@ const NcclApi* nccl_api();  // nullptr (+ error message) if libnccl cannot be lo
             return NCME_ERR_COMM;                                                                    \
         }                                                                                            \
     } while (0)
+
+// Collective: expose [base, base+bytes) to the ranks in `peers` (and map theirs).  local0/stride/nvec describe where
+// the vectors live inside the allocation (see RegBuf).  Idempotent for an already registered base.
+int comm_register(ncme_comm* c, void* base, size_t bytes, int64_t local0, int64_t stride, int64_t nvec, const int* peers,
+                  int npeers);
+// Collective: unmap the peers' views of `base` on every rank (call before freeing it).
+int comm_unregister(ncme_comm* c, void* base);
+// pointer to the local rows of the same vector on rank q, or nullptr if x_local is not inside a registered buffer
+const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q);
 
 // in-place sum over ranks of `count` doubles on the device (stream-ordered on `st`)
 int comm_allreduce_sum(ncme_comm* c, double* buf_dev, size_t count, cudaStream_t st);

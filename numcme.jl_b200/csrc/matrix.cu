@@ -144,7 +144,7 @@ __device__ __forceinline__ void decode_cols(const MatvecArgs& a, int s, int64_t 
     }
 }
 
-template <int S, int ROWS, bool C8>
+template <int S, int ROWS, bool C8, bool P2P = false>
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
     const int nt = a.do_sinks ? a.ntasks : 0;
     if ((int)blockIdx.x < nt) {
@@ -198,7 +198,15 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int j = 0; j < ROWS; ++j) g[s][j] = __ldg(a.x + c[s][j]);
+        for (int j = 0; j < ROWS; ++j) {
+            if (P2P) {   // boundary rows of a sharded matrix: halo entries are read from the neighbour's HBM (NVLink)
+                const uint32_t cc = c[s][j];
+                const double* src = cc < a.lo_end ? a.x_lo : (cc >= a.hi_begin ? a.x_hi : a.x);
+                g[s][j] = src[cc];
+            } else {
+                g[s][j] = __ldg(a.x + c[s][j]);
+            }
+        }
     // ---- arithmetic
     double d[ROWS];
 #pragma unroll
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_
     a.y[i] = acc;
 }
 
-template <int ROWS, bool C8>
+template <int ROWS, bool C8, bool P2P = false>
 static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
     const int64_t rows_per_block = (int64_t)MV_THREADS * ROWS;
     const int64_t nrows = a.row_end - a.row_begin;
@@ -264,7 +272,7 @@ static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
     switch (a.nslots) {
 #define NCME_CASE(SS)                                              \
     case SS:                                                       \
-        k_fsp_matvec<SS, ROWS, C8><<<grid, MV_THREADS, 0, st>>>(a); \
+        k_fsp_matvec<SS, ROWS, C8, P2P><<<grid, MV_THREADS, 0, st>>>(a); \
         break;
         NCME_CASE(1) NCME_CASE(2) NCME_CASE(3) NCME_CASE(4) NCME_CASE(5) NCME_CASE(6) NCME_CASE(7) NCME_CASE(8)
         NCME_CASE(9) NCME_CASE(10) NCME_CASE(11) NCME_CASE(12) NCME_CASE(13) NCME_CASE(14) NCME_CASE(15) NCME_CASE(16)
@@ -273,6 +281,15 @@ static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
             return -1;
     }
     return 0;
+}
+
+// boundary rows with peer-memory gathers
+static int matvec_launch_p2p(ncme_matrix* A, const MatvecArgs& a) {
+    NCME_REQUIRE(a.nslots >= 1 && a.nslots <= 16, "peer-memory halo supports up to 16 slots");
+    launch_rows<1, false, true>(A, a);
+    A->ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
 }
 
 int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
@@ -362,6 +379,109 @@ int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st) {
     return NCME_OK;
 }
 
+// ---- cross-GPU flag synchronisation for the peer-memory halo (no NCCL in the loop) -----------------------------
+struct SyncArgs {
+    int nsig, nwait;
+    unsigned int* sig[8];          // peer memory: slots to store the epoch into
+    const unsigned int* wait[8];   // local memory: slots that must reach the epoch
+    unsigned int epoch;
+    unsigned int* err;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// one thread: publish, then (optionally) wait.  Waits are bounded (2 s): a lost peer raises an error flag instead of
+// hanging the GPU.
+__global__ void k_p2p_sync(const __grid_constant__ SyncArgs a) {
+    if (threadIdx.x != 0) return;
+    if (a.nsig) {
+        __threadfence_system();
+        for (int k = 0; k < a.nsig; ++k) *((volatile unsigned int*)a.sig[k]) = a.epoch;
+    }
+    if (a.nwait) {
+        const unsigned long long t0 = global_ns();
+        for (int k = 0; k < a.nwait; ++k) {
+            const volatile unsigned int* f = a.wait[k];
+            while ((int)(*f - a.epoch) < 0) {
+                if (global_ns() - t0 > 2000000000ull) {
+                    atomicExch(a.err, 1u);
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+static int p2p_sync(ncme_matrix* A, const SyncArgs& sa) {
+    if (sa.nsig == 0 && sa.nwait == 0) return NCME_OK;
+    k_p2p_sync<<<1, 32, 0, A->ctx->stream>>>(sa);
+    A->ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+// Halo of x read straight from the neighbours' HBM by the boundary rows (CUDA IPC + NVLink); flags replace the
+// collective: ready(e) before reading, done(e) before the owner may overwrite.
+static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, const double* xhi, int reduce_sinks) {
+    ncme_comm* c = A->comm;
+    const unsigned int e = ++c->epoch;
+    const int me = c->rank;
+    SyncArgs ready_sig{}, ready_wait{}, done{};
+    ready_sig.epoch = ready_wait.epoch = done.epoch = e;
+    ready_sig.err = ready_wait.err = done.err = &c->my_flags->error;
+    for (int q : A->readers) {                               // they read my x: tell them it is complete
+        ready_sig.sig[ready_sig.nsig++] = &c->peer_flags[q]->ready[me];
+        done.wait[done.nwait++] = &c->my_flags->done[q];      // ... and later wait until they are through with it
+    }
+    for (int q : {A->plo, A->phi}) {
+        if (q < 0) continue;
+        ready_wait.wait[ready_wait.nwait++] = &c->my_flags->ready[q];
+        done.sig[done.nsig++] = &c->peer_flags[q]->done[me];
+    }
+    // padded position c -> peer address: low halo c in [0, hl): global ext_lo + c; high halo c >= hl + n + R
+    a.lo_end = (uint32_t)A->hl;
+    a.hi_begin = (uint32_t)(A->hl + A->n + A->nr);
+    a.x_lo = xlo ? xlo + (A->ext_lo - A->plo_row_lo) : a.x;
+    a.x_hi = xhi ? xhi + (A->row_hi - A->phi_row_lo) - (int64_t)a.hi_begin : a.x;
+    NCME_TRY(p2p_sync(A, ready_sig));
+    const bool interior = A->b1 > A->b0;
+    if (interior) {
+        MatvecArgs in = a;
+        in.row_begin = A->b0;
+        in.row_end = A->b1;
+        in.do_sinks = 1;
+        NCME_TRY(matvec_launch(A, in));
+    }
+    NCME_TRY(p2p_sync(A, ready_wait));
+    if (!interior) {
+        NCME_TRY(matvec_launch_p2p(A, a));
+    } else {
+        if (A->b0 > 0) {
+            MatvecArgs lo = a;
+            lo.row_begin = 0;
+            lo.row_end = A->b0;
+            lo.do_sinks = 0;
+            NCME_TRY(matvec_launch_p2p(A, lo));
+        }
+        if (A->b1 < A->n) {
+            MatvecArgs hi = a;
+            hi.row_begin = A->b1;
+            hi.row_end = A->n;
+            hi.do_sinks = 0;
+            NCME_TRY(matvec_launch_p2p(A, hi));
+        }
+    }
+    NCME_TRY(p2p_sync(A, done));
+    c->p2p_matvecs++;
+    if (reduce_sinks) NCME_TRY(comm_allreduce_sum(c, a.y + A->n, (size_t)A->nr, A->ctx->stream));
+    return NCME_OK;
+}
+
 int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, double* y_local, double beta, int reduce_sinks) {
     MatvecArgs a;
     matvec_fill_args(A, coef, &a);
@@ -372,6 +492,16 @@ int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, doubl
     ncme_comm* c = A->comm;
     if (!c || c->nranks == 1) return matvec_launch(A, a);
     cudaStream_t st = A->ctx->stream;
+    if (c->p2p_ok && A->p2p_eligible && beta == 0.0) {
+        // registered on every rank or on none (registration is collective), so all ranks take the same branch
+        const double* xlo = A->plo >= 0 ? comm_peer_vector(c, x_local, A->plo) : nullptr;
+        const double* xhi = A->phi >= 0 ? comm_peer_vector(c, x_local, A->phi) : nullptr;
+        bool registered = false;
+        for (const auto& r : c->regs)
+            registered |= ((const char*)x_local >= (const char*)r.base && (const char*)x_local < (const char*)r.base + r.bytes);
+        if (registered && (A->plo < 0 || xlo) && (A->phi < 0 || xhi)) return matvec_dist_p2p(A, a, xlo, xhi, reduce_sinks);
+    }
+    c->nccl_matvecs++;
     static const bool no_overlap_env = getenv("NCME_NO_OVERLAP") != nullptr;   // experiments only
     const bool overlap = A->b1 > A->b0 && !no_overlap_env;
     if (!overlap) {
@@ -750,6 +880,31 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
             if (isect(A->ext_lo, row_lo, qlo, qhi, &s0, &s1)) A->halo_recv.push_back({q, s0 - row_lo, s1 - s0});
             if (isect(row_hi, A->ext_hi, qlo, qhi, &s0, &s1)) A->halo_recv.push_back({q, s0 - row_lo + nr, s1 - s0});
         }
+        // peer-memory eligibility, evaluated for EVERY rank from the gathered table so that all ranks agree
+        bool all_ok = true;
+        A->readers.clear();
+        A->plo = A->phi = -1;
+        for (int r = 0; r < P; ++r) {
+            const int64_t rlo = (int64_t)h[4 * r], rhi = (int64_t)h[4 * r + 1], relo = (int64_t)h[4 * r + 2],
+                          rehi = (int64_t)h[4 * r + 3];
+            int owner_lo = -1, owner_hi = -1;
+            for (int q = 0; q < P; ++q) {
+                if (q == r) continue;
+                const int64_t qlo = (int64_t)h[4 * q], qhi = (int64_t)h[4 * q + 1];
+                if (relo < rlo && qlo <= relo && rlo <= qhi) owner_lo = q;
+                if (rehi > rhi && qlo <= rhi && rehi <= qhi) owner_hi = q;
+            }
+            if ((relo < rlo && owner_lo < 0) || (rehi > rhi && owner_hi < 0)) all_ok = false;
+            if (r == me) {
+                A->plo = owner_lo;
+                A->phi = owner_hi;
+                if (owner_lo >= 0) A->plo_row_lo = (int64_t)h[4 * owner_lo];
+                if (owner_hi >= 0) A->phi_row_lo = (int64_t)h[4 * owner_hi];
+            }
+            if (owner_lo == me || owner_hi == me) A->readers.push_back(r);
+        }
+        if (A->readers.size() > 8) all_ok = false;
+        A->p2p_eligible = all_ok;
     }
 
     // ---- sink lists (rows ascending inside each reaction) and structural counts
@@ -868,6 +1023,19 @@ int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t
     }
     *out = A;
     return NCME_OK;
+}
+
+int ncme_matrix_register_buffer(ncme_matrix* A, void* base_dev, size_t bytes, int64_t local0) {
+    NCME_REQUIRE(A && base_dev, "null argument");
+    if (!A->comm) return NCME_OK;
+    const int peers[2] = {A->plo, A->phi};
+    return comm_register(A->comm, base_dev, bytes, local0, 0, 1, peers, 2);
+}
+
+int ncme_matrix_unregister_buffer(ncme_matrix* A, void* base_dev) {
+    NCME_REQUIRE(A && base_dev, "null argument");
+    if (!A->comm) return NCME_OK;
+    return comm_unregister(A->comm, base_dev);
 }
 
 int ncme_matrix_shard_info(ncme_matrix* A, int64_t info[8]) {

@@ -37,6 +37,11 @@ struct ncme_matrix {
         int64_t count;
     };
     std::vector<HaloSeg> halo_send, halo_recv;
+    // peer-memory halo (CUDA IPC): possible when each halo side lies inside ONE neighbouring rank's block
+    bool p2p_eligible = false;        // same value on every rank
+    int plo = -1, phi = -1;           // ranks that own my low / high halo (-1: no halo on that side)
+    int64_t plo_row_lo = 0, phi_row_lo = 0;
+    std::vector<int> readers;         // ranks whose halo lies in my block (they read my vectors)
 
     int nslots = 0;
     int slot_coef_src[NCME_MAX_REACTIONS] = {0};   // reaction whose time factor scales the slot, -1 => 1.0
@@ -104,6 +109,9 @@ struct MatvecArgs {
     const double* xd;   // x_local: entry of row i is xd[i]
     double* y;
     double beta;
+    const double* x_lo;   // P2P launches: x_lo[c] for padded positions c < lo_end (peer memory over NVLink)
+    const double* x_hi;   //               x_hi[c] for c >= hi_begin
+    uint32_t lo_end, hi_begin;
     int64_t row_begin, row_end;  // rows handled by this launch
     int do_sinks;                // 1: the sink-task CTAs run in this launch
 };

@@ -178,6 +178,7 @@ struct OdeSystem {
     int64_t hl = 0, hh = 0;      // halo margins every RHS input must carry
     int64_t len_global = 0;      // number of entries of the global vector (error norm)
     int64_t n_global = 0;        // sharded: global number of state rows (output gather)
+    int peers[2] = {-1, -1};     // sharded: ranks whose vectors this rank reads (peer-memory halo)
     std::function<int(double, const double*, double*)> rhs;
 };
 
@@ -198,8 +199,28 @@ static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, dou
     // every vector that can be a matvec input carries the halo margins: [hl | n rows | R sinks | hh]
     const size_t hl = round_up<size_t>((size_t)sys.hl, 32), hh = round_up<size_t>((size_t)sys.hh, 32);
     const size_t Npad = hl + round_up<size_t>((size_t)N, 32) + hh;
-    NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 10 * sizeof(double), false));
-    ws.base = ctx->solve_ws;
+    // Sharded runs: a fresh allocation registered for peer access (CUDA IPC) for the duration of the segment, so the
+    // neighbours can pull halo entries of any stage vector straight from this GPU's HBM.
+    struct SharedWs {
+        ncme_comm* c = nullptr;
+        double* p = nullptr;
+        ~SharedWs() {
+            if (p) {
+                comm_unregister(c, p);
+                cudaFree(p);
+            }
+        }
+    } shared;
+    if (comm) {
+        NCME_CUDA(cudaMalloc(&shared.p, Npad * 10 * sizeof(double)));
+        shared.c = comm;
+        NCME_CUDA(cudaMemsetAsync(shared.p, 0, Npad * 10 * sizeof(double), s));
+        NCME_TRY(comm_register(comm, shared.p, Npad * 10 * sizeof(double), (int64_t)hl, (int64_t)Npad, 10, sys.peers, 2));
+        ws.base = shared.p;
+    } else {
+        NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 10 * sizeof(double), false));
+        ws.base = ctx->solve_ws;
+    }
     for (int j = 0; j < 7; ++j) ws.k[j] = ws.base + Npad * j + hl;
     ws.ytmp = ws.base + Npad * 7 + hl;
     ws.ua = ws.base + Npad * 8 + hl;
@@ -285,6 +306,14 @@ static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, dou
         if (src != u) NCME_CUDA(cudaMemcpyAsync(u, src, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         NCME_TRY(comm_allreduce_sum(comm, u + n, (size_t)R, s));
         NCME_CUDA(cudaStreamSynchronize(s));
+        if (comm && comm->my_flags) {
+            unsigned int perr = 0;
+            NCME_CUDA(cudaMemcpy(&perr, &comm->my_flags->error, sizeof(perr), cudaMemcpyDeviceToHost));
+            if (perr) {
+                set_error("peer-memory halo: a neighbouring rank did not signal within 2 s");
+                return NCME_ERR_COMM;
+            }
+        }
         st->launches = ctx->launches - launches0;
         return NCME_OK;
     };
@@ -498,6 +527,8 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     sys.hh = A->hh;
     sys.len_global = A->n_global + A->nr;
     sys.n_global = A->n_global;
+    sys.peers[0] = A->plo;
+    sys.peers[1] = A->phi;
     sys.rhs = [&](double t, const double* x, double* y) -> int {
         if (coef_fn) coef_fn(t, coef, user);
         return matvec_dist(A, coef, x, y, 0.0, /*reduce_sinks=*/0);

@@ -61,6 +61,11 @@ class Comm:
         L.check(L.load().ncme_comm_allgatherv(self._h, C.c_void_p(device_ptr(local)), C.c_void_p(device_ptr(full)),
                                               L.ptr(cn, C.c_int64), L.ptr(dp, C.c_int64)))
 
+    def info(self) -> dict:
+        v = (C.c_int64 * 4)()
+        L.check(L.load().ncme_comm_info(self._h, v))
+        return {"p2p": bool(v[0]), "p2p_matvecs": int(v[1]), "nccl_matvecs": int(v[2]), "nccl_halo_bytes": int(v[3])}
+
     def close(self):
         if getattr(self, "_h", None):
             L.load().ncme_comm_destroy(self._h)
@@ -78,7 +83,10 @@ class ShardedVector:
     """Local slice [rows row_lo..row_hi | R sink entries] of an FSP vector, allocated with the halo margins a
     sharded matvec input needs (ncme_matrix_shard_info)."""
 
-    def __init__(self, A, fill=None):
+    def __init__(self, A, fill=None, register=False):
+        """``register=True`` (collective over the ranks) exposes the buffer for the peer-memory halo."""
+        self._A = A
+        self._registered = False
         info = A.shard_info()
         self.hl, self.hh = info["halo_lo"], info["halo_hi"]
         self.nloc = info["row_hi"] - info["row_lo"]
@@ -88,3 +96,12 @@ class ShardedVector:
         self.v = self._buf.view(self.hl, self.nloc + self.R)
         if fill is not None:
             self.v.upload(fill)
+        if register and info["nranks"] > 1:
+            L.check(L.load().ncme_matrix_register_buffer(A.handle, C.c_void_p(self._buf.ptr), self._buf.n * 8, self.hl))
+            self._registered = True
+
+    def unregister(self):
+        """collective"""
+        if self._registered:
+            L.check(L.load().ncme_matrix_unregister_buffer(self._A.handle, C.c_void_p(self._buf.ptr)))
+            self._registered = False

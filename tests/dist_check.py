@@ -45,6 +45,18 @@ def main():
     y = ys.to_host()
     assert np.array_equal(y[:hi - lo], y_ref[lo:hi]), "state rows differ from the single-GPU result"
     assert np.abs(y[hi - lo:] - y_ref[n:]).max() <= 1e-12 * np.abs(y_ref[n:]).max(), "sink rows differ"
+    # same through the peer-memory halo (CUDA IPC): registered input buffer, no NCCL in the matvec
+    before = comm.info()
+    xr = pkg.ShardedVector(A_sh, fill=np.concatenate([x[lo:hi], x[n:]]), register=True)
+    for rep in range(5):
+        xr.v.upload(np.concatenate([x[lo:hi], x[n:]]) * (1.0 + rep))     # overwrite between matvecs: exercises ready/done
+        pkg.matvec_(ys, 2.5, A_sh, xr.v)
+        y2 = ys.to_host()
+        assert np.allclose(y2[:hi - lo], y_ref[lo:hi] * (1.0 + rep), rtol=1e-14, atol=0), "peer-memory halo: state rows differ"
+    after = comm.info()
+    if after["p2p"]:
+        assert after["p2p_matvecs"] - before["p2p_matvecs"] == 5 and after["nccl_matvecs"] == before["nccl_matvecs"]
+    xr.unregister()
     gsum = torch.tensor([y[:hi - lo].sum()], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(gsum)
     ones = pkg.ShardedVector(A_sh, fill=np.ones(hi - lo + 6))
@@ -79,7 +91,7 @@ def main():
     assert f1.stats["steps"] == f2.stats["steps"]
     dist.barrier()
     if rank == 0:
-        print(f"DIST_CHECK_OK world={world} n={n} halo=({info['halo_lo']},{info['halo_hi']}) "
+        print(f"DIST_CHECK_OK world={world} n={n} comm={comm.info()} halo=({info['halo_lo']},{info['halo_hi']}) "
               f"interior=[{info['interior_begin']},{info['interior_end']})")
     dist.destroy_process_group()
 
