@@ -207,8 +207,10 @@ int ncme_matrix_register_buffer(ncme_matrix* mat, void* base_dev, size_t bytes, 
 int ncme_matrix_unregister_buffer(ncme_matrix* mat, void* base_dev);
 /* info = {peer-memory transport available, #matvecs through peer memory, #matvecs through NCCL, halo bytes sent by NCCL} */
 int ncme_comm_info(ncme_comm* comm, int64_t info[4]);
-/* As ncme_matvec, but the nr sink entries of y_dev are left as this rank's partial sums (their sum over the ranks
- * is the result): what the native integrator does per stage, deferring the reduction to one all-reduce per step. */
+/* The matvec as the native integrator issues it per stage: the nr sink entries of y_dev are left as this rank's
+ * partial sums (their sum over the ranks is the result; one all-reduce per step instead of one per stage), and the
+ * caller promises not to overwrite x_dev before its NEXT matvec on this matrix has been issued (the integrator
+ * alternates input buffers), which lets the peer-memory halo drop its "done" handshake. */
 int ncme_matvec_local(ncme_matrix* mat, const double* coef, const double* x_dev, double* y_dev);
 /* info = {row_lo, row_hi, halo_lo, halo_hi, n_global, interior_begin, interior_end, nranks} */
 int ncme_matrix_shard_info(ncme_matrix* mat, int64_t info[8]);

@@ -59,6 +59,12 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ------------------------------------------------------------------------------ sink rows ------
 // y[n+r] = c_r * sum over the sink entries of reaction r.  One CTA per (reaction, <=SINK_CHUNK
 // entries) task writes a partial; the last CTA to finish adds the partials of each reaction in task
@@ -151,13 +157,38 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
         sink_task(a);
         return;
     }
-    const int64_t i0 = a.row_begin + ((int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x) * ROWS;
-    if (i0 >= a.row_end) return;
+    int64_t i0 = a.row_begin + ((int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x) * ROWS;
+    int64_t row_end = a.row_end;
+    if (P2P) {
+        // boundary rows of a sharded matrix: wait (bounded) until the neighbours have published this matvec's input
+        if (a.nwait) {
+            if (threadIdx.x == 0) {
+                const unsigned long long t0 = global_ns();
+                for (int k = 0; k < a.nwait; ++k) {
+                    const volatile unsigned int* f = a.wait_flag[k];
+                    while ((int)(*f - a.epoch) < 0) {
+                        if (global_ns() - t0 > 2000000000ull) {
+                            atomicExch(a.err_flag, 1u);
+                            break;
+                        }
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+        const int64_t nb1 = (a.row_end - a.row_begin + MV_THREADS * ROWS - 1) / (MV_THREADS * ROWS);
+        if ((int64_t)(blockIdx.x - nt) >= nb1) {   // second range
+            i0 = a.row_begin2 + ((int64_t)(blockIdx.x - nt - nb1) * MV_THREADS + threadIdx.x) * ROWS;
+            row_end = a.row_end2;
+        }
+    }
+    if (i0 >= row_end) return;
 
     // ---- first-level loads: all independent, all issued before the first use (one exposed DRAM latency)
     double xi[ROWS];
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) xi[j] = (i0 + j < a.row_end) ? __ldg(a.xd + i0 + j) : 0.0;
+    for (int j = 0; j < ROWS; ++j) xi[j] = (i0 + j < row_end) ? __ldg(a.xd + i0 + j) : 0.0;
     uint32_t c[S][ROWS];
     double v[S][ROWS];
     int2 desc[C8 ? S : 1];
@@ -232,7 +263,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
     }
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
-        if (i0 + j < a.row_end) {
+        if (i0 + j < row_end) {
             double out = acc[j];
             if (a.beta != 0.0) out += a.beta * a.y[i0 + j];
             a.y[i0 + j] = out;
@@ -266,7 +297,9 @@ template <int ROWS, bool C8, bool P2P = false>
 static int launch_rows(ncme_matrix* A, const MatvecArgs& a) {
     const int64_t rows_per_block = (int64_t)MV_THREADS * ROWS;
     const int64_t nrows = a.row_end - a.row_begin;
-    const unsigned grid = (unsigned)((a.do_sinks ? a.ntasks : 0) + (nrows + rows_per_block - 1) / rows_per_block);
+    const int64_t nrows2 = P2P ? (a.row_end2 - a.row_begin2) : 0;
+    const unsigned grid = (unsigned)((a.do_sinks ? a.ntasks : 0) + (nrows + rows_per_block - 1) / rows_per_block +
+                                     (nrows2 + rows_per_block - 1) / rows_per_block);
     if (grid == 0) return 0;
     cudaStream_t st = A->ctx->stream;
     switch (a.nslots) {
@@ -347,6 +380,10 @@ int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a) {
     a->sink_counter = A->sink_counter;
     a->row_begin = 0;
     a->row_end = A->n;
+    a->row_begin2 = a->row_end2 = 0;
+    a->nwait = 0;
+    a->epoch = 0;
+    a->err_flag = nullptr;
     a->do_sinks = 1;
     return NCME_OK;
 }
@@ -388,12 +425,6 @@ struct SyncArgs {
     unsigned int* err;
 };
 
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // one thread: publish, then (optionally) wait.  Waits are bounded (2 s): a lost peer raises an error flag instead of
 // hanging the GPU.
 __global__ void k_p2p_sync(const __grid_constant__ SyncArgs a) {
@@ -425,22 +456,33 @@ static int p2p_sync(ncme_matrix* A, const SyncArgs& sa) {
     return NCME_OK;
 }
 
-// Halo of x read straight from the neighbours' HBM by the boundary rows (CUDA IPC + NVLink); flags replace the
-// collective: ready(e) before reading, done(e) before the owner may overwrite.
-static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, const double* xhi, int reduce_sinks) {
+// Halo of x read straight from the neighbours' HBM by the boundary rows (CUDA IPC + NVLink).  Flags replace the
+// collective: ready(e) is published before the interior rows start and awaited inside the boundary-rows kernel;
+// done(e) protects the input against being overwritten while a neighbour still reads it -- skipped when the caller
+// alternates input buffers, because observing ready(e+1) from a neighbour already implies it finished matvec e.
+static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, const double* xhi, int flags) {
     ncme_comm* c = A->comm;
     const unsigned int e = ++c->epoch;
     const int me = c->rank;
-    SyncArgs ready_sig{}, ready_wait{}, done{};
-    ready_sig.epoch = ready_wait.epoch = done.epoch = e;
-    ready_sig.err = ready_wait.err = done.err = &c->my_flags->error;
+    SyncArgs ready_sig{}, done{};
+    ready_sig.epoch = done.epoch = e;
+    ready_sig.err = done.err = &c->my_flags->error;
+    a.nwait = 0;
+    a.epoch = e;
+    a.err_flag = &c->my_flags->error;
+    auto add_wait = [&](int q) {
+        for (int k = 0; k < a.nwait; ++k)
+            if (a.wait_flag[k] == &c->my_flags->ready[q]) return;
+        if (a.nwait < 4) a.wait_flag[a.nwait++] = &c->my_flags->ready[q];
+    };
     for (int q : A->readers) {                               // they read my x: tell them it is complete
         ready_sig.sig[ready_sig.nsig++] = &c->peer_flags[q]->ready[me];
-        done.wait[done.nwait++] = &c->my_flags->done[q];      // ... and later wait until they are through with it
+        done.wait[done.nwait++] = &c->my_flags->done[q];
+        add_wait(q);                                         // (their ready(e) also certifies they are past e-1)
     }
     for (int q : {A->plo, A->phi}) {
         if (q < 0) continue;
-        ready_wait.wait[ready_wait.nwait++] = &c->my_flags->ready[q];
+        add_wait(q);
         done.sig[done.nsig++] = &c->peer_flags[q]->done[me];
     }
     // padded position c -> peer address: low halo c in [0, hl): global ext_lo + c; high halo c >= hl + n + R
@@ -456,29 +498,19 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
         in.row_end = A->b1;
         in.do_sinks = 1;
         NCME_TRY(matvec_launch(A, in));
-    }
-    NCME_TRY(p2p_sync(A, ready_wait));
-    if (!interior) {
-        NCME_TRY(matvec_launch_p2p(A, a));
+        MatvecArgs bd = a;                                   // both boundary ranges in one launch
+        bd.row_begin = 0;
+        bd.row_end = A->b0;
+        bd.row_begin2 = A->b1;
+        bd.row_end2 = A->n;
+        bd.do_sinks = 0;
+        NCME_TRY(matvec_launch_p2p(A, bd));
     } else {
-        if (A->b0 > 0) {
-            MatvecArgs lo = a;
-            lo.row_begin = 0;
-            lo.row_end = A->b0;
-            lo.do_sinks = 0;
-            NCME_TRY(matvec_launch_p2p(A, lo));
-        }
-        if (A->b1 < A->n) {
-            MatvecArgs hi = a;
-            hi.row_begin = A->b1;
-            hi.row_end = A->n;
-            hi.do_sinks = 0;
-            NCME_TRY(matvec_launch_p2p(A, hi));
-        }
+        NCME_TRY(matvec_launch_p2p(A, a));
     }
-    NCME_TRY(p2p_sync(A, done));
+    if (!(flags & 2)) NCME_TRY(p2p_sync(A, done));
     c->p2p_matvecs++;
-    if (reduce_sinks) NCME_TRY(comm_allreduce_sum(c, a.y + A->n, (size_t)A->nr, A->ctx->stream));
+    if (flags & 1) NCME_TRY(comm_allreduce_sum(c, a.y + A->n, (size_t)A->nr, A->ctx->stream));
     return NCME_OK;
 }
 
@@ -534,7 +566,7 @@ int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, doubl
             NCME_TRY(matvec_launch(A, hi));
         }
     }
-    if (reduce_sinks) NCME_TRY(comm_allreduce_sum(c, y_local + A->n, (size_t)A->nr, st));
+    if (reduce_sinks & 1) NCME_TRY(comm_allreduce_sum(c, y_local + A->n, (size_t)A->nr, st));
     return NCME_OK;
 }
 
@@ -1127,7 +1159,7 @@ int ncme_matvec_local(ncme_matrix* A, const double* coef, const double* x_dev, d
     bool need_coef = false;
     for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] == NCME_SEPARABLE_TV);
     NCME_REQUIRE(coef || !need_coef, "coef is null but the matrix has separable time-varying reactions");
-    return matvec_dist(A, coef, x_dev, y_dev, 0.0, 0);
+    return matvec_dist(A, coef, x_dev, y_dev, 0.0, 2);
 }
 
 int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, double* y_host, double beta) {

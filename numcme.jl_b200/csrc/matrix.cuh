@@ -112,6 +112,11 @@ struct MatvecArgs {
     const double* x_lo;   // P2P launches: x_lo[c] for padded positions c < lo_end (peer memory over NVLink)
     const double* x_hi;   //               x_hi[c] for c >= hi_begin
     uint32_t lo_end, hi_begin;
+    int nwait;                         // P2P launches: every CTA first waits until these flags reach `epoch`
+    const unsigned int* wait_flag[4];
+    unsigned int epoch;
+    unsigned int* err_flag;
+    int64_t row_begin2, row_end2;      // P2P launches: optional second row range (high boundary rows)
     int64_t row_begin, row_end;  // rows handled by this launch
     int do_sinks;                // 1: the sink-task CTAs run in this launch
 };
@@ -121,6 +126,8 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a);
 // y_local = A(t) x_local for a (possibly sharded) matrix.  Sharded: exchanges the halo of x in place (x_local must
 // have hl doubles of margin before it and hh after its nr sink entries); the nr sink entries of y hold this rank's
 // partial sums unless reduce_sinks != 0.
+// reduce_sinks: bit 0 = all-reduce the sink entries; bit 1 = the caller alternates input buffers between consecutive
+// matvecs (the integrator does), so the peer-memory path may skip the "done" handshake.
 int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, double* y_local, double beta, int reduce_sinks);
 int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st);
 int sens_describe(ncme_sensmatrix* SA, ncme_matrix** A, int* npar, int* nent);

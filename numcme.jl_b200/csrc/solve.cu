@@ -127,6 +127,7 @@ struct Workspace {       // views into the context's grow-only caches
     double* base = nullptr;
     double* k[7];
     double* ytmp;
+    double* ytmp2;   // consecutive RHS inputs alternate buffers (lets the peer-memory halo skip its "done" handshake)
     double* ua;
     double* ub;
     double* full = nullptr;     // n_global + R, for gathered output slices (sharded runs)
@@ -212,19 +213,20 @@ static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, dou
         }
     } shared;
     if (comm) {
-        NCME_CUDA(cudaMalloc(&shared.p, Npad * 10 * sizeof(double)));
+        NCME_CUDA(cudaMalloc(&shared.p, Npad * 11 * sizeof(double)));
         shared.c = comm;
-        NCME_CUDA(cudaMemsetAsync(shared.p, 0, Npad * 10 * sizeof(double), s));
-        NCME_TRY(comm_register(comm, shared.p, Npad * 10 * sizeof(double), (int64_t)hl, (int64_t)Npad, 10, sys.peers, 2));
+        NCME_CUDA(cudaMemsetAsync(shared.p, 0, Npad * 11 * sizeof(double), s));
+        NCME_TRY(comm_register(comm, shared.p, Npad * 11 * sizeof(double), (int64_t)hl, (int64_t)Npad, 11, sys.peers, 2));
         ws.base = shared.p;
     } else {
-        NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 10 * sizeof(double), false));
+        NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 11 * sizeof(double), false));
         ws.base = ctx->solve_ws;
     }
     for (int j = 0; j < 7; ++j) ws.k[j] = ws.base + Npad * j + hl;
     ws.ytmp = ws.base + Npad * 7 + hl;
     ws.ua = ws.base + Npad * 8 + hl;
     ws.ub = ws.base + Npad * 9 + hl;
+    ws.ytmp2 = ws.base + Npad * 10 + hl;
     if (save_fn) {
         NCME_TRY(cache_reserve(&ctx->solve_pinned, &ctx->solve_pinned_bytes, (size_t)Nglob * sizeof(double), true));
         ws.pinned = ctx->solve_pinned;
@@ -384,7 +386,7 @@ static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, dou
                 cs[1 + j] = h * DP_A[i][j];
                 xs[1 + j] = ws.k[j];
             }
-            double* dst = (i == 6) ? unext : ws.ytmp;
+            double* dst = (i == 6) ? unext : ((i & 1) ? ws.ytmp : ws.ytmp2);
             NCME_TRY(lincomb(1 + i, cs, xs, dst));
             NCME_TRY(rhs(t + DP_C[i] * h, dst, ws.k[i]));
         }
@@ -531,7 +533,7 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     sys.peers[1] = A->phi;
     sys.rhs = [&](double t, const double* x, double* y) -> int {
         if (coef_fn) coef_fn(t, coef, user);
-        return matvec_dist(A, coef, x, y, 0.0, /*reduce_sinks=*/0);
+        return matvec_dist(A, coef, x, y, 0.0, /*no sink reduction, inputs alternate buffers*/ 2);
     };
     if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, u_dev, opts, stats);
     set_error("unknown integrator method %d", opts->method);
