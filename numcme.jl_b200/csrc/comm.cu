@@ -151,6 +151,41 @@ int comm_unregister(ncme_comm* c, void* base) {
     return NCME_OK;
 }
 
+int comm_workspace(ncme_comm* c, size_t bytes, int64_t local0, int64_t stride, int64_t nvec, const int* peers, int npeers,
+                   double** out) {
+    cudaStream_t st = c->ctx->stream;
+    // layout or size changed anywhere => everybody re-allocates (keeps the registration symmetric)
+    const bool same = c->ws_base && c->ws_bytes >= bytes && c->ws_local0 == local0 && c->ws_stride == stride &&
+                      c->ws_nvec == nvec;
+    double v = same ? 0.0 : 1.0;
+    NCME_CUDA(cudaMemcpyAsync(c->scratch, &v, sizeof(double), cudaMemcpyHostToDevice, st));
+    NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, st));
+    NCME_CUDA(cudaMemcpyAsync(&v, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    if (v != 0.0) {
+        if (c->ws_base) {
+            NCME_TRY(comm_unregister(c, c->ws_base));
+            cudaFree(c->ws_base);
+            c->ws_base = nullptr;
+            c->ws_bytes = 0;
+        }
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&c->ws_base, want);
+        if (e != cudaSuccess) {
+            set_error("integrator workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return NCME_ERR_NOMEM;
+        }
+        c->ws_bytes = want;
+        c->ws_local0 = local0;
+        c->ws_stride = stride;
+        c->ws_nvec = nvec;
+        NCME_CUDA(cudaMemsetAsync(c->ws_base, 0, want, st));
+        NCME_TRY(comm_register(c, c->ws_base, want, local0, stride, nvec, peers, npeers));
+    }
+    *out = c->ws_base;
+    return NCME_OK;
+}
+
 const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q) {
     for (const auto& r : c->regs) {
         const char* b = (const char*)r.base;
@@ -242,6 +277,7 @@ int ncme_comm_destroy(ncme_comm* c) {
     for (int q = 0; q < NCME_MAX_RANKS; ++q)
         if (c->peer_flags[q]) cudaIpcCloseMemHandle(c->peer_flags[q]);
     if (c->my_flags) cudaFree(c->my_flags);
+    if (c->ws_base) cudaFree(c->ws_base);
     cudaGetLastError();
     if (c->nccl && nccl_api()) nccl_api()->CommDestroy(c->nccl);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);

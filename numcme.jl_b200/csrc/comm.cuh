@@ -41,6 +41,10 @@ struct ncme_comm {
     unsigned int epoch = 0;
     std::vector<RegBuf> regs;
     int64_t p2p_matvecs = 0, nccl_matvecs = 0;
+    // grow-only integrator workspace, registered for peer access (re-allocation is a collective decision)
+    double* ws_base = nullptr;
+    size_t ws_bytes = 0;
+    int64_t ws_local0 = -1, ws_stride = -1, ws_nvec = -1;
 };
 
 namespace ncme {
@@ -75,6 +79,9 @@ int comm_register(ncme_comm* c, void* base, size_t bytes, int64_t local0, int64_
                   int npeers);
 // Collective: unmap the peers' views of `base` on every rank (call before freeing it).
 int comm_unregister(ncme_comm* c, void* base);
+// Collective: make sure the registered integrator workspace holds `bytes` with the given vector layout.
+int comm_workspace(ncme_comm* c, size_t bytes, int64_t local0, int64_t stride, int64_t nvec, const int* peers, int npeers,
+                   double** out);
 // pointer to the local rows of the same vector on rank q, or nullptr if x_local is not inside a registered buffer
 const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q);
 

@@ -493,18 +493,28 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
     NCME_TRY(p2p_sync(A, ready_sig));
     const bool interior = A->b1 > A->b0;
     if (interior) {
-        MatvecArgs in = a;
-        in.row_begin = A->b0;
-        in.row_end = A->b1;
-        in.do_sinks = 1;
-        NCME_TRY(matvec_launch(A, in));
+        // boundary rows (peer loads over NVLink, waiting for the neighbours inside the kernel) run on the
+        // high-priority stream CONCURRENTLY with the interior rows; they write disjoint rows of y
+        cudaStream_t st = A->ctx->stream;
+        NCME_CUDA(cudaEventRecord(c->ev_ready, st));
+        NCME_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
         MatvecArgs bd = a;                                   // both boundary ranges in one launch
         bd.row_begin = 0;
         bd.row_end = A->b0;
         bd.row_begin2 = A->b1;
         bd.row_end2 = A->n;
         bd.do_sinks = 0;
-        NCME_TRY(matvec_launch_p2p(A, bd));
+        A->ctx->stream = c->comm_stream;
+        int rc = matvec_launch_p2p(A, bd);
+        A->ctx->stream = st;
+        NCME_TRY(rc);
+        NCME_CUDA(cudaEventRecord(c->ev_done, c->comm_stream));
+        MatvecArgs in = a;
+        in.row_begin = A->b0;
+        in.row_end = A->b1;
+        in.do_sinks = 1;
+        NCME_TRY(matvec_launch(A, in));
+        NCME_CUDA(cudaStreamWaitEvent(st, c->ev_done, 0));
     } else {
         NCME_TRY(matvec_launch_p2p(A, a));
     }

@@ -200,24 +200,10 @@ static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, dou
     // every vector that can be a matvec input carries the halo margins: [hl | n rows | R sinks | hh]
     const size_t hl = round_up<size_t>((size_t)sys.hl, 32), hh = round_up<size_t>((size_t)sys.hh, 32);
     const size_t Npad = hl + round_up<size_t>((size_t)N, 32) + hh;
-    // Sharded runs: a fresh allocation registered for peer access (CUDA IPC) for the duration of the segment, so the
-    // neighbours can pull halo entries of any stage vector straight from this GPU's HBM.
-    struct SharedWs {
-        ncme_comm* c = nullptr;
-        double* p = nullptr;
-        ~SharedWs() {
-            if (p) {
-                comm_unregister(c, p);
-                cudaFree(p);
-            }
-        }
-    } shared;
+    // Sharded runs: the workspace is registered for peer access (CUDA IPC), so the neighbours can pull halo entries
+    // of any stage vector straight from this GPU's HBM.
     if (comm) {
-        NCME_CUDA(cudaMalloc(&shared.p, Npad * 11 * sizeof(double)));
-        shared.c = comm;
-        NCME_CUDA(cudaMemsetAsync(shared.p, 0, Npad * 11 * sizeof(double), s));
-        NCME_TRY(comm_register(comm, shared.p, Npad * 11 * sizeof(double), (int64_t)hl, (int64_t)Npad, 11, sys.peers, 2));
-        ws.base = shared.p;
+        NCME_TRY(comm_workspace(comm, Npad * 11 * sizeof(double), (int64_t)hl, (int64_t)Npad, 11, sys.peers, 2, &ws.base));
     } else {
         NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, Npad * 11 * sizeof(double), false));
         ws.base = ctx->solve_ws;
