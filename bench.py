@@ -132,7 +132,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="matvec kernel variant: rows per thread (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", action="store_true", help="skip the fixed-space solve leg")
-    ap.add_argument("--solve-t", type=float, default=2.0, help="horizon of the solve leg")
+    ap.add_argument("--solve-t", type=float, default=10.0, help="horizon of the solve leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -152,6 +152,11 @@ __device__ __forceinline__ void decode_cols(const MatvecArgs& a, int s, int64_t 
 
 template <int S, int ROWS, bool C8, bool P2P = false>
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
+    if (a.nsig && blockIdx.x == 0 && threadIdx.x == 0) {
+        // everything enqueued before this kernel has completed: the input vector is final -> tell the readers
+        __threadfence_system();
+        for (int k = 0; k < a.nsig; ++k) *((volatile unsigned int*)a.sig_flag[k]) = a.epoch;
+    }
     const int nt = a.do_sinks ? a.ntasks : 0;
     if ((int)blockIdx.x < nt) {
         sink_task(a);
@@ -382,6 +387,7 @@ int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a) {
     a->row_end = A->n;
     a->row_begin2 = a->row_end2 = 0;
     a->nwait = 0;
+    a->nsig = 0;
     a->epoch = 0;
     a->err_flag = nullptr;
     a->do_sinks = 1;
@@ -480,6 +486,11 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
         done.wait[done.nwait++] = &c->my_flags->done[q];
         add_wait(q);                                         // (their ready(e) also certifies they are past e-1)
     }
+    const bool sig_in_kernel = ready_sig.nsig <= 4;          // published by CTA 0 of the first matvec kernel
+    if (sig_in_kernel) {
+        a.nsig = ready_sig.nsig;
+        for (int k = 0; k < ready_sig.nsig; ++k) a.sig_flag[k] = ready_sig.sig[k];
+    }
     for (int q : {A->plo, A->phi}) {
         if (q < 0) continue;
         add_wait(q);
@@ -490,7 +501,7 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
     a.hi_begin = (uint32_t)(A->hl + A->n + A->nr);
     a.x_lo = xlo ? xlo + (A->ext_lo - A->plo_row_lo) : a.x;
     a.x_hi = xhi ? xhi + (A->row_hi - A->phi_row_lo) - (int64_t)a.hi_begin : a.x;
-    NCME_TRY(p2p_sync(A, ready_sig));
+    if (!sig_in_kernel) NCME_TRY(p2p_sync(A, ready_sig));
     const bool interior = A->b1 > A->b0;
     if (interior) {
         // boundary rows (peer loads over NVLink, waiting for the neighbours inside the kernel) run on the
@@ -503,7 +514,7 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
         bd.row_end = A->b0;
         bd.row_begin2 = A->b1;
         bd.row_end2 = A->n;
-        bd.do_sinks = 0;
+        bd.do_sinks = 0;   // (this kernel's CTA 0 publishes "ready" before it starts waiting: no rank can starve another)
         A->ctx->stream = c->comm_stream;
         int rc = matvec_launch_p2p(A, bd);
         A->ctx->stream = st;
@@ -513,6 +524,7 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
         in.row_begin = A->b0;
         in.row_end = A->b1;
         in.do_sinks = 1;
+        in.nsig = 0;
         NCME_TRY(matvec_launch(A, in));
         NCME_CUDA(cudaStreamWaitEvent(st, c->ev_done, 0));
     } else {

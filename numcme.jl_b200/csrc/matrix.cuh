@@ -112,6 +112,8 @@ struct MatvecArgs {
     const double* x_lo;   // P2P launches: x_lo[c] for padded positions c < lo_end (peer memory over NVLink)
     const double* x_hi;   //               x_hi[c] for c >= hi_begin
     uint32_t lo_end, hi_begin;
+    int nsig;                          // sharded: CTA 0 first publishes `epoch` into these peer flags ("my x is ready")
+    unsigned int* sig_flag[4];
     int nwait;                         // P2P launches: every CTA first waits until these flags reach `epoch`
     const unsigned int* wait_flag[4];
     unsigned int epoch;
