@@ -592,6 +592,51 @@ int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, doubl
     return NCME_OK;
 }
 
+// diag(A(t))_i = sum_d cd_d(t) diag[d][i]   (Jacobi preconditioner of the BDF/GMRES integrator)
+struct DiagArgs {
+    int64_t n, ld;
+    int ndiag;
+    const double* diag;
+    double coef[NCME_MAX_REACTIONS + 1];
+    double* out;
+};
+__global__ void k_matrix_diag(const __grid_constant__ DiagArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double d = 0.0;
+    for (int k = 0; k < a.ndiag; ++k) d = fma(a.coef[k], a.diag[(int64_t)k * a.ld + i], d);
+    a.out[i] = d;
+}
+
+int matrix_diag(ncme_matrix* A, const double* coef, double* out) {
+    if (A->n == 0) return NCME_OK;
+    MatvecArgs m;
+    matvec_fill_args(A, coef, &m);
+    DiagArgs a;
+    a.n = A->n;
+    a.ld = A->ld;
+    a.ndiag = A->ndiag;
+    a.diag = A->diag.p;
+    for (int k = 0; k < A->ndiag; ++k) a.coef[k] = m.diag_coef[k];
+    a.out = out;
+    k_matrix_diag<<<(unsigned)((A->n + 255) / 256), 256, 0, A->ctx->stream>>>(a);
+    A->ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+int matvec_sinks_only(ncme_matrix* A, const double* coef, const double* x_local, double* y_local) {
+    MatvecArgs a;
+    matvec_fill_args(A, coef, &a);
+    a.xd = x_local;
+    a.x = x_local - A->hl;
+    a.y = y_local;
+    a.beta = 0.0;
+    a.row_begin = a.row_end = 0;
+    a.do_sinks = 1;
+    return matvec_launch(A, a);
+}
+
 // ------------------------------------------------------------------------------ K6 assembly ----
 struct SlotReactions {
     int count;

@@ -132,6 +132,8 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a);
 // matvecs (the integrator does), so the peer-memory path may skip the "done" handshake.
 int matvec_dist(ncme_matrix* A, const double* coef, const double* x_local, double* y_local, double beta, int reduce_sinks);
 int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st);
+int matrix_diag(ncme_matrix* A, const double* coef, double* out);                                 // out[0..n) = diag(A(t))
+int matvec_sinks_only(ncme_matrix* A, const double* coef, const double* x_local, double* y_local);  // the nr sink rows only
 int sens_describe(ncme_sensmatrix* SA, ncme_matrix** A, int* npar, int* nent);
 
 }  // namespace ncme

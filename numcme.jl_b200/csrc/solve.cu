@@ -13,6 +13,7 @@
 
 #include "comm.cuh"
 #include "matrix.cuh"
+#include "ode.cuh"
 #include "vec.cuh"
 
 namespace ncme {
@@ -134,7 +135,7 @@ struct Workspace {       // views into the context's grow-only caches
     double* pinned = nullptr;
 };
 
-static int cache_reserve(double** p, size_t* have, size_t want, bool pinned) {
+int cache_reserve(double** p, size_t* have, size_t want, bool pinned) {
     if (*have >= want) return NCME_OK;
     if (*p) {
         if (pinned)
@@ -169,25 +170,63 @@ static double sink_dense_sum(const double* tails, int R, double h, double theta)
     return s;
 }
 
-// What the integrator needs to know about du/dt = F(t) u.
-struct OdeSystem {
-    ncme_ctx* ctx = nullptr;
-    ncme_comm* comm = nullptr;   // row-sharded FSP vectors only
-    int64_t len = 0;             // local vector length
-    int64_t sink_off = 0;        // the R event-sink entries are [sink_off, sink_off + R)
-    int R = 0;
-    int64_t hl = 0, hh = 0;      // halo margins every RHS input must carry
-    int64_t len_global = 0;      // number of entries of the global vector (error norm)
-    int64_t n_global = 0;        // sharded: global number of state rows (output gather)
-    int peers[2] = {-1, -1};     // sharded: ranks whose vectors this rank reads (peer-memory halo)
-    std::function<int(double, const double*, double*)> rhs;
-};
-
 __global__ void k_zero_tail(double* p, int R) {
     if ((int)threadIdx.x < R) p[threadIdx.x] = 0.0;
 }
 
-static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0, double t1, double* u,
+int SliceSaver::init(const OdeSystem& s, ncme_save_fn f, void* u, ncme_solve_stats* stats) {
+    sys = &s;
+    fn = f;
+    user = u;
+    st = stats;
+    if (!fn) return NCME_OK;
+    ncme_ctx* ctx = s.ctx;
+    ncme_comm* comm = s.comm;
+    cudaStream_t stream = ctx->stream;
+    NCME_TRY(cache_reserve(&ctx->solve_pinned, &ctx->solve_pinned_bytes, (size_t)s.len_global * sizeof(double), true));
+    pinned = ctx->solve_pinned;
+    if (comm) {
+        NCME_TRY(cache_reserve(&ctx->solve_full, &ctx->solve_full_bytes, (size_t)s.len_global * sizeof(double), false));
+        full = ctx->solve_full;
+        counts.resize(comm->nranks);
+        displs.resize(comm->nranks);
+        double mine = (double)s.sink_off;
+        NCME_CUDA(cudaMemcpyAsync(comm->scratch + comm->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, stream));
+        NCME_NCCL(nccl_api()->AllGather(comm->scratch + comm->rank, comm->scratch, 1, ncclDouble, comm->nccl, stream));
+        std::vector<double> hc(comm->nranks);
+        NCME_CUDA(cudaMemcpyAsync(hc.data(), comm->scratch, sizeof(double) * comm->nranks, cudaMemcpyDeviceToHost, stream));
+        NCME_CUDA(cudaStreamSynchronize(stream));
+        int64_t off = 0;
+        for (int r = 0; r < comm->nranks; ++r) {
+            counts[r] = (int64_t)hc[r];
+            displs[r] = off;
+            off += counts[r];
+        }
+    }
+    return NCME_OK;
+}
+
+// `v_dev` holds per-rank partial sink entries on sharded runs
+int SliceSaver::save(double t, const double* v_dev) {
+    if (!fn) return NCME_OK;
+    cudaStream_t stream = sys->ctx->stream;
+    ncme_comm* comm = sys->comm;
+    const double* src = v_dev;
+    if (comm) {
+        const int64_t n = sys->sink_off;
+        NCME_TRY(comm_allgatherv(comm, v_dev, full, counts.data(), displs.data(), stream));
+        NCME_CUDA(cudaMemcpyAsync(full + sys->n_global, v_dev + n, (size_t)sys->R * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        NCME_TRY(comm_allreduce_sum(comm, full + sys->n_global, (size_t)sys->R, stream));
+        src = full;
+    }
+    NCME_CUDA(cudaMemcpyAsync(pinned, src, (size_t)sys->len_global * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    NCME_CUDA(cudaStreamSynchronize(stream));
+    fn(t, pinned, user);
+    st->nsaved++;
+    return NCME_OK;
+}
+
+int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0, double t1, double* u,
                      const ncme_solve_opts* o, ncme_solve_stats* st) {
     ncme_ctx* ctx = sys.ctx;
     ncme_comm* comm = sys.comm;          // nullptr on a single GPU
@@ -213,53 +252,13 @@ static int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, dou
     ws.ua = ws.base + Npad * 8 + hl;
     ws.ub = ws.base + Npad * 9 + hl;
     ws.ytmp2 = ws.base + Npad * 10 + hl;
-    if (save_fn) {
-        NCME_TRY(cache_reserve(&ctx->solve_pinned, &ctx->solve_pinned_bytes, (size_t)Nglob * sizeof(double), true));
-        ws.pinned = ctx->solve_pinned;
-    }
-    if (save_fn && comm) {
-        NCME_TRY(cache_reserve(&ctx->solve_full, &ctx->solve_full_bytes, (size_t)Nglob * sizeof(double), false));
-        ws.full = ctx->solve_full;
-    }
-
     auto rhs = [&](double t, const double* x, double* y) -> int {
         st->rhs_evals++;
         return sys.rhs(t, x, y);
     };
-    // hand a slice to the host: sharded runs gather [all state rows | reduced sinks] on every rank first.
-    // `v_dev` holds per-rank partial sink entries (see below).
-    std::vector<int64_t> counts, displs;
-    if (comm) {
-        counts.resize(comm->nranks);
-        displs.resize(comm->nranks);
-        double mine = (double)n;
-        NCME_CUDA(cudaMemcpyAsync(comm->scratch + comm->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
-        NCME_NCCL(nccl_api()->AllGather(comm->scratch + comm->rank, comm->scratch, 1, ncclDouble, comm->nccl, s));
-        std::vector<double> hc(comm->nranks);
-        NCME_CUDA(cudaMemcpyAsync(hc.data(), comm->scratch, sizeof(double) * comm->nranks, cudaMemcpyDeviceToHost, s));
-        NCME_CUDA(cudaStreamSynchronize(s));
-        int64_t off = 0;
-        for (int r = 0; r < comm->nranks; ++r) {
-            counts[r] = (int64_t)hc[r];
-            displs[r] = off;
-            off += counts[r];
-        }
-    }
-    auto save = [&](double t, const double* v_dev) -> int {
-        if (!save_fn) return NCME_OK;
-        const double* src = v_dev;
-        if (comm) {
-            NCME_TRY(comm_allgatherv(comm, v_dev, ws.full, counts.data(), displs.data(), s));
-            NCME_CUDA(cudaMemcpyAsync(ws.full + sys.n_global, v_dev + n, (size_t)R * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            NCME_TRY(comm_allreduce_sum(comm, ws.full + sys.n_global, (size_t)R, s));
-            src = ws.full;
-        }
-        NCME_CUDA(cudaMemcpyAsync(ws.pinned, src, (size_t)Nglob * sizeof(double), cudaMemcpyDeviceToHost, s));
-        NCME_CUDA(cudaStreamSynchronize(s));
-        save_fn(t, ws.pinned, user);
-        st->nsaved++;
-        return NCME_OK;
-    };
+    SliceSaver saver;
+    NCME_TRY(saver.init(sys, save_fn, user, st));
+    auto save = [&](double t, const double* v_dev) -> int { return saver.save(t, v_dev); };
     auto lincomb = [&](int kterms, const double* cs, const double* const* xs, double* out) -> int {
         double c2[8];
         const double* x2[8];
@@ -521,7 +520,21 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
         if (coef_fn) coef_fn(t, coef, user);
         return matvec_dist(A, coef, x, y, 0.0, /*no sink reduction, inputs alternate buffers*/ 2);
     };
+    sys.rhs_safe = [&](double t, const double* x, double* y) -> int {
+        if (coef_fn) coef_fn(t, coef, user);
+        return matvec_dist(A, coef, x, y, 0.0, 0);
+    };
+    sys.n_impl = A->n;
+    sys.jac_diag = [&](double t, double* out) -> int {
+        if (coef_fn) coef_fn(t, coef, user);
+        return matrix_diag(A, coef, out);
+    };
+    sys.rhs_sinks = [&](double t, const double* x, double* y) -> int {
+        if (coef_fn) coef_fn(t, coef, user);
+        return matvec_sinks_only(A, coef, x, y);
+    };
     if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, u_dev, opts, stats);
+    if (opts->method == 1) return solve_bdf(sys, save_fn, user, t0, t1, u_dev, opts, stats);
     set_error("unknown integrator method %d", opts->method);
     return NCME_ERR_ARG;
 }

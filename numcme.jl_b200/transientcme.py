@@ -32,6 +32,12 @@ class NativeRK45:
     method = 0
 
 
+class NativeBDF:
+    """Device-resident variable-order BDF (NDF) + matrix-free Jacobi-preconditioned GMRES (libncme method 1): the
+    counterpart of the ``CVODE_BDF(linear_solver=:GMRES)`` every example of the reference uses."""
+    method = 1
+
+
 class RStepAdapter:
     """rstepadapters.jl:12-16"""
     selective = False

@@ -92,6 +92,11 @@ def main():
     for a, b in zip(f1.p, f2.p):
         assert np.abs(a.values - b.values).max() < 1e-12
     assert f1.stats["steps"] == f2.stats["steps"]
+    b1 = pkg.solve(model, pfull, (0.0, 0.5), pkg.NativeBDF(), saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-7, ctx=ctx)
+    b2 = pkg.solve(model, pfull, (0.0, 0.5), pkg.NativeBDF(), saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-7, comm=comm)
+    for a, b, c3 in zip(b1.p, b2.p, f1.p):
+        assert np.abs(a.values - b.values).max() < 1e-9, "sharded BDF differs from single-GPU BDF"
+        assert np.abs(a.values - c3.values).max() < 1e-6, "BDF differs from the explicit integrator"
     dist.barrier()
     if rank == 0:
         print(f"DIST_CHECK_OK world={world} n={n} comm={comm.info()} halo=({info['halo_lo']},{info['halo_hi']}) "

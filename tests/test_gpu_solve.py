@@ -175,3 +175,69 @@ def test_vector_ops(pkg, ctx):
     assert pkg.DeviceVector.from_host(ctx, a2).any_nonfinite()
     assert np.array_equal(da.view(10, 20).to_host(), a[10:30])
     assert da.sum() == da.sum()                                  # deterministic
+
+
+# ---- the stiff integrator (BDF/NDF + GMRES, method 1) against the same references ------------------------------
+def test_bdf_fixed_space(pkg):
+    model = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, fspmat_propensities("tv")), FSPMAT_THETA)
+    sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])
+    sp.expand_(20)
+    p0 = pkg.FspVectorSparse.from_pairs(sp, [([1, 0, 0], 1.0)])
+    touts = np.arange(0.0, 121.0, 20.0)
+    sol = pkg.solve(model, p0, (0.0, 120.0), pkg.NativeBDF(), odertol=1e-4, odeatol=1e-14, saveat=touts)
+    assert len(sol) == len(touts)
+    for p, s in zip(sol.p, sol.sinks):
+        assert p.sum() + s.sum() == pytest.approx(1.0, abs=1e-9)
+    tight = pkg.solve(model, p0, (0.0, 120.0), pkg.NativeBDF(), odertol=1e-8, odeatol=1e-13, saveat=touts)
+    ref = solve_fixed(TELEGRAPH_S, fspmat_propensities("tv"), FSPMAT_THETA, sp.get_states(), p0.values, (0.0, 120.0),
+                      saveat=touts, odeatol=1e-13, odertol=1e-10, method="LSODA")
+    for k in range(len(touts)):
+        assert np.abs(tight.p[k].values - ref["p"][k]).max() < 5e-7
+        assert np.abs(tight.sinks[k] - ref["sinks"][k]).max() < 5e-7
+    loose = pkg.solve(model, p0, (0.0, 120.0), pkg.NativeBDF(), odertol=1e-4, odeatol=1e-8, saveat=touts)
+    for k in range(len(touts)):
+        assert np.abs(loose.p[k].values - ref["p"][k]).max() < 2e-3
+
+
+def test_bdf_adaptive_and_poisson(pkg):
+    import math
+    S = np.array([[1], [-1]]).T
+    lam, gam = 10.0, 0.5
+    model = pkg.CmeModel(S, [pkg.propensity(lambda x, p: p[0] + 0.0 * x[0]), pkg.propensity(lambda x, p: p[1] * x[0])],
+                         [lam, gam])
+    alg = pkg.AdaptiveFspSparse(ode_method=pkg.NativeBDF(), space_adapter=pkg.RStepAdapter(10, 10, False))
+    sol = pkg.solve(model, pkg.FspVectorSparse([[0]], [1.0]), (0.0, 4.0), alg, saveat=[1.0, 4.0], fsptol=1e-8,
+                    odeatol=1e-13, odertol=1e-8)
+    assert sol.stats["adapts"] >= 1
+    for k, t in enumerate([1.0, 4.0]):
+        mu = lam / gam * (1 - math.exp(-gam * t))
+        assert np.abs(sol.p[k].values - poisson.pmf(sol.p[k].states[:, 0], mu)).max() < 1e-6
+    # telegraph adaptive (examples/telegraph_cme.jl) : BDF vs explicit integrator
+    tm = pkg.workloads.telegraph_model()
+    p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
+    a = pkg.solve(tm, p0, (0.0, 300.0), pkg.AdaptiveFspSparse(pkg.NativeBDF(), pkg.RStepAdapter(5, 10, True)),
+                  saveat=[150.0, 300.0], odeatol=1e-12, odertol=1e-7)
+    b = pkg.solve(tm, p0, (0.0, 300.0), pkg.AdaptiveFspSparse(pkg.NativeRK45(), pkg.RStepAdapter(5, 10, True)),
+                  saveat=[150.0, 300.0], odeatol=1e-12, odertol=1e-8)
+    for k in range(2):
+        x, y = _align(a.p[k].states, a.p[k].values, b.p[k].states, b.p[k].values)
+        assert np.abs(x - y).max() < 3e-6
+        assert a.p[k].sum() + a.sinks[k].sum() == pytest.approx(1.0, abs=1e-8)
+
+
+def test_bdf_stiff_is_cheaper_than_explicit(pkg):
+    """A stiff birth-death chain (death rate up to 2000): the BDF needs far fewer RHS evaluations than DP5."""
+    S = np.array([[1], [-1]]).T
+    model = pkg.CmeModel(S, [pkg.propensity(lambda x, p: p[0] + 0.0 * x[0]), pkg.propensity(lambda x, p: p[1] * x[0])],
+                         [20.0, 1.0])
+    sp = pkg.StateSpaceSparse(S, [[0]])
+    sp.expand_(2000)
+    p0 = pkg.FspVectorSparse.from_pairs(sp, [([0], 1.0)])
+    r = {}
+    for name, m in (("bdf", pkg.NativeBDF()), ("rk", pkg.NativeRK45())):
+        r[name] = pkg.solve(model, p0, (0.0, 5.0), m, saveat=[5.0], odertol=1e-5, odeatol=1e-10)
+    mu = 20.0 * (1 - np.exp(-5.0))
+    for name in r:
+        st = r[name].p[0].states[:, 0]
+        assert np.abs(r[name].p[0].values - poisson.pmf(st, mu)).max() < 1e-4, name
+    assert r["bdf"].stats["rhs_evals"] < 0.25 * r["rk"].stats["rhs_evals"], (r["bdf"].stats, r["rk"].stats)
