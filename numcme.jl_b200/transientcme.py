@@ -28,13 +28,15 @@ EPS = float(np.finfo(np.float64).eps)
 
 
 class NativeRK45:
-    """Device-resident Dormand-Prince 5(4) (libncme method 0).  The value ``None`` means the same."""
+    """Device-resident explicit Dormand-Prince 5(4) (libncme method 0): exact linear invariants, best for non-stiff
+    problems and tight tolerances."""
     method = 0
 
 
 class NativeBDF:
     """Device-resident variable-order BDF (NDF) + matrix-free Jacobi-preconditioned GMRES (libncme method 1): the
-    counterpart of the ``CVODE_BDF(linear_solver=:GMRES)`` every example of the reference uses."""
+    counterpart of the ``CVODE_BDF(linear_solver=:GMRES)`` every example of the reference uses.  ``ode_method=None``
+    selects it."""
     method = 1
 
 
@@ -148,7 +150,7 @@ class _Segment:
 
 def _method_code(ode_method):
     if ode_method is None:
-        return 0
+        return 1          # the native counterpart of the reference's CVODE_BDF(linear_solver=:GMRES)
     if hasattr(ode_method, "method"):
         return int(ode_method.method)
     raise L.ArgumentError("ode_method must be None (native device integrator) or a Native* method object; "

@@ -72,7 +72,7 @@ def main():
     # ---- adaptive solve: telegraph, sharded vs single GPU (same adaptation decisions expected)
     tm = pkg.workloads.telegraph_model()
     p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
-    alg = pkg.AdaptiveFspSparse(None, pkg.RStepAdapter(5, 10, True))
+    alg = pkg.AdaptiveFspSparse(pkg.NativeRK45(), pkg.RStepAdapter(5, 10, True))
     touts = [50.0, 150.0, 300.0]
     s1 = pkg.solve(tm, p0, (0.0, 300.0), alg, saveat=touts, odeatol=1e-12, odertol=1e-8, ctx=ctx)
     s2 = pkg.solve(tm, p0, (0.0, 300.0), alg, saveat=touts, odeatol=1e-12, odertol=1e-8, comm=comm)
@@ -87,8 +87,8 @@ def main():
     sp0 = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0, 0], ctx=ctx)
     sp0.expand_(40)
     pfull = pkg.FspVectorSparse.from_pairs(sp0, [([0, 0, 0], 1.0)])
-    f1 = pkg.solve(model, pfull, (0.0, 0.5), None, saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-8, ctx=ctx)
-    f2 = pkg.solve(model, pfull, (0.0, 0.5), None, saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-8, comm=comm)
+    f1 = pkg.solve(model, pfull, (0.0, 0.5), pkg.NativeRK45(), saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-8, ctx=ctx)
+    f2 = pkg.solve(model, pfull, (0.0, 0.5), pkg.NativeRK45(), saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-8, comm=comm)
     for a, b in zip(f1.p, f2.p):
         assert np.abs(a.values - b.values).max() < 1e-12
     assert f1.stats["steps"] == f2.stats["steps"]

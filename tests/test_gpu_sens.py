@@ -103,7 +103,7 @@ def test_sens_solve(pkg):
     props, grads, pattern, _ = sens_telegraph()
     model = _sensmodel(pkg, TELEGRAPH_S, props, grads, pattern, SENS_THETA)
     ic = pkg.forwardsens_initial_condition([[1, 0, 0]], [1.0], [[0.0] for _ in range(5)])
-    alg = pkg.AdaptiveForwardSensFspSparse(ode_method=None, space_adapter=pkg.ForwardSensRStepAdapter(10, 10, True))
+    alg = pkg.AdaptiveForwardSensFspSparse(ode_method=pkg.NativeRK45(), space_adapter=pkg.ForwardSensRStepAdapter(10, 10, True))
     touts = [10.0, 40.0]
     sol = pkg.solve(model, ic, (0.0, 40.0), alg, saveat=touts, fsptol=1e-8, odeatol=1e-12, odertol=1e-8)
     assert sol.stats["adapts"] >= 1
@@ -113,7 +113,7 @@ def test_sens_solve(pkg):
         for ip in range(5):
             assert abs(sol.S[k][ip].values.sum() + sol.dsinks[k][ip].sum()) <= 1e-8
     # probability block == plain solve
-    plain_alg = pkg.AdaptiveFspSparse(None, pkg.RStepAdapter(10, 10, True))
+    plain_alg = pkg.AdaptiveFspSparse(pkg.NativeRK45(), pkg.RStepAdapter(10, 10, True))
 
     def plain(theta):
         m = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, props), theta)
