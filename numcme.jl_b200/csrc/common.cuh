@@ -67,6 +67,9 @@ struct ncme_ctx {
     double* stage_dev_x = nullptr;
     double* stage_dev_y = nullptr;
     size_t stage_dev_bytes = 0;
+    // host-buffer matvec pipeline: copy streams + per-chunk events
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[16] = {nullptr}, ev_comp[16] = {nullptr}, ev_start = nullptr;
     // grow-only caches of the native integrator (re-used by every segment of a solve)
     double* solve_ws = nullptr;
     size_t solve_ws_bytes = 0;

@@ -70,6 +70,13 @@ int ncme_ctx_destroy(ncme_ctx* ctx) {
     if (ctx->solve_ws) cudaFree(ctx->solve_ws);
     if (ctx->solve_full) cudaFree(ctx->solve_full);
     if (ctx->solve_pinned) cudaFreeHost(ctx->solve_pinned);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    for (int k = 0; k < 16; ++k) {
+        if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+    }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return NCME_OK;

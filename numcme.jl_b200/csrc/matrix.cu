@@ -762,6 +762,16 @@ __global__ void k_compress_cols(const uint32_t* __restrict__ col, int64_t ld, in
     }
 }
 
+// per row chunk: the highest padded x position its gathers touch (host-buffer pipeline)
+__global__ void k_chunk_reach(const uint32_t* __restrict__ col, int64_t ld, int64_t n, int nslots, int64_t chunk_rows,
+                              unsigned int* __restrict__ reach /*[nchunks]*/) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned int m = 0;
+    for (int s = 0; s < nslots; ++s) m = max(m, col[(int64_t)s * ld + i]);
+    atomicMax(&reach[i / chunk_rows], m);
+}
+
 __global__ void k_bit_flags(const uint32_t* __restrict__ mask, int64_t n, int r, uint32_t* __restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = (mask[i] >> r) & 1u;
@@ -933,6 +943,29 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         ctx->launches++;
     }
     NCME_CUDA(cudaGetLastError());
+    // ---- row chunks of the host-buffer pipeline (single GPU): how far ahead each chunk's gathers reach
+    A->pipe_chunks = 0;
+    if (!A->comm && n >= 16 * 4096 && nslots > 0) {
+        const int NC = 8;
+        const int64_t chunk_rows = round_up<int64_t>((n + NC - 1) / NC, 64);
+        unsigned int* d_reach = nullptr;
+        NCME_CUDA(cudaMalloc(&d_reach, 16 * sizeof(unsigned int)));
+        NCME_CUDA(cudaMemsetAsync(d_reach, 0, 16 * sizeof(unsigned int), st));
+        k_chunk_reach<<<nblk(n), 256, 0, st>>>(A->col.p, A->ld, n, nslots, chunk_rows, d_reach);
+        ctx->launches++;
+        unsigned int h_reach[16];
+        NCME_CUDA(cudaMemcpyAsync(h_reach, d_reach, sizeof(h_reach), cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_reach);
+        int nc = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+            A->pipe_row[nc] = r0;
+            A->pipe_need_hi[nc] = (int64_t)h_reach[nc] + 1;
+            ++nc;
+        }
+        A->pipe_row[nc] = n;
+        A->pipe_chunks = nc;
+    }
     // ---- byte-compressed column indices for the matvec fast path
     A->nchunks = A->ld / 64;
     if (nslots > 0) {
@@ -1244,10 +1277,59 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
         ctx->stage_dev_bytes = bytes;
     }
     cudaStream_t st = ctx->stream;
-    NCME_CUDA(cudaMemcpyAsync(ctx->stage_dev_x, x_host, bytes, cudaMemcpyHostToDevice, st));
-    if (beta != 0.0) NCME_CUDA(cudaMemcpyAsync(ctx->stage_dev_y, y_host, bytes, cudaMemcpyHostToDevice, st));
-    NCME_TRY(ncme_matvec(A, coef, ctx->stage_dev_x, ctx->stage_dev_y, beta));
-    NCME_CUDA(cudaMemcpyAsync(y_host, ctx->stage_dev_y, bytes, cudaMemcpyDeviceToHost, st));
+    if (beta != 0.0 || A->pipe_chunks < 2) {
+        NCME_CUDA(cudaMemcpyAsync(ctx->stage_dev_x, x_host, bytes, cudaMemcpyHostToDevice, st));
+        if (beta != 0.0) NCME_CUDA(cudaMemcpyAsync(ctx->stage_dev_y, y_host, bytes, cudaMemcpyHostToDevice, st));
+        NCME_TRY(ncme_matvec(A, coef, ctx->stage_dev_x, ctx->stage_dev_y, beta));
+        NCME_CUDA(cudaMemcpyAsync(y_host, ctx->stage_dev_y, bytes, cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        return NCME_OK;
+    }
+    // ---- pipelined: H2D of x (chunk c+1), rows of chunk c, D2H of y (chunk c-1) overlap on three streams.
+    // Chunk c may start once x is on the device up to the furthest entry its gathers reach (pipe_need_hi).
+    if (!ctx->h2d_stream) {
+        NCME_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        NCME_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 16; ++k) {
+            NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+            NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+        }
+        NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    }
+    const int nc = A->pipe_chunks;
+    double* xd = ctx->stage_dev_x;
+    double* yd = ctx->stage_dev_y;
+    NCME_CUDA(cudaEventRecord(ctx->ev_start, st));                       // order after earlier work on the context
+    NCME_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_start, 0));
+    NCME_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_start, 0));
+    for (int c = 0; c < nc; ++c) {
+        const int64_t r0 = A->pipe_row[c];
+        const int64_t r1 = (c == nc - 1) ? A->N : A->pipe_row[c + 1];  // the last chunk carries the sink entries
+        NCME_CUDA(cudaMemcpyAsync(xd + r0, x_host + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        NCME_CUDA(cudaEventRecord(ctx->ev_h2d[c], ctx->h2d_stream));
+    }
+    MatvecArgs a;
+    matvec_fill_args(A, coef, &a);
+    a.xd = xd;
+    a.x = xd;
+    a.y = yd;
+    a.beta = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        int need = c;
+        while (need < nc - 1 && A->pipe_row[need + 1] < A->pipe_need_hi[c]) ++need;
+        NCME_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[need], 0));
+        MatvecArgs ac = a;
+        ac.row_begin = A->pipe_row[c];
+        ac.row_end = A->pipe_row[c + 1];
+        ac.do_sinks = (c == nc - 1) ? 1 : 0;                             // sink rows read x everywhere: last
+        NCME_TRY(matvec_launch(A, ac));
+        NCME_CUDA(cudaEventRecord(ctx->ev_comp[c], st));
+        NCME_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_comp[c], 0));
+        const int64_t r0 = A->pipe_row[c];
+        const int64_t r1 = (c == nc - 1) ? A->N : A->pipe_row[c + 1];
+        NCME_CUDA(cudaMemcpyAsync(y_host + r0, yd + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    NCME_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
     NCME_CUDA(cudaStreamSynchronize(st));
     return NCME_OK;
 }

@@ -73,6 +73,11 @@ struct ncme_matrix {
     ncme::DevArray<double> sink_partial; // [ntasks]
     unsigned int* sink_counter = nullptr;
 
+    // host-buffer pipeline: row chunks and, per chunk, the last row index its gathers reach (+1)
+    int pipe_chunks = 0;
+    int64_t pipe_row[17] = {0};
+    int64_t pipe_need_hi[16] = {0};
+
     // reference-structure statistics
     int nterms = 0;
     int64_t nnz_term[NCME_MAX_REACTIONS + 1] = {0};
