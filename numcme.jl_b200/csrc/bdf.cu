@@ -143,19 +143,48 @@ struct ApplyArgs {
     unsigned int* counter;
     double* result;
 };
+// KB = number of basis vectors dotted (k+1 rounded up to a multiple of 4; the surplus pointers alias V_0 and their
+// results are ignored): fully unrolled, no predication, all loads of an element independent.
+template <int KB>
 __global__ void __launch_bounds__(BT) k_gm_apply_dots(const __grid_constant__ ApplyArgs a) {
-    double v[RED_SLOTS];
+    double v[KB + 1];
 #pragma unroll
-    for (int s = 0; s < RED_SLOTS; ++s) v[s] = 0.0;
+    for (int s = 0; s <= KB; ++s) v[s] = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * BT) {
         const double w = (a.z[i] - a.c * a.Az[i]) * a.ps[i];
+        double vj[KB > 0 ? KB : 1];
+#pragma unroll
+        for (int j = 0; j < KB; ++j) vj[j] = a.V.p[j][i];
         a.w[i] = w;
 #pragma unroll
-        for (int j = 0; j < GM_M + 1; ++j)
-            if (j <= a.k) v[j] = fma(w, a.V.p[j][i], v[j]);
-        v[RED_SLOTS - 1] = fma(w, w, v[RED_SLOTS - 1]);
+        for (int j = 0; j < KB; ++j) v[j] = fma(w, vj[j], v[j]);
+        v[KB] = fma(w, w, v[KB]);
     }
-    block_reduce_store<RED_SLOTS>(v, RED_SLOTS, a.partials, a.counter, a.result);
+    // slot layout expected by the host: [0..k] dots, [RED_SLOTS-1] = <w,w>
+    double full[RED_SLOTS];
+#pragma unroll
+    for (int s = 0; s < RED_SLOTS; ++s) full[s] = 0.0;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) full[j] = v[j];
+    full[RED_SLOTS - 1] = v[KB];
+    block_reduce_store<RED_SLOTS>(full, RED_SLOTS, a.partials, a.counter, a.result);
+}
+
+static int launch_apply_dots(ncme_ctx* ctx, const ApplyArgs& aa, unsigned grid) {
+    cudaStream_t s = ctx->stream;
+    const int kb = aa.k < 0 ? 0 : ((aa.k + 1 + 3) / 4) * 4;
+    switch (kb) {
+        case 0: k_gm_apply_dots<0><<<grid, BT, 0, s>>>(aa); break;
+        case 4: k_gm_apply_dots<4><<<grid, BT, 0, s>>>(aa); break;
+        case 8: k_gm_apply_dots<8><<<grid, BT, 0, s>>>(aa); break;
+        case 12: k_gm_apply_dots<12><<<grid, BT, 0, s>>>(aa); break;
+        case 16: k_gm_apply_dots<16><<<grid, BT, 0, s>>>(aa); break;
+        case 20: k_gm_apply_dots<20><<<grid, BT, 0, s>>>(aa); break;
+        default: k_gm_apply_dots<24><<<grid, BT, 0, s>>>(aa); break;
+    }
+    ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
 }
 
 // v_{k+1} = (w - sum_j h_j V_j) * inv ;  z = v_{k+1} * scale
@@ -385,6 +414,10 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     const size_t hl = round_up<size_t>((size_t)sys.hl, 32), hh = round_up<size_t>((size_t)sys.hh, 32);
     const size_t Npad = hl + round_up<size_t>((size_t)N, 32) + hh;
     const int NV = (MAX_ORDER + 3) + 3 + 7 + (GM_M + 1);
+    // partial sums of the fused Krylov inner products: one slot row per CTA (deterministic two-stage reduction)
+    const int GM_BLOCKS = 148 * 8;
+    NCME_TRY(cache_reserve(&ctx->gm_partials, &ctx->gm_partials_bytes, (size_t)GM_BLOCKS * RED_SLOTS * sizeof(double), false));
+    double* gm_partials = ctx->gm_partials;
     double* base = nullptr;
     if (comm) {
         NCME_TRY(comm_workspace(comm, Npad * NV * sizeof(double), (int64_t)hl, (int64_t)Npad, NV, sys.peers, 2, &base));
@@ -415,6 +448,7 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     const double rtol = o->rtol > 0 ? o->rtol : 1e-4, atol = o->atol > 0 ? o->atol : 1e-6;
     const int64_t max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
     const double tspan = t1 - t0;
+    const unsigned gm_grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(GM_BLOCKS, (n + (int64_t)BT * 2 - 1) / ((int64_t)BT * 2)));
 
     // NDF coefficients (Shampine & Reichelt; same constants as scipy's BDF)
     const double kappa[MAX_ORDER + 1] = {0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0};
@@ -588,12 +622,10 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
                     for (int j = 0; j <= k; ++j) aa.V.p[j] = V[j];
                     for (int j = k + 1; j < GM_M + 2; ++j) aa.V.p[j] = V[0];
                     aa.w = w;
-                    aa.partials = ctx->red_partials;
+                    aa.partials = gm_partials;
                     aa.counter = ctx->red_counter;
                     aa.result = ctx->red_result_dev;
-                    k_gm_apply_dots<<<red_grid(n), BT, 0, s>>>(aa);
-                    ctx->launches++;
-                    NCME_CUDA(cudaGetLastError());
+                    NCME_TRY(launch_apply_dots(ctx, aa, gm_grid));
                     NCME_TRY(fetch(RED_SLOTS));
                     const double* hh = ctx->red_result_host;
                     double ww = hh[RED_SLOTS - 1], hsq = 0.0;
@@ -688,11 +720,10 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
                     aa.c = 0.0;
                     for (int j = 0; j < GM_M + 2; ++j) aa.V.p[j] = V[0];
                     aa.w = w;
-                    aa.partials = ctx->red_partials;
+                    aa.partials = gm_partials;
                     aa.counter = ctx->red_counter;
                     aa.result = ctx->red_result_dev;
-                    k_gm_apply_dots<<<red_grid(n), BT, 0, s>>>(aa);
-                    ctx->launches++;
+                    NCME_TRY(launch_apply_dots(ctx, aa, gm_grid));
                     NCME_TRY(fetch(RED_SLOTS));
                     beta = sqrt(std::max(ctx->red_result_host[RED_SLOTS - 1], 0.0));
                     if (!(beta > 0.0)) break;

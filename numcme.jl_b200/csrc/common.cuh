@@ -77,6 +77,8 @@ struct ncme_ctx {
     size_t solve_pinned_bytes = 0;
     double* solve_full = nullptr;
     size_t solve_full_bytes = 0;
+    double* gm_partials = nullptr;      // per-CTA partial sums of the fused Krylov inner products
+    size_t gm_partials_bytes = 0;
 };
 
 namespace ncme {

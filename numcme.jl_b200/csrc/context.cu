@@ -69,6 +69,7 @@ int ncme_ctx_destroy(ncme_ctx* ctx) {
     if (ctx->stage_dev_y) cudaFree(ctx->stage_dev_y);
     if (ctx->solve_ws) cudaFree(ctx->solve_ws);
     if (ctx->solve_full) cudaFree(ctx->solve_full);
+    if (ctx->gm_partials) cudaFree(ctx->gm_partials);
     if (ctx->solve_pinned) cudaFreeHost(ctx->solve_pinned);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
