@@ -756,7 +756,8 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
             NCME_CUDA(cudaGetLastError());
         }
         // ---- local error test; the same D2H carries the sink tails of D_0..D_{k+1}, d (event) and ypred
-        const int ntail = sinks_explicit ? order + 4 : 0;
+        const int ntail = R > 0 ? order + 4 : 0;   // sink tails are always fetched (event); their error is added
+                                                   // on the host only when they are not part of the implicit rows
         ErrArgs ea{};
         ea.n = n;
         ea.d = d;
@@ -805,7 +806,7 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
         NCME_CUDA(cudaGetLastError());
         // new difference tails of the sinks, on the host (the update is linear)
         double nd[MAX_ORDER + 3][NCME_MAX_REACTIONS] = {};
-        if (sinks_explicit) {
+        if (R > 0) {
             for (int r = 0; r < R; ++r) {
                 const double ds = tails[(size_t)(order + 2) * R + r];
                 nd[order + 2][r] = ds - tails[(size_t)(order + 1) * R + r];
@@ -845,7 +846,7 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
         };
         double t_hi = t_new;
         bool event = false;
-        if (o->check_event && sinks_explicit) {
+        if (o->check_event && R > 0) {
             if (!have_g) {
                 double s0 = 0.0;
                 for (int r = 0; r < R; ++r) s0 += tails[r];   // D_0 before the step = u(t)

@@ -566,7 +566,20 @@ extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn
         coef_fn(t, cf.data(), user);
         return ncme_sens_matvec(SA, cf.data(), cf.data() + A->nr, x, y);
     };
+    // BDF: the whole block vector is implicit; Jacobian = [A 0; dA A] => block-Jacobi diagonal = diag(A) per block
+    // (zero on the sink rows)
+    sys.n_impl = sys.len;
+    sys.jac_diag = [&](double t, double* out) -> int {
+        coef_fn(t, cf.data(), user);
+        cudaStream_t st = A->ctx->stream;
+        NCME_CUDA(cudaMemsetAsync(out, 0, (size_t)sys.len * sizeof(double), st));
+        NCME_TRY(matrix_diag(A, cf.data(), out));
+        for (int b = 1; b <= npar; ++b)
+            NCME_CUDA(cudaMemcpyAsync(out + (size_t)b * A->N, out, (size_t)A->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return NCME_OK;
+    };
     if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, U_dev, opts, stats);
+    if (opts->method == 1) return solve_bdf(sys, save_fn, user, t0, t1, U_dev, opts, stats);
     set_error("unknown integrator method %d", opts->method);
     return NCME_ERR_ARG;
 }

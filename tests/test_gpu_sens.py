@@ -133,3 +133,25 @@ def test_sens_solve(pkg):
         fd = (on_states(plain(tp).p[1], st) - on_states(plain(tm).p[1], st)) / (2 * h)
         s = sol.S[1][ip].values
         assert np.abs(fd - s).max() <= 2e-4 * max(np.abs(s).max(), 1e-3), (ip, np.abs(fd - s).max(), np.abs(s).max())
+
+
+def test_sens_solve_bdf_matches_explicit(pkg):
+    """test/test_sensfsp.jl passes CVODE_BDF(GMRES); the native BDF on the block system agrees with the explicit one."""
+    props, grads, pattern, _ = sens_telegraph()
+    model = _sensmodel(pkg, TELEGRAPH_S, props, grads, pattern, SENS_THETA)
+    ic = pkg.forwardsens_initial_condition([[1, 0, 0]], [1.0], [[0.0] for _ in range(5)])
+    out = {}
+    for name, m, rt in (("bdf", None, 1e-7), ("rk", pkg.NativeRK45(), 1e-8)):
+        alg = pkg.AdaptiveForwardSensFspSparse(ode_method=m, space_adapter=pkg.ForwardSensRStepAdapter(10, 10, False))
+        out[name] = pkg.solve(model, ic, (0.0, 30.0), alg, saveat=[30.0], fsptol=1e-8, odeatol=1e-12, odertol=rt)
+    a, b = out["bdf"], out["rk"]
+    assert a.stats["adapts"] >= 1
+
+    def on(fv, states):
+        d = fv.state2idx
+        return np.array([fv.values[d[tuple(s)] - 1] if tuple(s) in d else 0.0 for s in states.tolist()])
+    st = b.p[0].states
+    assert np.abs(on(a.p[0], st) - b.p[0].values).max() < 2e-6
+    for ip in range(5):
+        sb = b.S[0][ip].values
+        assert np.abs(on(a.S[0][ip], st) - sb).max() <= 2e-5 * max(np.abs(sb).max(), 1e-2), ip
