@@ -76,3 +76,49 @@ M3D_LEVELS = 390    # n = 10 039 316
 
 def simplex_count(d: int, L: int) -> int:
     return math.comb(L + d, d)
+
+
+# ---- Hog1p (examples/hog1p.jl:6-82): NS = 6 (G0..G3, RNAnuc, RNAcyt), R = 13, P = 14 -----------------------------
+HOG_R1, HOG_R2, HOG_ETA, HOG_A, HOG_M = 6.1e-3, 6.9e-3, 5.9, 9.3e9, 2.2e-2
+
+
+def hog1p_signal(t):
+    u = (1.0 - math.exp(-HOG_R1 * t)) * math.exp(-HOG_R2 * t)
+    return HOG_A * (u / (1.0 + u / HOG_M)) ** HOG_ETA
+
+
+# parameter order: k01 k10 a k12 k21 k23 k32 l0 l1 l2 l3 gnuc ktrans gcyt
+HOG1P_THETA = [2.6e-3, 1.9e01, 0.0, 7.63e-3, 1.2e-2, 4e-3, 3.1e-3, 5.9e-4, 1.7e-1, 1.0, 3e-2, 2.2e-6, 2.6e-1, 8.3e-3]
+
+
+def hog1p_model(theta=HOG1P_THETA, separable=True) -> CmeModel:
+    """The 13-reaction Hog1p-driven gene model of examples/hog1p.jl.  Reaction 2 (G1 -> G0) has the time-varying rate
+    max(0, k10 - a*Hog1p(t)): Catalyst import makes it a joint propensity in the reference (catalyst_interface.jl:21-27);
+    it is rank-1, so the separable form is offered as well."""
+    S = np.zeros((6, 13), dtype=np.int64)
+    def rx(r, frm=None, to=None, plus=None, minus=None):
+        if frm is not None:
+            S[frm, r] -= 1
+            S[to, r] += 1
+        if plus is not None:
+            S[plus, r] += 1
+        if minus is not None:
+            S[minus, r] -= 1
+    rx(0, 0, 1); rx(1, 1, 0); rx(2, 1, 2); rx(3, 2, 1); rx(4, 2, 3); rx(5, 3, 2)
+    rx(6, plus=4); rx(7, plus=4); rx(8, plus=4); rx(9, plus=4)
+    rx(10, minus=4); rx(11, minus=4, plus=5); rx(12, minus=5)
+    k10t = lambda t, p: max(0.0, p[1] - p[2] * hog1p_signal(t))
+    props = [propensity(lambda x, p: p[0] * x[0])]
+    if separable:
+        props.append(propensity(lambda x, p: 1.0 * x[1], k10t))
+    else:
+        props.append(propensity(lambda t, x, p: k10t(t, p) * x[1]))
+    props += [
+        propensity(lambda x, p: p[3] * x[1]), propensity(lambda x, p: p[4] * x[2]),
+        propensity(lambda x, p: p[5] * x[2]), propensity(lambda x, p: p[6] * x[3]),
+        propensity(lambda x, p: p[7] * x[0]), propensity(lambda x, p: p[8] * x[1]),
+        propensity(lambda x, p: p[9] * x[2]), propensity(lambda x, p: p[10] * x[3]),
+        propensity(lambda x, p: p[11] * x[4]), propensity(lambda x, p: p[12] * x[4]),
+        propensity(lambda x, p: p[13] * x[5]),
+    ]
+    return CmeModel(S, props, list(theta))
