@@ -9,6 +9,8 @@
 // (rank == stored value) are stream-compacted in rank order, which reproduces the sequential result.
 #include "space.cuh"
 
+#include <algorithm>
+
 namespace ncme {
 
 // ------------------------------------------------------------------------------------ kernels ---
@@ -202,6 +204,26 @@ __global__ void k_lookup(HashView h, const uint64_t* __restrict__ q, int64_t m, 
     out[i] = (v == NONE32) ? 0u : v + 1u;
 }
 
+// exact per-species maxima of the packed keys (key re-layout decisions)
+__global__ void k_species_max(KeyLayout L, const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ mx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t key = i < n ? keys[i] : 0ull;     // no early return: the whole warp takes part in the shuffles
+    for (int s = 0; s < L.ns; ++s) {
+        unsigned long long v = (key >> L.shift[s]) & L.mask[s];
+        for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if ((threadIdx.x & 31) == 0) atomicMax(&mx[s], v);
+    }
+}
+
+__global__ void k_repack_keys(KeyLayout from, KeyLayout to, uint64_t* __restrict__ keys, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    uint64_t nk = 0;
+    for (int s = 0; s < from.ns; ++s) nk |= ((key >> from.shift[s]) & from.mask[s]) << to.shift[s];
+    keys[i] = nk;
+}
+
 // --------------------------------------------------------------------------------- host side ---
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
@@ -349,6 +371,79 @@ __global__ void k_compact_vector(const uint32_t* __restrict__ keep, const uint32
     if (i < n && keep[i]) out[pos[i]] = in[i];
 }
 
+static int bitlen(uint64_t v) {
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+// The 63 key bits start as an equal split; when a species is about to outgrow its field the budget is re-divided
+// from the observed maxima (all keys re-packed, table rebuilt).  NCME_ERR_KEYWIDTH only if 63 bits cannot hold it.
+int space_ensure_key_room(ncme_space* sp, const int64_t* inc) {
+    const int ns = sp->ns;
+    bool tight = false;
+    for (int s = 0; s < ns; ++s) tight |= (uint64_t)(sp->ub[s] + inc[s]) > sp->layout.mask[s];
+    if (!tight) return NCME_OK;
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t st = ctx->stream;
+    // the host bound is pessimistic (+inc per level): get the exact maxima first
+    if (sp->n > 0) {
+        unsigned long long* d_mx = nullptr;
+        NCME_CUDA(cudaMalloc(&d_mx, sizeof(unsigned long long) * NCME_MAX_SPECIES));
+        NCME_CUDA(cudaMemsetAsync(d_mx, 0, sizeof(unsigned long long) * NCME_MAX_SPECIES, st));
+        k_species_max<<<(unsigned)((sp->n + 255) / 256), 256, 0, st>>>(sp->layout, sp->keys.p, sp->n, d_mx);
+        ctx->launches++;
+        unsigned long long h_mx[NCME_MAX_SPECIES];
+        NCME_CUDA(cudaMemcpyAsync(h_mx, d_mx, sizeof(h_mx), cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_mx);
+        for (int s = 0; s < ns; ++s) sp->ub[s] = (int64_t)h_mx[s];
+    }
+    tight = false;
+    for (int s = 0; s < ns; ++s) tight |= (uint64_t)(sp->ub[s] + inc[s]) > sp->layout.mask[s];
+    if (!tight) return NCME_OK;
+    int need[NCME_MAX_SPECIES], total = 0;
+    for (int s = 0; s < ns; ++s) {
+        need[s] = std::max(1, bitlen((uint64_t)(sp->ub[s] + inc[s])));
+        total += need[s];
+    }
+    if (total > 63) {
+        set_error("the reachable states no longer fit a 64-bit packed key (%d species need %d bits)", ns, total);
+        return NCME_ERR_KEYWIDTH;
+    }
+    // hand the spare bits to the species that can still grow, round robin (one doubling each per round)
+    int spare = 63 - total;
+    while (spare > 0) {
+        bool any = false;
+        for (int s = 0; s < ns && spare > 0; ++s)
+            if (inc[s] > 0 && need[s] < 62) {
+                need[s]++;
+                spare--;
+                any = true;
+            }
+        if (!any) break;
+    }
+    KeyLayout to{};
+    to.ns = ns;
+    int sh = 0;
+    for (int s = 0; s < ns; ++s) {
+        to.shift[s] = sh;
+        to.mask[s] = (1ull << need[s]) - 1;
+        sh += need[s];
+    }
+    if (sp->n > 0) {
+        k_repack_keys<<<(unsigned)((sp->n + 255) / 256), 256, 0, st>>>(sp->layout, to, sp->keys.p, sp->n);
+        ctx->launches++;
+        NCME_CUDA(cudaGetLastError());
+    }
+    sp->layout = to;
+    sp->relayouts++;
+    return space_rebuild_table(sp, 4 * (uint64_t)(sp->n + 256));
+}
+
 static int space_alloc(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, ncme_space** out) {
     NCME_REQUIRE(ctx && out && stoich, "null argument");
     NCME_REQUIRE(ns >= 1 && ns <= NCME_MAX_SPECIES, "species count must be in 1..%d", NCME_MAX_SPECIES);
@@ -415,6 +510,13 @@ int ncme_space_create(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int6
         if ((st = space_reserve_rows(sp, n0 > 1024 ? n0 : 1024)) != NCME_OK) break;
         if ((st = space_rebuild_table(sp, 4 * (uint64_t)(n0 + 256))) != NCME_OK) break;
         if (n0 == 0) break;
+        {   // widen the key fields first if an initial state needs it
+            int64_t mx[NCME_MAX_SPECIES] = {0}, zero[NCME_MAX_SPECIES] = {0};
+            for (int64_t i = 0; i < n0; ++i)
+                for (int s2 = 0; s2 < ns; ++s2) mx[s2] = std::max(mx[s2], states0[(size_t)i * ns + s2]);
+            for (int s2 = 0; s2 < ns; ++s2) sp->ub[s2] = mx[s2];
+            if ((st = space_ensure_key_room(sp, zero)) != NCME_OK) break;
+        }
         std::vector<uint64_t> ck((size_t)n0);
         for (int64_t i = 0; i < n0; ++i) {
             int rc = space_pack_host(sp, states0 + (size_t)i * ns, &ck[(size_t)i]);
@@ -452,6 +554,13 @@ int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, i
     int st = NCME_OK;
     do {
         if ((st = space_reserve_rows(sp, n > 1024 ? n : 1024)) != NCME_OK) break;
+        {
+            int64_t mx[NCME_MAX_SPECIES] = {0}, zero[NCME_MAX_SPECIES] = {0};
+            for (int64_t i = 0; i < n; ++i)
+                for (int s2 = 0; s2 < ns; ++s2) mx[s2] = std::max(mx[s2], states[(size_t)i * ns + s2]);
+            for (int s2 = 0; s2 < ns; ++s2) sp->ub[s2] = mx[s2];
+            if ((st = space_ensure_key_room(sp, zero)) != NCME_OK) break;
+        }
         std::vector<uint64_t> hk((size_t)n);
         std::vector<uint32_t> hm((size_t)n, 0u), hp((size_t)n * nr);
         for (int64_t i = 0; i < n && st == NCME_OK; ++i) {
@@ -559,7 +668,12 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
         ctx->launches++;
         const uint32_t* frontier = sp->frontier.p;
         int64_t fbase = 0;
+        int64_t inc[NCME_MAX_SPECIES] = {0};   // largest possible growth of each species in one level
+        for (int k = 0; k < nreact; ++k)
+            for (int s2 = 0; s2 < sp->ns; ++s2) inc[s2] = std::max(inc[s2], sp->stoich[(size_t)reacts[k] * sp->ns + s2]);
         for (int level = 0; level < expansionlevel && F > 0; ++level) {
+            if ((st = space_ensure_key_room(sp, inc)) != NCME_OK) break;
+            for (int s2 = 0; s2 < sp->ns; ++s2) sp->ub[s2] += inc[s2];
             const int64_t ncand = (int64_t)F * nreact;
             if ((st = sp->cand_key.reserve((size_t)ncand, s, false)) != NCME_OK) break;
             k_gen_candidates<<<nblk(ncand), 256, 0, s>>>(sp->layout, sp->sdev, sp->keys.p, frontier, fbase, (int64_t)F,

@@ -71,6 +71,8 @@ struct ncme_space {
     ncme::DevArray<uint32_t> scan_scratch;
     ncme::DevArray<uint32_t> frontier;
     int* err_flag = nullptr;  // device int: key-width overflow seen
+    int relayouts = 0;
+    int64_t ub[NCME_MAX_SPECIES] = {0};  // host upper bound of every species count present in the space (key re-layout)
     int64_t last_delete_nold = -1;  // >= 0: flags/pos hold the keep flags / compaction map of the last deletion
     int64_t last_delete_nnew = 0;
 
@@ -84,5 +86,7 @@ int space_addstates(ncme_space* sp, int64_t ncand, int64_t* added);
 int space_reserve_rows(ncme_space* sp, int64_t nrows);
 int space_delete_flagged(ncme_space* sp);  // keep flags in sp->flags[0..n)
 int space_rebuild_table(ncme_space* sp, uint64_t min_slots);
+// make sure every species can grow by inc[s] without overflowing its key field (re-packs all keys if needed)
+int space_ensure_key_room(ncme_space* sp, const int64_t* inc);
 int space_pack_host(const ncme_space* sp, const int64_t* state, uint64_t* key_out);  // 0 ok, 1 negative, <0 error
 }  // namespace ncme

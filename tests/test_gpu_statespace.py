@@ -120,3 +120,31 @@ def test_three_species_million(pkg):
     assert ((sc[:, 1] != 0) == (~on_boundary)).all()          # predecessor through -e1 is x+e1
     j = sc[:, 0][st[:, 0] > 0].astype(np.int64) - 1
     assert np.array_equal(st[j] + S[:, 0], st[st[:, 0] > 0])
+
+
+def test_key_relayout_when_a_species_outgrows_its_field(pkg):
+    """6 species start with 10 key bits each (max count 1023); a species that grows past that triggers a re-division
+    of the 63-bit budget instead of an error -- ordering and connectivity stay index-exact."""
+    S = np.zeros((6, 3), dtype=np.int64)
+    S[5, 0] = 1          # birth of species 6
+    S[5, 1] = -1         # death of species 6
+    S[0, 2], S[1, 2] = -1, 1   # G0 -> G1
+    sp = pkg.StateSpaceSparse(S, [[1, 0, 0, 0, 0, 0]])
+    sp.expand_(1500)
+    osp = StateSpaceOracleFast(S, [[1, 0, 0, 0, 0, 0]], bits_per_species=[4, 4, 4, 4, 4, 40])
+    osp.expand(1500)
+    assert sp.get_states()[:, 5].max() == 1500 > 1023
+    _same(sp, osp)
+    assert sp.lookup([[0, 1, 0, 0, 0, 1499], [1, 0, 0, 0, 0, 1501]]).tolist() == [int(osp._index.lookup(osp._pack(np.array([[0, 1, 0, 0, 0, 1499]])))[0]), 0]
+    sp.deleteat_([3, 4, 5])
+    osp.deleteat([3, 4, 5])
+    sp.expand_(3)
+    osp.expand(3)
+    _same(sp, osp)
+    # an initial state that does not fit the equal split
+    sp2 = pkg.StateSpaceSparse(S, [[0, 1, 0, 0, 0, 5000]])
+    assert sp2.get_states().tolist() == [[0, 1, 0, 0, 0, 5000]]
+    sp2.expand_(2)
+    osp2 = StateSpaceOracleFast(S, [[0, 1, 0, 0, 0, 5000]], bits_per_species=[4, 4, 4, 4, 4, 40])
+    osp2.expand(2)
+    _same(sp2, osp2)
