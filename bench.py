@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--levels", type=int, default=None, help="expansion depth of the M-3D simplex (default 390)")
     ap.add_argument("--rows", type=int, default=0, help="matvec kernel variant: rows per thread (0 = auto)")
+    ap.add_argument("--pipe", default="", help="experiments: ROWS,STAGES of the shared-memory pipelined matvec kernel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", action="store_true", help="skip the fixed-space solve leg")
     ap.add_argument("--solve-t", type=float, default=10.0, help="horizon of the solve leg")
@@ -184,6 +185,8 @@ def main():
     t_assemble = time.perf_counter() - t_build - t_expand
     if args.rows:
         A.set_tuning(args.rows)
+    if args.pipe:
+        A.set_pipe(*[int(v) for v in args.pipe.split(",")])
     n = space.get_state_count()
     R = 6
     info = A.shard_info()

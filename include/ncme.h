@@ -137,6 +137,10 @@ int ncme_matrix_stats(ncme_matrix* mat, int* nterms, int64_t* nnz_per_term, int6
  * DRAM traffic but latency-bound in its current form, so off by default). */
 int ncme_matrix_set_tuning(ncme_matrix* mat, int rows_per_thread);
 
+/* Experiments: select the shared-memory (cp.async) pipelined matvec kernel, `rows` rows per thread and `stages`
+ * pipeline stages ((1,4), (2,4), (2,2), (1,2) are instantiated, for 4 or 6 slots); rows = 0 switches it off.
+ * Bitwise identical results; measured slower than the default register-staged kernel (profiles/README.md). */
+int ncme_matrix_set_pipe(ncme_matrix* mat, int rows, int stages);
 /* info = {#(64-row chunk, slot) pairs, #pairs that fell back to 32-bit indices, compression enabled, #slots} */
 int ncme_matrix_compression_info(ncme_matrix* mat, int64_t info[4]);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ncme_matrix_set_joint_values": (cint, [p_void, cint, p_f64]),
     "ncme_matrix_set_tuning": (cint, [p_void, cint]),
     "ncme_matvec": (cint, [p_void, p_f64, p_void, p_void, f64]),
+    "ncme_matrix_set_pipe": (cint, [p_void, cint, cint]),
     "ncme_matrix_compression_info": (cint, [p_void, p_i64]),
     "ncme_matvec_local": (cint, [p_void, p_f64, p_void, p_void]),
     "ncme_matvec_host": (cint, [p_void, p_f64, p_void, p_void, f64]),

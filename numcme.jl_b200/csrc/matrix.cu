@@ -276,6 +276,179 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------------------ K1, pipelined --
+// Same arithmetic as k_fsp_matvec, different data movement: the once-read matrix streams (values, diagonals,
+// byte-compressed column indices, chunk descriptors) are staged through shared memory with a 4-stage cp.async
+// pipeline, so the bytes in flight per SM (3 stages x ~18-36 KB per CTA, 2-3 CTAs) no longer depend on registers or
+// occupancy -- which is what kept the byte-compressed variant of the register-staged kernel latency-bound.  Only the
+// gathers of x and x_i/y go through the normal load/store path.  Persistent CTAs walk the row tiles round-robin.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+template <int S, int D, int ROWS, int PIPE_STAGES>
+struct PipeLayout {
+    static constexpr int TILE = MV_THREADS * ROWS;
+    static constexpr int VAL_B = S * TILE * 8;
+    static constexpr int DIAG_B = D * TILE * 8;
+    static constexpr int COL_B = S * TILE;
+    static constexpr int DESC_B = ((TILE / 64) * S * 8 + 15) / 16 * 16;
+    static constexpr int STAGE_B = VAL_B + DIAG_B + COL_B + DESC_B;
+    static constexpr int SMEM_B = STAGE_B * PIPE_STAGES;
+};
+
+template <int S, int D, int ROWS, int PIPE_STAGES>
+__global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_pipe(const __grid_constant__ MatvecArgs a) {
+    using L = PipeLayout<S, D, ROWS, PIPE_STAGES>;
+    constexpr int TILE = L::TILE;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nt = a.do_sinks ? a.ntasks : 0;
+    if ((int)blockIdx.x < nt) {
+        sink_task(a);
+        return;
+    }
+    const int64_t G = (int64_t)gridDim.x - nt;
+    const int64_t b = (int64_t)blockIdx.x - nt;
+    const int64_t tile_lo = a.row_begin / TILE;
+    const int64_t tile_hi = (a.row_end + TILE - 1) / TILE;   // exclusive
+    const int tid = threadIdx.x;
+
+    auto issue = [&](int64_t tl) {
+        const int64_t T = tile_lo + b + tl * G;
+        if (T < tile_hi) {
+            const int64_t r0 = T * TILE;
+            unsigned char* st = smem + (size_t)(tl % PIPE_STAGES) * L::STAGE_B;
+            // values: S rows of TILE doubles
+            for (int q = tid; q < L::VAL_B / 16; q += MV_THREADS) {
+                const int sl = q / (TILE / 2), o = q % (TILE / 2);
+                cp_async16(st + (size_t)q * 16, a.val + (int64_t)sl * a.ld + r0 + o * 2);
+            }
+            for (int q = tid; q < L::DIAG_B / 16; q += MV_THREADS) {
+                const int dl = q / (TILE / 2), o = q % (TILE / 2);
+                cp_async16(st + L::VAL_B + (size_t)q * 16, a.diag + (int64_t)dl * a.ld + r0 + o * 2);
+            }
+            for (int q = tid; q < L::COL_B / 16; q += MV_THREADS) {
+                const int sl = q / (TILE / 16), o = q % (TILE / 16);
+                cp_async16(st + L::VAL_B + L::DIAG_B + (size_t)q * 16, a.col8 + (int64_t)sl * a.ld + r0 + o * 16);
+            }
+            for (int q = tid; q < (TILE / 64) * S * 8 / 16; q += MV_THREADS)
+                cp_async16(st + L::VAL_B + L::DIAG_B + L::COL_B + (size_t)q * 16,
+                           reinterpret_cast<const unsigned char*>(a.cdesc + (r0 >> 6) * S) + (size_t)q * 16);
+        }
+        cp_async_commit();   // (possibly empty) group: keeps the group count aligned with the tile counter
+    };
+
+#pragma unroll
+    for (int p = 0; p < PIPE_STAGES - 1; ++p) issue(p);
+    for (int64_t tl = 0;; ++tl) {
+        const int64_t T = tile_lo + b + tl * G;
+        if (T >= tile_hi) break;
+        issue(tl + PIPE_STAGES - 1);
+        cp_async_wait<PIPE_STAGES - 1>();   // tile tl has landed
+        __syncthreads();
+        const unsigned char* st = smem + (size_t)(tl % PIPE_STAGES) * L::STAGE_B;
+        const double* sval = reinterpret_cast<const double*>(st);
+        const double* sdiag = reinterpret_cast<const double*>(st + L::VAL_B);
+        const unsigned char* scol = st + L::VAL_B + L::DIAG_B;
+        const int2* sdesc = reinterpret_cast<const int2*>(st + L::VAL_B + L::DIAG_B + L::COL_B);
+        const int l0 = tid * ROWS;                 // row inside the tile
+        const int64_t i0 = T * TILE + l0;
+        double xi[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) xi[j] = (i0 + j >= a.row_begin && i0 + j < a.row_end) ? __ldg(a.xd + i0 + j) : 0.0;
+        // Column indices.  The rare chunks that stayed on 32-bit indices are handled by a separate (warp-uniform for
+        // ROWS <= 2) path so that the common path contains no global load before the gathers: the compiler can then
+        // issue all S*ROWS gathers back to back instead of serialising them behind predicated loads.
+        uint32_t c[S][ROWS];
+        bool wide = false;
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl)
+#pragma unroll
+            for (int j = 0; j < ROWS; j += 64) wide |= (sdesc[((l0 + j) >> 6) * S + sl].y == 0);
+        if (!wide) {
+#pragma unroll
+            for (int sl = 0; sl < S; ++sl) {
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    const int2 desc = sdesc[((l0 + j) >> 6) * S + sl];
+                    const uint32_t d8 = scol[sl * TILE + l0 + j];
+                    const int k = (l0 + j) & 63;
+                    const int shift = desc.y == 2 ? k : (desc.y == 3 ? 63 - k : 0);
+                    c[sl][j] = (d8 == 255u) ? (a.self_off + (uint32_t)min(i0 + j, a.n - 1)) : (uint32_t)(desc.x + (int)d8 + shift);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int sl = 0; sl < S; ++sl) ld_stream<ROWS>(a.col + (int64_t)sl * a.ld + i0, c[sl]);
+        }
+        double g[S][ROWS];
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl)
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) g[sl][j] = __ldg(a.x + c[sl][j]);
+        double acc[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            double dsum = 0.0;
+#pragma unroll
+            for (int dl = 0; dl < D; ++dl) dsum = fma(a.diag_coef[dl], sdiag[dl * TILE + l0 + j], dsum);
+            acc[j] = dsum * xi[j];
+        }
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl) {
+            const double cs = a.slot_coef[sl];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) acc[j] = fma(cs * sval[sl * TILE + l0 + j], g[sl][j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            if (i0 + j >= a.row_begin && i0 + j < a.row_end) {
+                double out = acc[j];
+                if (a.beta != 0.0) out += a.beta * a.y[i0 + j];
+                a.y[i0 + j] = out;
+            }
+        }
+        __syncthreads();   // the stage may be refilled by the next iteration's issue
+    }
+    cp_async_wait<0>();
+}
+
+template <int S, int D, int ROWS, int PIPE_STAGES>
+static int launch_pipe_sdr(ncme_matrix* A, const MatvecArgs& a) {
+    using L = PipeLayout<S, D, ROWS, PIPE_STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        NCME_CUDA(cudaFuncSetAttribute(k_fsp_matvec_pipe<S, D, ROWS, PIPE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_B));
+        configured = true;
+    }
+    const int per_sm = std::max(1, std::min(4, (int)(220 * 1024 / L::SMEM_B)));
+    const int64_t ntiles = (a.row_end + L::TILE - 1) / L::TILE - a.row_begin / L::TILE;
+    const int64_t G = std::max<int64_t>(1, std::min<int64_t>((int64_t)A->ctx->sm_count * per_sm, ntiles));
+    const unsigned grid = (unsigned)((a.do_sinks ? a.ntasks : 0) + G);
+    k_fsp_matvec_pipe<S, D, ROWS, PIPE_STAGES><<<grid, MV_THREADS, L::SMEM_B, A->ctx->stream>>>(a);
+    A->ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+// returns 1 if no pipelined instantiation covers (slots, diagonals)
+template <int ROWS, int PIPE_STAGES>
+static int launch_pipe(ncme_matrix* A, const MatvecArgs& a) {
+#define NCME_PIPE(SS, DD) \
+    if (a.nslots == SS && a.ndiag == DD) return launch_pipe_sdr<SS, DD, ROWS, PIPE_STAGES>(A, a);
+    // experimental kernel: instantiated for the benchmark shapes only (4 / 6 slots, 1 / 2 diagonal arrays)
+    NCME_PIPE(4, 1) NCME_PIPE(4, 2) NCME_PIPE(6, 1) NCME_PIPE(6, 2)
+#undef NCME_PIPE
+    return 1;
+}
+
 // Generic slot count (> 16 slots): same data flow without the register tile.
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_constant__ MatvecArgs a) {
     const int nt = a.do_sinks ? a.ntasks : 0;
@@ -337,6 +510,17 @@ int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
     // vector loads of x[i0..] / y are not used (scalar), but the matrix streams need i0 % ROWS == 0 only.
     int rc = -1;
     const bool c8 = A->use_c8 && A->col8.p != nullptr;
+    if (A->use_pipe && A->col8.p != nullptr && a.row_end - a.row_begin >= A->pipe_min_rows) {
+        int prc = 1;
+        switch (A->use_pipe) {   // rows per thread + 10 * stages
+            case 41: prc = launch_pipe<1, 4>(A, a); break;
+            case 42: prc = launch_pipe<2, 4>(A, a); break;
+            case 22: prc = launch_pipe<2, 2>(A, a); break;
+            case 21: prc = launch_pipe<1, 2>(A, a); break;
+            default: break;
+        }
+        if (prc <= 0) return prc;   // launched (0) or failed (< 0); 1 = no instantiation, fall through
+    }
     if (a.nslots >= 1 && a.nslots <= 16) {
         if (rows == 4 && a.nslots <= 8)
             rc = c8 ? launch_rows<4, true>(A, a) : launch_rows<4, false>(A, a);
@@ -843,7 +1027,7 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     A->n_global = ng;
     A->row_lo = row_lo;
     A->row_hi = row_hi;
-    A->ld = round_up<int64_t>(n > 0 ? n : 1, 64);
+    A->ld = round_up<int64_t>(n > 0 ? n : 1, 512);   // multiple of the largest row tile of the pipelined kernel
     for (int r = 0; r < nr; ++r) {
         NCME_REQUIRE(kind[r] >= 0 && kind[r] <= 2, "bad reaction kind");
         A->kind[r] = kind[r];
@@ -1170,6 +1354,13 @@ int ncme_matrix_unregister_buffer(ncme_matrix* A, void* base_dev) {
     return comm_unregister(A->comm, base_dev);
 }
 
+int ncme_matrix_set_pipe(ncme_matrix* A, int rows, int stages) {   // experiments: shared-memory pipelined kernel variant
+    NCME_REQUIRE(A, "null matrix");
+    A->use_pipe = rows > 0 ? rows + 10 * stages : 0;
+    A->pipe_min_rows = 0;
+    return NCME_OK;
+}
+
 int ncme_matrix_shard_info(ncme_matrix* A, int64_t info[8]) {
     NCME_REQUIRE(A && info, "null argument");
     info[0] = A->row_lo;
@@ -1208,12 +1399,17 @@ int ncme_matrix_size(ncme_matrix* A, int64_t* rows, int64_t* cols) {
 }
 
 int ncme_matrix_set_tuning(ncme_matrix* A, int rows_per_thread) {
-    // rows_per_thread: 0 (auto), 1, 2, 4; add 16 to use the byte-compressed column indices (experimental)
+    // rows_per_thread: 0 (auto), 1, 2, 4; +16: byte-compressed column indices in the register-staged kernel;
+    // +32 / +64: shared-memory pipelined kernel with 1 / 2 rows per thread; +128: never use the pipelined kernel
     const int rows = rows_per_thread & 15;
-    NCME_REQUIRE(A && (rows == 0 || rows == 1 || rows == 2 || rows == 4) && (rows_per_thread & ~31) == 0,
-                 "rows_per_thread must be 0, 1, 2 or 4 (+16: byte-compressed column indices)");
+    NCME_REQUIRE(A && (rows == 0 || rows == 1 || rows == 2 || rows == 4) && (rows_per_thread & ~255) == 0,
+                 "rows_per_thread must be 0, 1, 2 or 4 (+16 / +32 / +64 / +128 select kernel variants)");
     A->tune_rows = rows;
     A->use_c8 = (rows_per_thread & 16) ? 1 : 0;
+    if (rows_per_thread & 32) A->use_pipe = 41;
+    if (rows_per_thread & 64) A->use_pipe = 42;
+    if (rows_per_thread & 128) A->use_pipe = 0;
+    if (rows_per_thread & (32 | 64)) A->pipe_min_rows = 0;
     return NCME_OK;
 }
 

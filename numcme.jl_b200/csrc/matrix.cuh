@@ -61,6 +61,8 @@ struct ncme_matrix {
     int64_t nchunks = 0;
     int64_t wide_chunks = 0;          // chunk-slots that fell back to 32-bit indices
     int use_c8 = 0;                   // off by default: measured slower than 32-bit indices (profiles/README.md)
+    int use_pipe = 0;                 // shared-memory pipelined kernel: 0 off, 1 / 2 = rows per thread
+    int64_t pipe_min_rows = 1 << 18;  // below this the register-staged kernel is used
 
     // sink rows: entries grouped by reaction, rows ascending inside a reaction
     int64_t nsink = 0;

@@ -79,6 +79,9 @@ class FspMatrixSparse:
         return {"nterms": nt.value, "nnz_per_term": [nnz[k] for k in range(nt.value)],
                 "algorithmic_bytes": ab.value, "device_bytes": db.value}
 
+    def set_pipe(self, rows: int, stages: int):
+        L.check(L.load().ncme_matrix_set_pipe(self._h, int(rows), int(stages)))
+
     def compression_info(self) -> dict:
         info = (C.c_int64 * 4)()
         L.check(L.load().ncme_matrix_compression_info(self._h, info))

@@ -59,7 +59,7 @@ def test_separable_equals_joint(pkg):  # test/test_fspmat.jl:68
         assert np.linalg.norm(pkg.matvec(t, A1, v) - pkg.matvec(t, A2, v)) <= 1e-15
 
 
-@pytest.mark.parametrize("rows", [0, 1, 2, 4, 16, 17, 18, 20])   # +16: byte-compressed column indices
+@pytest.mark.parametrize("rows", [0, 1, 2, 4, 16, 17, 18, 20, 32, 64])   # +16: byte-compressed indices; +32/+64: smem-pipelined kernel
 def test_rectangular_telegraph_all_kernel_variants(pkg, rows):
     props, grads, pattern, states = sens_telegraph()
     sp = pkg.StateSpaceSparse(TELEGRAPH_S, states)
@@ -127,7 +127,7 @@ def test_m2d_100k_vs_oracle(pkg):
     v /= v.sum()
     ref = OA.matvec(0.0, v)
     outs = []
-    for rows in (1, 2, 4, 17, 18, 20):
+    for rows in (1, 2, 4, 17, 18, 20, 32, 64):
         A.set_tuning(rows)
         outs.append(pkg.matvec(0.0, A, v))
         assert _relerr(outs[-1], ref) <= RTOL
