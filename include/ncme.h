@@ -255,7 +255,9 @@ typedef struct ncme_solve_opts {
     const double* save_t;
     double h_init;        /* 0 = automatic */
     int64_t max_steps;    /* 0 = 10^8 */
-    int method;           /* 0 = Dormand-Prince 5(4) explicit; 1 = BDF/GMRES (see ncme_solve_segment docs) */
+    int method;           /* 0 = Dormand-Prince 5(4) explicit; 1 = BDF/GMRES (see ncme_solve_segment docs): one fused
+                           * kernel per step attempt for unsharded matrices up to NCME_BDF_FUSED_MAX_ROWS (env,
+                           * default 3e6) rows, launch-per-operation otherwise; 2 / 3 force the latter / the former */
 } ncme_solve_opts;
 
 typedef struct ncme_solve_stats {

@@ -15,7 +15,8 @@ from .statespace import (StateSpaceSparse, expand_, deleteat_, get_state_count, 
 from .fspmatrix import FspMatrixSparse, matvec_, matvecadd_, matvec, get_rowcount, get_colcount
 from .sensmatrix import ForwardSensFspMatrixSparse, sens_matvec_
 from .fspvector import FspVectorSparse, FspOutputSparse, FspOutputSliceSparse
-from .transientcme import (solve, AdaptiveFspSparse, RStepAdapter, SelectiveRStepAdapter, NativeRK45, NativeBDF, init_, adapt_)
+from .transientcme import (solve, AdaptiveFspSparse, RStepAdapter, SelectiveRStepAdapter, NativeRK45, NativeBDF, NativeBDFClassic,
+                           NativeBDFFused, init_, adapt_)
 from .forwardsenscme import (ForwardSensFspInitialConditionSparse, forwardsens_initial_condition, ForwardSensRStepAdapter,
                              AdaptiveForwardSensFspSparse, ForwardSensFspOutputSparse, ForwardSensFspOutputSliceSparse)
 from .parallel import Comm, ShardedVector, shard_bounds

@@ -1,0 +1,989 @@
+// Fused-step variant of the native BDF/NDF + Jacobi-GMRES integrator (bdf.cu): ONE kernel launch per step attempt.
+//
+// Why: the launch-per-operation integrator of bdf.cu needs ~34 launches and ~10 device->host scalar fetches per
+// step (one per Krylov iteration).  That is irrelevant at 10^7 states (a matvec is 150 us) but it is all the cost of
+// the reference's own example configurations (telegraph: 70 states, toggle switch: 10^3, Hog1p: 10^4..10^5 --
+// SURVEY.md H4): 83 steps took 26 ms, against 5.45 ms for the reference's whole adaptive solve on a laptop CPU
+// (docs/src/examples/telegraph.md:89).  Here the whole step -- pending rescaling of the difference array, predictor,
+// A(t_new)*y_pred, Jacobi/weight setup, restarted GMRES(24) (matvec, Gram-Schmidt inner products, Givens rotations,
+// stopping test), solution update, explicit sink rows, total-mass projection, local error test, update of the
+// differences and the order-selection norms -- runs inside one persistent kernel: a single CTA (`__syncthreads`
+// between phases) for up to ~1000 rows, a cooperative grid (grid-wide barriers) above.  All reductions are
+// two-stage and ordered (bitwise reproducible); every CTA redundantly combines the partials and runs the small
+// Hessenberg/Givens recurrences, so no broadcast step is needed.  The host only sees one result record per step
+// (error norm, sink tails for the event function, iteration counts) and keeps the step-size / order controller,
+// the sink event and the output slices, exactly as in bdf.cu.  All RHS evaluations of a BDF step are at t_new, so
+// time-varying coefficients c_r(t_new) are passed by value with the launch (one host callback per step attempt).
+//
+// Replaces, like bdf.cu: DE.init / DE.step! with CVODE_BDF(linear_solver=:GMRES) (src/transientcme/sparse/fspsolve.jl:158-161).
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "matrix.cuh"
+#include "ode.cuh"
+#include "vec.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ncme {
+
+namespace {
+
+constexpr int FBT = 512;              // threads per CTA
+constexpr int FW = FBT / 32;          // warps per CTA
+constexpr int MAXO = 5;               // maximum BDF order
+constexpr int GM = 24;                // Krylov dimension before restart
+constexpr int NSLOT = GM + 2;         // widest reduction (k+1 inner products + <w,w>)
+constexpr int MAXR = NCME_MAX_REACTIONS;
+
+struct StepResult {                   // written by CTA 0 straight into pinned (device-mapped) host memory
+    double error_sumsq;               // sum over ALL entries (states + sinks) of (d / (atol + rtol |ynew|))^2
+    double error_norm;
+    double ord_sm, ord_sp;            // order-selection sums over the state rows (new differences)
+    double beta0, resid;
+    double ms0, ms1, ms2;             // mass defect diagnostics
+    int lin_ok, accepted, kiters, rhs_evals, restarts, pad0;
+    volatile unsigned int seq;        // written last (after a system-scope fence): the host polls it
+    int pad1;
+    double sink_old0[MAXR];           // sink entries of D_0 before the step (u(t))
+    double nd[MAXO + 3][MAXR];        // sink entries of the NEW differences D_0..D_{order+2} (valid when accepted)
+};
+
+struct StepArgs {
+    // matrix (single GPU: padded position == row index)
+    const uint32_t* col;
+    const double* val;
+    const double* diag;
+    int64_t n, ld, N;
+    int nslots, ndiag, R, G;
+    double slot_coef[MAXR];
+    double diag_coef[MAXR + 1];
+    double sink_coef[MAXR];
+    const uint32_t* sink_row;
+    const double* sink_val;
+    int64_t sink_ptr[MAXR + 1];
+    // vectors (each of stride `stride` inside one workspace)
+    double* D;        // D_j = D + j*stride, j < MAXO+3
+    double* V;        // V_j = V + j*stride, j <= GM
+    double *ypred, *ynew, *z, *psi, *scale, *ps, *w, *d;
+    int64_t stride;
+    // step description
+    int order, have_change;
+    double P[MAXO + 1][MAXO + 1];     // pending rescaling of the differences: D_r <- sum_j P[j][r] D_j
+    double gamma[MAXO + 1];
+    double inv_alpha, c, atol, rtol, err_const, lin_tol, sqrtn, massfix_limit;
+    double Nglob;
+    // scratch
+    double* partials;                 // [2][G][NSLOT]
+    double* sinkbuf;                  // [2][MAXR]: sum val*x, sum val*|x|
+    StepResult* res;                  // device alias of the pinned host record
+    unsigned int seq;
+};
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    return x;
+}
+
+struct Shared {
+    double w[FW][NSLOT];
+    double res[NSLOT];
+    double H[GM + 1][GM];
+    double cs[GM], sn[GM], g[GM + 1], y[GM + 1], hcol[GM + 1];
+    double inv_hk1, resid;
+    int stop, ok;
+    double sink_d[MAXR];
+};
+
+template <bool MULTI>
+__device__ __forceinline__ void grid_barrier() {
+    if (MULTI)
+        cg::this_grid().sync();
+    else
+        __syncthreads();
+}
+
+// Ordered two-stage reduction of nv <= NV values; afterwards sh.res[0..nv) holds the totals in EVERY CTA (identical
+// bits everywhere: same partials, same summation order).  Contains a grid-wide barrier when MULTI.
+template <int NV, bool MULTI>
+__device__ __forceinline__ void reduce_all(double (&v)[NV], int nv, const StepArgs& a, int& parity, Shared& sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NV; ++s) {
+        if (s < nv) {
+            const double x = warp_sum(v[s]);
+            if (lane == 0) sh.w[wid][s] = x;
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nv) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < FW; ++w) t += sh.w[w][threadIdx.x];
+        if (MULTI)
+            a.partials[((size_t)parity * a.G + blockIdx.x) * NSLOT + threadIdx.x] = t;
+        else
+            sh.res[threadIdx.x] = t;
+    }
+    if (MULTI) {
+        cg::this_grid().sync();
+        const double* P = a.partials + (size_t)parity * a.G * NSLOT;
+        for (int s = wid; s < nv; s += FW) {
+            double t = 0.0;
+            for (int b = lane; b < a.G; b += 32) t += __ldcg(P + (size_t)b * NSLOT + s);
+            t = warp_sum(t);
+            if (lane == 0) sh.res[s] = t;
+        }
+        parity ^= 1;
+    }
+    __syncthreads();
+}
+
+// (A x)_i and diag(A)_i for one state row
+__device__ __forceinline__ double row_apply(const StepArgs& a, const double* x, int64_t i, double& jd) {
+    double acc = 0.0;
+    const uint32_t* cp = a.col + i;
+    const double* vp = a.val + i;
+#pragma unroll 4
+    for (int s = 0; s < a.nslots; ++s) {
+        const uint32_t c = __ldg(cp + (size_t)s * a.ld);
+        const double v = __ldg(vp + (size_t)s * a.ld);
+        acc = fma(a.slot_coef[s] * v, x[c], acc);
+    }
+    double dg = 0.0;
+    for (int d = 0; d < a.ndiag; ++d) dg = fma(a.diag_coef[d], __ldg(a.diag + (size_t)d * a.ld + i), dg);
+    jd = dg;
+    return fma(dg, x[i], acc);
+}
+
+// sinkbuf[r] = c_r * sum_k sink_val[k] x[sink_row[k]], sinkbuf[MAXR + r] = same with |x|; ends with a grid barrier
+template <bool MULTI>
+__device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Shared& sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (!MULTI) {
+        for (int r = wid; r < a.R; r += FW) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int64_t k = a.sink_ptr[r] + lane; k < a.sink_ptr[r + 1]; k += 32) {
+                const double v = __ldg(a.sink_val + k), xv = x[__ldg(a.sink_row + k)];
+                s0 = fma(v, xv, s0);
+                s1 = fma(v, fabs(xv), s1);
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            if (lane == 0) {
+                a.sinkbuf[r] = a.sink_coef[r] * s0;
+                a.sinkbuf[MAXR + r] = a.sink_coef[r] * s1;
+            }
+        }
+    } else {
+        for (int r = blockIdx.x; r < a.R; r += a.G) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int64_t k = a.sink_ptr[r] + threadIdx.x; k < a.sink_ptr[r + 1]; k += FBT) {
+                const double v = __ldg(a.sink_val + k), xv = x[__ldg(a.sink_row + k)];
+                s0 = fma(v, xv, s0);
+                s1 = fma(v, fabs(xv), s1);
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            __syncthreads();   // sh.w may still be read by the previous round
+            if (lane == 0) {
+                sh.w[wid][0] = s0;
+                sh.w[wid][1] = s1;
+            }
+            __syncthreads();
+            if (threadIdx.x < 2) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < FW; ++w) t += sh.w[w][threadIdx.x];
+                a.sinkbuf[threadIdx.x * MAXR + r] = a.sink_coef[r] * t;
+            }
+        }
+    }
+    grid_barrier<MULTI>();
+}
+
+// Krylov iteration k: w = (z - c A z) ps, inner products with V_0..V_k (KB = k+1 rounded up to a multiple of 4; the
+// surplus products are garbage-free duplicates of V_0 and ignored), <w,w> in slot KB.
+template <int KB, bool MULTI>
+__device__ __forceinline__ void krylov_apply(const StepArgs& a, int k, int& parity, Shared& sh) {
+    double v[KB + 1];
+#pragma unroll
+    for (int s = 0; s <= KB; ++s) v[s] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * FBT + threadIdx.x; i < a.n; i += (int64_t)a.G * FBT) {
+        double jd;
+        const double Az = row_apply(a, a.z, i, jd);
+        const double w = (a.z[i] - a.c * Az) * a.ps[i];
+        a.w[i] = w;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+            const double vj = a.V[(size_t)(j <= k ? j : 0) * a.stride + i];
+            v[j] = fma(w, vj, v[j]);
+        }
+        v[KB] = fma(w, w, v[KB]);
+    }
+    reduce_all<KB + 1, MULTI>(v, KB + 1, a, parity, sh);
+    // results: sh.res[0..k] = h_j, sh.res[KB] = <w,w>
+    if (threadIdx.x == 0) {
+        double ww = sh.res[KB], hsq = 0.0;
+        for (int j = 0; j <= k; ++j) {
+            sh.hcol[j] = sh.res[j];
+            sh.H[j][k] = sh.res[j];
+            hsq += sh.res[j] * sh.res[j];
+        }
+        double hk1sq = ww - hsq;   // |w - sum h_j v_j|^2 by Pythagoras
+        if (!(hk1sq > 0.0)) hk1sq = 0.0;
+        const double hk1 = sqrt(hk1sq);
+        sh.H[k + 1][k] = hk1;
+        for (int j = 0; j < k; ++j) {
+            const double tmp = sh.cs[j] * sh.H[j][k] + sh.sn[j] * sh.H[j + 1][k];
+            sh.H[j + 1][k] = -sh.sn[j] * sh.H[j][k] + sh.cs[j] * sh.H[j + 1][k];
+            sh.H[j][k] = tmp;
+        }
+        const double den = hypot(sh.H[k][k], sh.H[k + 1][k]);
+        if (!(den > 0.0) || !(ww == ww)) {
+            sh.ok = 0;
+            sh.stop = 1;
+        } else {
+            sh.cs[k] = sh.H[k][k] / den;
+            sh.sn[k] = sh.H[k + 1][k] / den;
+            sh.H[k][k] = den;
+            sh.H[k + 1][k] = 0.0;
+            sh.g[k + 1] = -sh.sn[k] * sh.g[k];
+            sh.g[k] = sh.cs[k] * sh.g[k];
+            sh.resid = fabs(sh.g[k + 1]);
+            const bool happy = hk1 <= 1e-14 * sqrt(fmax(ww, 1e-300));
+            sh.stop = (sh.resid / a.sqrtn <= a.lin_tol || happy || k + 1 == GM) ? 1 : 0;
+            sh.inv_hk1 = hk1 > 0.0 ? 1.0 / hk1 : 0.0;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepArgs a) {
+    __shared__ Shared sh;
+    int parity = 0;
+    const int64_t gtid = (int64_t)blockIdx.x * FBT + threadIdx.x, gstride = (int64_t)a.G * FBT;
+    const int order = a.order;
+    double* const D = a.D;
+    const int64_t st = a.stride;
+    int rhs_evals = 0, kiters = 0, restarts = 0;
+
+    // ---- P0: pending rescaling of the differences, predictor y_pred = sum D_j, psi = sum gamma_j D_j / alpha_k
+    for (int64_t i = gtid; i < a.N; i += gstride) {
+        double in[MAXO + 1];
+#pragma unroll
+        for (int j = 0; j <= MAXO; ++j) in[j] = j <= order ? D[(size_t)j * st + i] : 0.0;
+        if (a.have_change) {
+            double out[MAXO + 1];
+#pragma unroll
+            for (int r = 0; r <= MAXO; ++r) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j <= MAXO; ++j) s = fma(a.P[j][r], in[j], s);
+                out[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r <= MAXO; ++r)
+                if (r <= order) {
+                    D[(size_t)r * st + i] = out[r];
+                    in[r] = out[r];
+                }
+        }
+        double y = in[0], p = 0.0;
+#pragma unroll
+        for (int j = 1; j <= MAXO; ++j)
+            if (j <= order) {
+                y += in[j];
+                p = fma(a.gamma[j], in[j], p);
+            }
+        a.ypred[i] = y;
+        a.psi[i] = p * a.inv_alpha;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.R) a.res->sink_old0[threadIdx.x] = D[a.n + threadIdx.x];
+    grid_barrier<MULTI>();
+
+    // ---- P1: A y_pred, Jacobi preconditioner and error weights, right-hand side w0, beta^2 = |w0|^2
+    double v1[1] = {0.0};
+    for (int64_t i = gtid; i < a.n; i += gstride) {
+        double jd;
+        const double Ay = row_apply(a, a.ypred, i, jd);
+        const double sc = a.atol + a.rtol * fabs(a.ypred[i]);
+        const double p = 1.0 / ((1.0 - a.c * jd) * sc);
+        const double w = (a.c * Ay - a.psi[i]) * p;
+        a.scale[i] = sc;
+        a.ps[i] = p;
+        a.w[i] = w;
+        v1[0] = fma(w, w, v1[0]);
+    }
+    rhs_evals++;
+    reduce_all<1, MULTI>(v1, 1, a, parity, sh);
+    double beta = sqrt(fmax(sh.res[0], 0.0));
+    const double beta0 = beta;
+    bool lin_ok = (beta == beta);
+    double resid = beta;
+    double ms0 = 0.0, ms1 = 0.0;
+
+    if (!(beta / a.sqrtn > a.lin_tol * 1e-3)) {
+        // right-hand side already negligible: d = 0
+        double v2[2] = {0.0, 0.0};
+        for (int64_t i = gtid; i < a.n; i += gstride) {
+            a.d[i] = 0.0;
+            const double yn = a.ypred[i];
+            a.ynew[i] = yn;
+            v2[0] += a.psi[i];
+            v2[1] += fabs(yn);
+        }
+        reduce_all<2, MULTI>(v2, 2, a, parity, sh);
+        ms0 = sh.res[0];
+        ms1 = sh.res[1];
+    } else {
+        bool have_d = false;
+        while (true) {
+            // ---- P2: v_0 = w / beta, z = v_0 * scale
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                sh.g[0] = beta;
+                sh.ok = 1;
+                sh.stop = 0;
+                sh.resid = beta;
+            }
+            {
+                const double inv = 1.0 / beta;
+                for (int64_t i = gtid; i < a.n; i += gstride) {
+                    const double x = a.w[i] * inv;
+                    a.V[i] = x;
+                    a.z[i] = x * a.scale[i];
+                }
+            }
+            grid_barrier<MULTI>();
+            int k = 0;
+            for (; k < GM; ++k) {
+                // ---- P3: fused matvec + Gram-Schmidt inner products + Givens update
+                const int kb = ((k + 1 + 3) / 4) * 4;
+                switch (kb) {
+                    case 4: krylov_apply<4, MULTI>(a, k, parity, sh); break;
+                    case 8: krylov_apply<8, MULTI>(a, k, parity, sh); break;
+                    case 12: krylov_apply<12, MULTI>(a, k, parity, sh); break;
+                    case 16: krylov_apply<16, MULTI>(a, k, parity, sh); break;
+                    case 20: krylov_apply<20, MULTI>(a, k, parity, sh); break;
+                    default: krylov_apply<24, MULTI>(a, k, parity, sh); break;
+                }
+                rhs_evals++;
+                kiters++;
+                if (sh.stop) {
+                    ++k;
+                    break;
+                }
+                // ---- P4: v_{k+1} = (w - sum h_j v_j) / h_{k+1,k}, z = v_{k+1} * scale
+                {
+                    const double inv = sh.inv_hk1;
+                    for (int64_t i = gtid; i < a.n; i += gstride) {
+                        double x = a.w[i];
+                        for (int j = 0; j <= k; ++j) x = fma(-sh.hcol[j], a.V[(size_t)j * st + i], x);
+                        x *= inv;
+                        a.V[(size_t)(k + 1) * st + i] = x;
+                        a.z[i] = x * a.scale[i];
+                    }
+                }
+                grid_barrier<MULTI>();
+            }
+            if (!sh.ok) {
+                lin_ok = false;
+                break;
+            }
+            resid = sh.resid;
+            // ---- back substitution H y = g (thread 0), then P5: d = scale * sum y_j V_j, ynew = ypred + d
+            if (threadIdx.x == 0) {
+                for (int i = k - 1; i >= 0; --i) {
+                    double acc = sh.g[i];
+                    for (int j = i + 1; j < k; ++j) acc -= sh.H[i][j] * sh.y[j];
+                    sh.y[i] = acc / sh.H[i][i];
+                }
+            }
+            __syncthreads();
+            double v2[2] = {0.0, 0.0};
+            for (int64_t i = gtid; i < a.n; i += gstride) {
+                double x = 0.0;
+                for (int j = 0; j < k; ++j) x = fma(sh.y[j], a.V[(size_t)j * st + i], x);
+                x *= a.scale[i];
+                if (have_d) x += a.d[i];
+                a.d[i] = x;
+                const double yn = a.ypred[i] + x;
+                a.ynew[i] = yn;
+                v2[0] += x + a.psi[i];
+                v2[1] += fabs(yn);
+            }
+            have_d = true;
+            reduce_all<2, MULTI>(v2, 2, a, parity, sh);
+            ms0 = sh.res[0];
+            ms1 = sh.res[1];
+            if (resid / a.sqrtn <= a.lin_tol) break;
+            if (++restarts > 3) {
+                lin_ok = false;
+                break;
+            }
+            // restart: residual of the current d, r = (c A ynew - psi - d) ps
+            double v3[1] = {0.0};
+            for (int64_t i = gtid; i < a.n; i += gstride) {
+                double jd;
+                const double Ay = row_apply(a, a.ynew, i, jd);
+                const double w = (a.c * Ay - a.psi[i] - a.d[i]) * a.ps[i];
+                a.w[i] = w;
+                v3[0] = fma(w, w, v3[0]);
+            }
+            rhs_evals++;
+            reduce_all<1, MULTI>(v3, 1, a, parity, sh);
+            beta = sqrt(fmax(sh.res[0], 0.0));
+            if (!(beta > 0.0)) break;
+        }
+    }
+
+    StepResult* res = a.res;
+    if (!lin_ok) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            res->lin_ok = 0;
+            res->accepted = 0;
+            res->kiters = kiters;
+            res->rhs_evals = rhs_evals;
+            res->restarts = restarts;
+            res->beta0 = beta0;
+            res->resid = resid;
+            res->error_norm = 1e300;
+            res->error_sumsq = 1e300;
+            __threadfence_system();
+            res->seq = a.seq;
+        }
+        return;
+    }
+
+    // ---- P6: explicit sink rows (they never feed back) and the total-mass projection of the inexact solve.
+    // 1^T A = 0, so an exact step has sum_all(d + psi) = 0; the defect is removed by the relative rescaling
+    // d_i -= defect |ynew_i| / sum|ynew| (see bdf.cu).  The sink rows are linear in ynew: S(ynew + delta) follows from
+    // S(ynew) and S(|ynew|) without a second pass.
+    sink_rows<MULTI>(a, a.ynew, sh);
+    double ms2 = 0.0;
+    for (int r = 0; r < a.R; ++r) ms2 += a.c * __ldcg(a.sinkbuf + r);
+    const double defect = ms0 + ms2;
+    const bool fix = (fabs(defect) <= a.massfix_limit * ms1) && (ms1 > 0.0);
+    const double fixfac = fix ? -defect / ms1 : 0.0;
+    // ---- P7: apply the projection to the state rows, local error test
+    double v4[1] = {0.0};
+    for (int64_t i = gtid; i < a.n; i += gstride) {
+        double dd = a.d[i], yn = a.ynew[i];
+        if (fix) {
+            const double delta = fixfac * fabs(yn);
+            dd += delta;
+            yn += delta;
+            a.d[i] = dd;
+            a.ynew[i] = yn;
+        }
+        const double q = dd / (a.atol + a.rtol * fabs(yn));
+        v4[0] = fma(q, q, v4[0]);
+    }
+    if ((int)threadIdx.x < a.R) {   // every CTA keeps the sink increments (needed for the update of rows n..n+R)
+        const int r = threadIdx.x;
+        const double S = __ldcg(a.sinkbuf + r) + fixfac * __ldcg(a.sinkbuf + MAXR + r);
+        sh.sink_d[r] = a.c * S - a.psi[a.n + r];
+    }
+    reduce_all<1, MULTI>(v4, 1, a, parity, sh);
+    double sumsq = sh.res[0];
+    for (int r = 0; r < a.R; ++r) {
+        const double ds = sh.sink_d[r], yn = a.ypred[a.n + r] + ds;
+        const double q = ds / (a.atol + a.rtol * fabs(yn));
+        sumsq += q * q;
+    }
+    const double error_norm = a.err_const * sqrt(sumsq / a.Nglob);
+    const bool accept = (error_norm <= 1.0);
+
+    double ord_sm = 0.0, ord_sp = 0.0;
+    if (accept) {
+        // ---- P8: D_{k+2} = d - D_{k+1}; D_{k+1} = d; D_j += D_{j+1} (j = k..0); order-selection norms of the new D
+        double v5[2] = {0.0, 0.0};
+        for (int64_t i = gtid; i < a.N; i += gstride) {
+            const double dd = i < a.n ? a.d[i] : sh.sink_d[i - a.n];
+            const double dp = dd - D[(size_t)(order + 1) * st + i];
+            D[(size_t)(order + 2) * st + i] = dp;
+            D[(size_t)(order + 1) * st + i] = dd;
+            double run = dd, dm = 0.0;
+            for (int j = order; j >= 0; --j) {
+                run += D[(size_t)j * st + i];
+                D[(size_t)j * st + i] = run;
+                if (j == order) dm = run;
+            }
+            if (i < a.n) {
+                const double inv = 1.0 / (a.atol + a.rtol * fabs(run));
+                const double qm = order > 1 ? dm * inv : 0.0, qp = order < MAXO ? dp * inv : 0.0;
+                v5[0] = fma(qm, qm, v5[0]);
+                v5[1] = fma(qp, qp, v5[1]);
+            }
+        }
+        reduce_all<2, MULTI>(v5, 2, a, parity, sh);
+        ord_sm = sh.res[0];
+        ord_sp = sh.res[1];
+        // new sink tails for the host's event function (rows n..n+R were updated before the barrier above)
+        if (blockIdx.x == 0 && (int)threadIdx.x < a.R)
+            for (int j = 0; j <= order + 2; ++j) res->nd[j][threadIdx.x] = __ldcg(D + (size_t)j * st + a.n + threadIdx.x);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        res->lin_ok = 1;
+        res->accepted = accept ? 1 : 0;
+        res->kiters = kiters;
+        res->rhs_evals = rhs_evals;
+        res->restarts = restarts;
+        res->beta0 = beta0;
+        res->resid = resid;
+        res->error_sumsq = sumsq;
+        res->error_norm = (error_norm == error_norm) ? error_norm : 1e300;
+        res->ord_sm = ord_sm;
+        res->ord_sp = ord_sp;
+        res->ms0 = ms0;
+        res->ms1 = ms1;
+        res->ms2 = ms2;
+        __threadfence_system();   // cumulative: also orders the tails written by the other threads of this CTA
+        res->seq = a.seq;
+    }
+}
+
+void compute_R(int order, double factor, double R[MAXO + 1][MAXO + 1]) {
+    double M[MAXO + 1][MAXO + 1] = {};
+    for (int j = 0; j <= order; ++j) M[0][j] = 1.0;
+    for (int i = 1; i <= order; ++i)
+        for (int j = 1; j <= order; ++j) M[i][j] = ((double)i - 1.0 - factor * j) / (double)i;
+    for (int j = 0; j <= order; ++j) {
+        double run = 1.0;
+        for (int i = 0; i <= order; ++i) {
+            run *= M[i][j];
+            R[i][j] = run;
+        }
+    }
+    R[0][0] = 1.0;
+    for (int i = 1; i <= order; ++i) R[i][0] = 0.0;
+}
+
+// output slices with the device->host copies queued behind the step kernels and the host callbacks deferred to the
+// next synchronisation that happens anyway (no extra stream sync per saved step)
+struct LazySaver {
+    ncme_ctx* ctx = nullptr;
+    ncme_save_fn fn = nullptr;
+    void* user = nullptr;
+    ncme_solve_stats* st = nullptr;
+    double* pinned = nullptr;
+    size_t len = 0;
+    int nslots = 0;
+    std::vector<std::pair<double, int>> pending;
+    int init(ncme_ctx* c, size_t n, ncme_save_fn f, void* u, ncme_solve_stats* stats) {
+        ctx = c;
+        fn = f;
+        user = u;
+        st = stats;
+        len = n;
+        if (!fn) return NCME_OK;
+        nslots = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)16 << 20) / (len * sizeof(double))));
+        NCME_TRY(cache_reserve(&ctx->solve_pinned, &ctx->solve_pinned_bytes, (size_t)nslots * len * sizeof(double), true));
+        pinned = ctx->solve_pinned;
+        return NCME_OK;
+    }
+    void delivered() {   // call right after a stream synchronisation
+        for (auto& p : pending) {
+            fn(p.first, pinned + (size_t)p.second * len, user);
+            st->nsaved++;
+        }
+        pending.clear();
+    }
+    int flush() {
+        if (pending.empty()) return NCME_OK;
+        NCME_CUDA(cudaStreamSynchronize(ctx->stream));
+        delivered();
+        return NCME_OK;
+    }
+    int save(double t, const double* v_dev) {
+        if (!fn) return NCME_OK;
+        if ((int)pending.size() == nslots) NCME_TRY(flush());
+        const int slot = (int)pending.size();
+        NCME_CUDA(cudaMemcpyAsync(pinned + (size_t)slot * len, v_dev, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        pending.emplace_back(t, slot);
+        return NCME_OK;
+    }
+};
+
+}  // namespace
+
+bool bdf_fused_eligible(const ncme_matrix* A) {
+    return A->comm == nullptr && A->hl == 0 && A->hh == 0 && A->n >= 1 && A->nr <= MAXR;
+}
+
+int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
+                    double* u, const ncme_solve_opts* o, ncme_solve_stats* st) {
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t s = ctx->stream;
+    NCME_REQUIRE(bdf_fused_eligible(A), "fused BDF step kernel: single-GPU FSP matrices only");
+    const int64_t n = A->n, N = A->N;
+    const int R = A->nr;
+    const int64_t launches0 = ctx->launches;
+
+    // ---- grid: one CTA up to 2 rows per thread, a cooperative grid above (bounded by co-residency)
+    static int occ_cached = 0;
+    if (!occ_cached) {
+        int occ = 0;
+        NCME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bdf_step<true>, FBT, 0));
+        occ_cached = std::max(1, occ);
+    }
+    const int maxG = std::min(occ_cached, 2) * ctx->sm_count;
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(maxG, (n + (int64_t)FBT * 2 - 1) / ((int64_t)FBT * 2)));
+
+    // ---- workspace
+    const size_t stride = round_up<size_t>((size_t)N, 32);
+    const int NV = (MAXO + 3) + 8 + (GM + 1);
+    const size_t extra = (size_t)2 * G * NSLOT + 2 * MAXR + 64;
+    NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, (stride * NV + extra) * sizeof(double), false));
+    double* base = ctx->solve_ws;
+    NCME_CUDA(cudaMemsetAsync(base, 0, (stride * NV + extra) * sizeof(double), s));
+    int slot = 0;
+    auto vec = [&]() { return base + stride * (slot++); };
+    double* D[MAXO + 3];
+    for (int j = 0; j < MAXO + 3; ++j) D[j] = vec();
+    double* ypred = vec();
+    double* ynew = vec();
+    double* z = vec();
+    double* psi = vec();
+    double* scale = vec();
+    double* ps = vec();
+    double* w = vec();
+    double* d = vec();
+    double* V = base + stride * slot;
+    slot += GM + 1;
+    double* partials = base + stride * NV;
+    double* sinkbuf = partials + (size_t)2 * G * NSLOT;
+    static_assert(sizeof(StepResult) <= 1024 * sizeof(double), "StepResult must fit the context's pinned scalars");
+    StepResult* res_host = reinterpret_cast<StepResult*>(ctx->red_result_host);
+    StepResult* res_dev = nullptr;
+    NCME_CUDA(cudaHostGetDevicePointer((void**)&res_dev, (void*)res_host, 0));
+    unsigned int seq = 0;
+    res_host->seq = 0;
+
+    LazySaver saver;
+    NCME_TRY(saver.init(ctx, (size_t)N, save_fn, user, st));
+    const double rtol = o->rtol > 0 ? o->rtol : 1e-4, atol = o->atol > 0 ? o->atol : 1e-6;
+    const int64_t max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
+    const double tspan = t1 - t0;
+
+    const double kappa[MAXO + 1] = {0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0};
+    double gamma[MAXO + 1], alpha[MAXO + 1], error_const[MAXO + 2];
+    gamma[0] = 0;
+    for (int k = 1; k <= MAXO; ++k) gamma[k] = gamma[k - 1] + 1.0 / k;
+    for (int k = 0; k <= MAXO; ++k) alpha[k] = (1 - kappa[k]) * gamma[k];
+    for (int k = 0; k <= MAXO; ++k) error_const[k] = kappa[k] * gamma[k] + 1.0 / (k + 1);
+    error_const[MAXO + 1] = 1.0 / (MAXO + 2);
+
+    double coef[NCME_MAX_REACTIONS];
+    for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
+
+    // pending rescaling of the difference array, composed on the host and applied by the next step kernel
+    double P[MAXO + 1][MAXO + 1] = {};
+    bool have_change = false;
+    auto queue_change = [&](int order, double factor) {
+        double Rm[MAXO + 1][MAXO + 1] = {}, Um[MAXO + 1][MAXO + 1] = {}, RU[MAXO + 1][MAXO + 1] = {};
+        compute_R(order, factor, Rm);
+        compute_R(order, 1.0, Um);
+        for (int i = 0; i <= order; ++i)
+            for (int j = 0; j <= order; ++j) {
+                double v = 0.0;
+                for (int q = 0; q <= order; ++q) v += Rm[i][q] * Um[q][j];
+                RU[i][j] = v;
+            }
+        if (!have_change) {
+            memcpy(P, RU, sizeof(P));
+        } else {
+            double T[MAXO + 1][MAXO + 1] = {};
+            for (int i = 0; i <= order; ++i)
+                for (int j = 0; j <= order; ++j) {
+                    double v = 0.0;
+                    for (int q = 0; q <= order; ++q) v += P[i][q] * RU[q][j];
+                    T[i][j] = v;
+                }
+            memcpy(P, T, sizeof(P));
+        }
+        have_change = true;
+    };
+    // apply a pending rescaling now (needed before dense output is evaluated on D at a segment end: never, D_0 is
+    // invariant under the rescaling and dense output happens before any change is queued)
+    auto finish = [&](const double* src) -> int {
+        if (src != u) NCME_CUDA(cudaMemcpyAsync(u, src, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        saver.delivered();
+        st->launches = ctx->launches - launches0;
+        return NCME_OK;
+    };
+
+    NCME_CUDA(cudaMemcpyAsync(D[0], u, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    st->t_final = t0;
+    st->event_hit = 0;
+    int isave = 0;
+    while (isave < o->nsave && o->save_t[isave] < t0) ++isave;
+    if (o->save_every_step) NCME_TRY(saver.save(t0, D[0]));
+    while (isave < o->nsave && o->save_t[isave] == t0) {
+        NCME_TRY(saver.save(t0, D[0]));
+        ++isave;
+    }
+    if (!(tspan > 0)) return finish(D[0]);
+
+    // ---- initial step size (Hairer's rule on the WRMS norms of u and f(t0, u)), D_1 = h f(t0, u)
+    if (coef_fn) coef_fn(t0, coef, user);
+    NCME_TRY(matvec_dist(A, coef, D[0], ynew, 0.0, 0));
+    st->rhs_evals++;
+    double h_abs = o->h_init;
+    if (!(h_abs > 0)) {
+        double d0 = 0, d1 = 0;
+        NCME_TRY(ncme_vec_wrms(ctx, N, D[0], D[0], D[0], atol, rtol, &d0));
+        NCME_TRY(ncme_vec_wrms(ctx, N, ynew, D[0], D[0], atol, rtol, &d1));
+        saver.delivered();
+        h_abs = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h_abs = std::min(h_abs, tspan);
+    }
+    {
+        const double cs[1] = {h_abs};
+        const double* xs[1] = {ynew};
+        NCME_TRY(ncme_vec_lincomb(ctx, N, 1, cs, xs, D[1]));
+    }
+    int order = 1, n_equal_steps = 0;
+    double t = t0;
+    double g_prev = 0.0;
+    bool have_g = false;
+    const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+    const double lin_tol = 5e-3;   // WRMS residual of the linear solve = CVODE's 0.05 x Newton tolerance 0.1
+
+    StepArgs sa{};
+    sa.col = A->col.p;
+    sa.val = A->val.p;
+    sa.diag = A->diag.p;
+    sa.n = n;
+    sa.ld = A->ld;
+    sa.N = N;
+    sa.nslots = A->nslots;
+    sa.ndiag = A->ndiag;
+    sa.R = R;
+    sa.G = G;
+    sa.sink_row = A->sink_row.p;
+    sa.sink_val = A->sink_val.p;
+    for (int r = 0; r <= R; ++r) sa.sink_ptr[r] = A->sink_ptr[r];
+    sa.D = D[0];
+    sa.V = V;
+    sa.ypred = ypred;
+    sa.ynew = ynew;
+    sa.z = z;
+    sa.psi = psi;
+    sa.scale = scale;
+    sa.ps = ps;
+    sa.w = w;
+    sa.d = d;
+    sa.stride = (int64_t)stride;
+    for (int k = 0; k <= MAXO; ++k) sa.gamma[k] = gamma[k];
+    sa.atol = atol;
+    sa.rtol = rtol;
+    sa.lin_tol = lin_tol;
+    sa.sqrtn = sqrt((double)std::max<int64_t>(1, n));
+    sa.massfix_limit = 10.0 * rtol;
+    sa.Nglob = (double)N;
+    sa.partials = partials;
+    sa.sinkbuf = sinkbuf;
+    sa.res = res_dev;
+
+    while (t < t1) {
+        if (st->steps + st->rejected >= max_steps) {
+            set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)max_steps, t);
+            return NCME_ERR_SOLVER;
+        }
+        if (h_abs < hmin) {
+            set_error("integrator (BDF): step size underflow at t = %g", t);
+            return NCME_ERR_SOLVER;
+        }
+        double t_new = t + h_abs;
+        if (t_new > t1 || t1 - t_new < 1e-12 * tspan) {
+            t_new = t1;
+            queue_change(order, fabs(t_new - t) / h_abs);
+            n_equal_steps = 0;
+        }
+        const double h = t_new - t;
+        h_abs = fabs(h);
+        const double c = h / alpha[order];
+
+        // ---- one launch: the whole step attempt at t_new
+        if (coef_fn) coef_fn(t_new, coef, user);
+        {
+            MatvecArgs ma;
+            matvec_fill_args(A, coef, &ma);
+            for (int q = 0; q < A->nslots; ++q) sa.slot_coef[q] = ma.slot_coef[q];
+            for (int q = 0; q < A->ndiag; ++q) sa.diag_coef[q] = ma.diag_coef[q];
+            for (int q = 0; q < R; ++q) sa.sink_coef[q] = ma.sink_coef[q];
+        }
+        sa.order = order;
+        sa.have_change = have_change ? 1 : 0;
+        memcpy(sa.P, P, sizeof(P));
+        have_change = false;
+        sa.inv_alpha = 1.0 / alpha[order];
+        sa.c = c;
+        sa.err_const = error_const[order];
+        sa.seq = ++seq;
+        if (G == 1) {
+            k_bdf_step<false><<<1, FBT, 0, s>>>(sa);
+        } else {
+            void* kargs[1] = {(void*)&sa};
+            NCME_CUDA(cudaLaunchCooperativeKernel((const void*)k_bdf_step<true>, dim3(G), dim3(FBT), kargs, 0, s));
+        }
+        ctx->launches++;
+        NCME_CUDA(cudaGetLastError());
+        // the kernel writes its result record into pinned host memory and publishes the sequence number last: poll
+        // it (cheaper than a copy + stream synchronisation); the stream is queried now and then to catch faults
+        for (unsigned spin = 1; res_host->seq != seq; ++spin) {
+            if ((spin & 0xFFFF) == 0) {
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q == cudaSuccess) {
+                    if (res_host->seq == seq) break;
+                    set_error("fused BDF step kernel finished without publishing its result");
+                    return NCME_ERR_SOLVER;
+                }
+                if (q != cudaErrorNotReady) NCME_CUDA(q);
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        saver.delivered();   // copies queued before the kernel have completed (stream order)
+        const StepResult& rs = *res_host;
+        st->rhs_evals += rs.rhs_evals;
+
+        if (!rs.lin_ok) {   // linear solver failed: halve the step (CVODE's reaction to a convergence failure)
+            st->rejected++;
+            h_abs *= 0.5;
+            queue_change(order, 0.5);
+            n_equal_steps = 0;
+            continue;
+        }
+        const double safety = 0.9;
+        const double error_norm = rs.error_norm;
+        if (!rs.accepted) {
+            st->rejected++;
+            const double factor = (error_norm < 1e299) ? std::max(0.2, safety * pow(error_norm, -1.0 / (order + 1))) : 0.2;
+            h_abs *= factor;
+            queue_change(order, factor);
+            n_equal_steps = 0;
+            continue;
+        }
+        // ---- accepted: the kernel has already updated the differences
+        st->steps++;
+        n_equal_steps++;
+        const double(*nd)[MAXR] = rs.nd;
+        auto sink_sum_at = [&](double tt) {
+            double sum = 0.0;
+            for (int r = 0; r < R; ++r) {
+                double p = 1.0, y = nd[0][r];
+                for (int j = 1; j <= order; ++j) {
+                    p *= (tt - (t_new - (j - 1) * h)) / (h * j);
+                    y += nd[j][r] * p;
+                }
+                sum += y;
+            }
+            return sum;
+        };
+        auto dense_to = [&](double tt, double* out) -> int {
+            double cs[MAXO + 1];
+            const double* xs[MAXO + 1];
+            cs[0] = 1.0;
+            xs[0] = D[0];
+            double p = 1.0;
+            for (int j = 1; j <= order; ++j) {
+                p *= (tt - (t_new - (j - 1) * h)) / (h * j);
+                cs[j] = p;
+                xs[j] = D[j];
+            }
+            return ncme_vec_lincomb(ctx, N, order + 1, cs, xs, out);
+        };
+        double t_hi = t_new;
+        bool event = false;
+        if (o->check_event && R > 0) {
+            if (!have_g) {
+                double s0 = 0.0;
+                for (int r = 0; r < R; ++r) s0 += rs.sink_old0[r];
+                g_prev = s0 - o->event_slope * t;
+                have_g = true;
+            }
+            const int NS_ = 16;
+            double ga = g_prev, ta = t;
+            for (int q = 1; q <= NS_; ++q) {
+                const double tb = t + (t_new - t) * q / NS_;
+                const double gb = sink_sum_at(tb) - o->event_slope * tb;
+                if (ga <= 0.0 && gb > 0.0) {
+                    double lo = ta, hi = tb;
+                    for (int it = 0; it < 60; ++it) {
+                        const double mid = 0.5 * (lo + hi);
+                        if (sink_sum_at(mid) - o->event_slope * mid > 0.0)
+                            hi = mid;
+                        else
+                            lo = mid;
+                    }
+                    t_hi = hi;
+                    event = true;
+                    break;
+                }
+                ga = gb;
+                ta = tb;
+            }
+            if (!event) g_prev = ga;
+        }
+        while (isave < o->nsave && o->save_t[isave] <= t_hi + 1e-14 * fabs(t_hi)) {
+            const double ts = o->save_t[isave];
+            if (ts >= t_new && !event) {
+                NCME_TRY(saver.save(ts, D[0]));
+            } else {
+                NCME_TRY(saver.flush());   // z is about to be overwritten: deliver what still points at it
+                NCME_TRY(dense_to(std::min(ts, t_new), z));
+                NCME_TRY(saver.save(ts, z));
+            }
+            ++isave;
+        }
+        if (event) {
+            NCME_TRY(saver.flush());
+            NCME_TRY(dense_to(t_hi, z));
+            st->t_final = t_hi;
+            st->event_hit = 1;
+            st->h_last = h_abs;
+            return finish(z);
+        }
+        t = t_new;
+        st->h_last = h_abs;
+        if (o->save_every_step) NCME_TRY(saver.save(t, D[0]));
+        if (t >= t1) break;
+        if (n_equal_steps < order + 1) continue;
+        // ---- order / step-size selection (norms of the new differences came back with the step result)
+        double sm = rs.ord_sm, sp = rs.ord_sp;
+        for (int r = 0; r < R; ++r) {
+            const double inv = 1.0 / (atol + rtol * fabs(nd[0][r]));
+            if (order > 1) sm += (nd[order][r] * inv) * (nd[order][r] * inv);
+            if (order < MAXO) sp += (nd[order + 2][r] * inv) * (nd[order + 2][r] * inv);
+        }
+        const double INF = 1e300;
+        const double em = order > 1 ? error_const[order - 1] * sqrt(sm / (double)N) : INF;
+        const double ep = order < MAXO ? error_const[order + 1] * sqrt(sp / (double)N) : INF;
+        const double norms[3] = {em, error_norm, ep};
+        double factors[3];
+        for (int q = 0; q < 3; ++q)
+            factors[q] = norms[q] >= INF ? 0.0 : (norms[q] > 0 ? pow(norms[q], -1.0 / (order + q)) : 1e9);
+        int best = 1;
+        for (int q = 0; q < 3; ++q)
+            if (factors[q] > factors[best]) best = q;
+        order += best - 1;
+        const double factor = std::min(10.0, safety * factors[best]);
+        h_abs *= factor;
+        queue_change(order, factor);
+        n_equal_steps = 0;
+    }
+    st->t_final = t;
+    return finish(D[0]);
+}
+
+}  // namespace ncme

@@ -83,19 +83,23 @@ struct ncme_ctx {
 
 namespace ncme {
 
-// Device array with capacity growth (contents preserved).
+// Device array with capacity growth (contents preserved).  Storage comes from the device's stream-ordered memory
+// pool (cudaMallocAsync; release threshold raised by ncme_ctx_create so freed blocks are re-used without returning to
+// the driver): the per-adapt rebuilds of spaces and matrices (fspsolve.jl:175-176) make dozens of small allocations,
+// and cudaMalloc/cudaFree (implicit device synchronisation) dominated the small example configurations.
 template <typename T>
 struct DevArray {
     T* p = nullptr;
     size_t cap = 0;
+    cudaStream_t last_stream = nullptr;   // stream the storage was last (re)allocated on; frees are ordered on it
     int reserve(size_t n, cudaStream_t s, bool keep = true) {
         if (n <= cap) return NCME_OK;
         size_t ncap = cap ? cap : 256;
         while (ncap < n) ncap = ncap + ncap / 2 + 256;
         T* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)&q, ncap * sizeof(T), s);
         if (e != cudaSuccess) {
-            set_error("cudaMalloc(%zu bytes) failed: %s", ncap * sizeof(T), cudaGetErrorString(e));
+            set_error("cudaMallocAsync(%zu bytes) failed: %s", ncap * sizeof(T), cudaGetErrorString(e));
             return NCME_ERR_NOMEM;
         }
         if (p && keep && cap) {
@@ -106,15 +110,16 @@ struct DevArray {
             }
         }
         if (p) {
-            cudaStreamSynchronize(s);
-            cudaFree(p);
+            if (last_stream != s) cudaStreamSynchronize(last_stream);   // work queued on the old stream may still use p
+            cudaFreeAsync(p, s);
         }
         p = q;
         cap = ncap;
+        last_stream = s;
         return NCME_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, last_stream);
         p = nullptr;
         cap = 0;
     }

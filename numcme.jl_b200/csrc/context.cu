@@ -36,6 +36,14 @@ int ncme_ctx_create(int device, ncme_ctx** out) {
     NCME_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     NCME_CUDA(cudaGetDeviceProperties(&prop, device));
+    {   // keep freed blocks of the stream-ordered pool (DevArray) cached instead of returning them to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     ncme_ctx* ctx = new ncme_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;

@@ -956,6 +956,50 @@ __global__ void k_chunk_reach(const uint32_t* __restrict__ col, int64_t ld, int6
     atomicMax(&reach[i / chunk_rows], m);
 }
 
+// counts[r] = rows with a predecessor through reaction r; counts[NCME_MAX_REACTIONS + r] = rows whose sink flag r is set
+__global__ void __launch_bounds__(256) k_count_structure(const uint32_t* __restrict__ pred, int64_t ld, int64_t row_lo,
+                                                         const uint32_t* __restrict__ sinkmask, int64_t n, int nr,
+                                                         uint32_t validmask, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int sh[2 * NCME_MAX_REACTIONS];
+    if (threadIdx.x < 2 * NCME_MAX_REACTIONS) sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n;
+    const uint32_t m = in ? (sinkmask[row_lo + i] & validmask) : 0u;
+    for (int r = 0; r < nr; ++r) {
+        const bool hp = in && pred[(int64_t)r * ld + row_lo + i] != NONE32;
+        const unsigned bp = __ballot_sync(0xffffffffu, hp), bs = __ballot_sync(0xffffffffu, (m >> r) & 1u);
+        if ((threadIdx.x & 31) == 0) {
+            if (bp) atomicAdd(&sh[r], (unsigned)__popc(bp));
+            if (bs) atomicAdd(&sh[NCME_MAX_REACTIONS + r], (unsigned)__popc(bs));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * NCME_MAX_REACTIONS && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// flags[q * n + i] = sink flag of reaction r0 + q at local row i
+__global__ void k_sink_flags_group(const uint32_t* __restrict__ mask, int64_t n, int r0, int g, uint32_t validmask,
+                                   uint32_t* __restrict__ flags) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)g * n) return;
+    const int q = (int)(t / n);
+    const int64_t i = t - (int64_t)q * n;
+    flags[t] = ((mask[i] & validmask) >> (r0 + q)) & 1u;
+}
+
+__global__ void k_fill_sinks_group(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n, int g,
+                                   int r0, const double* __restrict__ G, int64_t ng, int64_t row_lo, int64_t base,
+                                   uint32_t* __restrict__ sink_row, double* __restrict__ sink_val) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)g * n || !flags[t]) return;
+    const int q = (int)(t / n);
+    const int64_t i = t - (int64_t)q * n;
+    const int64_t k = base + pos[t];
+    sink_row[k] = (uint32_t)i;
+    sink_val[k] = G[(int64_t)(r0 + q) * ng + row_lo + i];
+}
+
 __global__ void k_bit_flags(const uint32_t* __restrict__ mask, int64_t n, int r, uint32_t* __restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = (mask[i] >> r) & 1u;
@@ -1002,6 +1046,32 @@ static bool zero_stoich(const ncme_space* sp, int r) {
     for (int s = 0; s < sp->ns; ++s)
         if (sp->stoich[(size_t)r * sp->ns + s] != 0) return false;
     return true;
+}
+
+// Byte-compressed column indices for the experimental matvec variants (ncme_matrix_set_tuning(+16/+32/+64),
+// ncme_matrix_set_pipe): built on first use, the default 32-bit kernel never needs them.
+static int matrix_ensure_compressed(ncme_matrix* A) {
+    if (A->col8.p || A->nslots == 0) return NCME_OK;
+    ncme_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nslots = A->nslots;
+    const int64_t n = A->n;
+    A->nchunks = A->ld / 64;
+    NCME_TRY(A->col8.reserve((size_t)A->ld * nslots, st, false));
+    NCME_TRY(A->cdesc.reserve((size_t)A->nchunks * nslots, st, false));
+    unsigned long long* d_wide = nullptr;
+    NCME_CUDA(cudaMalloc(&d_wide, sizeof(unsigned long long)));
+    NCME_CUDA(cudaMemsetAsync(d_wide, 0, sizeof(unsigned long long), st));
+    const int64_t nwarps = A->nchunks * nslots;
+    k_compress_cols<<<nblk(nwarps * 32), 256, 0, st>>>(A->col.p, A->ld, n, A->nchunks, nslots, (uint32_t)A->hl,
+                                                       A->col8.p, A->cdesc.p, d_wide);
+    ctx->launches++;
+    unsigned long long hw = 0;
+    NCME_CUDA(cudaMemcpyAsync(&hw, d_wide, sizeof(hw), cudaMemcpyDeviceToHost, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_wide);
+    A->wide_chunks = (int64_t)hw;
+    return NCME_OK;
 }
 
 static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A, ncme_comm* comm) {
@@ -1150,24 +1220,9 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         A->pipe_row[nc] = n;
         A->pipe_chunks = nc;
     }
-    // ---- byte-compressed column indices for the matvec fast path
+    // byte-compressed column indices (experimental kernel variants) are built on demand: matrix_ensure_compressed
     A->nchunks = A->ld / 64;
-    if (nslots > 0) {
-        NCME_TRY(A->col8.reserve((size_t)A->ld * nslots, st, false));
-        NCME_TRY(A->cdesc.reserve((size_t)A->nchunks * nslots, st, false));
-        unsigned long long* d_wide = nullptr;
-        NCME_CUDA(cudaMalloc(&d_wide, sizeof(unsigned long long)));
-        NCME_CUDA(cudaMemsetAsync(d_wide, 0, sizeof(unsigned long long), st));
-        const int64_t nwarps = A->nchunks * nslots;
-        k_compress_cols<<<nblk(nwarps * 32), 256, 0, st>>>(A->col.p, A->ld, n, A->nchunks, nslots, (uint32_t)A->hl,
-                                                           A->col8.p, A->cdesc.p, d_wide);
-        ctx->launches++;
-        unsigned long long hw = 0;
-        NCME_CUDA(cudaMemcpyAsync(&hw, d_wide, sizeof(hw), cudaMemcpyDeviceToHost, st));
-        NCME_CUDA(cudaStreamSynchronize(st));
-        cudaFree(d_wide);
-        A->wide_chunks = (int64_t)hw;
-    }
+    A->wide_chunks = 0;
     // ---- halo plan: who owns what I need, who needs what I own
     if (A->comm) {
         double mine[4] = {(double)row_lo, (double)row_hi, (double)A->ext_lo, (double)A->ext_hi};
@@ -1223,48 +1278,51 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         A->p2p_eligible = all_ok;
     }
 
-    // ---- sink lists (rows ascending inside each reaction) and structural counts
-    DevArray<uint32_t> flags, pos, scratch;
-    NCME_TRY(flags.reserve((size_t)(n > 0 ? n : 1), st, false));
-    NCME_TRY(pos.reserve((size_t)(n > 0 ? n : 1), st, false));
-    NCME_TRY(scratch.reserve(scan_scratch_elems(n > 0 ? n : 1), st, false));
+    // ---- structural counts (one kernel, one device->host fetch) and sink lists (rows ascending inside each reaction)
     int64_t npred[NCME_MAX_REACTIONS] = {0};
     std::vector<uint64_t> nsink_r((size_t)nr, 0);
-    int rc = NCME_OK;
-    for (int r = 0; r < nr && n > 0 && rc == NCME_OK; ++r) {
-        k_pred_flags<<<nblk(n), 256, 0, st>>>(sp->pred.p + (size_t)r * sp->ld + row_lo, n, flags.p);
-        ctx->launches++;
-        uint64_t tot = 0;
-        rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, &tot);
-        npred[r] = (int64_t)tot;
-    }
-    // two passes over the sink flags: count, then fill
+    uint32_t validmask = 0;
+    for (int r = 0; r < nr; ++r)
+        if (!zero_stoich(sp, r)) validmask |= 1u << r;
     A->sink_ptr[0] = 0;
-    for (int r = 0; r < nr && rc == NCME_OK; ++r) {
-        uint64_t tot = 0;
-        if (n > 0) {
-            k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p + row_lo, n, r, flags.p);
-            ctx->launches++;
-            rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, &tot);
+    if (n > 0) {
+        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->red_result_dev);
+        unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->red_result_host);
+        NCME_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2 * NCME_MAX_REACTIONS, st));
+        k_count_structure<<<nblk(n), 256, 0, st>>>(sp->pred.p, sp->ld, row_lo, sp->sinkmask.p, n, nr, validmask, d_cnt);
+        ctx->launches++;
+        NCME_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long) * 2 * NCME_MAX_REACTIONS, cudaMemcpyDeviceToHost, st));
+        NCME_CUDA(cudaStreamSynchronize(st));
+        for (int r = 0; r < nr; ++r) {
+            npred[r] = (int64_t)h_cnt[r];
+            nsink_r[(size_t)r] = h_cnt[NCME_MAX_REACTIONS + r];
         }
-        nsink_r[(size_t)r] = zero_stoich(sp, r) ? 0 : tot;
-        A->sink_ptr[r + 1] = A->sink_ptr[r] + (int64_t)nsink_r[(size_t)r];
     }
-    if (rc == NCME_OK) {
-        A->nsink = A->sink_ptr[nr];
-        rc = A->sink_row.reserve((size_t)(A->nsink > 0 ? A->nsink : 1), st, false);
-        if (rc == NCME_OK) rc = A->sink_val.reserve((size_t)(A->nsink > 0 ? A->nsink : 1), st, false);
+    for (int r = 0; r < nr; ++r) A->sink_ptr[r + 1] = A->sink_ptr[r] + (int64_t)nsink_r[(size_t)r];
+    A->nsink = A->sink_ptr[nr];
+    NCME_TRY(A->sink_row.reserve((size_t)(A->nsink > 0 ? A->nsink : 1), st, false));
+    NCME_TRY(A->sink_val.reserve((size_t)(A->nsink > 0 ? A->nsink : 1), st, false));
+    DevArray<uint32_t> flags, pos, scratch;
+    int rc = NCME_OK;
+    if (A->nsink > 0) {
+        // reactions are processed in groups whose reaction-major flag array (g x n) is scanned at once: the scan
+        // position of an entry is then its offset inside the group's part of the sink list
+        const int64_t group = std::max<int64_t>(1, std::min<int64_t>(nr, ((int64_t)1 << 24) / n));
+        NCME_TRY(flags.reserve((size_t)(group * n), st, false));
+        NCME_TRY(pos.reserve((size_t)(group * n), st, false));
+        NCME_TRY(scratch.reserve(scan_scratch_elems(group * n), st, false));
+        for (int r0 = 0; r0 < nr && rc == NCME_OK; r0 += (int)group) {
+            const int g = (int)std::min<int64_t>(group, nr - r0);
+            if (A->sink_ptr[r0 + g] == A->sink_ptr[r0]) continue;
+            k_sink_flags_group<<<nblk((int64_t)g * n), 256, 0, st>>>(sp->sinkmask.p + row_lo, n, r0, g, validmask, flags.p);
+            ctx->launches++;
+            rc = exclusive_scan_u32(ctx, flags.p, pos.p, (int64_t)g * n, scratch.p, scratch.cap, nullptr);
+            k_fill_sinks_group<<<nblk((int64_t)g * n), 256, 0, st>>>(flags.p, pos.p, n, g, r0, G.p, ng, row_lo, A->sink_ptr[r0],
+                                                                    A->sink_row.p, A->sink_val.p);
+            ctx->launches++;
+        }
     }
-    for (int r = 0; r < nr && rc == NCME_OK && n > 0; ++r) {
-        if (nsink_r[(size_t)r] == 0) continue;
-        k_bit_flags<<<nblk(n), 256, 0, st>>>(sp->sinkmask.p + row_lo, n, r, flags.p);
-        ctx->launches++;
-        rc = exclusive_scan_u32(ctx, flags.p, pos.p, n, scratch.p, scratch.cap, nullptr);
-        k_fill_sinks<<<nblk(n), 256, 0, st>>>(flags.p, pos.p, n, G.p + (size_t)r * ng + row_lo, A->sink_row.p + A->sink_ptr[r],
-                                              A->sink_val.p + A->sink_ptr[r]);
-        ctx->launches++;
-    }
-    if (rc == NCME_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+    if (rc == NCME_OK && cudaGetLastError() != cudaSuccess) {
         set_error("matrix assembly failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = NCME_ERR_CUDA;
     }
@@ -1291,7 +1349,8 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     NCME_TRY(A->tasks.reserve(tasks.size(), st, false));
     NCME_TRY(A->sink_partial.reserve(tasks.size(), st, false));
     NCME_CUDA(cudaMemcpyAsync(A->tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-    NCME_CUDA(cudaMalloc(&A->sink_counter, sizeof(unsigned)));
+    NCME_TRY(A->sink_counter_mem.reserve(1, st, false));
+    A->sink_counter = A->sink_counter_mem.p;
     NCME_CUDA(cudaMemsetAsync(A->sink_counter, 0, sizeof(unsigned), st));
     NCME_CUDA(cudaStreamSynchronize(st));
 
@@ -1358,6 +1417,7 @@ int ncme_matrix_set_pipe(ncme_matrix* A, int rows, int stages) {   // experiment
     NCME_REQUIRE(A, "null matrix");
     A->use_pipe = rows > 0 ? rows + 10 * stages : 0;
     A->pipe_min_rows = 0;
+    if (A->use_pipe) NCME_TRY(matrix_ensure_compressed(A));
     return NCME_OK;
 }
 
@@ -1386,7 +1446,7 @@ int ncme_matrix_destroy(ncme_matrix* A) {
     A->sink_val.release();
     A->tasks.release();
     A->sink_partial.release();
-    if (A->sink_counter) cudaFree(A->sink_counter);
+    A->sink_counter_mem.release();
     delete A;
     return NCME_OK;
 }
@@ -1410,6 +1470,7 @@ int ncme_matrix_set_tuning(ncme_matrix* A, int rows_per_thread) {
     if (rows_per_thread & 64) A->use_pipe = 42;
     if (rows_per_thread & 128) A->use_pipe = 0;
     if (rows_per_thread & (32 | 64)) A->pipe_min_rows = 0;
+    if (A->use_c8 || A->use_pipe) NCME_TRY(matrix_ensure_compressed(A));
     return NCME_OK;
 }
 
@@ -1532,6 +1593,7 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
 
 int ncme_matrix_compression_info(ncme_matrix* A, int64_t info[4]) {
     NCME_REQUIRE(A && info, "null argument");
+    NCME_TRY(matrix_ensure_compressed(A));
     info[0] = A->nchunks * A->nslots;   // (64-row chunk, slot) pairs
     info[1] = A->wide_chunks;           // of which kept on 32-bit column indices
     info[2] = A->use_c8;

@@ -74,6 +74,7 @@ struct ncme_matrix {
     ncme::DevArray<int4> tasks;          // (reaction, begin, end, -)
     ncme::DevArray<double> sink_partial; // [ntasks]
     unsigned int* sink_counter = nullptr;
+    ncme::DevArray<unsigned int> sink_counter_mem;
 
     // host-buffer pipeline: row chunks and, per chunk, the last row index its gathers reach (+1)
     int pipe_chunks = 0;

@@ -6,6 +6,8 @@
 #include "comm.cuh"
 #include "common.cuh"
 
+struct ncme_matrix;
+
 namespace ncme {
 
 struct OdeSystem {
@@ -35,6 +37,11 @@ int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
               const ncme_solve_opts* o, ncme_solve_stats* st);
 int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0, double t1, double* u,
               const ncme_solve_opts* o, ncme_solve_stats* st);
+
+// bdf_fused.cu: the same BDF/GMRES algorithm with ONE kernel launch per step attempt (unsharded FSP matrices)
+bool bdf_fused_eligible(const ncme_matrix* A);
+int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
+                    double* u, const ncme_solve_opts* o, ncme_solve_stats* st);
 
 // gathers a slice [all state rows | reduced sinks] on every rank and hands it to the host callback
 struct SliceSaver {

@@ -156,11 +156,7 @@ extern "C" int ncme_space_prune_by_mass(ncme_space* sp, const double* p_dev, dou
         if ((rc = idx.reserve((size_t)n2, s, false)) != NCME_OK) break;
         if ((rc = excl.reserve((size_t)n, s, false)) != NCME_OK) break;
         if ((rc = scratch.reserve(scan_scratch_elems(n), s, false)) != NCME_OK) break;
-        if (cudaMalloc(&cnt, sizeof(unsigned long long)) != cudaSuccess) {
-            set_error("cudaMalloc failed");
-            rc = NCME_ERR_NOMEM;
-            break;
-        }
+        cnt = reinterpret_cast<unsigned long long*>(ctx->red_result_dev + 900);   // context scratch scalar
         cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s);
         k_sort_init<<<nblk(n2), 256, 0, s>>>(p_dev, n, n2, key.p, idx.p);
         k_bitonic_local_sort<<<(unsigned)(n2 / BS_TILE), BS_THREADS, 0, s>>>(key.p, idx.p);
@@ -204,6 +200,5 @@ extern "C" int ncme_space_prune_by_mass(ncme_space* sp, const double* p_dev, dou
     idx.release();
     excl.release();
     scratch.release();
-    if (cnt) cudaFree(cnt);
     return rc;
 }

@@ -7,6 +7,7 @@
 //           sqrt(mean((err_i / (atol + rtol*max(|u_i|,|unew_i|)))^2)) and 4th-order dense output
 //           (Hairer's dopri5 continuous extension) for saveat and for locating the sink event.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <functional>
@@ -534,7 +535,23 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
         return matvec_sinks_only(A, coef, x, y);
     };
     if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, u_dev, opts, stats);
-    if (opts->method == 1) return solve_bdf(sys, save_fn, user, t0, t1, u_dev, opts, stats);
+    if (opts->method == 1 || opts->method == 2 || opts->method == 3) {
+        // BDF: one fused kernel per step attempt (bdf_fused.cu) where launch latency dominates, the
+        // launch-per-operation integrator (bdf.cu) for sharded matrices and for very large state spaces
+        bool fused = false;
+        if (opts->method == 3) {
+            NCME_REQUIRE(bdf_fused_eligible(A), "method 3 (fused BDF step kernel) needs an unsharded matrix");
+            fused = true;
+        } else if (opts->method == 1 && bdf_fused_eligible(A)) {
+            static const long long max_rows = [] {
+                const char* e = getenv("NCME_BDF_FUSED_MAX_ROWS");
+                return e ? atoll(e) : 3000000LL;
+            }();
+            fused = (long long)A->n <= max_rows;
+        }
+        if (fused) return solve_bdf_fused(A, coef_fn, save_fn, user, t0, t1, u_dev, opts, stats);
+        return solve_bdf(sys, save_fn, user, t0, t1, u_dev, opts, stats);
+    }
     set_error("unknown integrator method %d", opts->method);
     return NCME_ERR_ARG;
 }
@@ -579,7 +596,7 @@ extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn
         return NCME_OK;
     };
     if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, U_dev, opts, stats);
-    if (opts->method == 1) return solve_bdf(sys, save_fn, user, t0, t1, U_dev, opts, stats);
+    if (opts->method >= 1 && opts->method <= 3) return solve_bdf(sys, save_fn, user, t0, t1, U_dev, opts, stats);
     set_error("unknown integrator method %d", opts->method);
     return NCME_ERR_ARG;
 }

@@ -60,12 +60,11 @@ __device__ __forceinline__ int shifted_key(const KeyLayout& L, const StoichDev& 
 // frontier == nullptr means the frontier is the index range [fbase, fbase + F).
 __global__ void k_gen_candidates(KeyLayout L, StoichDev S, const uint64_t* __restrict__ keys,
                                  const uint32_t* __restrict__ frontier, int64_t fbase, int64_t F, int nreact,
-                                 const int* __restrict__ reacts /*device, nreact, 0-based*/, uint64_t* __restrict__ cand_key,
-                                 int* err_flag) {
+                                 const ReactList reacts /*0-based*/, uint64_t* __restrict__ cand_key, int* err_flag) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= F * nreact) return;
     const int64_t f = F - 1 - c / nreact;
-    const int r = reacts[c % nreact];
+    const int r = reacts.r[c % nreact];
     const int64_t idx = frontier ? (int64_t)frontier[f] : fbase + f;
     uint64_t nk;
     const int rc = shifted_key(L, S, keys[idx], r, +1, &nk);
@@ -227,6 +226,169 @@ __global__ void k_repack_keys(KeyLayout from, KeyLayout to, uint64_t* __restrict
 // --------------------------------------------------------------------------------- host side ---
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+
+// ---------------------------------------------------------------- small spaces: all levels in ONE launch ----
+// expand! on a space of a few thousand states is pure launch/synchronisation latency in the per-level pipeline above
+// (8 launches + a host round trip per level; the reference's example configurations expand 5-20 levels per adapt
+// event).  One CTA runs the SAME algorithm -- candidate ranks, atomicMin on the table value, ordered compaction of the
+// winners, connectivity of the new states -- for as many levels as the pre-reserved capacities allow, with
+// __syncthreads() between the phases; the host continues with the general path if a level does not fit.
+struct ExpandSmallArgs {
+    HashView h;
+    KeyLayout L;
+    StoichDev S;
+    ReactList reacts;
+    uint32_t reactmask;
+    uint64_t* keys;
+    uint32_t* pred;
+    int64_t ld;
+    uint32_t* sinkmask;
+    uint64_t* cand_key;
+    uint32_t* cand_slot;
+    uint32_t* frontier;
+    int64_t n0, cand_cap;
+    uint64_t tcap;
+    int levels;
+    int* err_flag;
+    long long* out;   // [0] states after, [1] levels done, [2] states added by the last level done, [3] stopped for capacity
+};
+constexpr int XS_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t block_flag_scan(bool flag, uint32_t* warp_tot, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    const uint32_t excl = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[wid] = __popc(b);
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < XS_THREADS / 32; ++w) {
+        const uint32_t v = warp_tot[w];
+        if (w < wid) off += v;
+        tot += v;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + excl;
+}
+
+__global__ void __launch_bounds__(XS_THREADS) k_expand_small(const __grid_constant__ ExpandSmallArgs a) {
+    __shared__ uint32_t warp_tot[XS_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int nreact = a.reacts.n, nr = a.S.nr;
+    int64_t n = a.n0;
+    // explorables = states with a sink flag on one of the expansion reactions (:165-173), ascending
+    uint32_t running = 0;
+    for (int64_t base = 0; base < n; base += XS_THREADS) {
+        const int64_t i = base + tid;
+        const bool flag = i < n && (a.sinkmask[i] & a.reactmask);
+        uint32_t total;
+        const uint32_t pos = block_flag_scan(flag, warp_tot, &total);
+        if (flag) a.frontier[running + pos] = (uint32_t)i;
+        running += total;
+    }
+    __syncthreads();
+    int64_t F = running, fbase = 0;
+    bool use_list = true;
+    int done = 0, stopped = 0;
+    int64_t last_added = 0;
+    for (int level = 0; level < a.levels && F > 0; ++level) {
+        const int64_t ncand = F * nreact;
+        if (ncand > a.cand_cap || n + ncand > a.ld || 2ull * (uint64_t)(n + ncand) > a.tcap) {
+            stopped = 1;
+            break;
+        }
+        const uint32_t n_old = (uint32_t)n;
+        // candidates (LIFO over the frontier, reactions ascending :176-186) and the first loop of _addstates! (:219-226)
+        for (int64_t c = tid; c < ncand; c += XS_THREADS) {
+            const int64_t f = F - 1 - c / nreact;
+            const int r = a.reacts.r[c % nreact];
+            const int64_t idx = use_list ? (int64_t)a.frontier[f] : fbase + f;
+            uint64_t nk;
+            const int rc = shifted_key(a.L, a.S, a.keys[idx], r, +1, &nk);
+            if (rc == 2) atomicExch(a.err_flag, 1);
+            const uint64_t key = rc == 0 ? nk : EMPTY_KEY;
+            a.cand_key[c] = key;
+            uint32_t cs = NONE32;
+            if (key != EMPTY_KEY) {
+                uint64_t slot = hash64(key) & a.h.capmask;
+                while (true) {
+                    const uint64_t prev = atomicCAS((unsigned long long*)&a.h.keys[slot], (unsigned long long)EMPTY_KEY,
+                                                    (unsigned long long)key);
+                    if (prev == EMPTY_KEY || prev == key) {
+                        const uint32_t before = atomicMin(&a.h.vals[slot], n_old + (uint32_t)c);
+                        cs = (before < n_old) ? NONE32 : (uint32_t)slot;
+                        break;
+                    }
+                    slot = (slot + 1) & a.h.capmask;
+                }
+            }
+            a.cand_slot[c] = cs;
+        }
+        __syncthreads();
+        // winners in rank order -> new indices; commit
+        running = 0;
+        for (int64_t base = 0; base < ncand; base += XS_THREADS) {
+            const int64_t c = base + tid;
+            uint32_t slot = NONE32;
+            bool flag = false;
+            if (c < ncand) {
+                slot = a.cand_slot[c];
+                flag = slot != NONE32 && a.h.vals[slot] == n_old + (uint32_t)c;
+            }
+            uint32_t total;
+            const uint32_t pos = block_flag_scan(flag, warp_tot, &total);
+            if (flag) {
+                const uint32_t i = n_old + running + pos;
+                a.keys[i] = a.cand_key[c];
+                a.h.vals[slot] = i;
+                a.sinkmask[i] = 0u;
+                for (int r = 0; r < nr; ++r) a.pred[(int64_t)r * a.ld + i] = NONE32;
+            }
+            running += total;
+        }
+        __syncthreads();
+        const int64_t m = running, n_new = n + m;
+        // connectivity of the new states (:241-266)
+        for (int64_t t = tid; t < m * nr; t += XS_THREADS) {
+            const int64_t i = n + t / nr;
+            const int r = (int)(t % nr);
+            const uint64_t key = a.keys[i];
+            uint64_t k2;
+            if (shifted_key(a.L, a.S, key, r, -1, &k2) == 0) {
+                const uint32_t j = hash_lookup(a.h, k2);
+                if (j != NONE32) {
+                    a.pred[(int64_t)r * a.ld + i] = j;
+                    atomicAnd(&a.sinkmask[j], ~(1u << r));
+                }
+            }
+            const int rc = shifted_key(a.L, a.S, key, r, +1, &k2);
+            if (rc == 0) {
+                const uint32_t j = hash_lookup(a.h, k2);
+                if (j == NONE32)
+                    atomicOr(&a.sinkmask[i], 1u << r);
+                else
+                    a.pred[(int64_t)r * a.ld + j] = (uint32_t)i;
+            } else if (rc == 2) {
+                atomicOr(&a.sinkmask[i], 1u << r);
+            }
+        }
+        __syncthreads();
+        use_list = false;
+        fbase = n;
+        F = m;
+        last_added = m;
+        n = n_new;
+        ++done;
+    }
+    if (tid == 0) {
+        a.out[0] = n;
+        a.out[1] = done;
+        a.out[2] = last_added;
+        a.out[3] = stopped;
+    }
+}
+
 #define LAUNCH(ctx, kern, n, ...)                                          \
     do {                                                                   \
         if ((n) > 0) {                                                     \
@@ -338,7 +500,9 @@ int space_delete_flagged(ncme_space* sp) {
     if ((int64_t)m == n) return NCME_OK;
     DevArray<uint64_t> k2;
     DevArray<uint32_t> p2, m2;
-    const int64_t ld2 = round_up<int64_t>((int64_t)m > 1024 ? (int64_t)m : 1024, 64);
+    // keep head-room for the expansion that follows every prune (adapt!, rstepadapters.jl:44-49) instead of shrinking
+    // to fit and re-growing (re-layout of the slot-major predecessor table) a moment later
+    const int64_t ld2 = round_up<int64_t>(std::max<int64_t>(1024, std::min<int64_t>(sp->ld, 2 * (int64_t)m + 8192)), 64);
     NCME_TRY(k2.reserve((size_t)ld2, s, false));
     NCME_TRY(m2.reserve((size_t)ld2, s, false));
     NCME_TRY(p2.reserve((size_t)ld2 * sp->nr, s, false));
@@ -625,59 +789,137 @@ int ncme_space_destroy(ncme_space* sp) {
     return NCME_OK;
 }
 
+// small spaces: run as many levels as fit the (generously pre-reserved) capacities in one single-CTA launch.
+// Returns the levels done and the size of the last level's batch of new states (the next frontier).
+static int expand_small(ncme_space* sp, int levels, const ReactList& reacts, uint32_t reactmask, const int64_t* inc,
+                        int* levels_done, int64_t* last_added, bool* frontier_empty) {
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t s = ctx->stream;
+    *levels_done = 0;
+    *last_added = 0;
+    *frontier_empty = false;
+    constexpr int64_t SMALL_N = 1 << 16, CAND_CAP = 1 << 16;
+    while (*levels_done < levels && sp->n <= SMALL_N) {
+        // how many levels can the key fields take without a re-layout?
+        int64_t safe = levels - *levels_done;
+        for (int q = 0; q < sp->ns; ++q)
+            if (inc[q] > 0) safe = std::min<int64_t>(safe, ((int64_t)sp->layout.mask[q] - sp->ub[q]) / inc[q]);
+        if (safe <= 0) {
+            NCME_TRY(space_ensure_key_room(sp, inc));
+            safe = 1;
+        }
+        const int64_t want_rows = 2 * sp->n + 8192;
+        NCME_TRY(space_reserve_rows(sp, want_rows));
+        if (4 * (uint64_t)sp->ld > sp->tcap) NCME_TRY(space_rebuild_table(sp, 4 * (uint64_t)sp->ld));
+        NCME_TRY(sp->cand_key.reserve((size_t)CAND_CAP, s, false));
+        NCME_TRY(sp->cand_slot.reserve((size_t)CAND_CAP, s, false));
+        NCME_TRY(sp->frontier.reserve((size_t)sp->ld, s, false));
+        ExpandSmallArgs a{};
+        a.h = sp->hview();
+        a.L = sp->layout;
+        a.S = sp->sdev;
+        a.reacts = reacts;
+        a.reactmask = reactmask;
+        a.keys = sp->keys.p;
+        a.pred = sp->pred.p;
+        a.ld = sp->ld;
+        a.sinkmask = sp->sinkmask.p;
+        a.cand_key = sp->cand_key.p;
+        a.cand_slot = sp->cand_slot.p;
+        a.frontier = sp->frontier.p;
+        a.n0 = sp->n;
+        a.cand_cap = CAND_CAP;
+        a.tcap = sp->tcap;
+        a.levels = (int)safe;
+        a.err_flag = sp->err_flag;
+        long long* out_dev = reinterpret_cast<long long*>(ctx->red_result_dev);
+        long long* out_host = reinterpret_cast<long long*>(ctx->red_result_host);
+        a.out = out_dev;
+        k_expand_small<<<1, XS_THREADS, 0, s>>>(a);
+        ctx->launches++;
+        NCME_CUDA(cudaGetLastError());
+        NCME_CUDA(cudaMemcpyAsync(out_host, out_dev, 4 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        const int done = (int)out_host[1];
+        if (out_host[0] != sp->n) sp->version++;
+        sp->n = out_host[0];
+        for (int q = 0; q < sp->ns; ++q) sp->ub[q] += inc[q] * done;
+        *levels_done += done;
+        if (done > 0) *last_added = out_host[2];
+        if (done > 0 && out_host[2] == 0) {   // the frontier died out
+            *frontier_empty = true;
+            return NCME_OK;
+        }
+        if (done == 0 && !out_host[3]) {      // nothing to explore at all
+            *frontier_empty = true;
+            return NCME_OK;
+        }
+        if (out_host[3] && done == 0) break;  // a single level exceeds the small-path capacities: general path
+    }
+    return NCME_OK;
+}
+
 int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32_t* onlyreactions) {
     NCME_REQUIRE(sp, "null space");
     if (expansionlevel <= 0 || sp->n == 0) return NCME_OK;
     ncme_ctx* ctx = sp->ctx;
     sp->last_delete_nold = -1;
-    int reacts[NCME_MAX_REACTIONS];
-    int nreact = 0;
+    ReactList reacts{};
     uint32_t reactmask = 0;
     if (nonly <= 0) {
-        for (int r = 0; r < sp->nr; ++r) reacts[nreact++] = r;
+        for (int r = 0; r < sp->nr; ++r) reacts.r[reacts.n++] = r;
     } else {
         NCME_REQUIRE(onlyreactions && nonly <= NCME_MAX_REACTIONS, "bad onlyreactions");
         for (int k = 0; k < nonly; ++k) {
             NCME_REQUIRE(onlyreactions[k] >= 1 && onlyreactions[k] <= sp->nr, "onlyreactions entry out of range");
-            reacts[nreact++] = onlyreactions[k] - 1;
+            reacts.r[reacts.n++] = onlyreactions[k] - 1;
         }
     }
-    for (int k = 0; k < nreact; ++k) reactmask |= 1u << reacts[k];
-    int* reacts_dev = nullptr;
-    NCME_CUDA(cudaMalloc(&reacts_dev, sizeof(int) * NCME_MAX_REACTIONS));
+    const int nreact = reacts.n;
+    for (int k = 0; k < nreact; ++k) reactmask |= 1u << reacts.r[k];
+    int64_t inc[NCME_MAX_SPECIES] = {0};   // largest possible growth of each species in one level
+    for (int k = 0; k < nreact; ++k)
+        for (int s2 = 0; s2 < sp->ns; ++s2) inc[s2] = std::max(inc[s2], sp->stoich[(size_t)reacts.r[k] * sp->ns + s2]);
+    cudaStream_t s = ctx->stream;
     int st = NCME_OK;
     do {
-        if (cudaMemcpyAsync(reacts_dev, reacts, sizeof(int) * nreact, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
-            set_error("cudaMemcpyAsync failed");
-            st = NCME_ERR_CUDA;
+        int level0 = 0;
+        int64_t last_added = 0;
+        bool dead = false;
+        if ((st = expand_small(sp, expansionlevel, reacts, reactmask, inc, &level0, &last_added, &dead)) != NCME_OK) break;
+        if (dead || level0 >= expansionlevel) {
+            st = check_overflow(sp);
             break;
         }
-        // explorables = states with a sink flag on one of the expansion reactions (:165-173)
-        cudaStream_t s = ctx->stream;
-        if ((st = sp->flags.reserve((size_t)sp->n, s, false)) != NCME_OK) break;
-        if ((st = sp->pos.reserve((size_t)sp->n, s, false)) != NCME_OK) break;
-        if ((st = sp->scan_scratch.reserve(scan_scratch_elems(sp->n), s, false)) != NCME_OK) break;
-        k_frontier_flags<<<nblk(sp->n), 256, 0, s>>>(sp->sinkmask.p, sp->n, reactmask, sp->flags.p);
-        ctx->launches++;
-        uint64_t F = 0;
-        if ((st = exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, sp->n, sp->scan_scratch.p, sp->scan_scratch.cap, &F)) != NCME_OK)
-            break;
-        if (F == 0) break;
-        if ((st = sp->frontier.reserve((size_t)F, s, false)) != NCME_OK) break;
-        k_compact_indices<<<nblk(sp->n), 256, 0, s>>>(sp->flags.p, sp->pos.p, sp->n, sp->frontier.p);
-        ctx->launches++;
-        const uint32_t* frontier = sp->frontier.p;
+        // ---- general path (one kernel pipeline per level)
+        const uint32_t* frontier = nullptr;
         int64_t fbase = 0;
-        int64_t inc[NCME_MAX_SPECIES] = {0};   // largest possible growth of each species in one level
-        for (int k = 0; k < nreact; ++k)
-            for (int s2 = 0; s2 < sp->ns; ++s2) inc[s2] = std::max(inc[s2], sp->stoich[(size_t)reacts[k] * sp->ns + s2]);
-        for (int level = 0; level < expansionlevel && F > 0; ++level) {
+        uint64_t F = 0;
+        if (level0 > 0) {   // continue from the last batch of new states
+            fbase = sp->n - last_added;
+            F = (uint64_t)last_added;
+        } else {
+            // explorables = states with a sink flag on one of the expansion reactions (:165-173)
+            if ((st = sp->flags.reserve((size_t)sp->n, s, false)) != NCME_OK) break;
+            if ((st = sp->pos.reserve((size_t)sp->n, s, false)) != NCME_OK) break;
+            if ((st = sp->scan_scratch.reserve(scan_scratch_elems(sp->n), s, false)) != NCME_OK) break;
+            k_frontier_flags<<<nblk(sp->n), 256, 0, s>>>(sp->sinkmask.p, sp->n, reactmask, sp->flags.p);
+            ctx->launches++;
+            if ((st = exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, sp->n, sp->scan_scratch.p, sp->scan_scratch.cap, &F)) != NCME_OK)
+                break;
+            if (F == 0) break;
+            if ((st = sp->frontier.reserve((size_t)F, s, false)) != NCME_OK) break;
+            k_compact_indices<<<nblk(sp->n), 256, 0, s>>>(sp->flags.p, sp->pos.p, sp->n, sp->frontier.p);
+            ctx->launches++;
+            frontier = sp->frontier.p;
+        }
+        for (int level = level0; level < expansionlevel && F > 0; ++level) {
             if ((st = space_ensure_key_room(sp, inc)) != NCME_OK) break;
             for (int s2 = 0; s2 < sp->ns; ++s2) sp->ub[s2] += inc[s2];
             const int64_t ncand = (int64_t)F * nreact;
             if ((st = sp->cand_key.reserve((size_t)ncand, s, false)) != NCME_OK) break;
             k_gen_candidates<<<nblk(ncand), 256, 0, s>>>(sp->layout, sp->sdev, sp->keys.p, frontier, fbase, (int64_t)F,
-                                                         nreact, reacts_dev, sp->cand_key.p, sp->err_flag);
+                                                         nreact, reacts, sp->cand_key.p, sp->err_flag);
             ctx->launches++;
             int64_t added = 0;
             const int64_t n_before = sp->n;
@@ -695,7 +937,6 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
         st = check_overflow(sp);
     } while (0);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(reacts_dev);
     return st;
 }
 

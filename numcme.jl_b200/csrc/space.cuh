@@ -18,6 +18,12 @@ struct StoichDev {
     int16_t s[NCME_MAX_REACTIONS][NCME_MAX_SPECIES];
 };
 
+// reactions an expansion goes through (0-based), passed by value to the kernels
+struct ReactList {
+    int n;
+    int r[NCME_MAX_REACTIONS];
+};
+
 __host__ __device__ inline uint64_t hash64(uint64_t k) {
     k ^= k >> 33;
     k *= 0xff51afd7ed558ccdULL;

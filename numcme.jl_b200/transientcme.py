@@ -40,6 +40,16 @@ class NativeBDF:
     method = 1
 
 
+class NativeBDFClassic(NativeBDF):
+    """method 2: force the launch-per-operation BDF of csrc/bdf.cu (what sharded and very large problems use)."""
+    method = 2
+
+
+class NativeBDFFused(NativeBDF):
+    """method 3: force the one-kernel-per-step BDF of csrc/bdf_fused.cu (the default below ~3e6 states on one GPU)."""
+    method = 3
+
+
 class RStepAdapter:
     """rstepadapters.jl:12-16"""
     selective = False

@@ -243,3 +243,75 @@ def test_bdf_stiff_is_cheaper_than_explicit(pkg):
         st = r[name].p[0].states[:, 0]
         assert np.abs(r[name].p[0].values - poisson.pmf(st, mu)).max() < 1e-4, name
     assert r["bdf"].stats["rhs_evals"] < 0.25 * r["rk"].stats["rhs_evals"], (r["bdf"].stats, r["rk"].stats)
+
+
+# ---- fused-step BDF (csrc/bdf_fused.cu, one kernel per step attempt) against the launch-per-operation BDF ---------
+@pytest.mark.parametrize("levels", [20, 400])      # 41 states: one CTA (__syncthreads); 801 states: still one CTA
+def test_bdf_fused_matches_classic_fixed(pkg, levels):
+    model = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, fspmat_propensities("tv")), FSPMAT_THETA)
+    sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])
+    sp.expand_(levels)
+    p0 = pkg.FspVectorSparse.from_pairs(sp, [([1, 0, 0], 1.0)])
+    touts = np.arange(0.0, 121.0, 20.0)
+    ref = solve_fixed(TELEGRAPH_S, fspmat_propensities("tv"), FSPMAT_THETA, sp.get_states(), p0.values, (0.0, 120.0),
+                      saveat=touts, odeatol=1e-13, odertol=1e-10, method="LSODA")
+    out = {}
+    for name, m in (("classic", pkg.NativeBDFClassic()), ("fused", pkg.NativeBDFFused())):
+        out[name] = pkg.solve(model, p0, (0.0, 120.0), m, odertol=1e-8, odeatol=1e-13, saveat=touts)
+        for k in range(len(touts)):
+            assert np.abs(out[name].p[k].values - ref["p"][k]).max() < 5e-7, name
+            assert np.abs(out[name].sinks[k] - ref["sinks"][k]).max() < 5e-7, name
+            assert out[name].p[k].sum() + out[name].sinks[k].sum() == pytest.approx(1.0, abs=1e-9)
+    f, c = out["fused"].stats, out["classic"].stats
+    print("fused", f, "classic", c)
+    assert f["launches"] < 0.2 * c["launches"]                         # one launch per step attempt (+ dense output)
+    assert abs(f["steps"] - c["steps"]) <= 0.1 * c["steps"] + 2        # same controller, same algorithm
+    # every-step output and bitwise reproducibility of the fused path
+    a = pkg.solve(model, p0, (0.0, 120.0), pkg.NativeBDFFused(), odertol=1e-4, odeatol=1e-14)
+    b = pkg.solve(model, p0, (0.0, 120.0), pkg.NativeBDFFused(), odertol=1e-4, odeatol=1e-14)
+    assert len(a) == a.stats["steps"] + 1 and a.t == b.t
+    assert all(np.array_equal(x.values, y.values) for x, y in zip(a.p, b.p))
+
+
+def test_bdf_fused_cooperative_grid(pkg):
+    """20 301 states (examples/2dstate_exploration.jl as shipped): 20 CTAs, grid-wide barriers; and a 2-D model large
+    enough for the full co-resident grid.  Checked against the explicit integrator and the classic BDF."""
+    model = pkg.workloads.m2d_model()
+    for levels, tol in ((200, 2e-6), (700, 2e-6)):
+        sp = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0])
+        sp.expand_(levels)
+        p0 = pkg.FspVectorSparse.from_pairs(sp, [([0, 0], 1.0)])
+        res = {}
+        for name, m, rt in (("fused", pkg.NativeBDFFused(), 1e-7), ("classic", pkg.NativeBDFClassic(), 1e-7),
+                            ("rk", pkg.NativeRK45(), 1e-9)):
+            res[name] = pkg.solve(model, p0, (0.0, 2.0), m, saveat=[0.5, 2.0], odertol=rt, odeatol=1e-13)
+        print(levels, {k: (v.stats["steps"], v.stats["rhs_evals"], v.stats["launches"], round(v.stats["wall_s"], 4))
+                       for k, v in res.items()})
+        for k in range(2):
+            assert np.abs(res["fused"].p[k].values - res["rk"].p[k].values).max() < tol
+            assert np.abs(res["classic"].p[k].values - res["rk"].p[k].values).max() < tol
+            assert res["fused"].p[k].sum() + res["fused"].sinks[k].sum() == pytest.approx(1.0, abs=1e-9)
+        # product-form Poisson marginals: mean x1 = 10 (1 - e^-t), mean x2 = 16 (1 - e^-t/2)
+        st = res["fused"].p[1].states
+        v = res["fused"].p[1].values
+        assert (v * st[:, 0]).sum() == pytest.approx(10.0 * (1 - math.exp(-2.0)), rel=1e-5)
+        assert (v * st[:, 1]).sum() == pytest.approx(16.0 * (1 - math.exp(-1.0)), rel=1e-5)
+
+
+def test_bdf_fused_adaptive_event_and_timevarying(pkg):
+    """Adaptive solves (sink event inside a fused step, dense output at the event, prune/expand in between) with a
+    separable and a joint time-varying reaction: fused == classic within the solver tolerance."""
+    touts = np.arange(0.0, 3601.0, 600.0)
+    p0 = pkg.FspVectorSparse([[0, 0]], [1.0])
+    for sep in (True, False):
+        model = pkg.workloads.toggle_model(separable=sep)
+        out = {}
+        for name, m in (("fused", pkg.NativeBDFFused()), ("classic", pkg.NativeBDFClassic())):
+            out[name] = pkg.solve(model, p0, (0.0, 3600.0), pkg.AdaptiveFspSparse(m, pkg.RStepAdapter(20, 5, True)),
+                                  saveat=touts, odertol=1e-7, odeatol=1e-14)
+        assert out["fused"].stats["adapts"] >= 1
+        for k in range(len(touts)):
+            a, b = _align(out["fused"].p[k].states, out["fused"].p[k].values, out["classic"].p[k].states,
+                          out["classic"].p[k].values)
+            assert np.abs(a - b).max() < 5e-6
+            assert out["fused"].p[k].sum() + out["fused"].sinks[k].sum() == pytest.approx(1.0, abs=1e-7)
