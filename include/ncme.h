@@ -103,6 +103,14 @@ int ncme_space_download_connectivity(ncme_space* space, int64_t first, int64_t c
                                      uint32_t* sink_conn_out);
 /* get(state2idx, x, 0) for m states                sparsestatespace.jl:33 (Dict lookups :221,247,258) */
 int ncme_space_lookup(ncme_space* space, int64_t m, const int64_t* states, uint32_t* idx_out);
+/* sum(p, dims): marginal of a device-resident probability vector over the (1-based) species `dims`
+ *                                                   src/fspvector/fspvector.jl:66-99 (used by examples/hog1p.jl:104-105)
+ * p_dev: device, n doubles (entry i belongs to state i).  The reduced states come out in the order of their first
+ * occurrence in the state list, like the reference; states_out is row-major nred x (NS - #dims), vals_out nred doubles
+ * (both host).  *nred is always set; nothing is written when cap < *nred or an output pointer is NULL (size query).
+ * Values are accumulated with fp64 atomics: equal to the reference's sequential sums up to summation order. */
+int ncme_space_marginal(ncme_space* space, const double* p_dev, int ndims, const int32_t* dims, int64_t cap, int64_t* nred,
+                        int64_t* states_out, double* vals_out);
 
 /* ---------------------------------------------------------------- FspMatrixSparse ------------ */
 /* FspMatrixSparse{Float64}(space, propensities; parameters)   src/fspmatrix/sparse/fspsparsematrix.jl:47-108
@@ -257,7 +265,7 @@ typedef struct ncme_solve_opts {
     int64_t max_steps;    /* 0 = 10^8 */
     int method;           /* 0 = Dormand-Prince 5(4) explicit; 1 = BDF/GMRES (see ncme_solve_segment docs): one fused
                            * kernel per step attempt for unsharded matrices up to NCME_BDF_FUSED_MAX_ROWS (env,
-                           * default 3e6) rows, launch-per-operation otherwise; 2 / 3 force the latter / the former */
+                           * default 2e6) rows, launch-per-operation otherwise; 2 / 3 force the latter / the former */
 } ncme_solve_opts;
 
 typedef struct ncme_solve_stats {

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ncme_space_download_states": (cint, [p_void, i64, i64, p_i64]),
     "ncme_space_download_connectivity": (cint, [p_void, i64, i64, p_u32, p_u32]),
     "ncme_space_lookup": (cint, [p_void, i64, p_i64, p_u32]),
+    "ncme_space_marginal": (cint, [p_void, p_void, cint, p_i32, i64, p_i64, p_i64, p_f64]),
     "ncme_matrix_create": (cint, [p_void, p_i32, p_f64, C.POINTER(p_void)]),
     "ncme_matrix_destroy": (cint, [p_void]),
     "ncme_matrix_size": (cint, [p_void, p_i64, p_i64]),

@@ -138,6 +138,9 @@ struct Workspace {       // views into the context's grow-only caches
 
 int cache_reserve(double** p, size_t* have, size_t want, bool pinned) {
     if (*have >= want) return NCME_OK;
+    // grow-only with head-room: adaptive solves call this once per segment with a slightly larger state space each
+    // time, and cudaMallocHost / cudaMalloc + their frees cost more than a whole small segment
+    want = std::max<size_t>(want + std::min<size_t>(want / 2, (size_t)256 << 20), (size_t)4 << 20);
     if (*p) {
         if (pinned)
             cudaFreeHost(*p);
@@ -545,7 +548,7 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
         } else if (opts->method == 1 && bdf_fused_eligible(A)) {
             static const long long max_rows = [] {
                 const char* e = getenv("NCME_BDF_FUSED_MAX_ROWS");
-                return e ? atoll(e) : 3000000LL;
+                return e ? atoll(e) : 2000000LL;   // measured cross-over on B200 (tools/bdf_crossover.py)
             }();
             fused = (long long)A->n <= max_rows;
         }

@@ -389,6 +389,44 @@ __global__ void __launch_bounds__(XS_THREADS) k_expand_small(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------ marginals: sum(p, dims) on the device ----------
+// Reference: Base.sum(p::FspVectorSparse, dims) (src/fspvector/fspvector.jl:66-99): reduced states in order of first
+// occurrence, values accumulated in state order.  Device version: the reduced key of a state is its packed key with
+// the summed-out fields masked away; a temporary open-addressing table maps every reduced key to the smallest state
+// index carrying it (atomicMin), those first occurrences are stream-compacted in index order (= the reference's
+// order of the reduced states), then every state adds its probability to its bucket.
+__global__ void k_marg_insert(HashView h, const uint64_t* __restrict__ keys, int64_t n, uint64_t keepmask,
+                              uint32_t* __restrict__ slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i] & keepmask;
+    uint64_t slot = hash64(key) & h.capmask;
+    while (true) {
+        const uint64_t prev = atomicCAS((unsigned long long*)&h.keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+        if (prev == EMPTY_KEY || prev == key) {
+            atomicMin(&h.vals[slot], (uint32_t)i);
+            slot_of[i] = (uint32_t)slot;
+            return;
+        }
+        slot = (slot + 1) & h.capmask;
+    }
+}
+__global__ void k_marg_flags(HashView h, const uint32_t* __restrict__ slot_of, int64_t n, uint32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = h.vals[slot_of[i]] == (uint32_t)i ? 1u : 0u;
+}
+__global__ void k_marg_accumulate(HashView h, const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ flags,
+                                  const uint32_t* __restrict__ pos, const uint64_t* __restrict__ keys, uint64_t keepmask,
+                                  const double* __restrict__ p, int64_t n, uint64_t* __restrict__ rkeys,
+                                  double* __restrict__ rvals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t first = h.vals[slot_of[i]];
+    const uint32_t j = pos[first];
+    if (flags[i]) rkeys[j] = keys[i] & keepmask;
+    atomicAdd(&rvals[j], p[i]);
+}
+
 #define LAUNCH(ctx, kern, n, ...)                                          \
     do {                                                                   \
         if ((n) > 0) {                                                     \
@@ -1033,6 +1071,76 @@ int ncme_space_lookup(ncme_space* sp, int64_t m, const int64_t* states, uint32_t
     NCME_CUDA(cudaMemcpyAsync(idx_out, sp->cand_slot.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     NCME_CUDA(cudaStreamSynchronize(ctx->stream));
     return NCME_OK;
+}
+
+int ncme_space_marginal(ncme_space* sp, const double* p_dev, int ndims, const int32_t* dims, int64_t cap, int64_t* nred,
+                        int64_t* states_out, double* vals_out) {
+    NCME_REQUIRE(sp && p_dev && nred && ndims >= 1 && dims, "null argument");
+    uint32_t drop = 0;
+    for (int k = 0; k < ndims; ++k) {
+        NCME_REQUIRE(dims[k] >= 1 && dims[k] <= sp->ns, "Input dimensions must be between 1 and %d.", sp->ns);
+        drop |= 1u << (dims[k] - 1);
+    }
+    int keep[NCME_MAX_SPECIES], nkeep = 0;
+    uint64_t keepmask = 0;
+    for (int q = 0; q < sp->ns; ++q)
+        if (!(drop & (1u << q))) {
+            keep[nkeep++] = q;
+            keepmask |= sp->layout.mask[q] << sp->layout.shift[q];
+        }
+    const int64_t n = sp->n;
+    *nred = 0;
+    if (n == 0) return NCME_OK;
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t s = ctx->stream;
+    sp->last_delete_nold = -1;   // flags/pos scratch is reused
+    uint64_t tcap = 1024;
+    while (tcap < 2 * (uint64_t)n) tcap <<= 1;
+    DevArray<uint64_t> tk, rkeys;
+    DevArray<uint32_t> tv, slot_of;
+    DevArray<double> rvals;
+    NCME_TRY(tk.reserve(tcap, s, false));
+    NCME_TRY(tv.reserve(tcap, s, false));
+    NCME_TRY(slot_of.reserve((size_t)n, s, false));
+    NCME_TRY(sp->flags.reserve((size_t)n, s, false));
+    NCME_TRY(sp->pos.reserve((size_t)n, s, false));
+    NCME_TRY(sp->scan_scratch.reserve(scan_scratch_elems(n), s, false));
+    NCME_CUDA(cudaMemsetAsync(tk.p, 0xFF, tcap * sizeof(uint64_t), s));
+    NCME_CUDA(cudaMemsetAsync(tv.p, 0xFF, tcap * sizeof(uint32_t), s));
+    const HashView h{tk.p, tv.p, tcap - 1};
+    int rc = NCME_OK;
+    do {
+        k_marg_insert<<<nblk(n), 256, 0, s>>>(h, sp->keys.p, n, keepmask, slot_of.p);
+        k_marg_flags<<<nblk(n), 256, 0, s>>>(h, slot_of.p, n, sp->flags.p);
+        ctx->launches += 2;
+        uint64_t m = 0;
+        if ((rc = exclusive_scan_u32(ctx, sp->flags.p, sp->pos.p, n, sp->scan_scratch.p, sp->scan_scratch.cap, &m)) != NCME_OK) break;
+        *nred = (int64_t)m;
+        if (cap < (int64_t)m || !states_out || !vals_out) break;   // size query (or too small): count only
+        if ((rc = rkeys.reserve((size_t)m, s, false)) != NCME_OK) break;
+        if ((rc = rvals.reserve((size_t)m, s, false)) != NCME_OK) break;
+        cudaMemsetAsync(rvals.p, 0, (size_t)m * sizeof(double), s);
+        k_marg_accumulate<<<nblk(n), 256, 0, s>>>(h, slot_of.p, sp->flags.p, sp->pos.p, sp->keys.p, keepmask, p_dev, n, rkeys.p,
+                                                  rvals.p);
+        ctx->launches++;
+        std::vector<uint64_t> hk((size_t)m);
+        if (cudaMemcpyAsync(hk.data(), rkeys.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaMemcpyAsync(vals_out, rvals.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            set_error("marginal: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = NCME_ERR_CUDA;
+            break;
+        }
+        for (uint64_t j = 0; j < m; ++j)
+            for (int q = 0; q < nkeep; ++q)
+                states_out[(size_t)j * nkeep + q] = (int64_t)((hk[(size_t)j] >> sp->layout.shift[keep[q]]) & sp->layout.mask[keep[q]]);
+    } while (0);
+    tk.release();
+    tv.release();
+    slot_of.release();
+    rkeys.release();
+    rvals.release();
+    return rc;
 }
 
 }  // extern "C"

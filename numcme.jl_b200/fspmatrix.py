@@ -20,10 +20,53 @@ from .device import DeviceVector, device_ptr, is_device, vec_len
 from .statespace import StateSpaceSparse
 
 
+# probe times of the rank-1 (separability) test of joint time-varying propensities: irregular, spread over several
+# decades so that switch-like time factors are sampled on both sides when they switch inside [0, 1e4]
+_PROBE_TIMES = (0.0, 0.7310585786300049, 19.098300562505255, 738.90560989306495, 5459.8150033144236, 28813.3)
+
+
+def detect_rank1(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
+    """is the joint propensity ``f(t, x, p)`` a product ``c(t) g(x)`` on ``states``?
+    Evaluates f over all states at a few probe times; separable iff every evaluation is a scalar multiple of the first
+    non-vanishing one (same support, ratio constant to ``rtol``).  Returns ``(g, sentinels)`` -- the state factor
+    ``g = f(t_ref, .)`` and up to four state indices on which the time factor ``c(t) = f(t, x*, p) / g(x*)`` is
+    evaluated (the first) and cross-checked (the others) at run time -- or ``None``."""
+    n = states.shape[0]
+    if n == 0:
+        return None
+    g = None
+    for t in probe_times:
+        v = eval_over_states(f, states, parameters, t=t)
+        if not np.all(np.isfinite(v)):
+            return None
+        if g is None:
+            if np.any(v != 0.0):
+                g = v
+            continue
+        supp = g != 0.0
+        if np.any(v[~supp] != 0.0):
+            return None
+        ratio = v[supp] / g[supp]
+        if np.abs(ratio - ratio[0]).max() > rtol * max(abs(ratio[0]), 1e-300) and np.abs(ratio).max() > 0.0:
+            return None
+    if g is None:
+        return None            # vanishes at every probe time: leave it on the exact (joint) path
+    order = np.argsort(-np.abs(g), kind="stable")
+    nz = order[: int(np.count_nonzero(g))]
+    sent = [int(nz[0])] + [int(nz[k]) for k in (len(nz) // 3, 2 * len(nz) // 3, len(nz) - 1) if 0 < k < len(nz)]
+    return g, list(dict.fromkeys(sent))
+
+
 class FspMatrixSparse:
-    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=(), comm=None):
+    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=(), comm=None, detect_separable=True):
         """``comm`` (a parallel.Comm) restricts the matrix to this rank's row block (K8); vectors are then the
-        local slices ``[rows | R sinks]`` and matvec inputs need halo margins (see parallel.ShardedVector)."""
+        local slices ``[rows | R sinks]`` and matvec inputs need halo margins (see parallel.ShardedVector).
+
+        ``detect_separable``: joint time-varying propensities (what the Catalyst import produces,
+        catalyst_interface.jl:19-27) need n host closure calls and an upload per distinct ``t``
+        (``_update_sparsematrix!``, fspsparsematrix.jl:154-166).  When such a propensity is numerically a product
+        c(t) g(x) on the current states (``detect_rank1``) it is put on the separable path instead -- one host call per
+        right-hand side, nothing uploaded -- and cross-checked on sentinel states at every ``t``."""
         self.ctx = space.ctx
         self.comm = comm
         self.parameters = parameters
@@ -42,12 +85,27 @@ class FspMatrixSparse:
         self.timeinvariant_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "ti"]
         self.separabletv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "sep"]
         self.jointtv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "joint"]
+        # what the device matrix does with each reaction (differs from the user's classification above only for joint
+        # propensities found to be rank-1 separable)
+        self._tfactor = {}                 # 1-based reaction id -> callable t -> c(t)
+        self._rank1 = {}                   # 1-based reaction id -> (g, sentinel indices) of detected reactions
         propvals = np.zeros((self.nr, max(n, 1)), dtype=np.float64)
         for r, a in enumerate(self.propensities):
             if a.kind == "ti":
                 propvals[r, :n] = eval_over_states(a.f, self.states, parameters)
             elif a.kind == "sep":
                 propvals[r, :n] = eval_over_states(a.statefactor, self.states, parameters)
+                self._tfactor[r + 1] = (lambda t, a=a: float(a.tfactor(t, self.parameters)))
+            elif detect_separable:
+                found = detect_rank1(a.f, self.states, parameters)
+                if found is not None:
+                    g, sent = found
+                    propvals[r, :n] = g
+                    self.kinds[r] = SEPARABLE_TV
+                    self._rank1[r + 1] = (g, sent)
+                    self._tfactor[r + 1] = self._make_rank1_tfactor(r + 1, a.f, g, sent)
+        self.device_separable_ids = sorted(self._tfactor)
+        self.device_joint_ids = [r for r in self.jointtv_propensity_ids if r not in self._rank1]
         propvals = np.ascontiguousarray(propvals[:, :n]) if n else propvals
         h = L.p_void()
         L.check(L.load().ncme_matrix_create_sharded(space.handle, comm.handle if comm is not None else None,
@@ -96,18 +154,31 @@ class FspMatrixSparse:
     def set_tuning(self, rows_per_thread: int):
         L.check(L.load().ncme_matrix_set_tuning(self._h, int(rows_per_thread)))
 
+    def _make_rank1_tfactor(self, rid, f, g, sent):
+        xs = [[int(v) for v in self.states[i]] for i in sent]
+        gs = [float(g[i]) for i in sent]
+
+        def tfactor(t):
+            c = float(f(t, xs[0], self.parameters)) / gs[0]
+            for x, gv in zip(xs[1:], gs[1:]):          # sentinels: the product form must hold at every t actually used
+                ck = float(f(t, x, self.parameters)) / gv
+                if abs(ck - c) > 1e-9 * max(abs(c), abs(ck), 1e-300):
+                    raise L.NcmeError(f"propensity {rid} was classified as c(t) g(x) on the probe times but is not "
+                                      f"separable at t = {t!r}; build the matrix with detect_separable=False")
+            return c
+        return tfactor
+
     # -- time-dependent pieces evaluated on the host (they are opaque closures, as in the reference)
     def coefficients(self, t: float) -> np.ndarray:
-        th = self.parameters
-        for r in self.separabletv_propensity_ids:
-            self._coef[r - 1] = float(self.propensities[r - 1].tfactor(t, th))
+        for r in self.device_separable_ids:
+            self._coef[r - 1] = self._tfactor[r](t)
         return self._coef
 
     def _refresh_joint(self, t: float):
         if t == self.t_cache:
             return
         self.t_cache = t
-        for r in self.jointtv_propensity_ids:
+        for r in self.device_joint_ids:
             vals = eval_over_states(self.propensities[r - 1].f, self.states, self.parameters, t=t)
             L.check(L.load().ncme_matrix_set_joint_values(self._h, r, L.ptr(vals, C.c_double)))
 

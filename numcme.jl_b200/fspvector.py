@@ -56,18 +56,18 @@ class FspVectorSparse:
             raise ArgumentError(f"Input dimensions must be between 1 and {ns}.")
         keep = [k for k in range(ns) if (k + 1) not in dims]
         red = self.states[:, keep]
-        order = {}
-        rstates, rvals = [], []
-        for i in range(red.shape[0]):
-            key = tuple(int(v) for v in red[i])
-            j = order.get(key)
-            if j is None:
-                order[key] = len(rstates)
-                rstates.append(key)
-                rvals.append(self.values[i])
-            else:
-                rvals[j] += self.values[i]
-        return FspVectorSparse(np.asarray(rstates, dtype=np.int64).reshape(len(rstates), len(keep)), np.asarray(rvals))
+        m = red.shape[0]
+        if m == 0 or not keep:
+            tot = np.array([self.values.sum()]) if m else np.zeros(0)
+            return FspVectorSparse(np.zeros((tot.size, len(keep)), dtype=np.int64), tot)
+        # reduced states in order of first occurrence, values accumulated in state order (np.bincount adds its weights
+        # sequentially by index: the same sums, in the same order, as the reference's loop)
+        uniq, first, inv = np.unique(red, axis=0, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        vals = np.bincount(rank[np.asarray(inv).reshape(-1)], weights=self.values, minlength=order.size)
+        return FspVectorSparse(uniq[order], vals)
 
     def to_array(self):
         """Array(p)  (fspvector.jl:107-129)"""

@@ -24,7 +24,9 @@ from .statespace import StateSpaceSparse
 
 class ForwardSensFspMatrixSparse:
     def __init__(self, model: CmeModelWithSensitivity, space: StateSpaceSparse):
-        self.fspmatrix = A = FspMatrixSparse(space, get_propensities(model), parameters=get_parameters(model))
+        # the derivative entries below follow the user's classification of every reaction: no separability detection
+        self.fspmatrix = A = FspMatrixSparse(space, get_propensities(model), parameters=get_parameters(model),
+                                             detect_separable=False)
         self.ctx = A.ctx
         self.parameters = get_parameters(model)
         self.parameter_count = P = len(self.parameters)

@@ -80,10 +80,16 @@ class StateSpaceSparse:
     def get_states(self, first: int = 0, count: int | None = None) -> np.ndarray:
         """States as an (n x NS) int64 array in index order (insertion order, as the reference)."""
         n = self.get_state_count()
+        whole = first == 0 and (count is None or count == n)
+        if whole and self._states_cache is not None and self._states_cache_n == n:
+            return self._states_cache          # read-only view of the last download; invalidated by every mutation
         count = n - first if count is None else count
         out = np.empty((count, self.ns), dtype=np.int64)
         if count:
             L.check(L.load().ncme_space_download_states(self._h, first, count, L.ptr(out, C.c_int64)))
+        if whole:
+            out.setflags(write=False)
+            self._states_cache, self._states_cache_n = out, n
         return out
 
     @property
@@ -112,17 +118,45 @@ class StateSpaceSparse:
             L.check(L.load().ncme_space_lookup(self._h, q.shape[0], L.ptr(q, C.c_int64), L.ptr(out, C.c_uint32)))
         return out
 
+    def marginal(self, p_dev, dims):
+        """``sum(p, dims)`` (fspvector.jl:66-99) for a DEVICE-resident probability vector over this space: the reduction
+        runs on the GPU (temporary hash table + compaction + fp64 atomics), only the reduced states and values come
+        back.  ``dims`` are the 1-based species summed out.  Returns an FspVectorSparse over the kept species."""
+        from .device import device_ptr, vec_len
+        from .fspvector import FspVectorSparse
+        n = self.get_state_count()
+        if vec_len(p_dev) < n:
+            raise L.ArgumentError("State and value lists must have equal lengths.")
+        dims = sorted(set(int(d) for d in dims))
+        if not dims or not (dims[0] >= 1 and dims[-1] <= self.ns):
+            raise L.ArgumentError(f"Input dimensions must be between 1 and {self.ns}.")
+        d = np.ascontiguousarray(dims, dtype=np.int32)
+        nkeep = self.ns - len(dims)
+        nred = C.c_int64()
+        ptr = C.c_void_p(device_ptr(p_dev))
+        L.check(L.load().ncme_space_marginal(self._h, ptr, d.size, L.ptr(d, C.c_int32), 0, C.byref(nred), None, None))
+        m = nred.value
+        st = np.zeros((m, max(nkeep, 0)), dtype=np.int64)
+        vals = np.zeros(m, dtype=np.float64)
+        if m:
+            L.check(L.load().ncme_space_marginal(self._h, ptr, d.size, L.ptr(d, C.c_int32), m, C.byref(nred),
+                                                 L.ptr(st, C.c_int64) if nkeep else L.ptr(np.zeros(1, dtype=np.int64), C.c_int64),
+                                                 L.ptr(vals, C.c_double)))
+        return FspVectorSparse(st, vals)
+
     def get_statedict(self) -> dict:
         """The reference's ``state2idx`` Dict, materialised on the host (debug / small spaces)."""
         return {tuple(int(v) for v in s): i + 1 for i, s in enumerate(self.get_states())}
 
     # -- mutation
     def expand_(self, expansionlevel: int, onlyreactions=()):
+        self._states_cache = None
         only = np.ascontiguousarray(list(onlyreactions), dtype=np.int32)
         L.check(L.load().ncme_space_expand(self._h, int(expansionlevel), only.size,
                                            L.ptr(only, C.c_int32) if only.size else None))
 
     def deleteat_(self, ids):
+        self._states_cache = None
         ids = np.ascontiguousarray(np.asarray(ids, dtype=np.int64).reshape(-1))
         if ids.size:
             L.check(L.load().ncme_space_delete(self._h, ids.size, L.ptr(ids, C.c_int64)))
@@ -131,6 +165,7 @@ class StateSpaceSparse:
         """The dropstates branch of adapt! on the device (rstepadapters.jl:40-46 / :93-99): deletes the
         ``dropcount`` least probable states; returns dropcount.  Follow with ``compact_vector``."""
         from .device import device_ptr
+        self._states_cache = None
         dc = C.c_int64()
         L.check(L.load().ncme_space_prune_by_mass(self._h, C.c_void_p(device_ptr(p_dev)), float(threshold),
                                                   1 if strict else 0, C.byref(dc)))

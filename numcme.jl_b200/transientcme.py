@@ -46,7 +46,7 @@ class NativeBDFClassic(NativeBDF):
 
 
 class NativeBDFFused(NativeBDF):
-    """method 3: force the one-kernel-per-step BDF of csrc/bdf_fused.cu (the default below ~3e6 states on one GPU)."""
+    """method 3: force the one-kernel-per-step BDF of csrc/bdf_fused.cu (the default below ~2e6 states on one GPU)."""
     method = 3
 
 
@@ -127,7 +127,7 @@ class _Segment:
         def coef_cb(t, coef_ptr, _user):
             c = A.coefficients(t)
             A._refresh_joint(t)
-            for r in A.separabletv_propensity_ids:
+            for r in A.device_separable_ids:
                 coef_ptr[r - 1] = c[r - 1]
 
         def save_cb(t, u_ptr, _user):
@@ -136,7 +136,7 @@ class _Segment:
 
         self._coef_cb = L.COEF_FN(coef_cb)
         self._save_cb = L.SAVE_FN(save_cb)
-        self.needs_coef = bool(A.separabletv_propensity_ids or A.jointtv_propensity_ids)
+        self.needs_coef = bool(A.device_separable_ids or A.device_joint_ids)
 
     def run(self, u: DeviceVector, t0, t1, saveat=None, save_every_step=False, event_slope=None):
         opts = L.SolveOpts()

@@ -27,12 +27,16 @@ def _to_pkg_props(pkg, oprops):
     return out
 
 
-@pytest.mark.parametrize("kind", ["ti", "tv", "tvj"])
+@pytest.mark.parametrize("kind", ["ti", "tv", "tvj", "tvj-exact"])
 def test_fspmat_jl_on_gpu(pkg, kind):  # test/test_fspmat.jl:41-68
     sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])
     sp.expand_(2)
+    detect = kind != "tvj-exact"      # "tvj": the joint propensity is found to be c(t) g(x); "-exact": _update_sparsematrix! path
+    kind = kind.split("-")[0]
     props = fspmat_propensities(kind)
-    A = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, props), parameters=FSPMAT_THETA)
+    A = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, props), parameters=FSPMAT_THETA, detect_separable=detect)
+    if kind == "tvj":
+        assert (A.device_joint_ids == []) == detect and A.jointtv_propensity_ids == [2]
     assert A.size(1) == sp.get_state_count() + sp.get_sink_count() == A.size(2)
     osp = StateSpaceOracle(TELEGRAPH_S, [1, 0, 0])
     osp.expand(2)
@@ -53,10 +57,13 @@ def test_separable_equals_joint(pkg):  # test/test_fspmat.jl:68
     sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])
     sp.expand_(2)
     A1 = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, fspmat_propensities("tv")), parameters=FSPMAT_THETA)
-    A2 = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, fspmat_propensities("tvj")), parameters=FSPMAT_THETA)
     v = np.ones(A1.size(1))
-    for t in (1.0, 0.0):
-        assert np.linalg.norm(pkg.matvec(t, A1, v) - pkg.matvec(t, A2, v)) <= 1e-15
+    for detect in (True, False):
+        A2 = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, fspmat_propensities("tvj")), parameters=FSPMAT_THETA,
+                                 detect_separable=detect)
+        for t in (1.0, 0.0):
+            assert np.linalg.norm(pkg.matvec(t, A1, v) - pkg.matvec(t, A2, v)) <= 1e-15
+        assert np.linalg.norm(pkg.matvec(0.0, A1, v) - pkg.matvec(0.0, A2, v)) == 0.0    # the reference asserts `≈ 0`
 
 
 @pytest.mark.parametrize("rows", [0, 1, 2, 4, 16, 17, 18, 20, 32, 64])   # +16: byte-compressed indices; +32/+64: smem-pipelined kernel
@@ -103,12 +110,35 @@ def test_joint_toggle(pkg):
     sp = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
     sp.expand_(40)
     mj, ms = pkg.workloads.toggle_model(separable=False), pkg.workloads.toggle_model(separable=True)
-    Aj = pkg.FspMatrixSparse(sp, mj.propensities, parameters=mj.parameters)
     As = pkg.FspMatrixSparse(sp, ms.propensities, parameters=ms.parameters)
     rng = np.random.default_rng(2)
-    v = rng.random(Aj.size(1))
-    for t in (0.0, 3600.0, 3601.0, 7000.0):
-        assert _relerr(pkg.matvec(t, Aj, v), pkg.matvec(t, As, v)) <= RTOL
+    v = rng.random(As.size(1))
+    for detect in (False, True):
+        Aj = pkg.FspMatrixSparse(sp, mj.propensities, parameters=mj.parameters, detect_separable=detect)
+        assert (Aj.device_joint_ids == []) == detect
+        for t in (0.0, 3600.0, 3601.0, 7000.0):
+            assert _relerr(pkg.matvec(t, Aj, v), pkg.matvec(t, As, v)) <= RTOL
+
+
+def test_rank1_detection(pkg):
+    """joint propensities that are numerically c(t) g(x) go to the separable path; genuinely
+    joint ones stay exact; a propensity that only looks separable on the probe times is caught by the sentinel states."""
+    import math
+    sp = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
+    sp.expand_(30)
+    base = pkg.workloads.toggle_model(separable=True)
+    nonsep = pkg.propensity(lambda t, x, p: 1e-3 * x[1] * (1.0 + np.sin(0.01 * t * (1.0 + x[0]))))
+    fake = pkg.propensity(lambda t, x, p: 1e-3 * x[1] * (1.0 + (1.0 if t == 5.0 else 0.0) * x[0]))
+    A = pkg.FspMatrixSparse(sp, base.propensities[:3] + [nonsep], parameters=base.parameters)
+    assert A.device_joint_ids == [4]
+    Ax = pkg.FspMatrixSparse(sp, base.propensities[:3] + [nonsep], parameters=base.parameters, detect_separable=False)
+    v = np.random.default_rng(4).random(A.size(1))
+    assert np.array_equal(pkg.matvec(12.5, A, v), pkg.matvec(12.5, Ax, v))
+    F = pkg.FspMatrixSparse(sp, base.propensities[:3] + [fake], parameters=base.parameters)
+    assert F.device_joint_ids == []                     # looks separable on the probe times ...
+    pkg.matvec(4.0, F, v)
+    with pytest.raises(pkg.NcmeError):                  # ... but the sentinels notice at the time where it is not
+        pkg.matvec(5.0, F, v)
 
 
 def test_m2d_100k_vs_oracle(pkg):
