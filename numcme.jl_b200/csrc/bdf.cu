@@ -459,7 +459,14 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     for (int k = 0; k <= MAX_ORDER; ++k) error_const[k] = kappa[k] * gamma[k] + 1.0 / (k + 1);
     error_const[MAX_ORDER + 1] = 1.0 / (MAX_ORDER + 2);
 
+    const bool host_reduce = comm_hostreduce_available(comm);
     auto fetch = [&](size_t count) -> int {   // reduced scalars -> pinned host
+        if (host_reduce && count <= (size_t)NCME_HOSTREDUCE_MAX) {
+            // sharded: this rank's partial sums go to the host, the ranks combine them through shared memory
+            NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
+            NCME_CUDA(cudaStreamSynchronize(s));
+            return comm_hostreduce_sum(comm, ctx->red_result_host, count);
+        }
         NCME_TRY(comm_allreduce_sum(comm, ctx->red_result_dev, count, s));
         NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
         NCME_CUDA(cudaStreamSynchronize(s));

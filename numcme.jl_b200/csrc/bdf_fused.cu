@@ -18,6 +18,7 @@
 // Replaces, like bdf.cu: DE.init / DE.step! with CVODE_BDF(linear_solver=:GMRES) (src/transientcme/sparse/fspsolve.jl:158-161).
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -39,6 +40,7 @@ constexpr int MAXO = 5;               // maximum BDF order
 constexpr int GM = 24;                // Krylov dimension before restart
 constexpr int NSLOT = GM + 2;         // widest reduction (k+1 inner products + <w,w>)
 constexpr int MAXR = NCME_MAX_REACTIONS;
+constexpr int SMEM_MAX_BYTES = 216 * 1024;   // dynamic shared memory of the SMEMV variant (+ ~10 KB static)
 
 struct StepResult {                   // written by CTA 0 straight into pinned (device-mapped) host memory
     double error_sumsq;               // sum over ALL entries (states + sinks) of (d / (atol + rtol |ynew|))^2
@@ -144,6 +146,11 @@ __device__ __forceinline__ void reduce_all(double (&v)[NV], int nv, const StepAr
     __syncthreads();
 }
 
+struct Vecs {   // where the per-step work vectors live (global workspace or shared memory)
+    double *ypred, *ynew, *z, *psi, *scale, *ps, *w, *d, *V;
+    int64_t vs;   // stride between Krylov vectors
+};
+
 // (A x)_i and diag(A)_i for one state row
 __device__ __forceinline__ double row_apply(const StepArgs& a, const double* x, int64_t i, double& jd) {
     double acc = 0.0;
@@ -210,53 +217,57 @@ __device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Sh
 // Krylov iteration k: w = (z - c A z) ps, inner products with V_0..V_k (KB = k+1 rounded up to a multiple of 4; the
 // surplus products are garbage-free duplicates of V_0 and ignored), <w,w> in slot KB.
 template <int KB, bool MULTI>
-__device__ __forceinline__ void krylov_apply(const StepArgs& a, int k, int& parity, Shared& sh) {
-    double v[KB + 1];
+__device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, int k, int& parity, Shared& sh) {
+    double acc[KB + 1];
 #pragma unroll
-    for (int s = 0; s <= KB; ++s) v[s] = 0.0;
+    for (int s = 0; s <= KB; ++s) acc[s] = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * FBT + threadIdx.x; i < a.n; i += (int64_t)a.G * FBT) {
         double jd;
-        const double Az = row_apply(a, a.z, i, jd);
-        const double w = (a.z[i] - a.c * Az) * a.ps[i];
-        a.w[i] = w;
+        const double Az = row_apply(a, v.z, i, jd);
+        const double w = (v.z[i] - a.c * Az) * v.ps[i];
+        v.w[i] = w;
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-            const double vj = a.V[(size_t)(j <= k ? j : 0) * a.stride + i];
-            v[j] = fma(w, vj, v[j]);
+            const double vj = v.V[(size_t)(j <= k ? j : 0) * v.vs + i];
+            acc[j] = fma(w, vj, acc[j]);
         }
-        v[KB] = fma(w, w, v[KB]);
+        acc[KB] = fma(w, w, acc[KB]);
     }
-    reduce_all<KB + 1, MULTI>(v, KB + 1, a, parity, sh);
-    // results: sh.res[0..k] = h_j, sh.res[KB] = <w,w>
+    reduce_all<KB + 1, MULTI>(acc, KB + 1, a, parity, sh);
+    // results: sh.res[0..k] = h_j, sh.res[KB] = <w,w>.  Thread 0 runs the Hessenberg/Givens recurrence: a serial chain, so
+    // the rotation coefficients are prefetched, and sqrt/one reciprocal replace hypot and the divisions
     if (threadIdx.x == 0) {
-        double ww = sh.res[KB], hsq = 0.0;
+        const double ww = sh.res[KB];
+        double hsq = 0.0;
         for (int j = 0; j <= k; ++j) {
-            sh.hcol[j] = sh.res[j];
-            sh.H[j][k] = sh.res[j];
-            hsq += sh.res[j] * sh.res[j];
+            const double hj = sh.res[j];
+            sh.hcol[j] = hj;
+            hsq = fma(hj, hj, hsq);
         }
         double hk1sq = ww - hsq;   // |w - sum h_j v_j|^2 by Pythagoras
         if (!(hk1sq > 0.0)) hk1sq = 0.0;
         const double hk1 = sqrt(hk1sq);
-        sh.H[k + 1][k] = hk1;
+        double hj = sh.res[0];     // running H[j][k] under the previous rotations
         for (int j = 0; j < k; ++j) {
-            const double tmp = sh.cs[j] * sh.H[j][k] + sh.sn[j] * sh.H[j + 1][k];
-            sh.H[j + 1][k] = -sh.sn[j] * sh.H[j][k] + sh.cs[j] * sh.H[j + 1][k];
-            sh.H[j][k] = tmp;
+            const double c = sh.cs[j], sn = sh.sn[j], hn = sh.res[j + 1];
+            sh.H[j][k] = fma(c, hj, sn * hn);
+            hj = fma(-sn, hj, c * hn);
         }
-        const double den = hypot(sh.H[k][k], sh.H[k + 1][k]);
-        if (!(den > 0.0) || !(ww == ww)) {
+        const double den = sqrt(fma(hj, hj, hk1sq));
+        if (!(den > 0.0) || !(ww == ww) || !(den < 1e300)) {
             sh.ok = 0;
             sh.stop = 1;
         } else {
-            sh.cs[k] = sh.H[k][k] / den;
-            sh.sn[k] = sh.H[k + 1][k] / den;
+            const double rden = 1.0 / den;
+            const double c = hj * rden, sn = hk1 * rden;
+            sh.cs[k] = c;
+            sh.sn[k] = sn;
             sh.H[k][k] = den;
-            sh.H[k + 1][k] = 0.0;
-            sh.g[k + 1] = -sh.sn[k] * sh.g[k];
-            sh.g[k] = sh.cs[k] * sh.g[k];
-            sh.resid = fabs(sh.g[k + 1]);
-            const bool happy = hk1 <= 1e-14 * sqrt(fmax(ww, 1e-300));
+            const double gk = sh.g[k];
+            sh.g[k + 1] = -sn * gk;
+            sh.g[k] = c * gk;
+            sh.resid = fabs(sn * gk);
+            const bool happy = hk1sq <= 1e-28 * fmax(ww, 1e-300);
             sh.stop = (sh.resid / a.sqrtn <= a.lin_tol || happy || k + 1 == GM) ? 1 : 0;
             sh.inv_hk1 = hk1 > 0.0 ? 1.0 / hk1 : 0.0;
         }
@@ -264,9 +275,29 @@ __device__ __forceinline__ void krylov_apply(const StepArgs& a, int k, int& pari
     __syncthreads();
 }
 
-template <bool MULTI>
+template <bool MULTI, bool SMEMV>
 __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepArgs a) {
     __shared__ Shared sh;
+    extern __shared__ __align__(16) double dyn_smem[];
+    Vecs v;
+    if (SMEMV) {
+        const int64_t vs = (a.N + 7) / 8 * 8;
+        double* q = dyn_smem;
+        v.ypred = q; q += vs;
+        v.ynew = q; q += vs;
+        v.z = q; q += vs;
+        v.psi = q; q += vs;
+        v.scale = q; q += vs;
+        v.ps = q; q += vs;
+        v.w = q; q += vs;
+        v.d = q; q += vs;
+        v.V = q;
+        v.vs = vs;
+    } else {
+        v.ypred = a.ypred; v.ynew = a.ynew; v.z = a.z; v.psi = a.psi; v.scale = a.scale; v.ps = a.ps; v.w = a.w; v.d = a.d;
+        v.V = a.V;
+        v.vs = a.stride;
+    }
     int parity = 0;
     const int64_t gtid = (int64_t)blockIdx.x * FBT + threadIdx.x, gstride = (int64_t)a.G * FBT;
     const int order = a.order;
@@ -302,8 +333,8 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
                 y += in[j];
                 p = fma(a.gamma[j], in[j], p);
             }
-        a.ypred[i] = y;
-        a.psi[i] = p * a.inv_alpha;
+        v.ypred[i] = y;
+        v.psi[i] = p * a.inv_alpha;
     }
     if (blockIdx.x == 0 && (int)threadIdx.x < a.R) a.res->sink_old0[threadIdx.x] = D[a.n + threadIdx.x];
     grid_barrier<MULTI>();
@@ -312,13 +343,13 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
     double v1[1] = {0.0};
     for (int64_t i = gtid; i < a.n; i += gstride) {
         double jd;
-        const double Ay = row_apply(a, a.ypred, i, jd);
-        const double sc = a.atol + a.rtol * fabs(a.ypred[i]);
+        const double Ay = row_apply(a, v.ypred, i, jd);
+        const double sc = a.atol + a.rtol * fabs(v.ypred[i]);
         const double p = 1.0 / ((1.0 - a.c * jd) * sc);
-        const double w = (a.c * Ay - a.psi[i]) * p;
-        a.scale[i] = sc;
-        a.ps[i] = p;
-        a.w[i] = w;
+        const double w = (a.c * Ay - v.psi[i]) * p;
+        v.scale[i] = sc;
+        v.ps[i] = p;
+        v.w[i] = w;
         v1[0] = fma(w, w, v1[0]);
     }
     rhs_evals++;
@@ -333,10 +364,10 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         // right-hand side already negligible: d = 0
         double v2[2] = {0.0, 0.0};
         for (int64_t i = gtid; i < a.n; i += gstride) {
-            a.d[i] = 0.0;
-            const double yn = a.ypred[i];
-            a.ynew[i] = yn;
-            v2[0] += a.psi[i];
+            v.d[i] = 0.0;
+            const double yn = v.ypred[i];
+            v.ynew[i] = yn;
+            v2[0] += v.psi[i];
             v2[1] += fabs(yn);
         }
         reduce_all<2, MULTI>(v2, 2, a, parity, sh);
@@ -356,9 +387,9 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
             {
                 const double inv = 1.0 / beta;
                 for (int64_t i = gtid; i < a.n; i += gstride) {
-                    const double x = a.w[i] * inv;
-                    a.V[i] = x;
-                    a.z[i] = x * a.scale[i];
+                    const double x = v.w[i] * inv;
+                    v.V[i] = x;
+                    v.z[i] = x * v.scale[i];
                 }
             }
             grid_barrier<MULTI>();
@@ -367,12 +398,12 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
                 // ---- P3: fused matvec + Gram-Schmidt inner products + Givens update
                 const int kb = ((k + 1 + 3) / 4) * 4;
                 switch (kb) {
-                    case 4: krylov_apply<4, MULTI>(a, k, parity, sh); break;
-                    case 8: krylov_apply<8, MULTI>(a, k, parity, sh); break;
-                    case 12: krylov_apply<12, MULTI>(a, k, parity, sh); break;
-                    case 16: krylov_apply<16, MULTI>(a, k, parity, sh); break;
-                    case 20: krylov_apply<20, MULTI>(a, k, parity, sh); break;
-                    default: krylov_apply<24, MULTI>(a, k, parity, sh); break;
+                    case 4: krylov_apply<4, MULTI>(a, v, k, parity, sh); break;
+                    case 8: krylov_apply<8, MULTI>(a, v, k, parity, sh); break;
+                    case 12: krylov_apply<12, MULTI>(a, v, k, parity, sh); break;
+                    case 16: krylov_apply<16, MULTI>(a, v, k, parity, sh); break;
+                    case 20: krylov_apply<20, MULTI>(a, v, k, parity, sh); break;
+                    default: krylov_apply<24, MULTI>(a, v, k, parity, sh); break;
                 }
                 rhs_evals++;
                 kiters++;
@@ -384,11 +415,11 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
                 {
                     const double inv = sh.inv_hk1;
                     for (int64_t i = gtid; i < a.n; i += gstride) {
-                        double x = a.w[i];
-                        for (int j = 0; j <= k; ++j) x = fma(-sh.hcol[j], a.V[(size_t)j * st + i], x);
+                        double x = v.w[i];
+                        for (int j = 0; j <= k; ++j) x = fma(-sh.hcol[j], v.V[(size_t)j * v.vs + i], x);
                         x *= inv;
-                        a.V[(size_t)(k + 1) * st + i] = x;
-                        a.z[i] = x * a.scale[i];
+                        v.V[(size_t)(k + 1) * v.vs + i] = x;
+                        v.z[i] = x * v.scale[i];
                     }
                 }
                 grid_barrier<MULTI>();
@@ -410,13 +441,13 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
             double v2[2] = {0.0, 0.0};
             for (int64_t i = gtid; i < a.n; i += gstride) {
                 double x = 0.0;
-                for (int j = 0; j < k; ++j) x = fma(sh.y[j], a.V[(size_t)j * st + i], x);
-                x *= a.scale[i];
-                if (have_d) x += a.d[i];
-                a.d[i] = x;
-                const double yn = a.ypred[i] + x;
-                a.ynew[i] = yn;
-                v2[0] += x + a.psi[i];
+                for (int j = 0; j < k; ++j) x = fma(sh.y[j], v.V[(size_t)j * v.vs + i], x);
+                x *= v.scale[i];
+                if (have_d) x += v.d[i];
+                v.d[i] = x;
+                const double yn = v.ypred[i] + x;
+                v.ynew[i] = yn;
+                v2[0] += x + v.psi[i];
                 v2[1] += fabs(yn);
             }
             have_d = true;
@@ -432,9 +463,9 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
             double v3[1] = {0.0};
             for (int64_t i = gtid; i < a.n; i += gstride) {
                 double jd;
-                const double Ay = row_apply(a, a.ynew, i, jd);
-                const double w = (a.c * Ay - a.psi[i] - a.d[i]) * a.ps[i];
-                a.w[i] = w;
+                const double Ay = row_apply(a, v.ynew, i, jd);
+                const double w = (a.c * Ay - v.psi[i] - v.d[i]) * v.ps[i];
+                v.w[i] = w;
                 v3[0] = fma(w, w, v3[0]);
             }
             rhs_evals++;
@@ -466,7 +497,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
     // 1^T A = 0, so an exact step has sum_all(d + psi) = 0; the defect is removed by the relative rescaling
     // d_i -= defect |ynew_i| / sum|ynew| (see bdf.cu).  The sink rows are linear in ynew: S(ynew + delta) follows from
     // S(ynew) and S(|ynew|) without a second pass.
-    sink_rows<MULTI>(a, a.ynew, sh);
+    sink_rows<MULTI>(a, v.ynew, sh);
     double ms2 = 0.0;
     for (int r = 0; r < a.R; ++r) ms2 += a.c * __ldcg(a.sinkbuf + r);
     const double defect = ms0 + ms2;
@@ -475,13 +506,13 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
     // ---- P7: apply the projection to the state rows, local error test
     double v4[1] = {0.0};
     for (int64_t i = gtid; i < a.n; i += gstride) {
-        double dd = a.d[i], yn = a.ynew[i];
+        double dd = v.d[i], yn = v.ynew[i];
         if (fix) {
             const double delta = fixfac * fabs(yn);
             dd += delta;
             yn += delta;
-            a.d[i] = dd;
-            a.ynew[i] = yn;
+            v.d[i] = dd;
+            v.ynew[i] = yn;
         }
         const double q = dd / (a.atol + a.rtol * fabs(yn));
         v4[0] = fma(q, q, v4[0]);
@@ -489,12 +520,12 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
     if ((int)threadIdx.x < a.R) {   // every CTA keeps the sink increments (needed for the update of rows n..n+R)
         const int r = threadIdx.x;
         const double S = __ldcg(a.sinkbuf + r) + fixfac * __ldcg(a.sinkbuf + MAXR + r);
-        sh.sink_d[r] = a.c * S - a.psi[a.n + r];
+        sh.sink_d[r] = a.c * S - v.psi[a.n + r];
     }
     reduce_all<1, MULTI>(v4, 1, a, parity, sh);
     double sumsq = sh.res[0];
     for (int r = 0; r < a.R; ++r) {
-        const double ds = sh.sink_d[r], yn = a.ypred[a.n + r] + ds;
+        const double ds = sh.sink_d[r], yn = v.ypred[a.n + r] + ds;
         const double q = ds / (a.atol + a.rtol * fabs(yn));
         sumsq += q * q;
     }
@@ -506,7 +537,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         // ---- P8: D_{k+2} = d - D_{k+1}; D_{k+1} = d; D_j += D_{j+1} (j = k..0); order-selection norms of the new D
         double v5[2] = {0.0, 0.0};
         for (int64_t i = gtid; i < a.N; i += gstride) {
-            const double dd = i < a.n ? a.d[i] : sh.sink_d[i - a.n];
+            const double dd = i < a.n ? v.d[i] : sh.sink_d[i - a.n];
             const double dp = dd - D[(size_t)(order + 1) * st + i];
             D[(size_t)(order + 2) * st + i] = dp;
             D[(size_t)(order + 1) * st + i] = dd;
@@ -632,11 +663,15 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     static int occ_cached = 0;
     if (!occ_cached) {
         int occ = 0;
-        NCME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bdf_step<true>, FBT, 0));
+        NCME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bdf_step<true, false>, FBT, 0));
         occ_cached = std::max(1, occ);
+        NCME_CUDA(cudaFuncSetAttribute(k_bdf_step<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_BYTES));
     }
     const int maxG = std::min(occ_cached, 2) * ctx->sm_count;
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>(maxG, (n + (int64_t)FBT * 2 - 1) / ((int64_t)FBT * 2)));
+    // tiny systems: work vectors + Krylov basis in shared memory (8 + GM + 1 vectors of round_up(N, 8) doubles)
+    const size_t smem_need = (size_t)(8 + GM + 1) * (size_t)((N + 7) / 8 * 8) * sizeof(double);
+    const size_t smem_bytes = (G == 1 && smem_need <= (size_t)SMEM_MAX_BYTES && !getenv("NCME_BDF_NO_SMEM")) ? smem_need : 0;
 
     // ---- workspace
     const size_t stride = round_up<size_t>((size_t)N, 32);
@@ -831,11 +866,13 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
         sa.c = c;
         sa.err_const = error_const[order];
         sa.seq = ++seq;
-        if (G == 1) {
-            k_bdf_step<false><<<1, FBT, 0, s>>>(sa);
+        if (smem_bytes) {
+            k_bdf_step<false, true><<<1, FBT, smem_bytes, s>>>(sa);
+        } else if (G == 1) {
+            k_bdf_step<false, false><<<1, FBT, 0, s>>>(sa);
         } else {
             void* kargs[1] = {(void*)&sa};
-            NCME_CUDA(cudaLaunchCooperativeKernel((const void*)k_bdf_step<true>, dim3(G), dim3(FBT), kargs, 0, s));
+            NCME_CUDA(cudaLaunchCooperativeKernel((const void*)k_bdf_step<true, false>, dim3(G), dim3(FBT), kargs, 0, s));
         }
         ctx->launches++;
         NCME_CUDA(cudaGetLastError());

@@ -3,7 +3,13 @@
 #include "comm.cuh"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <atomic>
 
 namespace ncme {
 
@@ -206,6 +212,102 @@ const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q)
     return nullptr;
 }
 
+// ---- host-side scalar all-reduce over POSIX shared memory -------------------------------------------------------
+}  // namespace ncme
+struct HostReduce {
+    struct alignas(128) Slot {
+        std::atomic<unsigned long long> seq;
+        double vals[NCME_HOSTREDUCE_MAX];
+    };
+    Slot slot[2][NCME_MAX_RANKS];   // double-buffered: a rank can be at most one reduction ahead of the slowest one
+};
+namespace ncme {
+
+static int comm_setup_hostreduce(ncme_comm* c) {
+    c->hr = nullptr;
+    if (c->nranks == 1 || c->nranks > NCME_MAX_RANKS || getenv("NCME_NO_HOSTREDUCE")) return NCME_OK;
+    struct {
+        char name[64];
+        char host[64];
+    } mine;
+    memset(&mine, 0, sizeof(mine));
+    gethostname(mine.host, sizeof(mine.host) - 1);
+    if (c->rank == 0) snprintf(mine.name, sizeof(mine.name), "/ncme_hr_%d_%p", (int)getpid(), (void*)c);
+    std::vector<char> all;
+    NCME_TRY(allgather_bytes(c, &mine, sizeof(mine), &all));
+    const decltype(mine)* g = (const decltype(mine)*)all.data();
+    bool same_host = true;
+    for (int q = 0; q < c->nranks; ++q) same_host &= strncmp(g[q].host, g[0].host, sizeof(mine.host)) == 0;
+    HostReduce* hr = nullptr;
+    int fd = -1;
+    if (same_host) {
+        if (c->rank == 0) {
+            fd = shm_open(g[0].name, O_CREAT | O_EXCL | O_RDWR, 0600);
+            if (fd >= 0 && ftruncate(fd, sizeof(HostReduce)) != 0) {
+                close(fd);
+                fd = -1;
+            }
+        }
+    }
+    // barrier 1: the segment exists (or not) before the others open it
+    double v = (c->rank == 0 && same_host && fd < 0) ? 1.0 : 0.0;
+    NCME_CUDA(cudaMemcpyAsync(c->scratch, &v, sizeof(double), cudaMemcpyHostToDevice, c->ctx->stream));
+    NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, c->ctx->stream));
+    NCME_CUDA(cudaMemcpyAsync(&v, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    bool ok = same_host && v == 0.0;
+    if (ok && c->rank != 0) fd = shm_open(g[0].name, O_RDWR, 0600);
+    if (ok && fd >= 0) {
+        void* m = mmap(nullptr, sizeof(HostReduce), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m != MAP_FAILED) hr = (HostReduce*)m;   // a fresh segment is zero-filled: every seq starts at 0
+    }
+    if (fd >= 0) close(fd);
+    // barrier 2: everybody mapped it (or the feature is off everywhere); then the name can go
+    v = (ok && hr) ? 0.0 : 1.0;
+    NCME_CUDA(cudaMemcpyAsync(c->scratch, &v, sizeof(double), cudaMemcpyHostToDevice, c->ctx->stream));
+    NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, c->ctx->stream));
+    NCME_CUDA(cudaMemcpyAsync(&v, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    if (c->rank == 0 && same_host) shm_unlink(g[0].name);
+    if (v != 0.0) {
+        if (hr) munmap(hr, sizeof(HostReduce));
+        hr = nullptr;
+    }
+    c->hr = hr;
+    c->hr_epoch = 0;
+    return NCME_OK;
+}
+
+bool comm_hostreduce_available(const ncme_comm* c) { return c && c->nranks > 1 && c->hr != nullptr; }
+
+int comm_hostreduce_sum(ncme_comm* c, double* vals, size_t count) {
+    if (!c || c->nranks == 1 || count == 0) return NCME_OK;
+    NCME_REQUIRE(c->hr && count <= (size_t)NCME_HOSTREDUCE_MAX, "host reduce unavailable or too many values");
+    const unsigned long long e = ++c->hr_epoch;
+    HostReduce::Slot* buf = c->hr->slot[e & 1];
+    HostReduce::Slot& me = buf[c->rank];
+    memcpy(me.vals, vals, count * sizeof(double));
+    me.seq.store(e, std::memory_order_release);
+    double acc[NCME_HOSTREDUCE_MAX];
+    for (size_t k = 0; k < count; ++k) acc[k] = 0.0;
+    for (int q = 0; q < c->nranks; ++q) {
+        unsigned long long spins = 0;
+        while (buf[q].seq.load(std::memory_order_acquire) != e) {
+            if (++spins > (1ull << 34)) {   // ~ a minute of spinning: a rank died
+                set_error("host all-reduce: rank %d never arrived (epoch %llu)", q, e);
+                return NCME_ERR_COMM;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        for (size_t k = 0; k < count; ++k) acc[k] += buf[q].vals[k];   // rank order: identical bits on every rank
+    }
+    memcpy(vals, acc, count * sizeof(double));
+    c->hr_reduces++;
+    return NCME_OK;
+}
+
 // Flags: every rank exports its PeerFlags block and maps everybody else's.
 static int comm_setup_p2p(ncme_comm* c) {
     c->p2p_ok = false;
@@ -276,6 +378,7 @@ int ncme_comm_destroy(ncme_comm* c) {
     c->regs.clear();
     for (int q = 0; q < NCME_MAX_RANKS; ++q)
         if (c->peer_flags[q]) cudaIpcCloseMemHandle(c->peer_flags[q]);
+    if (c->hr) munmap(c->hr, sizeof(HostReduce));
     if (c->my_flags) cudaFree(c->my_flags);
     if (c->ws_base) cudaFree(c->ws_base);
     cudaGetLastError();
@@ -322,6 +425,7 @@ int ncme_comm_create(ncme_ctx* ctx, int rank, int nranks, const char* uid128, nc
             return NCME_ERR_COMM;
         }
         int st = comm_setup_p2p(c);
+        if (st == NCME_OK) st = comm_setup_hostreduce(c);
         if (st != NCME_OK) {
             ncme_comm_destroy(c);
             return st;

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 constexpr int NCME_MAX_RANKS = 64;
+constexpr int NCME_HOSTREDUCE_MAX = 320;   // doubles per host-side all-reduce (1 + 9 R sink tails, R <= 32)
 
 // Flags each rank exposes to its peers through CUDA IPC (peer GPUs store into them over NVLink).
 struct PeerFlags {
@@ -41,6 +42,10 @@ struct ncme_comm {
     unsigned int epoch = 0;
     std::vector<RegBuf> regs;
     int64_t p2p_matvecs = 0, nccl_matvecs = 0;
+    // host-side all-reduce of step-control scalars through POSIX shared memory (all ranks live on one node)
+    struct HostReduce* hr = nullptr;
+    unsigned long long hr_epoch = 0;
+    int64_t hr_reduces = 0;
     // grow-only integrator workspace, registered for peer access (re-allocation is a collective decision)
     double* ws_base = nullptr;
     size_t ws_bytes = 0;
@@ -84,6 +89,14 @@ int comm_workspace(ncme_comm* c, size_t bytes, int64_t local0, int64_t stride, i
                    double** out);
 // pointer to the local rows of the same vector on rank q, or nullptr if x_local is not inside a registered buffer
 const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q);
+
+// Sum over ranks of `count` (<= NCME_HOSTREDUCE_MAX) HOST doubles, in place, summed in rank order on every rank
+// (bitwise identical results everywhere).  The integrators' step-control scalars (error norms, Krylov inner products,
+// sink tails) are needed on the HOST; an NCCL all-reduce costs a kernel launch + ~25 us of device latency before the
+// device->host copy can even start, the exchange through a shared-memory segment costs ~2 us.
+// Returns false when the shared segment is unavailable (the caller then uses comm_allreduce_sum on the device).
+bool comm_hostreduce_available(const ncme_comm* c);
+int comm_hostreduce_sum(ncme_comm* c, double* host_vals, size_t count);
 
 // in-place sum over ranks of `count` doubles on the device (stream-ordered on `st`)
 int comm_allreduce_sum(ncme_comm* c, double* buf_dev, size_t count, cudaStream_t st);

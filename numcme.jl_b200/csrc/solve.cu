@@ -385,9 +385,15 @@ int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
         k_rk_errnorm<<<(unsigned)nb, ST, 0, s>>>(ea);
         ctx->launches++;
         NCME_CUDA(cudaGetLastError());
-        NCME_TRY(comm_allreduce_sum(comm, ctx->red_result_dev, nres, s));   // one small all-reduce per step
-        NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * nres, cudaMemcpyDeviceToHost, s));
-        NCME_CUDA(cudaStreamSynchronize(s));
+        if (comm_hostreduce_available(comm) && nres <= NCME_HOSTREDUCE_MAX) {   // one small all-reduce per step:
+            NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * nres, cudaMemcpyDeviceToHost, s));
+            NCME_CUDA(cudaStreamSynchronize(s));                               // through shared host memory ...
+            NCME_TRY(comm_hostreduce_sum(comm, ctx->red_result_host, (size_t)nres));
+        } else {                                                                // ... or NCCL on the device
+            NCME_TRY(comm_allreduce_sum(comm, ctx->red_result_dev, nres, s));
+            NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * nres, cudaMemcpyDeviceToHost, s));
+            NCME_CUDA(cudaStreamSynchronize(s));
+        }
         const double* tails = ctx->red_result_host + 1;
         double sumsq = ctx->red_result_host[0];
         for (int r = 0; r < R; ++r) {   // sink rows, from the reduced tails

@@ -246,7 +246,8 @@ def test_bdf_stiff_is_cheaper_than_explicit(pkg):
 
 
 # ---- fused-step BDF (csrc/bdf_fused.cu, one kernel per step attempt) against the launch-per-operation BDF ---------
-@pytest.mark.parametrize("levels", [20, 400])      # 41 states: one CTA (__syncthreads); 801 states: still one CTA
+# 41 / 801 states: one CTA, work vectors in shared memory; 1001 states: one CTA, vectors in global memory
+@pytest.mark.parametrize("levels", [20, 400, 500])
 def test_bdf_fused_matches_classic_fixed(pkg, levels):
     model = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, fspmat_propensities("tv")), FSPMAT_THETA)
     sp = pkg.StateSpaceSparse(TELEGRAPH_S, [1, 0, 0])

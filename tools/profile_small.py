@@ -65,3 +65,23 @@ for meth, name in ((None, "bdf"),):
     print(f"mean {tot:.2f} ms; breakdown (ms per solve, calls per solve):")
     for k in sorted(acc, key=lambda k: -acc[k]):
         print(f"  {k:20s} {acc[k]/NREP*1e3:7.3f}  x{cnt[k]/NREP:.0f}")
+
+# ---- variants: no per-step output; fixed space (one segment)
+alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=pkg.RStepAdapter(5, 10, True))
+for label, kw in (("every step", {}), ("saveat=[300]", {"saveat": [300.0]})):
+    ts = []
+    for _ in range(8):
+        t0 = time.perf_counter()
+        sol = pkg.solve(model, p0, (0.0, 300.0), alg, **kw)
+        ts.append(time.perf_counter() - t0)
+    print(f"telegraph adaptive, {label}: best {min(ts)*1e3:.2f} ms median {sorted(ts)[len(ts)//2]*1e3:.2f} ms", sol.stats)
+sp = pkg.StateSpaceSparse(model.stoich_matrix, [1, 0, 0])
+sp.expand_(60)
+pf = pkg.FspVectorSparse.from_pairs(sp, [([1, 0, 0], 1.0)])
+for label, kw in (("every step", {}), ("saveat=[300]", {"saveat": [300.0]})):
+    ts = []
+    for _ in range(8):
+        t0 = time.perf_counter()
+        sol = pkg.solve(model, pf, (0.0, 300.0), None, **kw)
+        ts.append(time.perf_counter() - t0)
+    print(f"telegraph fixed space n={sp.get_state_count()}, {label}: best {min(ts)*1e3:.2f} ms", sol.stats)
