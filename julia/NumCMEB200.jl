@@ -159,7 +159,47 @@ function deleteat!(sp::StateSpaceSparseB200, ids::Vector{T}) where {T<:Integer}
     nothing
 end
 
+# sum(p, dims) for a device-resident probability vector over a device space        fspvector.jl:66-99
+# (reduced states in the order of their first occurrence, like the reference; values accumulated with fp64 atomics)
+function Base.sum(p::DeviceVector, sp::StateSpaceSparseB200{NS,NR}, dims::AbstractVector{<:Integer}) where {NS,NR}
+    d = Int32[x for x in unique(dims)]
+    nkeep = NS - length(d)
+    nred = Ref{Int64}(0)
+    check(ccall((:ncme_space_marginal, libncme), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Int64, Ref{Int64}, Ptr{Int64}, Ptr{Float64}),
+                sp.h, p.ptr, length(d), d, 0, nred, C_NULL, C_NULL))                       # size query
+    states = Vector{MVector{nkeep,Int64}}(undef, nred[]); vals = zeros(Float64, nred[])
+    nred[] > 0 && check(ccall((:ncme_space_marginal, libncme), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Int64, Ref{Int64}, Ptr{Cvoid}, Ptr{Float64}),
+                sp.h, p.ptr, length(d), d, nred[], nred, states, vals))
+    FspVectorSparse(states, vals)
+end
+
 # ------------------------------------------------------------------------------------------------ FspMatrixSparse
+# SURVEY H1: a JointTimeVaryingPropensity f(t,x,p) that is numerically c(t) g(x) on the current states is handed to the
+# library as separable (g = f(t_ref, .), c(t) = f(t, x*, p) / g(x*)): one host call per right-hand side instead of n
+# calls + an upload per distinct t (`_update_sparsematrix!`, fspsparsematrix.jl:154-166).  Same test as the executed
+# Python mirror (numcme.jl_b200/fspmatrix.py: detect_rank1); the product form is re-checked on sentinel states at
+# every t actually used.
+const _PROBE_TIMES = (0.0, 0.7310585786300049, 19.098300562505255, 738.90560989306495, 5459.8150033144236, 28813.3)
+function detect_rank1(f, states, θ; rtol = 1e-12)
+    g = nothing
+    for t in _PROBE_TIMES
+        v = Float64[f(t, x, θ) for x in states]
+        all(isfinite, v) || return nothing
+        if g === nothing
+            any(!iszero, v) && (g = v)
+            continue
+        end
+        supp = g .!= 0.0
+        any(!iszero, v[.!supp]) && return nothing
+        ratio = v[supp] ./ g[supp]
+        (maximum(abs, ratio) > 0 && maximum(abs, ratio .- ratio[1]) > rtol * max(abs(ratio[1]), 1e-300)) && return nothing
+    end
+    g === nothing && return nothing
+    nz = sortperm(abs.(g), rev = true)[1:count(!iszero, g)]
+    sent = unique([nz[1]; [nz[k] for k in (length(nz) ÷ 3, 2 * length(nz) ÷ 3, length(nz)) if 1 < k <= length(nz)]])
+    return g, sent
+end
+
 # reference: src/fspmatrix/sparse/fspsparsematrix.jl:9-27 (struct), :47-108 (ctor)
 mutable struct FspMatrixSparseB200{NS,NR} <: NumCME.AbstractFspMatrix
     ctx::Context
@@ -172,19 +212,38 @@ mutable struct FspMatrixSparseB200{NS,NR} <: NumCME.AbstractFspMatrix
     kinds::Vector{Int32}
     t_cache::Float64
     coef::Vector{Float64}
+    tfactors::Dict{Int,Any}      # reaction => t -> c_r(t) for every reaction the library treats as separable
 end
-function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, props::Vector{<:Propensity}; parameters = []) where {NS,NR}
+function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, props::Vector{<:Propensity}; parameters = [],
+                             detect_separable::Bool = true) where {NS,NR}
     states = get_states(space)                      # the host copy the reference keeps (`deepcopy(space.states)`, :97)
     n = length(states)
     kinds = Int32[!istimevarying(a) ? 0 : (istimeseparable(a) ? 1 : 2) for a in props]
     G = zeros(Float64, n, NR)                       # column r = state factor of reaction r: the ABI's reaction-major n x nr
+    tfactors = Dict{Int,Any}()
     for (r, a) in enumerate(props)                  # host evaluation of the opaque closures, once per (state, reaction) (:129)
         kinds[r] == 0 && (for i in 1:n; G[i, r] = a.f(states[i], parameters); end)
-        kinds[r] == 1 && (for i in 1:n; G[i, r] = a.statefactor(states[i], parameters); end)
+        kinds[r] == 1 && (for i in 1:n; G[i, r] = a.statefactor(states[i], parameters); end; tfactors[r] = t -> a.tfactor(t, parameters))
+        if kinds[r] == 2 && detect_separable
+            found = detect_rank1(a.f, states, parameters)
+            if found !== nothing
+                g, sent = found
+                G[:, r] .= g; kinds[r] = 1
+                tfactors[r] = function (t)
+                    c = a.f(t, states[sent[1]], parameters) / g[sent[1]]
+                    for k in sent[2:end]
+                        ck = a.f(t, states[k], parameters) / g[k]
+                        abs(ck - c) > 1e-9 * max(abs(c), abs(ck), 1e-300) &&
+                            error("propensity $r was classified as c(t) g(x) but is not separable at t = $t; pass detect_separable = false")
+                    end
+                    c
+                end
+            end
+        end
     end
     ref = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ncme_matrix_create, libncme), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ref{Ptr{Cvoid}}), space.h, kinds, G, ref))
-    A = FspMatrixSparseB200{NS,NR}(space.ctx, ref[], Vector{Any}(parameters), states, n + NR, n + NR, props, kinds, -Inf, ones(NR))
+    A = FspMatrixSparseB200{NS,NR}(space.ctx, ref[], Vector{Any}(parameters), states, n + NR, n + NR, props, kinds, -Inf, ones(NR), tfactors)
     finalizer(x -> ccall((:ncme_matrix_destroy, libncme), Cint, (Ptr{Cvoid},), x.h), A)
 end
 get_parameters(A::FspMatrixSparseB200) = A.parameters
@@ -202,8 +261,8 @@ end
 # re-evaluated on the host when t changes (:206-212) and uploaded
 function _prepare!(A::FspMatrixSparseB200, t::Real)
     θ = A.parameters
-    for (r, a) in enumerate(A.propensities)
-        A.kinds[r] == 1 && (A.coef[r] = a.tfactor(t, θ))
+    for (r, tf) in A.tfactors                       # separable reactions and joint ones found to be rank-1 (kinds[r] == 1)
+        A.coef[r] = tf(t)
     end
     if t != A.t_cache
         A.t_cache = t
@@ -309,7 +368,7 @@ function solve(model::CmeModel, p0::FspVectorSparse{NS,IntT,RealT}, tspan::Tuple
         u = DeviceVector(ctx, n + R); copyto!(view(u, 1:n), p)
         check(ccall((:ncme_h2d, libncme), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Csize_t), ctx.h, u.ptr + 8n, sinks, 8R))
         saved = Tuple{Float64,Vector{Float64}}[]; box = Ref((A, saved)); stats = SolveStats()
-        opts = SolveOpts(odertol, odeatol, fsptol / tend, 1, isempty(sv) ? 1 : 0, length(sv), pointer(sv), 0.0, 0, 0)
+        opts = SolveOpts(odertol, odeatol, fsptol / tend, 1, isempty(sv) ? 1 : 0, length(sv), pointer(sv), 0.0, 0, 1)   # method 1: native BDF/GMRES (fused step kernel below 2e6 rows)
         GC.@preserve box sv check(ccall((:ncme_solve_segment, libncme), Cint,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Ptr{Cvoid}, Ref{SolveOpts}, Ref{SolveStats}),
             A.h, ccoef, csave, pointer_from_objref(box), tnow, tend, u.ptr, opts, stats))

@@ -148,3 +148,67 @@ def test_key_relayout_when_a_species_outgrows_its_field(pkg):
     osp2 = StateSpaceOracleFast(S, [[0, 1, 0, 0, 0, 5000]], bits_per_species=[4, 4, 4, 4, 4, 40])
     osp2.expand(2)
     _same(sp2, osp2)
+
+
+def test_small_to_general_handover_index_exact(pkg):
+    """An expansion that starts in the single-launch path (k_expand_small), outgrows its pre-reserved capacity several
+    times and finally the 65 536-state limit, where the per-level pipeline takes over from the last batch of new
+    states: states and connectivity stay index-exact against the oracle (3 species, L = 75: 76 076 states)."""
+    S = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]]).T
+    sp, osp = pkg.StateSpaceSparse(S, [0, 0, 0]), StateSpaceOracleFast(S, [0, 0, 0])
+    sp.expand_(75)
+    osp.expand(75)
+    assert sp.get_state_count() == 76 * 77 * 78 // 6 > 65536
+    _same(sp, osp)
+    # ... and restricted expansions (SelectiveRStepAdapter) from there and from a small space
+    sp.expand_(2, onlyreactions=[1, 4])
+    osp.expand(2, onlyreactions=[1, 4])
+    _same(sp, osp)
+    sp2, osp2 = pkg.StateSpaceSparse(S, [[2, 1, 0], [0, 0, 3]]), StateSpaceOracleFast(S, [[2, 1, 0], [0, 0, 3]])
+    for only in ([2], [1, 3, 5], []):
+        sp2.expand_(4, onlyreactions=only)
+        osp2.expand(4, onlyreactions=only)
+        _same(sp2, osp2)
+
+
+def test_maximum_reaction_count_and_degenerate_spaces(pkg):
+    """R = 32 (NCME_MAX_REACTIONS) over 8 species incl. a zero-stoichiometry reaction and two reactions with identical
+    stoichiometry; a one-state space; a space emptied by deleteat!."""
+    from oracle.fspmatrix import FspMatrixOracle, OProp
+    rng = np.random.default_rng(17)
+    S = rng.integers(-1, 2, size=(8, 32))
+    S[:, 5] = 0                      # x -> x
+    S[:, 9] = S[:, 3]                # duplicate stoichiometry (merged into one slot, like Julia's sparse())
+    x0 = [2, 2, 2, 2, 2, 2, 2, 2]
+    sp, osp = pkg.StateSpaceSparse(S, x0), StateSpaceOracleFast(S, x0)
+    sp.expand_(2)
+    osp.expand(2)
+    _same(sp, osp)
+    props = [OProp("ti", f=(lambda x, p, r=r: (0.1 + 0.01 * r) * (1.0 + x[r % 8]))) for r in range(32)]
+    props[7] = OProp("sep", tfactor=lambda t, p: 1.0 + 0.5 * np.sin(t), statefactor=lambda x, p: 0.3 * x[2])
+    from test_gpu_matvec import _to_pkg_props
+    A = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, props), parameters=[])
+    OA = FspMatrixOracle(osp, props, [])
+    v = rng.random(A.size(1))
+    for t in (0.0, 1.3):
+        w, wr = pkg.matvec(t, A, v), OA.matvec(t, v)
+        assert np.abs(w - wr).max() <= 1e-12 * np.abs(wr).max()
+    # fused-step BDF with 32 sink rows
+    p0 = pkg.FspVectorSparse.from_pairs(sp, [(x0, 1.0)])
+    model = pkg.CmeModel(S, _to_pkg_props(pkg, props), [])
+    a = pkg.solve(model, p0, (0.0, 0.5), pkg.NativeBDFFused(), saveat=[0.5], odertol=1e-8, odeatol=1e-13)
+    b = pkg.solve(model, p0, (0.0, 0.5), pkg.NativeRK45(), saveat=[0.5], odertol=1e-9, odeatol=1e-13)
+    assert np.abs(a.p[0].values - b.p[0].values).max() < 1e-7 and np.abs(a.sinks[0] - b.sinks[0]).max() < 1e-7
+    assert a.p[0].sum() + a.sinks[0].sum() == pytest.approx(1.0, abs=1e-9)
+    # one state, no expansion: everything leaks into the sinks
+    one = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
+    m1 = pkg.workloads.m2d_model()
+    s1 = pkg.solve(m1, pkg.FspVectorSparse([[0, 0]], [1.0]), (0.0, 0.1), None, saveat=[0.1])
+    assert s1.p[0].values[0] == pytest.approx(np.exp(-1.8), rel=1e-4)       # exp(-(10 + 8) t)
+    assert s1.p[0].sum() + s1.sinks[0].sum() == pytest.approx(1.0, abs=1e-9)
+    # delete everything, then the space is empty and expansion is a no-op (nothing to explore)
+    one.expand_(2)
+    one.deleteat_(list(range(1, one.get_state_count() + 1)))
+    assert one.get_state_count() == 0 and one.get_states().shape == (0, 2)
+    one.expand_(3)
+    assert one.get_state_count() == 0
