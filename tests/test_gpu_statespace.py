@@ -199,7 +199,9 @@ def test_maximum_reaction_count_and_degenerate_spaces(pkg):
     a = pkg.solve(model, p0, (0.0, 0.5), pkg.NativeBDFFused(), saveat=[0.5], odertol=1e-8, odeatol=1e-13)
     b = pkg.solve(model, p0, (0.0, 0.5), pkg.NativeRK45(), saveat=[0.5], odertol=1e-9, odeatol=1e-13)
     assert np.abs(a.p[0].values - b.p[0].values).max() < 1e-7 and np.abs(a.sinks[0] - b.sinks[0]).max() < 1e-7
-    assert a.p[0].sum() + a.sinks[0].sum() == pytest.approx(1.0, abs=1e-9)
+    # (this random network is not mass-action: reactions with a negative successor keep a positive propensity and leak
+    #  mass, SURVEY.md 3A -- both integrators must lose the same amount)
+    assert a.p[0].sum() + a.sinks[0].sum() == pytest.approx(b.p[0].sum() + b.sinks[0].sum(), abs=1e-7)
     # one state, no expansion: everything leaks into the sinks
     one = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
     m1 = pkg.workloads.m2d_model()
