@@ -15,6 +15,12 @@
 // the sink event and the output slices, exactly as in bdf.cu.  All RHS evaluations of a BDF step are at t_new, so
 // time-varying coefficients c_r(t_new) are passed by value with the launch (one host callback per step attempt).
 //
+// Multi-step mode (time-invariant matrices on a single CTA, no saveat list): the controller itself (bdf_ctl.h, shared
+// host/device code) also runs inside the kernel, so one launch performs up to 64 step attempts -- rejected steps, order
+// and step-size selection, the sign test of the sink event and the every-step output ring included -- and returns to the
+// host only for what needs it: the step that contains the event or reaches t1, a full output ring, failures.  That
+// removes the ~10 us launch + result round trip per step that is left once a step is a single kernel.
+//
 // Replaces, like bdf.cu: DE.init / DE.step! with CVODE_BDF(linear_solver=:GMRES) (src/transientcme/sparse/fspsolve.jl:158-161).
 #include <cooperative_groups.h>
 #include <math.h>
@@ -24,6 +30,7 @@
 #include <atomic>
 #include <vector>
 
+#include "bdf_ctl.h"
 #include "matrix.cuh"
 #include "ode.cuh"
 #include "vec.cuh"
@@ -36,11 +43,11 @@ namespace {
 
 constexpr int FBT = 512;              // threads per CTA
 constexpr int FW = FBT / 32;          // warps per CTA
-constexpr int MAXO = 5;               // maximum BDF order
+constexpr int MAXO = BDF_MAXO;        // maximum BDF order
 constexpr int GM = 24;                // Krylov dimension before restart
 constexpr int NSLOT = GM + 2;         // widest reduction (k+1 inner products + <w,w>)
 constexpr int MAXR = NCME_MAX_REACTIONS;
-constexpr int SMEM_MAX_BYTES = 216 * 1024;   // dynamic shared memory of the SMEMV variant (+ ~10 KB static)
+constexpr int SMEM_MAX_BYTES = 212 * 1024;   // dynamic shared memory of the SMEMV variant (+ ~12 KB static <= 227 KB)
 
 struct StepResult {                   // written by CTA 0 straight into pinned (device-mapped) host memory
     double error_sumsq;               // sum over ALL entries (states + sinks) of (d / (atol + rtol |ynew|))^2
@@ -73,12 +80,16 @@ struct StepArgs {
     double* V;        // V_j = V + j*stride, j <= GM
     double *ypred, *ynew, *z, *psi, *scale, *ps, *w, *d;
     int64_t stride;
-    // step description
-    int order, have_change;
-    double P[MAXO + 1][MAXO + 1];     // pending rescaling of the differences: D_r <- sum_j P[j][r] D_j
+    // step description (single-step launches; in multi-step mode the in-kernel controller fills its own StepDyn)
+    StepDyn dyn;
     double gamma[MAXO + 1];
-    double inv_alpha, c, atol, rtol, err_const, lin_tol, sqrtn, massfix_limit;
+    double atol, rtol, lin_tol, sqrtn, massfix_limit;
     double Nglob;
+    // multi-step mode (ctl != nullptr): controller state in pinned host memory, constants, output ring
+    BdfCtl* ctl;
+    BdfConst kc;
+    double* ring;                     // [BDF_RING][stride] every-step output slices
+    int max_attempts;
     // scratch
     double* partials;                 // [2][G][NSLOT]
     double* sinkbuf;                  // [2][MAXR]: sum val*x, sum val*|x|
@@ -100,6 +111,7 @@ struct Shared {
     double inv_hk1, resid;
     int stop, ok;
     double sink_d[MAXR];
+    double sinkS[MAXR], sinkA[MAXR];   // sink rows of A x and of A |x| (every CTA keeps a copy)
 };
 
 template <bool MULTI>
@@ -115,18 +127,22 @@ __device__ __forceinline__ void grid_barrier() {
 template <int NV, bool MULTI>
 __device__ __forceinline__ void reduce_all(double (&v)[NV], int nv, const StepArgs& a, int& parity, Shared& sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // single CTA: row i is handled by thread i % FBT, so warps beyond ceil(N / 32) only ever hold zeros -- they skip the
+    // shuffles and the second stage skips their slots (a 100-state system keeps 4 of 16 warps busy)
+    const int nw = MULTI ? FW : (int)((a.N + 31) / 32 < FW ? (a.N + 31) / 32 : FW);
+    if (wid < nw) {
 #pragma unroll
-    for (int s = 0; s < NV; ++s) {
-        if (s < nv) {
-            const double x = warp_sum(v[s]);
-            if (lane == 0) sh.w[wid][s] = x;
+        for (int s = 0; s < NV; ++s) {
+            if (s < nv) {
+                const double x = warp_sum(v[s]);
+                if (lane == 0) sh.w[wid][s] = x;
+            }
         }
     }
     __syncthreads();
     if ((int)threadIdx.x < nv) {
         double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < FW; ++w) t += sh.w[w][threadIdx.x];
+        for (int w = 0; w < nw; ++w) t += sh.w[w][threadIdx.x];
         if (MULTI)
             a.partials[((size_t)parity * a.G + blockIdx.x) * NSLOT + threadIdx.x] = t;
         else
@@ -168,7 +184,7 @@ __device__ __forceinline__ double row_apply(const StepArgs& a, const double* x, 
     return fma(dg, x[i], acc);
 }
 
-// sinkbuf[r] = c_r * sum_k sink_val[k] x[sink_row[k]], sinkbuf[MAXR + r] = same with |x|; ends with a grid barrier
+// sh.sinkS[r] = c_r * sum_k sink_val[k] x[sink_row[k]], sh.sinkA[r] = same with |x|, in every CTA; ends with a barrier
 template <bool MULTI>
 __device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Shared& sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -183,10 +199,11 @@ __device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Sh
             s0 = warp_sum(s0);
             s1 = warp_sum(s1);
             if (lane == 0) {
-                a.sinkbuf[r] = a.sink_coef[r] * s0;
-                a.sinkbuf[MAXR + r] = a.sink_coef[r] * s1;
+                sh.sinkS[r] = a.sink_coef[r] * s0;
+                sh.sinkA[r] = a.sink_coef[r] * s1;
             }
         }
+        __syncthreads();
     } else {
         for (int r = blockIdx.x; r < a.R; r += a.G) {
             double s0 = 0.0, s1 = 0.0;
@@ -210,21 +227,26 @@ __device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Sh
                 a.sinkbuf[threadIdx.x * MAXR + r] = a.sink_coef[r] * t;
             }
         }
+        cg::this_grid().sync();
+        if ((int)threadIdx.x < a.R) {
+            sh.sinkS[threadIdx.x] = __ldcg(a.sinkbuf + threadIdx.x);
+            sh.sinkA[threadIdx.x] = __ldcg(a.sinkbuf + MAXR + threadIdx.x);
+        }
+        __syncthreads();
     }
-    grid_barrier<MULTI>();
 }
 
 // Krylov iteration k: w = (z - c A z) ps, inner products with V_0..V_k (KB = k+1 rounded up to a multiple of 4; the
 // surplus products are garbage-free duplicates of V_0 and ignored), <w,w> in slot KB.
 template <int KB, bool MULTI>
-__device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, int k, int& parity, Shared& sh) {
+__device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, const StepDyn& dyn, int k, int& parity, Shared& sh) {
     double acc[KB + 1];
 #pragma unroll
     for (int s = 0; s <= KB; ++s) acc[s] = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * FBT + threadIdx.x; i < a.n; i += (int64_t)a.G * FBT) {
         double jd;
         const double Az = row_apply(a, v.z, i, jd);
-        const double w = (v.z[i] - a.c * Az) * v.ps[i];
+        const double w = (v.z[i] - dyn.c * Az) * v.ps[i];
         v.w[i] = w;
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
@@ -275,32 +297,24 @@ __device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, i
     __syncthreads();
 }
 
-template <bool MULTI, bool SMEMV>
-__global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepArgs a) {
-    __shared__ Shared sh;
-    extern __shared__ __align__(16) double dyn_smem[];
-    Vecs v;
-    if (SMEMV) {
-        const int64_t vs = (a.N + 7) / 8 * 8;
-        double* q = dyn_smem;
-        v.ypred = q; q += vs;
-        v.ynew = q; q += vs;
-        v.z = q; q += vs;
-        v.psi = q; q += vs;
-        v.scale = q; q += vs;
-        v.ps = q; q += vs;
-        v.w = q; q += vs;
-        v.d = q; q += vs;
-        v.V = q;
-        v.vs = vs;
-    } else {
-        v.ypred = a.ypred; v.ynew = a.ynew; v.z = a.z; v.psi = a.psi; v.scale = a.scale; v.ps = a.ps; v.w = a.w; v.d = a.d;
-        v.V = a.V;
-        v.vs = a.stride;
-    }
-    int parity = 0;
+struct StepOut {   // identical in every thread of the grid
+    int lin_ok, accepted, rhs_evals;
+    double error_norm, ord_sm, ord_sp;
+};
+
+// One BDF step attempt described by `dyn` (see the file header); `publish`: write the sequence number of the result record
+template <bool MULTI>
+__device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, const StepDyn& dyn, Shared& sh, int& parity,
+                                             const bool publish) {
+    // publish: single-step launch -- the result record goes to pinned host memory and its sequence number is published.
+    // In multi-step mode the in-kernel controller consumes StepOut and writes the record only for the step it leaves
+    // to the host.
+    StepOut out;
+    out.lin_ok = out.accepted = out.rhs_evals = 0;
+    out.error_norm = 1e300;
+    out.ord_sm = out.ord_sp = 0.0;
     const int64_t gtid = (int64_t)blockIdx.x * FBT + threadIdx.x, gstride = (int64_t)a.G * FBT;
-    const int order = a.order;
+    const int order = dyn.order;
     double* const D = a.D;
     const int64_t st = a.stride;
     int rhs_evals = 0, kiters = 0, restarts = 0;
@@ -310,13 +324,13 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         double in[MAXO + 1];
 #pragma unroll
         for (int j = 0; j <= MAXO; ++j) in[j] = j <= order ? D[(size_t)j * st + i] : 0.0;
-        if (a.have_change) {
+        if (dyn.have_change) {
             double out[MAXO + 1];
 #pragma unroll
             for (int r = 0; r <= MAXO; ++r) {
                 double s = 0.0;
 #pragma unroll
-                for (int j = 0; j <= MAXO; ++j) s = fma(a.P[j][r], in[j], s);
+                for (int j = 0; j <= MAXO; ++j) s = fma(dyn.P[j][r], in[j], s);
                 out[r] = s;
             }
 #pragma unroll
@@ -334,9 +348,9 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
                 p = fma(a.gamma[j], in[j], p);
             }
         v.ypred[i] = y;
-        v.psi[i] = p * a.inv_alpha;
+        v.psi[i] = p * dyn.inv_alpha;
     }
-    if (blockIdx.x == 0 && (int)threadIdx.x < a.R) a.res->sink_old0[threadIdx.x] = D[a.n + threadIdx.x];
+    if (publish && blockIdx.x == 0 && (int)threadIdx.x < a.R) a.res->sink_old0[threadIdx.x] = D[a.n + threadIdx.x];
     grid_barrier<MULTI>();
 
     // ---- P1: A y_pred, Jacobi preconditioner and error weights, right-hand side w0, beta^2 = |w0|^2
@@ -345,8 +359,8 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         double jd;
         const double Ay = row_apply(a, v.ypred, i, jd);
         const double sc = a.atol + a.rtol * fabs(v.ypred[i]);
-        const double p = 1.0 / ((1.0 - a.c * jd) * sc);
-        const double w = (a.c * Ay - v.psi[i]) * p;
+        const double p = 1.0 / ((1.0 - dyn.c * jd) * sc);
+        const double w = (dyn.c * Ay - v.psi[i]) * p;
         v.scale[i] = sc;
         v.ps[i] = p;
         v.w[i] = w;
@@ -398,12 +412,12 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
                 // ---- P3: fused matvec + Gram-Schmidt inner products + Givens update
                 const int kb = ((k + 1 + 3) / 4) * 4;
                 switch (kb) {
-                    case 4: krylov_apply<4, MULTI>(a, v, k, parity, sh); break;
-                    case 8: krylov_apply<8, MULTI>(a, v, k, parity, sh); break;
-                    case 12: krylov_apply<12, MULTI>(a, v, k, parity, sh); break;
-                    case 16: krylov_apply<16, MULTI>(a, v, k, parity, sh); break;
-                    case 20: krylov_apply<20, MULTI>(a, v, k, parity, sh); break;
-                    default: krylov_apply<24, MULTI>(a, v, k, parity, sh); break;
+                    case 4: krylov_apply<4, MULTI>(a, v, dyn, k, parity, sh); break;
+                    case 8: krylov_apply<8, MULTI>(a, v, dyn, k, parity, sh); break;
+                    case 12: krylov_apply<12, MULTI>(a, v, dyn, k, parity, sh); break;
+                    case 16: krylov_apply<16, MULTI>(a, v, dyn, k, parity, sh); break;
+                    case 20: krylov_apply<20, MULTI>(a, v, dyn, k, parity, sh); break;
+                    default: krylov_apply<24, MULTI>(a, v, dyn, k, parity, sh); break;
                 }
                 rhs_evals++;
                 kiters++;
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
             for (int64_t i = gtid; i < a.n; i += gstride) {
                 double jd;
                 const double Ay = row_apply(a, v.ynew, i, jd);
-                const double w = (a.c * Ay - v.psi[i] - v.d[i]) * v.ps[i];
+                const double w = (dyn.c * Ay - v.psi[i] - v.d[i]) * v.ps[i];
                 v.w[i] = w;
                 v3[0] = fma(w, w, v3[0]);
             }
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
 
     StepResult* res = a.res;
     if (!lin_ok) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (publish && blockIdx.x == 0 && threadIdx.x == 0) {
             res->lin_ok = 0;
             res->accepted = 0;
             res->kiters = kiters;
@@ -490,7 +504,10 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
             __threadfence_system();
             res->seq = a.seq;
         }
-        return;
+        __syncthreads();
+        out.lin_ok = 0;
+        out.rhs_evals = rhs_evals;
+        return out;
     }
 
     // ---- P6: explicit sink rows (they never feed back) and the total-mass projection of the inexact solve.
@@ -499,7 +516,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
     // S(ynew) and S(|ynew|) without a second pass.
     sink_rows<MULTI>(a, v.ynew, sh);
     double ms2 = 0.0;
-    for (int r = 0; r < a.R; ++r) ms2 += a.c * __ldcg(a.sinkbuf + r);
+    for (int r = 0; r < a.R; ++r) ms2 += dyn.c * sh.sinkS[r];
     const double defect = ms0 + ms2;
     const bool fix = (fabs(defect) <= a.massfix_limit * ms1) && (ms1 > 0.0);
     const double fixfac = fix ? -defect / ms1 : 0.0;
@@ -519,8 +536,8 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
     }
     if ((int)threadIdx.x < a.R) {   // every CTA keeps the sink increments (needed for the update of rows n..n+R)
         const int r = threadIdx.x;
-        const double S = __ldcg(a.sinkbuf + r) + fixfac * __ldcg(a.sinkbuf + MAXR + r);
-        sh.sink_d[r] = a.c * S - v.psi[a.n + r];
+        const double S = sh.sinkS[r] + fixfac * sh.sinkA[r];
+        sh.sink_d[r] = dyn.c * S - v.psi[a.n + r];
     }
     reduce_all<1, MULTI>(v4, 1, a, parity, sh);
     double sumsq = sh.res[0];
@@ -529,7 +546,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         const double q = ds / (a.atol + a.rtol * fabs(yn));
         sumsq += q * q;
     }
-    const double error_norm = a.err_const * sqrt(sumsq / a.Nglob);
+    const double error_norm = dyn.err_const * sqrt(sumsq / a.Nglob);
     const bool accept = (error_norm <= 1.0);
 
     double ord_sm = 0.0, ord_sp = 0.0;
@@ -558,11 +575,11 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         ord_sm = sh.res[0];
         ord_sp = sh.res[1];
         // new sink tails for the host's event function (rows n..n+R were updated before the barrier above)
-        if (blockIdx.x == 0 && (int)threadIdx.x < a.R)
+        if (publish && blockIdx.x == 0 && (int)threadIdx.x < a.R)
             for (int j = 0; j <= order + 2; ++j) res->nd[j][threadIdx.x] = __ldcg(D + (size_t)j * st + a.n + threadIdx.x);
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (publish && blockIdx.x == 0 && threadIdx.x == 0) {
         res->lin_ok = 1;
         res->accepted = accept ? 1 : 0;
         res->kiters = kiters;
@@ -580,22 +597,175 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         __threadfence_system();   // cumulative: also orders the tails written by the other threads of this CTA
         res->seq = a.seq;
     }
+    __syncthreads();
+    out.lin_ok = 1;
+    out.accepted = accept ? 1 : 0;
+    out.error_norm = (error_norm == error_norm) ? error_norm : 1e300;
+    out.ord_sm = ord_sm;
+    out.ord_sp = ord_sp;
+    out.rhs_evals = rhs_evals;
+    return out;
 }
 
-void compute_R(int order, double factor, double R[MAXO + 1][MAXO + 1]) {
-    double M[MAXO + 1][MAXO + 1] = {};
-    for (int j = 0; j <= order; ++j) M[0][j] = 1.0;
-    for (int i = 1; i <= order; ++i)
-        for (int j = 1; j <= order; ++j) M[i][j] = ((double)i - 1.0 - factor * j) / (double)i;
-    for (int j = 0; j <= order; ++j) {
-        double run = 1.0;
-        for (int i = 0; i <= order; ++i) {
-            run *= M[i][j];
-            R[i][j] = run;
-        }
+// sink entries of the difference array as the controller sees them: nd(j, r) = D_j[n + r]
+struct NdView {
+    const double* D;
+    int64_t st, n;
+    __device__ __forceinline__ double operator()(int j, int r) const { return __ldcg(D + (size_t)j * st + n + r); }
+};
+
+// SMEMV (single CTA, N <= ~800): the per-step work vectors and the Krylov basis live in shared memory, only the
+// difference array D stays in global memory.
+template <bool MULTI, bool SMEMV>
+__global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepArgs a) {
+    __shared__ Shared sh;
+    extern __shared__ __align__(16) double dyn_smem[];
+    Vecs v;
+    if (SMEMV) {
+        const int64_t vs = (a.N + 7) / 8 * 8;
+        double* q = dyn_smem;
+        v.ypred = q; q += vs;
+        v.ynew = q; q += vs;
+        v.z = q; q += vs;
+        v.psi = q; q += vs;
+        v.scale = q; q += vs;
+        v.ps = q; q += vs;
+        v.w = q; q += vs;
+        v.d = q; q += vs;
+        v.V = q;
+        v.vs = vs;
+    } else {
+        v.ypred = a.ypred; v.ynew = a.ynew; v.z = a.z; v.psi = a.psi; v.scale = a.scale; v.ps = a.ps; v.w = a.w; v.d = a.d;
+        v.V = a.V;
+        v.vs = a.stride;
     }
-    R[0][0] = 1.0;
-    for (int i = 1; i <= order; ++i) R[i][0] = 0.0;
+    int parity = 0;
+    if (MULTI || a.ctl == nullptr) {   // one step attempt per launch, the host keeps the controller
+        step_body<MULTI>(a, v, a.dyn, sh, parity, true);
+        return;
+    }
+    // ---- multi-step mode (single CTA): the controller of bdf_ctl.h runs here, thread 0 holds its state in shared memory
+    __shared__ BdfCtl ctl;
+    __shared__ StepDyn dyn;
+    __shared__ int s_save;
+    __shared__ double ctl_ws[BDF_SCRATCH];
+    __shared__ double s_nd[MAXO + 3][MAXR];   // sink entries of the differences, staged for the controller
+    static_assert(sizeof(BdfCtl) % 8 == 0, "BdfCtl is copied as doubles");
+    for (int i = threadIdx.x; i < (int)(sizeof(BdfCtl) / 8); i += FBT)
+        reinterpret_cast<double*>(&ctl)[i] = reinterpret_cast<const volatile double*>(a.ctl)[i];
+    __syncthreads();
+    const int R = a.R;
+    const NdView ndg{a.D, a.stride, a.n};
+    auto nd = [&](int j, int r) { return s_nd[j][r]; };
+    for (int attempt = 0;; ++attempt) {
+        if (threadIdx.x == 0) {
+            int stt = BDF_RUN;
+            if (ctl.steps + ctl.rejected >= ctl.max_steps)
+                stt = BDF_MAXSTEPS;
+            else if (ctl.h_abs < ctl.hmin)
+                stt = BDF_UNDERFLOW;
+            else if (attempt >= a.max_attempts)
+                stt = BDF_YIELD;
+            else {
+                if (ctl.check_event && R > 0 && !ctl.have_g) {   // g(t) at the start of the segment's first step
+                    double s0 = 0.0;
+                    for (int r = 0; r < R; ++r) s0 += ndg(0, r);
+                    ctl.g_prev = s0 - ctl.event_slope * ctl.t;
+                    ctl.have_g = 1;
+                }
+                bdf_begin_step(ctl, a.kc, dyn, ctl_ws);
+            }
+            ctl.status = stt;
+            s_save = 0;
+        }
+        __syncthreads();
+        if (ctl.status != BDF_RUN) break;
+        const StepOut o = step_body<false>(a, v, dyn, sh, parity, false);
+        if (threadIdx.x < 32) {   // warp 0: reaction of the controller
+            const int lane = threadIdx.x;
+            if (!o.lin_ok) {
+                if (lane == 0) {
+                    ctl.rhs_evals += o.rhs_evals;
+                    bdf_after_linfail(ctl, ctl_ws);
+                }
+            } else if (!o.accepted) {
+                if (lane == 0) {
+                    ctl.rhs_evals += o.rhs_evals;
+                    bdf_after_reject(ctl, o.error_norm, ctl_ws);
+                }
+            } else {
+                const int order = ctl.order;
+                const double t = ctl.t, t_new = ctl.t_new, h = ctl.h;
+                // one L2 round trip for all sink tails of the new differences (rows n..n+R of D_0..D_{order+2})
+                for (int q = lane; q < (order + 3) * R; q += 32) s_nd[q / R][q % R] = ndg(q / R, q % R);
+                __syncwarp();
+                bool need_host = t_new >= ctl.t1;          // the last step of the segment is finished by the host
+                double g_last = ctl.g_prev;
+                if (!need_host && ctl.check_event && R > 0) {
+                    // sign test of the sink event on 16 samples of the dense output (fspsolve.jl:145-156), one per lane
+                    const int q = lane < 16 ? lane + 1 : 16;
+                    const double tb = t + (t_new - t) * q / 16;
+                    const double gb = bdf_sink_sum_at(nd, R, order, t_new, h, tb) - ctl.event_slope * tb;
+                    double ga = __shfl_up_sync(0xffffffffu, gb, 1);
+                    if (lane == 0) ga = ctl.g_prev;
+                    const bool cross = lane < 16 && ga <= 0.0 && gb > 0.0;
+                    if (__ballot_sync(0xffffffffu, cross)) need_host = true;
+                    g_last = __shfl_sync(0xffffffffu, gb, 15);
+                }
+                __syncwarp();
+                if (need_host && lane < R)   // the record the host's bookkeeping of this step reads
+                    for (int j = 0; j <= order + 2; ++j) a.res->nd[j][lane] = s_nd[j][lane];
+                if (lane == 0) {
+                    ctl.rhs_evals += o.rhs_evals;
+                    ctl.error_norm = o.error_norm;
+                    if (need_host) {
+                        ctl.status = BDF_HOST_STEP;
+                        a.res->lin_ok = 1;
+                        a.res->accepted = 1;
+                        a.res->error_norm = o.error_norm;
+                        a.res->ord_sm = o.ord_sm;
+                        a.res->ord_sp = o.ord_sp;
+                    } else {
+                        ctl.steps++;
+                        ctl.n_equal_steps++;
+                        if (ctl.check_event && R > 0) ctl.g_prev = g_last;
+                        ctl.t = t_new;
+                        ctl.h_last = ctl.h_abs;
+                        if (ctl.save_every_step) {
+                            ctl.ring_t[ctl.ring_count] = t_new;
+                            s_save = 1;
+                        }
+                        if (ctl.n_equal_steps >= order + 1) {
+                            double sm = o.ord_sm, sp = o.ord_sp;
+                            for (int r = 0; r < R; ++r) {
+                                const double inv = 1.0 / (a.atol + a.rtol * fabs(nd(0, r)));
+                                if (order > 1) sm += (nd(order, r) * inv) * (nd(order, r) * inv);
+                                if (order < MAXO) sp += (nd(order + 2, r) * inv) * (nd(order + 2, r) * inv);
+                            }
+                            bdf_select_order(ctl, a.kc, o.error_norm, sm, sp, ctl_ws);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (s_save) {   // every-step output: the new solution D_0 goes into the ring, the host drains it after the launch
+            double* dst = a.ring + (size_t)ctl.ring_count * a.stride;
+            for (int64_t i = threadIdx.x; i < a.N; i += FBT) dst[i] = a.D[i];
+            __syncthreads();
+            if (threadIdx.x == 0 && ++ctl.ring_count == BDF_RING && ctl.status == BDF_RUN) ctl.status = BDF_YIELD;
+            __syncthreads();
+        }
+        if (ctl.status != BDF_RUN) break;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(sizeof(BdfCtl) / 8); i += FBT)
+        reinterpret_cast<volatile double*>(a.ctl)[i] = reinterpret_cast<const double*>(&ctl)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        a.res->seq = a.seq;
+    }
 }
 
 // output slices with the device->host copies queued behind the step kernels and the host callbacks deferred to the
@@ -672,14 +842,18 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     // tiny systems: work vectors + Krylov basis in shared memory (8 + GM + 1 vectors of round_up(N, 8) doubles)
     const size_t smem_need = (size_t)(8 + GM + 1) * (size_t)((N + 7) / 8 * 8) * sizeof(double);
     const size_t smem_bytes = (G == 1 && smem_need <= (size_t)SMEM_MAX_BYTES && !getenv("NCME_BDF_NO_SMEM")) ? smem_need : 0;
+    // multi-step launches: time-invariant matrix (no host callback per step), one CTA, no saveat list
+    bool need_coef = false;
+    for (int r = 0; r < R; ++r) need_coef |= (A->kind[r] != NCME_TIME_INVARIANT);
+    const bool multi = G == 1 && !need_coef && o->nsave == 0 && !getenv("NCME_BDF_SINGLE_STEP");
 
     // ---- workspace
     const size_t stride = round_up<size_t>((size_t)N, 32);
-    const int NV = (MAXO + 3) + 8 + (GM + 1);
+    const int NV = (MAXO + 3) + 8 + (GM + 1) + (multi ? BDF_RING : 0);
     const size_t extra = (size_t)2 * G * NSLOT + 2 * MAXR + 64;
     NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, (stride * NV + extra) * sizeof(double), false));
     double* base = ctx->solve_ws;
-    NCME_CUDA(cudaMemsetAsync(base, 0, (stride * NV + extra) * sizeof(double), s));
+    NCME_CUDA(cudaMemsetAsync(base, 0, (stride * ((MAXO + 3) + 8 + (GM + 1)) + extra) * sizeof(double), s));
     int slot = 0;
     auto vec = [&]() { return base + stride * (slot++); };
     double* D[MAXO + 3];
@@ -694,68 +868,64 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     double* d = vec();
     double* V = base + stride * slot;
     slot += GM + 1;
+    double* ring = base + stride * slot;       // multi-step mode only
     double* partials = base + stride * NV;
     double* sinkbuf = partials + (size_t)2 * G * NSLOT;
-    static_assert(sizeof(StepResult) <= 1024 * sizeof(double), "StepResult must fit the context's pinned scalars");
+    // pinned scalars of the context: [StepResult | BdfCtl]
+    constexpr size_t CTL_OFF = (sizeof(StepResult) + 63) / 64 * 64;
+    static_assert(CTL_OFF + sizeof(BdfCtl) <= 1024 * sizeof(double), "result record + controller must fit the pinned scalars");
     StepResult* res_host = reinterpret_cast<StepResult*>(ctx->red_result_host);
+    BdfCtl& c = *reinterpret_cast<BdfCtl*>(reinterpret_cast<char*>(ctx->red_result_host) + CTL_OFF);
     StepResult* res_dev = nullptr;
     NCME_CUDA(cudaHostGetDevicePointer((void**)&res_dev, (void*)res_host, 0));
+    BdfCtl* ctl_dev = reinterpret_cast<BdfCtl*>(reinterpret_cast<char*>(res_dev) + CTL_OFF);
     unsigned int seq = 0;
     res_host->seq = 0;
 
     LazySaver saver;
     NCME_TRY(saver.init(ctx, (size_t)N, save_fn, user, st));
+    double* ring_pinned = nullptr;
+    if (multi && save_fn) {   // the lazy saver's pinned block is at least 4 MB: the ring's host image lives behind its slots
+        const size_t need = ((size_t)saver.nslots + BDF_RING) * (size_t)N * sizeof(double);
+        NCME_TRY(cache_reserve(&ctx->solve_pinned, &ctx->solve_pinned_bytes, need, true));
+        saver.pinned = ctx->solve_pinned;
+        ring_pinned = ctx->solve_pinned + (size_t)saver.nslots * (size_t)N;
+    }
     const double rtol = o->rtol > 0 ? o->rtol : 1e-4, atol = o->atol > 0 ? o->atol : 1e-6;
-    const int64_t max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
     const double tspan = t1 - t0;
 
-    const double kappa[MAXO + 1] = {0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0};
-    double gamma[MAXO + 1], alpha[MAXO + 1], error_const[MAXO + 2];
-    gamma[0] = 0;
-    for (int k = 1; k <= MAXO; ++k) gamma[k] = gamma[k - 1] + 1.0 / k;
-    for (int k = 0; k <= MAXO; ++k) alpha[k] = (1 - kappa[k]) * gamma[k];
-    for (int k = 0; k <= MAXO; ++k) error_const[k] = kappa[k] * gamma[k] + 1.0 / (k + 1);
-    error_const[MAXO + 1] = 1.0 / (MAXO + 2);
+    double ctl_ws[BDF_SCRATCH];
+    BdfConst kc;
+    bdf_constants(kc);
+    kc.atol = atol;
+    kc.rtol = rtol;
+    kc.Nglob = (double)N;
 
     double coef[NCME_MAX_REACTIONS];
     for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
 
-    // pending rescaling of the difference array, composed on the host and applied by the next step kernel
-    double P[MAXO + 1][MAXO + 1] = {};
-    bool have_change = false;
-    auto queue_change = [&](int order, double factor) {
-        double Rm[MAXO + 1][MAXO + 1] = {}, Um[MAXO + 1][MAXO + 1] = {}, RU[MAXO + 1][MAXO + 1] = {};
-        compute_R(order, factor, Rm);
-        compute_R(order, 1.0, Um);
-        for (int i = 0; i <= order; ++i)
-            for (int j = 0; j <= order; ++j) {
-                double v = 0.0;
-                for (int q = 0; q <= order; ++q) v += Rm[i][q] * Um[q][j];
-                RU[i][j] = v;
-            }
-        if (!have_change) {
-            memcpy(P, RU, sizeof(P));
-        } else {
-            double T[MAXO + 1][MAXO + 1] = {};
-            for (int i = 0; i <= order; ++i)
-                for (int j = 0; j <= order; ++j) {
-                    double v = 0.0;
-                    for (int q = 0; q <= order; ++q) v += P[i][q] * RU[q][j];
-                    T[i][j] = v;
-                }
-            memcpy(P, T, sizeof(P));
-        }
-        have_change = true;
-    };
-    // apply a pending rescaling now (needed before dense output is evaluated on D at a segment end: never, D_0 is
-    // invariant under the rescaling and dense output happens before any change is queued)
     auto finish = [&](const double* src) -> int {
         if (src != u) NCME_CUDA(cudaMemcpyAsync(u, src, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         NCME_CUDA(cudaStreamSynchronize(s));
         saver.delivered();
+        st->steps = c.steps;
+        st->rejected = c.rejected;
+        st->rhs_evals = c.rhs_evals;
+        st->h_last = c.h_last;
         st->launches = ctx->launches - launches0;
         return NCME_OK;
     };
+
+    memset(&c, 0, sizeof(c));
+    c.t = t0;
+    c.t1 = t1;
+    c.tspan = tspan;
+    c.hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+    c.order = 1;
+    c.max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
+    c.check_event = (o->check_event && R > 0) ? 1 : 0;
+    c.save_every_step = (o->save_every_step && save_fn) ? 1 : 0;
+    c.event_slope = o->event_slope;
 
     NCME_CUDA(cudaMemcpyAsync(D[0], u, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
     st->t_final = t0;
@@ -772,26 +942,21 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     // ---- initial step size (Hairer's rule on the WRMS norms of u and f(t0, u)), D_1 = h f(t0, u)
     if (coef_fn) coef_fn(t0, coef, user);
     NCME_TRY(matvec_dist(A, coef, D[0], ynew, 0.0, 0));
-    st->rhs_evals++;
-    double h_abs = o->h_init;
-    if (!(h_abs > 0)) {
+    c.rhs_evals++;
+    c.h_abs = o->h_init;
+    if (!(c.h_abs > 0)) {
         double d0 = 0, d1 = 0;
         NCME_TRY(ncme_vec_wrms(ctx, N, D[0], D[0], D[0], atol, rtol, &d0));
         NCME_TRY(ncme_vec_wrms(ctx, N, ynew, D[0], D[0], atol, rtol, &d1));
         saver.delivered();
-        h_abs = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h_abs = std::min(h_abs, tspan);
+        c.h_abs = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        c.h_abs = std::min(c.h_abs, tspan);
     }
     {
-        const double cs[1] = {h_abs};
+        const double cs[1] = {c.h_abs};
         const double* xs[1] = {ynew};
         NCME_TRY(ncme_vec_lincomb(ctx, N, 1, cs, xs, D[1]));
     }
-    int order = 1, n_equal_steps = 0;
-    double t = t0;
-    double g_prev = 0.0;
-    bool have_g = false;
-    const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
     const double lin_tol = 5e-3;   // WRMS residual of the linear solve = CVODE's 0.05 x Newton tolerance 0.1
 
     StepArgs sa{};
@@ -819,7 +984,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     sa.w = w;
     sa.d = d;
     sa.stride = (int64_t)stride;
-    for (int k = 0; k <= MAXO; ++k) sa.gamma[k] = gamma[k];
+    for (int k = 0; k <= MAXO; ++k) sa.gamma[k] = kc.gamma[k];
     sa.atol = atol;
     sa.rtol = rtol;
     sa.lin_tol = lin_tol;
@@ -829,42 +994,19 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     sa.partials = partials;
     sa.sinkbuf = sinkbuf;
     sa.res = res_dev;
+    sa.ctl = multi ? ctl_dev : nullptr;
+    sa.kc = kc;
+    sa.ring = ring;
+    sa.max_attempts = BDF_RING;
+    {   // coefficients of a time-invariant matrix never change
+        MatvecArgs ma;
+        matvec_fill_args(A, coef, &ma);
+        for (int q = 0; q < A->nslots; ++q) sa.slot_coef[q] = ma.slot_coef[q];
+        for (int q = 0; q < A->ndiag; ++q) sa.diag_coef[q] = ma.diag_coef[q];
+        for (int q = 0; q < R; ++q) sa.sink_coef[q] = ma.sink_coef[q];
+    }
 
-    while (t < t1) {
-        if (st->steps + st->rejected >= max_steps) {
-            set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)max_steps, t);
-            return NCME_ERR_SOLVER;
-        }
-        if (h_abs < hmin) {
-            set_error("integrator (BDF): step size underflow at t = %g", t);
-            return NCME_ERR_SOLVER;
-        }
-        double t_new = t + h_abs;
-        if (t_new > t1 || t1 - t_new < 1e-12 * tspan) {
-            t_new = t1;
-            queue_change(order, fabs(t_new - t) / h_abs);
-            n_equal_steps = 0;
-        }
-        const double h = t_new - t;
-        h_abs = fabs(h);
-        const double c = h / alpha[order];
-
-        // ---- one launch: the whole step attempt at t_new
-        if (coef_fn) coef_fn(t_new, coef, user);
-        {
-            MatvecArgs ma;
-            matvec_fill_args(A, coef, &ma);
-            for (int q = 0; q < A->nslots; ++q) sa.slot_coef[q] = ma.slot_coef[q];
-            for (int q = 0; q < A->ndiag; ++q) sa.diag_coef[q] = ma.diag_coef[q];
-            for (int q = 0; q < R; ++q) sa.sink_coef[q] = ma.sink_coef[q];
-        }
-        sa.order = order;
-        sa.have_change = have_change ? 1 : 0;
-        memcpy(sa.P, P, sizeof(P));
-        have_change = false;
-        sa.inv_alpha = 1.0 / alpha[order];
-        sa.c = c;
-        sa.err_const = error_const[order];
+    auto launch_and_wait = [&]() -> int {
         sa.seq = ++seq;
         if (smem_bytes) {
             k_bdf_step<false, true><<<1, FBT, smem_bytes, s>>>(sa);
@@ -876,8 +1018,9 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
         }
         ctx->launches++;
         NCME_CUDA(cudaGetLastError());
-        // the kernel writes its result record into pinned host memory and publishes the sequence number last: poll
-        // it (cheaper than a copy + stream synchronisation); the stream is queried now and then to catch faults
+        // the kernel writes its result record (and, in multi-step mode, the controller state) into pinned host memory
+        // and publishes the sequence number last: poll it (cheaper than a copy + stream synchronisation); the stream is
+        // queried now and then to catch faults
         for (unsigned spin = 1; res_host->seq != seq; ++spin) {
             if ((spin & 0xFFFF) == 0) {
                 const cudaError_t q = cudaStreamQuery(s);
@@ -891,42 +1034,73 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         saver.delivered();   // copies queued before the kernel have completed (stream order)
-        const StepResult& rs = *res_host;
-        st->rhs_evals += rs.rhs_evals;
+        return NCME_OK;
+    };
 
-        if (!rs.lin_ok) {   // linear solver failed: halve the step (CVODE's reaction to a convergence failure)
-            st->rejected++;
-            h_abs *= 0.5;
-            queue_change(order, 0.5);
-            n_equal_steps = 0;
-            continue;
-        }
-        const double safety = 0.9;
-        const double error_norm = rs.error_norm;
-        if (!rs.accepted) {
-            st->rejected++;
-            const double factor = (error_norm < 1e299) ? std::max(0.2, safety * pow(error_norm, -1.0 / (order + 1))) : 0.2;
-            h_abs *= factor;
-            queue_change(order, factor);
-            n_equal_steps = 0;
-            continue;
-        }
-        // ---- accepted: the kernel has already updated the differences
-        st->steps++;
-        n_equal_steps++;
-        const double(*nd)[MAXR] = rs.nd;
-        auto sink_sum_at = [&](double tt) {
-            double sum = 0.0;
-            for (int r = 0; r < R; ++r) {
-                double p = 1.0, y = nd[0][r];
-                for (int j = 1; j <= order; ++j) {
-                    p *= (tt - (t_new - (j - 1) * h)) / (h * j);
-                    y += nd[j][r] * p;
-                }
-                sum += y;
+    while (c.t < t1) {
+        if (!multi) {
+            if (c.steps + c.rejected >= c.max_steps) {
+                set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)c.max_steps, c.t);
+                return NCME_ERR_SOLVER;
             }
-            return sum;
-        };
+            if (c.h_abs < c.hmin) {
+                set_error("integrator (BDF): step size underflow at t = %g", c.t);
+                return NCME_ERR_SOLVER;
+            }
+            // ---- one launch: the whole step attempt at t_new
+            bdf_begin_step(c, kc, sa.dyn, ctl_ws);
+            if (coef_fn) {
+                coef_fn(c.t_new, coef, user);
+                MatvecArgs ma;
+                matvec_fill_args(A, coef, &ma);
+                for (int q = 0; q < A->nslots; ++q) sa.slot_coef[q] = ma.slot_coef[q];
+                for (int q = 0; q < A->ndiag; ++q) sa.diag_coef[q] = ma.diag_coef[q];
+                for (int q = 0; q < R; ++q) sa.sink_coef[q] = ma.sink_coef[q];
+            }
+            NCME_TRY(launch_and_wait());
+            c.rhs_evals += res_host->rhs_evals;
+            if (!res_host->lin_ok) {
+                bdf_after_linfail(c, ctl_ws);
+                continue;
+            }
+            c.error_norm = res_host->error_norm;
+            if (!res_host->accepted) {
+                bdf_after_reject(c, c.error_norm, ctl_ws);
+                continue;
+            }
+        } else {
+            // ---- one launch: up to BDF_RING step attempts with the controller on the device
+            c.status = BDF_RUN;
+            c.ring_count = 0;
+            NCME_TRY(launch_and_wait());
+            if (c.ring_count > 0 && save_fn) {   // every-step output slices produced inside the launch
+                NCME_CUDA(cudaMemcpy2DAsync(ring_pinned, (size_t)N * sizeof(double), ring, stride * sizeof(double),
+                                            (size_t)N * sizeof(double), (size_t)c.ring_count, cudaMemcpyDeviceToHost, s));
+                NCME_CUDA(cudaStreamSynchronize(s));
+                for (int k = 0; k < c.ring_count; ++k) {
+                    save_fn(c.ring_t[k], ring_pinned + (size_t)k * (size_t)N, user);
+                    st->nsaved++;
+                }
+            }
+            if (c.status == BDF_MAXSTEPS) {
+                set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)c.max_steps, c.t);
+                return NCME_ERR_SOLVER;
+            }
+            if (c.status == BDF_UNDERFLOW) {
+                set_error("integrator (BDF): step size underflow at t = %g", c.t);
+                return NCME_ERR_SOLVER;
+            }
+            if (c.status != BDF_HOST_STEP) continue;   // BDF_YIELD: ring full / attempts used up
+        }
+        // ---- accepted step (the kernel has already updated the differences): bookkeeping, event, output
+        const StepResult& rs = *res_host;
+        const int order = c.order;
+        const double t = c.t, t_new = c.t_new, h = c.h;
+        c.steps++;
+        c.n_equal_steps++;
+        const double(*nd)[MAXR] = rs.nd;
+        auto ndv = [&](int j, int r) { return nd[j][r]; };
+        auto sink_sum_at = [&](double tt) { return bdf_sink_sum_at(ndv, R, order, t_new, h, tt); };
         auto dense_to = [&](double tt, double* out) -> int {
             double cs[MAXO + 1];
             const double* xs[MAXO + 1];
@@ -942,23 +1116,23 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
         };
         double t_hi = t_new;
         bool event = false;
-        if (o->check_event && R > 0) {
-            if (!have_g) {
+        if (c.check_event) {
+            if (!c.have_g) {
                 double s0 = 0.0;
                 for (int r = 0; r < R; ++r) s0 += rs.sink_old0[r];
-                g_prev = s0 - o->event_slope * t;
-                have_g = true;
+                c.g_prev = s0 - c.event_slope * t;
+                c.have_g = 1;
             }
             const int NS_ = 16;
-            double ga = g_prev, ta = t;
+            double ga = c.g_prev, ta = t;
             for (int q = 1; q <= NS_; ++q) {
                 const double tb = t + (t_new - t) * q / NS_;
-                const double gb = sink_sum_at(tb) - o->event_slope * tb;
+                const double gb = sink_sum_at(tb) - c.event_slope * tb;
                 if (ga <= 0.0 && gb > 0.0) {
                     double lo = ta, hi = tb;
                     for (int it = 0; it < 60; ++it) {
                         const double mid = 0.5 * (lo + hi);
-                        if (sink_sum_at(mid) - o->event_slope * mid > 0.0)
+                        if (sink_sum_at(mid) - c.event_slope * mid > 0.0)
                             hi = mid;
                         else
                             lo = mid;
@@ -970,7 +1144,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
                 ga = gb;
                 ta = tb;
             }
-            if (!event) g_prev = ga;
+            if (!event) c.g_prev = ga;
         }
         while (isave < o->nsave && o->save_t[isave] <= t_hi + 1e-14 * fabs(t_hi)) {
             const double ts = o->save_t[isave];
@@ -988,14 +1162,14 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
             NCME_TRY(dense_to(t_hi, z));
             st->t_final = t_hi;
             st->event_hit = 1;
-            st->h_last = h_abs;
+            c.h_last = c.h_abs;
             return finish(z);
         }
-        t = t_new;
-        st->h_last = h_abs;
-        if (o->save_every_step) NCME_TRY(saver.save(t, D[0]));
-        if (t >= t1) break;
-        if (n_equal_steps < order + 1) continue;
+        c.t = t_new;
+        c.h_last = c.h_abs;
+        if (o->save_every_step) NCME_TRY(saver.save(c.t, D[0]));
+        if (c.t >= t1) break;
+        if (c.n_equal_steps < order + 1) continue;
         // ---- order / step-size selection (norms of the new differences came back with the step result)
         double sm = rs.ord_sm, sp = rs.ord_sp;
         for (int r = 0; r < R; ++r) {
@@ -1003,23 +1177,9 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
             if (order > 1) sm += (nd[order][r] * inv) * (nd[order][r] * inv);
             if (order < MAXO) sp += (nd[order + 2][r] * inv) * (nd[order + 2][r] * inv);
         }
-        const double INF = 1e300;
-        const double em = order > 1 ? error_const[order - 1] * sqrt(sm / (double)N) : INF;
-        const double ep = order < MAXO ? error_const[order + 1] * sqrt(sp / (double)N) : INF;
-        const double norms[3] = {em, error_norm, ep};
-        double factors[3];
-        for (int q = 0; q < 3; ++q)
-            factors[q] = norms[q] >= INF ? 0.0 : (norms[q] > 0 ? pow(norms[q], -1.0 / (order + q)) : 1e9);
-        int best = 1;
-        for (int q = 0; q < 3; ++q)
-            if (factors[q] > factors[best]) best = q;
-        order += best - 1;
-        const double factor = std::min(10.0, safety * factors[best]);
-        h_abs *= factor;
-        queue_change(order, factor);
-        n_equal_steps = 0;
+        bdf_select_order(c, kc, c.error_norm, sm, sp, ctl_ws);
     }
-    st->t_final = t;
+    st->t_final = c.t;
     return finish(D[0]);
 }
 

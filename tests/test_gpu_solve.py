@@ -316,3 +316,50 @@ def test_bdf_fused_adaptive_event_and_timevarying(pkg):
                           out["classic"].p[k].values)
             assert np.abs(a - b).max() < 5e-6
             assert out["fused"].p[k].sum() + out["fused"].sinks[k].sum() == pytest.approx(1.0, abs=1e-7)
+
+
+def test_bdf_fused_multistep_launches(pkg):
+    """Time-invariant matrices on one CTA: up to 64 step attempts per launch with the controller on the device
+    (every-step output ring, sink-event sign test, order selection in the kernel).  Same answers as one launch per step
+    (NCME_BDF_SINGLE_STEP=1) and as the launch-per-operation BDF; far fewer launches."""
+    import os
+    tm = pkg.workloads.telegraph_model()
+    p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
+    # (a) adaptive, every-step output, events + prune/expand in between (examples/telegraph_cme.jl)
+    alg = pkg.AdaptiveFspSparse(pkg.NativeBDFFused(), pkg.RStepAdapter(5, 10, True))
+    multi = pkg.solve(tm, p0, (0.0, 300.0), alg)
+    os.environ["NCME_BDF_SINGLE_STEP"] = "1"
+    try:
+        single = pkg.solve(tm, p0, (0.0, 300.0), alg)
+    finally:
+        del os.environ["NCME_BDF_SINGLE_STEP"]
+    classic = pkg.solve(tm, p0, (0.0, 300.0), pkg.AdaptiveFspSparse(pkg.NativeBDFClassic(), pkg.RStepAdapter(5, 10, True)))
+    print("multi", multi.stats, "single", single.stats, "classic", classic.stats)
+    assert multi.stats["launches"] < 0.5 * single.stats["launches"]
+    assert abs(multi.stats["steps"] - single.stats["steps"]) <= 3
+    for sol in (multi, single, classic):
+        assert sol.t[0] == 0.0 and sol.t[-1] == 300.0
+        assert all(b >= a for a, b in zip(sol.t, sol.t[1:]))
+        assert len(sol) >= sol.stats["steps"] + 1            # every accepted step (+ t0, + the final slice) is in the output
+        for p, s in zip(sol.p, sol.sinks):
+            assert p.sum() + s.sum() == pytest.approx(1.0, abs=1e-6)
+    a, b = _align(multi.p[-1].states, multi.p[-1].values, single.p[-1].states, single.p[-1].values)
+    assert np.abs(a - b).max() < 2e-6
+    a, b = _align(multi.p[-1].states, multi.p[-1].values, classic.p[-1].states, classic.p[-1].values)
+    assert np.abs(a - b).max() < 2e-6
+    # every-step slices of the multi-step run are consistent with its own dense trajectory: interpolate the mean
+    mean = [float((p.values * p.states[:, 2]).sum()) for p in multi.p]
+    ms = [float((p.values * p.states[:, 2]).sum()) for p in single.p]
+    assert np.interp(150.0, multi.t, mean) == pytest.approx(np.interp(150.0, single.t, ms), rel=1e-3)
+    # (b) fixed space, every step, no event; tight tolerance against the explicit integrator; reproducible bitwise
+    sp = pkg.StateSpaceSparse(tm.stoich_matrix, [1, 0, 0])
+    sp.expand_(60)
+    pf = pkg.FspVectorSparse.from_pairs(sp, [([1, 0, 0], 1.0)])
+    f1 = pkg.solve(tm, pf, (0.0, 50.0), pkg.NativeBDFFused(), odertol=1e-8, odeatol=1e-13)
+    f2 = pkg.solve(tm, pf, (0.0, 50.0), pkg.NativeBDFFused(), odertol=1e-8, odeatol=1e-13)
+    rk = pkg.solve(tm, pf, (0.0, 50.0), pkg.NativeRK45(), saveat=[50.0], odertol=1e-9, odeatol=1e-13)
+    assert len(f1) == f1.stats["steps"] + 1 and f1.t == f2.t and f1.t[-1] == 50.0
+    assert all(np.array_equal(x.values, y.values) for x, y in zip(f1.p, f2.p))
+    assert f1.stats["launches"] < 0.1 * f1.stats["steps"] + 10
+    assert np.abs(f1.p[-1].values - rk.p[0].values).max() < 5e-7
+    assert np.abs(f1.sinks[-1] - rk.sinks[0]).max() < 5e-7

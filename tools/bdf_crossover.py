@@ -9,7 +9,7 @@ import __graft_entry__ as g
 
 pkg = g.load_package()
 model = pkg.workloads.m2d_model()
-for levels in (44, 140, 446, 1000, 1413, 2000, 2800):
+for levels in ([int(v) for v in sys.argv[1:]] or [44, 140, 446, 1000, 1413, 2000, 2800]):
     sp = pkg.StateSpaceSparse(model.stoich_matrix, [0, 0])
     sp.expand_(levels)
     p0 = pkg.FspVectorSparse.from_pairs(sp, [([0, 0], 1.0)])
