@@ -210,6 +210,14 @@ int ncme_comm_allgatherv(ncme_comm* comm, const double* send_dev, double* recv_d
  * ncme_matvec on a sharded matrix returns globally reduced sink entries on every rank. */
 int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
                                ncme_matrix** out);
+/* Incremental constructor for the matrix that follows an adapt! (the reference rebuilds from scratch and re-evaluates
+ * every propensity at every state, src/transientcme/sparse/fspsolve.jl:176).  `prev` must be the matrix
+ * this space was last assembled into.  States that survived the prunes since then (always a prefix of the state list,
+ * *n_kept of them) take their state factors from `prev` on the device; propvals_new holds the factors of the *n_new
+ * states appended since (always the tail), reaction-major n_new x nr.  comm may be NULL. */
+int ncme_space_new_count(ncme_space* space, int64_t* n_kept, int64_t* n_new);
+int ncme_matrix_create_incremental(ncme_space* space, ncme_comm* comm, ncme_matrix* prev, const int32_t* kind,
+                                   const double* propvals_new, ncme_matrix** out);
 /* Peer-memory halo (CUDA IPC over NVLink).  COLLECTIVE: every rank registers the allocation that holds its matvec
  * input (base_dev from ncme_dmalloc / cudaMalloc, local rows starting local0 doubles into it, i.e. the halo_lo
  * margin).  Matvecs whose input lies in a registered allocation skip NCCL: the boundary rows read the neighbours'

@@ -246,6 +246,31 @@ function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, props::Vector{<
     A = FspMatrixSparseB200{NS,NR}(space.ctx, ref[], Vector{Any}(parameters), states, n + NR, n + NR, props, kinds, -Inf, ones(NR), tfactors)
     finalizer(x -> ccall((:ncme_matrix_destroy, libncme), Cint, (Ptr{Cvoid},), x.h), A)
 end
+# Rebuild after an adapt! (fspsolve.jl:176 rebuilds from scratch): only the states appended since `previous` was built
+# (always the tail of the state list) are evaluated on the host, the factors of the surviving states are carried over
+# on the device (SURVEY.md H8).  Falls back to the full constructor when `previous` is not the matrix the space was
+# last assembled into or a joint propensity found to be c(t) g(x) stops being so on the new states.
+function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, previous::FspMatrixSparseB200{NS,NR}) where {NS,NR}
+    props, parameters = previous.propensities, previous.parameters
+    nk = Ref{Int64}(0); nn = Ref{Int64}(0)
+    check(ccall((:ncme_space_new_count, libncme), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), space.h, nk, nn))
+    states = get_states(space)
+    n, nkept, nnew = length(states), Int(nk[]), Int(nn[])
+    any(previous.kinds[r] == 1 && !istimeseparable(props[r]) for r in 1:NR) &&         # rank-1 joint reactions: re-detect
+        return FspMatrixSparseB200(space, props; parameters)
+    nkept == 0 && return FspMatrixSparseB200(space, props; parameters)
+    G = zeros(Float64, nnew, NR)
+    for (r, a) in enumerate(props), i in 1:nnew
+        previous.kinds[r] == 0 && (G[i, r] = a.f(states[nkept+i], parameters))
+        previous.kinds[r] == 1 && (G[i, r] = a.statefactor(states[nkept+i], parameters))
+    end
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    code = ccall((:ncme_matrix_create_incremental, libncme), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                 space.h, C_NULL, previous.h, previous.kinds, G, ref)
+    code == 0 || return FspMatrixSparseB200(space, props; parameters)
+    A = FspMatrixSparseB200{NS,NR}(space.ctx, ref[], previous.parameters, states, n + NR, n + NR, props, copy(previous.kinds), -Inf, ones(NR), previous.tfactors)
+    finalizer(x -> ccall((:ncme_matrix_destroy, libncme), Cint, (Ptr{Cvoid},), x.h), A)
+end
 get_parameters(A::FspMatrixSparseB200) = A.parameters
 get_states(A::FspMatrixSparseB200) = A.states
 get_rowcount(A::FspMatrixSparseB200) = A.rowcount
@@ -383,7 +408,7 @@ function solve(model::CmeModel, p0::FspVectorSparse{NS,IntT,RealT}, tspan::Tuple
                 du = similar(u); matvec!(du, tnow, A, u); dsinks = du[n+1:n+R]
             end
             p = adapt!(space, adapter, copy(view(u, 1:n)), sinks, tnow, tend, fsptol; dsinks)
-            A = FspMatrixSparseB200(space, model.propensities; parameters = get_parameters(model))
+            A = FspMatrixSparseB200(space, A)                             # incremental rebuild (fspsolve.jl:176)
             sum(sinks) >= tnow * fsptol / tend && (sinks .-= eps())      # fspsolve.jl:179-181
             verbose && println("t = $(round(tnow, digits=2)). Update state space. New size: $(get_state_count(space)).")
         else

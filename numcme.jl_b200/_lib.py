@@ -59,6 +59,8 @@ SIGNATURES = {
     "ncme_space_lookup": (cint, [p_void, i64, p_i64, p_u32]),
     "ncme_space_marginal": (cint, [p_void, p_void, cint, p_i32, i64, p_i64, p_i64, p_f64]),
     "ncme_matrix_create": (cint, [p_void, p_i32, p_f64, C.POINTER(p_void)]),
+    "ncme_space_new_count": (cint, [p_void, p_i64, p_i64]),
+    "ncme_matrix_create_incremental": (cint, [p_void, p_void, p_void, p_i32, p_f64, C.POINTER(p_void)]),
     "ncme_matrix_destroy": (cint, [p_void]),
     "ncme_matrix_size": (cint, [p_void, p_i64, p_i64]),
     "ncme_matrix_set_joint_values": (cint, [p_void, cint, p_f64]),

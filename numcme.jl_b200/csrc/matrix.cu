@@ -1074,7 +1074,21 @@ static int matrix_ensure_compressed(ncme_matrix* A) {
     return NCME_OK;
 }
 
-static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A, ncme_comm* comm) {
+// G_new[r][i] = G_prev[r][origin[i]] for the surviving states (a prefix), the uploaded factors for the new tail
+__global__ void k_carry_factors(const double* __restrict__ Gprev, int64_t ngprev, const uint32_t* __restrict__ origin,
+                                int64_t nkept, const double* __restrict__ Gnew_tail, int64_t nnew, int nr,
+                                double* __restrict__ G, int64_t ng) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ng * nr) return;
+    const int r = (int)(t / ng);
+    const int64_t i = t - (int64_t)r * ng;
+    G[t] = i < nkept ? Gprev[(int64_t)r * ngprev + origin[i]] : Gnew_tail[(int64_t)r * nnew + (i - nkept)];
+}
+
+// prev != nullptr: incremental build -- `propvals` then holds the factors of the nnew = n - nkept states appended since
+// prev was built (reaction-major nnew x nr), everything else is carried over on the device.
+static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A, ncme_comm* comm,
+                        const ncme_matrix* prev = nullptr, int64_t nkept = 0) {
     ncme_ctx* ctx = sp->ctx;
     cudaStream_t st = ctx->stream;
     const int nr = sp->nr;
@@ -1148,13 +1162,29 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
 
     // ---- upload the state factors of ALL states (the values at predecessors outside the shard are needed;
     //      joint reactions start at zero, :87,129)
-    DevArray<double> G;
+    DevArray<double>& G = A->G;
     NCME_TRY(G.reserve((size_t)(ng > 0 ? ng : 1) * nr, st, false));
-    for (int r = 0; r < nr && ng > 0; ++r) {
-        if (kind[r] == NCME_JOINT_TV || !propvals)
-            NCME_CUDA(cudaMemsetAsync(G.p + (size_t)r * ng, 0, (size_t)ng * 8, st));
-        else
-            NCME_CUDA(cudaMemcpyAsync(G.p + (size_t)r * ng, propvals + (size_t)r * ng, (size_t)ng * 8, cudaMemcpyHostToDevice, st));
+    if (prev && ng > 0) {
+        const int64_t nnew = ng - nkept;
+        DevArray<double> tail;
+        NCME_TRY(tail.reserve((size_t)(nnew > 0 ? nnew : 1) * nr, st, false));
+        for (int r = 0; r < nr && nnew > 0; ++r) {
+            if (kind[r] == NCME_JOINT_TV || !propvals)
+                NCME_CUDA(cudaMemsetAsync(tail.p + (size_t)r * nnew, 0, (size_t)nnew * 8, st));
+            else
+                NCME_CUDA(cudaMemcpyAsync(tail.p + (size_t)r * nnew, propvals + (size_t)r * nnew, (size_t)nnew * 8, cudaMemcpyHostToDevice, st));
+        }
+        k_carry_factors<<<nblk(ng * nr), 256, 0, st>>>(prev->G.p, prev->n_global, sp->origin.p, nkept, tail.p, nnew, nr, G.p, ng);
+        ctx->launches++;
+        NCME_CUDA(cudaGetLastError());
+        tail.release();
+    } else {
+        for (int r = 0; r < nr && ng > 0; ++r) {
+            if (kind[r] == NCME_JOINT_TV || !propvals)
+                NCME_CUDA(cudaMemsetAsync(G.p + (size_t)r * ng, 0, (size_t)ng * 8, st));
+            else
+                NCME_CUDA(cudaMemcpyAsync(G.p + (size_t)r * ng, propvals + (size_t)r * ng, (size_t)ng * 8, cudaMemcpyHostToDevice, st));
+        }
     }
     // ---- predecessor window of the local rows -> halo extents and the halo-free interior row range
     ShardGeom geom{ng, row_lo, row_hi, row_lo, n, nr};
@@ -1326,7 +1356,6 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         set_error("matrix assembly failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = NCME_ERR_CUDA;
     }
-    G.release();
     flags.release();
     pos.release();
     scratch.release();
@@ -1370,6 +1399,9 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     A->nterms = nt;
     A->algorithmic_bytes = 16 * A->N;
     for (int k = 0; k < nt; ++k) A->algorithmic_bytes += 8 * A->nnz_term[k] + 4 * (A->nnz_term[k] - n);
+    // from now on the space tracks where its states were at this build (incremental constructor of the next matrix)
+    NCME_TRY(space_mark(sp));
+    A->space_mark = sp->mark_id;
     return NCME_OK;
 }
 
@@ -1392,6 +1424,41 @@ int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t
             NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
     ncme_matrix* A = new ncme_matrix();
     int st = matrix_build(space, kind, propvals, A, comm);
+    if (st != NCME_OK) {
+        ncme_matrix_destroy(A);
+        return st;
+    }
+    *out = A;
+    return NCME_OK;
+}
+
+int ncme_space_new_count(ncme_space* space, int64_t* n_kept, int64_t* n_new) {
+    NCME_REQUIRE(space && n_kept && n_new, "null argument");
+    if (space->mark_n < 0) {   // never marked: everything is new
+        *n_kept = 0;
+        *n_new = space->n;
+        return NCME_OK;
+    }
+    NCME_TRY(space_count_kept(space, n_kept));
+    *n_new = space->n - *n_kept;
+    return NCME_OK;
+}
+
+int ncme_matrix_create_incremental(ncme_space* space, ncme_comm* comm, ncme_matrix* prev, const int32_t* kind,
+                                   const double* propvals_new, ncme_matrix** out) {
+    NCME_REQUIRE(space && prev && kind && out, "null argument");
+    NCME_REQUIRE(prev->space_mark == space->mark_id && space->mark_n >= 0 && prev->G.p,
+                 "incremental build: `prev` is not the matrix this space was last assembled into");
+    NCME_REQUIRE(prev->nr == space->nr, "incremental build: reaction count changed");
+    for (int r = 0; r < space->nr; ++r) NCME_REQUIRE(prev->kind[r] == kind[r], "incremental build: reaction kinds changed");
+    if (comm && comm->nranks > 1)
+        for (int r = 0; r < space->nr; ++r)
+            NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
+    int64_t nkept = 0;
+    NCME_TRY(space_count_kept(space, &nkept));
+    NCME_REQUIRE(propvals_new || space->n == nkept, "propvals_new is null");
+    ncme_matrix* A = new ncme_matrix();
+    int st = matrix_build(space, kind, propvals_new, A, comm, prev, nkept);
     if (st != NCME_OK) {
         ncme_matrix_destroy(A);
         return st;
@@ -1442,6 +1509,7 @@ int ncme_matrix_destroy(ncme_matrix* A) {
     A->cdesc.release();
     A->val.release();
     A->diag.release();
+    A->G.release();
     A->sink_row.release();
     A->sink_val.release();
     A->tasks.release();

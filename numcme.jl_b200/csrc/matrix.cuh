@@ -54,6 +54,10 @@ struct ncme_matrix {
     ncme::DevArray<uint32_t> col;   // [nslots][ld]
     ncme::DevArray<double> val;     // [nslots][ld]
     ncme::DevArray<double> diag;    // [ndiag][ld]
+    // state factors G[r][i] of ALL states (reaction-major, stride n_global), kept for the incremental constructor of the
+    // matrix that follows an adapt! (H8): only the states added since are evaluated on the host
+    ncme::DevArray<double> G;
+    uint64_t space_mark = 0;        // mark of the space this matrix was built at
     // compressed column indices (K1 fast path): one byte per (slot,row) relative to a per-(slot, 64-row chunk)
     // descriptor {base:i32, mode:u32}; mode 0 = chunk stays on the 32-bit array (range does not fit)
     ncme::DevArray<uint8_t> col8;     // [nslots][ld]

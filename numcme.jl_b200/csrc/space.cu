@@ -169,12 +169,14 @@ __global__ void k_clear_flags_at(const uint32_t* __restrict__ ids0 /*0-based*/, 
 __global__ void k_compact_space(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, int64_t n,
                                 const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pred, int64_t ld,
                                 const uint32_t* __restrict__ sinkmask, int nr, uint64_t* __restrict__ keys2,
-                                uint32_t* __restrict__ pred2, int64_t ld2, uint32_t* __restrict__ sinkmask2) {
+                                uint32_t* __restrict__ pred2, int64_t ld2, uint32_t* __restrict__ sinkmask2,
+                                const uint32_t* __restrict__ origin, uint32_t* __restrict__ origin2) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !keep[i]) return;
     const uint32_t j = pos[i];
     keys2[j] = keys[i];
     sinkmask2[j] = sinkmask[i];
+    if (origin) origin2[j] = origin[i];
     for (int r = 0; r < nr; ++r) {
         uint32_t p = pred[(int64_t)r * ld + i];
         pred2[(int64_t)r * ld2 + j] = (p != NONE32 && keep[p]) ? pos[p] : NONE32;
@@ -459,6 +461,7 @@ int space_reserve_rows(ncme_space* sp, int64_t nrows) {
     nld = round_up<int64_t>(nld, 64);
     NCME_TRY(sp->keys.reserve((size_t)nld, st));
     NCME_TRY(sp->sinkmask.reserve((size_t)nld, st));
+    if (sp->mark_n >= 0) NCME_TRY(sp->origin.reserve((size_t)nld, st));
     // the slot-major table changes stride: re-lay it out
     DevArray<uint32_t> np;
     NCME_TRY(np.reserve((size_t)nld * sp->nr, st, false));
@@ -537,15 +540,17 @@ int space_delete_flagged(ncme_space* sp) {
     sp->last_delete_nnew = (int64_t)m;
     if ((int64_t)m == n) return NCME_OK;
     DevArray<uint64_t> k2;
-    DevArray<uint32_t> p2, m2;
+    DevArray<uint32_t> p2, m2, o2;
     // keep head-room for the expansion that follows every prune (adapt!, rstepadapters.jl:44-49) instead of shrinking
     // to fit and re-growing (re-layout of the slot-major predecessor table) a moment later
     const int64_t ld2 = round_up<int64_t>(std::max<int64_t>(1024, std::min<int64_t>(sp->ld, 2 * (int64_t)m + 8192)), 64);
     NCME_TRY(k2.reserve((size_t)ld2, s, false));
     NCME_TRY(m2.reserve((size_t)ld2, s, false));
     NCME_TRY(p2.reserve((size_t)ld2 * sp->nr, s, false));
+    const bool tracked = sp->mark_n >= 0;
+    if (tracked) NCME_TRY(o2.reserve((size_t)ld2, s, false));
     LAUNCH(ctx, k_compact_space, n, sp->flags.p, sp->pos.p, n, sp->keys.p, sp->pred.p, sp->ld, sp->sinkmask.p, sp->nr, k2.p,
-           p2.p, ld2, m2.p);
+           p2.p, ld2, m2.p, tracked ? sp->origin.p : nullptr, o2.p);
     NCME_CUDA(cudaStreamSynchronize(s));
     sp->keys.release();
     sp->pred.release();
@@ -553,6 +558,10 @@ int space_delete_flagged(ncme_space* sp) {
     sp->keys = k2;
     sp->pred = p2;
     sp->sinkmask = m2;
+    if (tracked) {
+        sp->origin.release();
+        sp->origin = o2;
+    }
     sp->ld = ld2;
     sp->n = (int64_t)m;
     sp->version++;
@@ -681,6 +690,45 @@ static int space_alloc(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, ncm
     }
     cudaMemsetAsync(sp->err_flag, 0, sizeof(int), ctx->stream);
     *out = sp;
+    return NCME_OK;
+}
+
+__global__ void k_iota_u32(uint32_t* p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void k_count_has_origin(const uint32_t* __restrict__ origin, int64_t n, unsigned long long* __restrict__ count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned b = __ballot_sync(0xffffffffu, i < n && origin[i] != NONE32);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+}
+
+int space_mark(ncme_space* sp) {
+    cudaStream_t s = sp->ctx->stream;
+    NCME_TRY(sp->origin.reserve((size_t)(sp->ld > 0 ? sp->ld : 1), s, false));
+    if (sp->n > 0) {
+        k_iota_u32<<<nblk(sp->n), 256, 0, s>>>(sp->origin.p, sp->n);
+        sp->ctx->launches++;
+        NCME_CUDA(cudaGetLastError());
+    }
+    sp->mark_n = sp->n;
+    sp->mark_id++;
+    return NCME_OK;
+}
+
+int space_count_kept(ncme_space* sp, int64_t* n_kept) {
+    *n_kept = 0;
+    if (sp->mark_n < 0 || sp->n == 0) return NCME_OK;
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t s = ctx->stream;
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->red_result_dev + 910);
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->red_result_host + 910);
+    NCME_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
+    k_count_has_origin<<<nblk(sp->n), 256, 0, s>>>(sp->origin.p, sp->n, d);
+    ctx->launches++;
+    NCME_CUDA(cudaMemcpyAsync(h, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    NCME_CUDA(cudaStreamSynchronize(s));
+    *n_kept = (int64_t)*h;
     return NCME_OK;
 }
 
@@ -822,6 +870,7 @@ int ncme_space_destroy(ncme_space* sp) {
     sp->pos.release();
     sp->scan_scratch.release();
     sp->frontier.release();
+    sp->origin.release();
     if (sp->err_flag) cudaFree(sp->err_flag);
     delete sp;
     return NCME_OK;
@@ -919,6 +968,7 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
     for (int k = 0; k < nreact; ++k)
         for (int s2 = 0; s2 < sp->ns; ++s2) inc[s2] = std::max(inc[s2], sp->stoich[(size_t)reacts.r[k] * sp->ns + s2]);
     cudaStream_t s = ctx->stream;
+    const int64_t n_at_entry = sp->n;
     int st = NCME_OK;
     do {
         int level0 = 0;
@@ -974,6 +1024,12 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
         }
         st = check_overflow(sp);
     } while (0);
+    if (st == NCME_OK && sp->mark_n >= 0 && sp->n > n_at_entry) {   // states added by this expansion have no origin
+        if ((st = sp->origin.reserve((size_t)sp->ld, s)) == NCME_OK) {
+            k_fill_u32<<<nblk(sp->n - n_at_entry), 256, 0, s>>>(sp->origin.p + n_at_entry, sp->n - n_at_entry, NONE32);
+            ctx->launches++;
+        }
+    }
     cudaStreamSynchronize(ctx->stream);
     return st;
 }

@@ -64,6 +64,12 @@ struct ncme_space {
     ncme::DevArray<uint64_t> keys;      // [ld]      packed state of index i (insertion order)
     ncme::DevArray<uint32_t> pred;      // [nr][ld]  pred[r][i] = j with x_i = x_j + s_r, NONE32 if absent
     ncme::DevArray<uint32_t> sinkmask;  // [ld]      bit r set <=> x_i + s_r >= 0 and not in the space
+    // incremental matrix assembly (H8): origin[i] = index state i had when the space was last marked (by a matrix
+    // build), NONE32 for states added since.  Deletions compact it with the states, expansions append NONE32 -- the
+    // surviving old states therefore always form a prefix and the new ones the tail.
+    ncme::DevArray<uint32_t> origin;    // [ld]
+    uint64_t mark_id = 0;               // bumped by every mark; a matrix remembers the mark it was built at
+    int64_t mark_n = -1;                // number of states at the mark (-1: never marked)
 
     ncme::DevArray<uint64_t> tkeys;     // open-addressing table
     ncme::DevArray<uint32_t> tvals;
@@ -95,4 +101,6 @@ int space_rebuild_table(ncme_space* sp, uint64_t min_slots);
 // make sure every species can grow by inc[s] without overflowing its key field (re-packs all keys if needed)
 int space_ensure_key_room(ncme_space* sp, const int64_t* inc);
 int space_pack_host(const ncme_space* sp, const int64_t* state, uint64_t* key_out);  // 0 ok, 1 negative, <0 error
+int space_mark(ncme_space* sp);                          // origin = identity; returns through sp->mark_id
+int space_count_kept(ncme_space* sp, int64_t* n_kept);   // states that already existed at the last mark (a prefix)
 }  // namespace ncme

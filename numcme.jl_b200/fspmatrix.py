@@ -25,23 +25,27 @@ from .statespace import StateSpaceSparse
 _PROBE_TIMES = (0.0, 0.7310585786300049, 19.098300562505255, 738.90560989306495, 5459.8150033144236, 28813.3)
 
 
-def detect_rank1(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
-    """SURVEY.md H1 / section 8(f) row 4: is the joint propensity ``f(t, x, p)`` a product ``c(t) g(x)`` on ``states``?
-    Evaluates f over all states at a few probe times; separable iff every evaluation is a scalar multiple of the first
-    non-vanishing one (same support, ratio constant to ``rtol``).  Returns ``(g, sentinels)`` -- the state factor
-    ``g = f(t_ref, .)`` and up to four state indices on which the time factor ``c(t) = f(t, x*, p) / g(x*)`` is
-    evaluated (the first) and cross-checked (the others) at run time -- or ``None``."""
+# below this many states the incremental rebuild (one more kernel + host round trip) costs more than it saves
+INCREMENTAL_MIN_STATES = 2048
+
+
+def _rank1_info(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
+    """Worker of ``detect_rank1``: returns ``None`` or a dict with the state factor ``g = f(t_ref, .)``, the sentinel
+    state indices, ``t_ref`` and the ratios ``c(t_k) / c(t_ref)`` at the other probe times (what an incremental rebuild
+    needs to validate states added later against the same factorisation)."""
     n = states.shape[0]
     if n == 0:
         return None
-    g = None
+    g, t_ref, ratios = None, None, []
     for t in probe_times:
         v = eval_over_states(f, states, parameters, t=t)
         if not np.all(np.isfinite(v)):
             return None
         if g is None:
             if np.any(v != 0.0):
-                g = v
+                g, t_ref = v, t
+            else:
+                ratios.append((t, 0.0))        # vanishes identically at this probe time
             continue
         supp = g != 0.0
         if np.any(v[~supp] != 0.0):
@@ -49,16 +53,42 @@ def detect_rank1(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
         ratio = v[supp] / g[supp]
         if np.abs(ratio - ratio[0]).max() > rtol * max(abs(ratio[0]), 1e-300) and np.abs(ratio).max() > 0.0:
             return None
+        ratios.append((t, float(ratio[0])))
     if g is None:
         return None            # vanishes at every probe time: leave it on the exact (joint) path
     order = np.argsort(-np.abs(g), kind="stable")
     nz = order[: int(np.count_nonzero(g))]
     sent = [int(nz[0])] + [int(nz[k]) for k in (len(nz) // 3, 2 * len(nz) // 3, len(nz) - 1) if 0 < k < len(nz)]
-    return g, list(dict.fromkeys(sent))
+    return {"g": g, "sent": list(dict.fromkeys(sent)), "t_ref": t_ref, "ratios": ratios, "rtol": rtol}
+
+
+def _rank1_extend(f, info, new_states, parameters):
+    """State factor of ``new_states`` under the factorisation found earlier, or ``None`` if they do not follow it."""
+    if new_states.shape[0] == 0:
+        return np.zeros(0)
+    g = eval_over_states(f, new_states, parameters, t=info["t_ref"])
+    if not np.all(np.isfinite(g)):
+        return None
+    for t, ratio in info["ratios"]:
+        v = eval_over_states(f, new_states, parameters, t=t)
+        if np.abs(v - ratio * g).max() > 1e-11 * max(np.abs(g).max() * abs(ratio), 1e-300) and np.abs(v - ratio * g).max() > 0.0:
+            return None
+    return g
+
+
+def detect_rank1(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
+    """SURVEY.md H1 / section 8(f) row 4: is the joint propensity ``f(t, x, p)`` a product ``c(t) g(x)`` on ``states``?
+    Evaluates f over all states at a few probe times; separable iff every evaluation is a scalar multiple of the first
+    non-vanishing one (same support, ratio constant to ``rtol``).  Returns ``(g, sentinels)`` -- the state factor
+    ``g = f(t_ref, .)`` and up to four state indices on which the time factor ``c(t) = f(t, x*, p) / g(x*)`` is
+    evaluated (the first) and cross-checked (the others) at run time -- or ``None``."""
+    info = _rank1_info(f, states, parameters, probe_times, rtol)
+    return None if info is None else (info["g"], info["sent"])
 
 
 class FspMatrixSparse:
-    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=(), comm=None, detect_separable=True):
+    def __init__(self, space: StateSpaceSparse, propensity_functions, parameters=(), comm=None, detect_separable=True,
+                 previous: "FspMatrixSparse | None" = None):
         """``comm`` (a parallel.Comm) restricts the matrix to this rank's row block (K8); vectors are then the
         local slices ``[rows | R sinks]`` and matvec inputs need halo margins (see parallel.ShardedVector).
 
@@ -66,7 +96,13 @@ class FspMatrixSparse:
         catalyst_interface.jl:19-27) need n host closure calls and an upload per distinct ``t``
         (``_update_sparsematrix!``, fspsparsematrix.jl:154-166).  When such a propensity is numerically a product
         c(t) g(x) on the current states (``detect_rank1``) it is put on the separable path instead -- one host call per
-        right-hand side, nothing uploaded -- and cross-checked on sentinel states at every ``t``."""
+        right-hand side, nothing uploaded -- and cross-checked on sentinel states at every ``t``.
+
+        ``previous``: the matrix this space was assembled into before its last prune / expand (the rebuild after an
+        ``adapt!``, fspsolve.jl:176).  Only the states added since are evaluated on the host and uploaded; the factors
+        of the surviving states are carried over on the device (``ncme_matrix_create_incremental``).  Any
+        mismatch (other propensities, a joint propensity that stops being separable on the new states, a space that was
+        assembled into another matrix in between) silently falls back to the full build."""
         self.ctx = space.ctx
         self.comm = comm
         self.parameters = parameters
@@ -81,14 +117,30 @@ class FspMatrixSparse:
         self.n = n
         self.nr = space.nr
         self.rowcount = self.colcount = n + space.get_sink_count()   # global size, as size(A) in the reference
-        self.kinds = np.array([a.kind_code for a in self.propensities], dtype=np.int32)
         self.timeinvariant_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "ti"]
         self.separabletv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "sep"]
         self.jointtv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "joint"]
-        # what the device matrix does with each reaction (differs from the user's classification above only for joint
+        self.incremental = False
+        h = None
+        if previous is not None and getattr(previous, "_h", None) and n >= max(1, INCREMENTAL_MIN_STATES):
+            h = self._build_incremental(space, previous, comm)
+        if h is None:
+            h = self._build_full(space, comm, detect_separable)
+        self._h = h
+        self.device_separable_ids = sorted(self._tfactor)
+        self.device_joint_ids = [r for r in self.jointtv_propensity_ids if r not in self._rank1]
+        info = self.shard_info()
+        self.local_len = info["row_hi"] - info["row_lo"] + self.nr
+        self.t_cache = -np.inf
+        self._coef = np.ones(self.nr, dtype=np.float64)
+
+    def _build_full(self, space, comm, detect_separable):
+        n, parameters = self.n, self.parameters
+        self.kinds = np.array([a.kind_code for a in self.propensities], dtype=np.int32)
+        # what the device matrix does with each reaction (differs from the user's classification only for joint
         # propensities found to be rank-1 separable)
         self._tfactor = {}                 # 1-based reaction id -> callable t -> c(t)
-        self._rank1 = {}                   # 1-based reaction id -> (g, sentinel indices) of detected reactions
+        self._rank1 = {}                   # 1-based reaction id -> factorisation info of detected reactions
         propvals = np.zeros((self.nr, max(n, 1)), dtype=np.float64)
         for r, a in enumerate(self.propensities):
             if a.kind == "ti":
@@ -97,24 +149,62 @@ class FspMatrixSparse:
                 propvals[r, :n] = eval_over_states(a.statefactor, self.states, parameters)
                 self._tfactor[r + 1] = (lambda t, a=a: float(a.tfactor(t, self.parameters)))
             elif detect_separable:
-                found = detect_rank1(a.f, self.states, parameters)
-                if found is not None:
-                    g, sent = found
+                info = _rank1_info(a.f, self.states, parameters)
+                if info is not None:
+                    g = info.pop("g")
                     propvals[r, :n] = g
                     self.kinds[r] = SEPARABLE_TV
-                    self._rank1[r + 1] = (g, sent)
-                    self._tfactor[r + 1] = self._make_rank1_tfactor(r + 1, a.f, g, sent)
-        self.device_separable_ids = sorted(self._tfactor)
-        self.device_joint_ids = [r for r in self.jointtv_propensity_ids if r not in self._rank1]
+                    info["sent_states"] = [[int(v) for v in self.states[i]] for i in info["sent"]]
+                    info["sent_g"] = [float(g[i]) for i in info["sent"]]
+                    self._rank1[r + 1] = info
+                    self._tfactor[r + 1] = self._make_rank1_tfactor(r + 1, a.f, info)
         propvals = np.ascontiguousarray(propvals[:, :n]) if n else propvals
         h = L.p_void()
         L.check(L.load().ncme_matrix_create_sharded(space.handle, comm.handle if comm is not None else None,
                                                     L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double), C.byref(h)))
-        self._h = h
-        info = self.shard_info()
-        self.local_len = info["row_hi"] - info["row_lo"] + self.nr
-        self.t_cache = -np.inf
-        self._coef = np.ones(self.nr, dtype=np.float64)
+        return h
+
+    def _build_incremental(self, space, previous, comm):
+        """Rebuild after an adapt!: evaluate the propensities of the appended states only (see ``previous``)."""
+        if len(previous.propensities) != len(self.propensities) or any(
+                a is not b for a, b in zip(previous.propensities, self.propensities)) or previous.comm is not comm:
+            return None
+        lib = L.load()
+        nk, nn = C.c_int64(), C.c_int64()
+        L.check(lib.ncme_space_new_count(space.handle, C.byref(nk), C.byref(nn)))
+        n_kept, n_new = nk.value, nn.value
+        if n_kept == 0:
+            return None
+        new_states = self.states[n_kept:]
+        th = self.parameters
+        propvals = np.zeros((self.nr, max(n_new, 1)), dtype=np.float64)
+        for r, a in enumerate(self.propensities):
+            if a.kind == "ti":
+                propvals[r, :n_new] = eval_over_states(a.f, new_states, th)
+            elif a.kind == "sep":
+                propvals[r, :n_new] = eval_over_states(a.statefactor, new_states, th)
+            elif (r + 1) in previous._rank1:
+                g = _rank1_extend(a.f, previous._rank1[r + 1], new_states, th)
+                if g is None:
+                    return None            # the new states do not follow the old factorisation: full build
+                propvals[r, :n_new] = g
+        self.kinds = previous.kinds.copy()
+        propvals = np.ascontiguousarray(propvals[:, :n_new]) if n_new else propvals
+        h = L.p_void()
+        st = lib.ncme_matrix_create_incremental(space.handle, comm.handle if comm is not None else None, previous._h,
+                                                L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double), C.byref(h))
+        if st != 0:
+            return None                    # e.g. the space was assembled into another matrix in between
+        self._rank1 = dict(previous._rank1)
+        self._tfactor = {}
+        for r, a in enumerate(self.propensities):
+            if a.kind == "sep":
+                self._tfactor[r + 1] = (lambda t, a=a: float(a.tfactor(t, self.parameters)))
+            elif (r + 1) in self._rank1:
+                self._tfactor[r + 1] = self._make_rank1_tfactor(r + 1, a.f, self._rank1[r + 1])
+        self.incremental = True
+        self.new_state_count = n_new
+        return h
 
     @property
     def handle(self):
@@ -154,9 +244,8 @@ class FspMatrixSparse:
     def set_tuning(self, rows_per_thread: int):
         L.check(L.load().ncme_matrix_set_tuning(self._h, int(rows_per_thread)))
 
-    def _make_rank1_tfactor(self, rid, f, g, sent):
-        xs = [[int(v) for v in self.states[i]] for i in sent]
-        gs = [float(g[i]) for i in sent]
+    def _make_rank1_tfactor(self, rid, f, info):
+        xs, gs = info["sent_states"], info["sent_g"]
 
         def tfactor(t):
             c = float(f(t, xs[0], self.parameters)) / gs[0]

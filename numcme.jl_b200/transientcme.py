@@ -309,8 +309,10 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
                 matvec_(du, tnow, A, dist.u.v)
                 dsinks = du.to_host(dist.nloc, R)
             p = adapt_(space, adapter, dist.gather(), sinks, tnow, tend, fsptol, dsinks=dsinks)
-            A.close()
-            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
+            A_old = A                                    # incremental rebuild: only the new states are evaluated (H8)
+            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm, previous=A_old)
+            A_old.close()
+            tot["incremental_builds"] = tot.get("incremental_builds", 0) + (1 if A.incremental else 0)
             tot["adapts"] += 1
             tot["matrix_builds"] += 1
             if sinks.sum() >= tnow * fsptol / tend:      # re-arm the event (fspsolve.jl:179-181)

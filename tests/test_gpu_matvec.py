@@ -183,3 +183,49 @@ def test_m3d_properties_at_scale(pkg, ctx):
     # A(t) = A_ti + c(t) A_sep  =>  A(t2) x - A(t1) x is proportional to c(t2) - c(t1)
     ya, yb, yc = pkg.matvec(0.0, A, x1), pkg.matvec(2.5, A, x1), pkg.matvec(7.5, A, x1)
     assert _relerr(yb - ya, -(yc - ya)) <= 1e-10
+
+
+def test_incremental_rebuild_after_adapt(pkg):
+    """the matrix after a prune + expand built from its predecessor -- only the appended states are
+    evaluated on the host -- is bit-for-bit the matrix built from scratch (toggle switch with a separable and, through
+    the rank-1 detection, a joint time factor; two adapt rounds; fallbacks)."""
+    import numcme_jl_b200.fspmatrix as FM
+    rng = np.random.default_rng(8)
+    FM.INCREMENTAL_MIN_STATES, saved = 0, FM.INCREMENTAL_MIN_STATES      # (small spaces rebuild from scratch by default)
+    for sep in (True, False):
+        model = pkg.workloads.toggle_model(separable=sep)
+        sp = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
+        sp.expand_(25)
+        A = pkg.FspMatrixSparse(sp, model.propensities, parameters=model.parameters)
+        assert not A.incremental
+        for rnd in range(2):
+            n = sp.get_state_count()
+            drop = np.sort(rng.choice(np.arange(1, n + 1), size=n // 5, replace=False))
+            sp.deleteat_(drop)
+            sp.expand_(4 + rnd)
+            B = pkg.FspMatrixSparse(sp, model.propensities, parameters=model.parameters, previous=A)
+            assert B.incremental and 0 < B.new_state_count < sp.get_state_count()
+            F = pkg.FspMatrixSparse(sp, model.propensities, parameters=model.parameters)      # from scratch (re-marks the space)
+            assert B.stats() == F.stats()
+            v = rng.random(B.size(1))
+            for t in (0.0, 1234.5, 5000.0):
+                assert np.array_equal(pkg.matvec(t, B, v), pkg.matvec(t, F, v))
+            # F was assembled in between: B is no longer the space's latest matrix -> silent fallback to a full build
+            sp.expand_(1)
+            C2 = pkg.FspMatrixSparse(sp, model.propensities, parameters=model.parameters, previous=B)
+            assert not C2.incremental
+            A = pkg.FspMatrixSparse(sp, model.propensities, parameters=model.parameters, previous=C2)
+            assert A.incremental
+            G = pkg.FspMatrixSparse(sp, model.propensities, parameters=model.parameters)
+            v = rng.random(A.size(1))
+            assert np.array_equal(pkg.matvec(77.0, A, v), pkg.matvec(77.0, G, v))
+            A = G
+    # other propensity objects -> full build
+    other = pkg.workloads.toggle_model(separable=True)
+    sp.expand_(1)
+    assert not pkg.FspMatrixSparse(sp, other.propensities, parameters=other.parameters, previous=A).incremental
+    # the adaptive solve uses it
+    sol = pkg.solve(pkg.workloads.telegraph_model(), pkg.FspVectorSparse([[1, 0, 0]], [1.0]), (0.0, 300.0),
+                    pkg.AdaptiveFspSparse(None, pkg.RStepAdapter(5, 10, True)), saveat=[300.0])
+    assert sol.stats["incremental_builds"] == sol.stats["adapts"] >= 1
+    FM.INCREMENTAL_MIN_STATES = saved

@@ -201,12 +201,12 @@ def test_maximum_reaction_count_and_degenerate_spaces(pkg):
     assert np.abs(a.p[0].values - b.p[0].values).max() < 1e-7 and np.abs(a.sinks[0] - b.sinks[0]).max() < 1e-7
     # (this random network is not mass-action: reactions with a negative successor keep a positive propensity and leak
     #  mass, SURVEY.md 3A -- both integrators must lose the same amount)
-    assert a.p[0].sum() + a.sinks[0].sum() == pytest.approx(b.p[0].sum() + b.sinks[0].sum(), abs=1e-7)
+    assert a.p[0].sum() + a.sinks[0].sum() == pytest.approx(b.p[0].sum() + b.sinks[0].sum(), abs=2e-5)   # 493 + 32 entries
     # one state, no expansion: everything leaks into the sinks
     one = pkg.StateSpaceSparse(TOGGLE_S, [0, 0])
     m1 = pkg.workloads.m2d_model()
     s1 = pkg.solve(m1, pkg.FspVectorSparse([[0, 0]], [1.0]), (0.0, 0.1), None, saveat=[0.1])
-    assert s1.p[0].values[0] == pytest.approx(np.exp(-1.8), rel=1e-4)       # exp(-(10 + 8) t)
+    assert s1.p[0].values[0] == pytest.approx(np.exp(-1.8), rel=2e-3)       # exp(-(10 + 8) t) at the default odertol = 1e-4
     assert s1.p[0].sum() + s1.sinks[0].sum() == pytest.approx(1.0, abs=1e-9)
     # delete everything, then the space is empty and expansion is a no-op (nothing to explore)
     one.expand_(2)
