@@ -268,9 +268,9 @@ def main():
         if world == 1:
             pkg.matvec_(yp.numpy(), tt, A, xp.numpy())        # ncme_matvec_host: H2D + kernel + D2H
         else:
-            x.v.upload(xp.numpy())
+            x.v.upload(xp.numpy())                            # pinned host -> this rank's shard
             pkg.matvec_(y, tt, A, x.v)
-            yp.numpy()[:] = y.to_host()
+            y.download_into(yp.numpy())                       # shard -> pinned host
     for _ in range(3):
         e2e_step()
     barrier()

@@ -143,6 +143,17 @@ class DeviceVector:
                                       out.nbytes))
         return out
 
+    def download_into(self, out: np.ndarray, start: int = 0):
+        """Device -> host into an existing contiguous float64 array (e.g. pinned memory): no allocation, no extra copy."""
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
+            raise L.ArgumentError("download_into needs a contiguous float64 numpy array")
+        if start < 0 or start + out.size > self.n:
+            raise L.ArgumentError("size mismatch in download_into")
+        if out.size:
+            L.check(L.load().ncme_d2h(self.ctx.handle, out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr + 8 * start),
+                                      out.nbytes))
+        return out
+
     def view(self, start: int, count: int) -> "DeviceVector":
         if start < 0 or count < 0 or start + count > self.n:
             raise L.ArgumentError("view out of range")
