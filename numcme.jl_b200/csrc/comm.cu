@@ -1,6 +1,8 @@
 // NCCL communicator of libncme (K8): creation from a unique id distributed by the host language
 // (torch.distributed / MPI / Julia Distributed), scalar all-reduce, all-gather-v.
 #include "comm.cuh"
+#include "hostreduce.h"
+static_assert(ncme::HR_MAX_RANKS >= NCME_MAX_RANKS && ncme::HR_MAX_VALUES >= NCME_HOSTREDUCE_MAX, "hostreduce.h limits");
 
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -212,17 +214,7 @@ const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q)
     return nullptr;
 }
 
-// ---- host-side scalar all-reduce over POSIX shared memory -------------------------------------------------------
-}  // namespace ncme
-struct HostReduce {
-    struct alignas(128) Slot {
-        std::atomic<unsigned long long> seq;
-        double vals[NCME_HOSTREDUCE_MAX];
-    };
-    Slot slot[2][NCME_MAX_RANKS];   // double-buffered: a rank can be at most one reduction ahead of the slowest one
-};
-namespace ncme {
-
+// ---- host-side scalar all-reduce over POSIX shared memory (protocol: hostreduce.h) ------------------------------
 static int comm_setup_hostreduce(ncme_comm* c) {
     c->hr = nullptr;
     if (c->nranks == 1 || c->nranks > NCME_MAX_RANKS || getenv("NCME_NO_HOSTREDUCE")) return NCME_OK;
@@ -239,38 +231,28 @@ static int comm_setup_hostreduce(ncme_comm* c) {
     bool same_host = true;
     for (int q = 0; q < c->nranks; ++q) same_host &= strncmp(g[q].host, g[0].host, sizeof(mine.host)) == 0;
     HostReduce* hr = nullptr;
-    int fd = -1;
-    if (same_host) {
-        if (c->rank == 0) {
-            fd = shm_open(g[0].name, O_CREAT | O_EXCL | O_RDWR, 0600);
-            if (fd >= 0 && ftruncate(fd, sizeof(HostReduce)) != 0) {
-                close(fd);
-                fd = -1;
-            }
-        }
+    bool created = false;
+    if (same_host && c->rank == 0) {
+        hr = hr_map(g[0].name, true);
+        created = hr != nullptr;
     }
     // barrier 1: the segment exists (or not) before the others open it
-    double v = (c->rank == 0 && same_host && fd < 0) ? 1.0 : 0.0;
+    double v = (c->rank == 0 && same_host && !created) ? 1.0 : 0.0;
     NCME_CUDA(cudaMemcpyAsync(c->scratch, &v, sizeof(double), cudaMemcpyHostToDevice, c->ctx->stream));
     NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, c->ctx->stream));
     NCME_CUDA(cudaMemcpyAsync(&v, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->ctx->stream));
     NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
-    bool ok = same_host && v == 0.0;
-    if (ok && c->rank != 0) fd = shm_open(g[0].name, O_RDWR, 0600);
-    if (ok && fd >= 0) {
-        void* m = mmap(nullptr, sizeof(HostReduce), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-        if (m != MAP_FAILED) hr = (HostReduce*)m;   // a fresh segment is zero-filled: every seq starts at 0
-    }
-    if (fd >= 0) close(fd);
+    const bool ok = same_host && v == 0.0;
+    if (ok && c->rank != 0) hr = hr_map(g[0].name, false);
     // barrier 2: everybody mapped it (or the feature is off everywhere); then the name can go
     v = (ok && hr) ? 0.0 : 1.0;
     NCME_CUDA(cudaMemcpyAsync(c->scratch, &v, sizeof(double), cudaMemcpyHostToDevice, c->ctx->stream));
     NCME_TRY(comm_allreduce_sum(c, c->scratch, 1, c->ctx->stream));
     NCME_CUDA(cudaMemcpyAsync(&v, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->ctx->stream));
     NCME_CUDA(cudaStreamSynchronize(c->ctx->stream));
-    if (c->rank == 0 && same_host) shm_unlink(g[0].name);
+    if (created) shm_unlink(g[0].name);
     if (v != 0.0) {
-        if (hr) munmap(hr, sizeof(HostReduce));
+        hr_unmap(hr);
         hr = nullptr;
     }
     c->hr = hr;
@@ -284,26 +266,11 @@ int comm_hostreduce_sum(ncme_comm* c, double* vals, size_t count) {
     if (!c || c->nranks == 1 || count == 0) return NCME_OK;
     NCME_REQUIRE(c->hr && count <= (size_t)NCME_HOSTREDUCE_MAX, "host reduce unavailable or too many values");
     const unsigned long long e = ++c->hr_epoch;
-    HostReduce::Slot* buf = c->hr->slot[e & 1];
-    HostReduce::Slot& me = buf[c->rank];
-    memcpy(me.vals, vals, count * sizeof(double));
-    me.seq.store(e, std::memory_order_release);
-    double acc[NCME_HOSTREDUCE_MAX];
-    for (size_t k = 0; k < count; ++k) acc[k] = 0.0;
-    for (int q = 0; q < c->nranks; ++q) {
-        unsigned long long spins = 0;
-        while (buf[q].seq.load(std::memory_order_acquire) != e) {
-            if (++spins > (1ull << 34)) {   // ~ a minute of spinning: a rank died
-                set_error("host all-reduce: rank %d never arrived (epoch %llu)", q, e);
-                return NCME_ERR_COMM;
-            }
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-        }
-        for (size_t k = 0; k < count; ++k) acc[k] += buf[q].vals[k];   // rank order: identical bits on every rank
+    const int late = hr_sum(c->hr, c->rank, c->nranks, e, vals, count, 1ull << 34);   // ~ a minute of spinning
+    if (late) {
+        set_error("host all-reduce: rank %d never arrived (epoch %llu)", late - 1, e);
+        return NCME_ERR_COMM;
     }
-    memcpy(vals, acc, count * sizeof(double));
     c->hr_reduces++;
     return NCME_OK;
 }
@@ -378,7 +345,7 @@ int ncme_comm_destroy(ncme_comm* c) {
     c->regs.clear();
     for (int q = 0; q < NCME_MAX_RANKS; ++q)
         if (c->peer_flags[q]) cudaIpcCloseMemHandle(c->peer_flags[q]);
-    if (c->hr) munmap(c->hr, sizeof(HostReduce));
+    hr_unmap(c->hr);
     if (c->my_flags) cudaFree(c->my_flags);
     if (c->ws_base) cudaFree(c->ws_base);
     cudaGetLastError();

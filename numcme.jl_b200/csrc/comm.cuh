@@ -27,6 +27,10 @@ struct RegBuf {
     int64_t peer_stride[NCME_MAX_RANKS] = {0};
 };
 
+namespace ncme {
+struct HostReduce;
+}
+
 struct ncme_comm {
     ncme_ctx* ctx = nullptr;
     int rank = 0, nranks = 1;
@@ -43,7 +47,7 @@ struct ncme_comm {
     std::vector<RegBuf> regs;
     int64_t p2p_matvecs = 0, nccl_matvecs = 0;
     // host-side all-reduce of step-control scalars through POSIX shared memory (all ranks live on one node)
-    struct HostReduce* hr = nullptr;
+    ncme::HostReduce* hr = nullptr;
     unsigned long long hr_epoch = 0;
     int64_t hr_reduces = 0;
     // grow-only integrator workspace, registered for peer access (re-allocation is a collective decision)
