@@ -13,7 +13,8 @@ using NumCME
 using StaticArrays: MVector
 import NumCME: expand!, deleteat!, get_state_count, get_sink_count, get_states, get_statedict,
     get_state_connectivity, get_sink_connectivity, get_stoich_matrix, matvec!, matvecadd!, matvec,
-    get_rowcount, get_colcount, get_parameters, get_propensities, init!, adapt!, solve
+    get_rowcount, get_colcount, get_parameters, get_propensities, init!, adapt!, solve, get_propensity_gradients,
+    get_gradient_sparsity_patterns, get_parameter_count
 import Base: size, *
 import LinearAlgebra: mul!
 
@@ -319,6 +320,61 @@ matvec(t, A::FspMatrixSparseB200, v) = (w = similar(v); matvec!(w, t, A, v); w)
 # addition (the reference imports mul! but defines no method, fspsparsematrix.jl:1): mul! at the cached time
 mul!(y, A::FspMatrixSparseB200, x) = (matvec!(y, isfinite(A.t_cache) ? A.t_cache : 0.0, A, x); y)
 
+# ------------------------------------------------------------------------------------------------ ForwardSensFspMatrixSparse
+# reference: src/forwardsensfspmatrix/forwardsensfspmatrixsparse/sensfspmatrixsparse.jl:9-22 (struct), :31-95 (ctor),
+# :97-142 (matvec!).  Vector layout [p; s_1; ...; s_P], each block n + R long.  A(t) is read once for all P + 1 blocks
+# and every dA/dtheta entry is streamed once (ncme_sens_matvec, one fused launch).
+mutable struct ForwardSensFspMatrixSparseB200{NS,NR} <: NumCME.ForwardSensFspMatrix
+    fspmatrix::FspMatrixSparseB200{NS,NR}
+    h::Ptr{Cvoid}
+    propensity_gradients::Vector{<:PropensityGradient}
+    entries::Vector{Tuple{Int,Int}}          # (reaction, parameter) pairs of the gradient sparsity pattern, parameter-major
+    dcoef::Vector{Float64}
+end
+function ForwardSensFspMatrixSparseB200(model::CmeModelWithSensitivity, space::StateSpaceSparseB200{NS,NR}) where {NS,NR}
+    θ = get_parameters(model)
+    # the derivative entries follow the user's classification of every reaction: no separability detection here
+    A = FspMatrixSparseB200(space, get_propensities(model); parameters = θ, detect_separable = false)
+    grads = get_propensity_gradients(model)
+    pattern = get_gradient_sparsity_patterns(model)
+    P = get_parameter_count(model)
+    ents = [(r, ip) for ip in 1:P for r in 1:NR if pattern[r, ip]]       # the reference's order (nzrange over CSC columns)
+    n = length(A.states)
+    dvals = zeros(Float64, n, max(length(ents), 1))                       # entry-major nentries x n for the ABI
+    for (e, (r, ip)) in enumerate(ents)
+        g = grads[r]
+        A.kinds[r] == 0 && (for i in 1:n; dvals[i, e] = g.pardiffs[ip](A.states[i], θ); end)
+        A.kinds[r] == 1 && (for i in 1:n; dvals[i, e] = g.statefactor_pardiffs[ip](A.states[i], θ); end)
+    end
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ncme_sensmatrix_create, libncme), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                A.h, P, length(ents), Int32[r for (r, _) in ents], Int32[ip for (_, ip) in ents], dvals, ref))
+    SA = ForwardSensFspMatrixSparseB200{NS,NR}(A, ref[], grads, ents, zeros(max(length(ents), 1)))
+    finalizer(x -> ccall((:ncme_sensmatrix_destroy, libncme), Cint, (Ptr{Cvoid},), x.h), SA)
+end
+get_propensity_gradients(SA::ForwardSensFspMatrixSparseB200) = SA.propensity_gradients
+
+# matvec!(out, t, SA, vs)                                         sensfspmatrixsparse.jl:97
+function matvec!(out::DeviceVector, t::Real, SA::ForwardSensFspMatrixSparseB200, vs::DeviceVector)
+    A = SA.fspmatrix
+    θ = A.parameters
+    P = length(θ)
+    (length(out) == (P + 1) * A.rowcount && length(vs) == (P + 1) * A.rowcount) ||
+        throw(DimensionMismatch("matvec!: expected vectors of length $((P + 1) * A.rowcount)"))
+    coef = _prepare!(A, t)
+    for (e, (r, ip)) in enumerate(SA.entries)
+        if A.kinds[r] == 1                                               # d tfactor / d theta_ip   (:124-132)
+            SA.dcoef[e] = SA.propensity_gradients[r].tfactor_pardiffs[ip](t, θ)
+        elseif A.kinds[r] == 2                                           # joint: d f / d theta_ip over all states (:134-139, see Q6)
+            vals = Float64[SA.propensity_gradients[r].pardiffs[ip](t, x, θ) for x in A.states]
+            check(ccall((:ncme_sensmatrix_set_joint_values, libncme), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), SA.h, e - 1, vals))
+        end
+    end
+    check(ccall((:ncme_sens_matvec, libncme), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}),
+                SA.h, coef, SA.dcoef, vs.ptr, out.ptr))
+    nothing
+end
+
 # ------------------------------------------------------------------------------------------------ adapters
 # init!(space, adapter, p, t, fsptol)            rstepadapters.jl:23 / :74
 function init!(space::StateSpaceSparseB200, adapter::Union{RStepAdapter,SelectiveRStepAdapter}, p::DeviceVector, t, fsptol)
@@ -418,6 +474,6 @@ function solve(model::CmeModel, p0::FspVectorSparse{NS,IntT,RealT}, tspan::Tuple
     out
 end
 
-export Context, DeviceVector, StateSpaceSparseB200, FspMatrixSparseB200, lincomb!, wrms, axpy!
+export Context, DeviceVector, StateSpaceSparseB200, FspMatrixSparseB200, ForwardSensFspMatrixSparseB200, lincomb!, wrms, axpy!
 
 end # module

@@ -65,5 +65,6 @@ def test_julia_ccalls_match_the_abi(pkg):
     # the entry points of the hot path are all bound
     for must in ("ncme_space_create", "ncme_space_expand", "ncme_space_delete", "ncme_matrix_create", "ncme_matvec",
                  "ncme_matvec_host", "ncme_solve_segment", "ncme_space_prune_by_mass", "ncme_space_compact_vector",
-                 "ncme_space_marginal", "ncme_matrix_create_incremental", "ncme_space_new_count"):
+                 "ncme_space_marginal", "ncme_matrix_create_incremental", "ncme_space_new_count", "ncme_sensmatrix_create",
+                 "ncme_sens_matvec", "ncme_sensmatrix_set_joint_values"):
         assert must in used, f"the Julia glue does not bind {must}"
