@@ -57,3 +57,23 @@ def test_prune_rule():  # rstepadapters.jl:41-43 vs :93-95 (>= vs >)
     assert a.drop_ids(p, 1.0, 1.0, 2e-9).tolist() == [2]
     thr_exact = 1.0 - (p.sum() - np.cumsum(np.sort(p))[0])
     assert len(a.drop_ids(p, 1.0, 1.0, thr_exact)) >= len(b.drop_ids(p, 1.0, 1.0, thr_exact))
+
+
+def test_telegraph_moments_analytic():
+    """Second independent pin of transient VALUES (the reference's tests pin none): the telegraph model
+    (examples/telegraph_cme.jl) has closed-form means.  P(gene on) = k01/(k01+k10) (1 - exp(-(k01+k10) t)) from the off
+    state, and the mean mRNA count solves m' = lam * P_on(t) - gam * m."""
+    k01, k10, lam, gam = 0.05, 0.1, 5.0, 0.5
+    props = [OProp("ti", f=lambda x, p: p[0] * x[0]), OProp("ti", f=lambda x, p: p[1] * x[1]),
+             OProp("ti", f=lambda x, p: p[2] * x[1]), OProp("ti", f=lambda x, p: p[3] * x[2])]
+    touts = [5.0, 20.0, 60.0]
+    sol = solve_adaptive(TELEGRAPH_S, props, [k01, k10, lam, gam], [[1, 0, 0]], [1.0], (0.0, 60.0),
+                         RStepAdapterOracle(5, 10, True), saveat=touts, fsptol=1e-8, odeatol=1e-13, odertol=1e-9, method="LSODA")
+    s = k01 + k10
+    for k, t in enumerate(touts):
+        st, p = sol["states"][k], sol["p"][k]
+        pon = k01 / s * (1 - math.exp(-s * t))
+        # m(t) = lam k01/s [ (1 - e^{-gam t})/gam - (e^{-s t} - e^{-gam t})/(gam - s) ]
+        m = lam * k01 / s * ((1 - math.exp(-gam * t)) / gam - (math.exp(-s * t) - math.exp(-gam * t)) / (gam - s))
+        assert float((p * st[:, 1]).sum()) == pytest.approx(pon, abs=2e-7)
+        assert float((p * st[:, 2]).sum()) == pytest.approx(m, abs=2e-6)
