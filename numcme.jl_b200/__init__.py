@@ -14,10 +14,11 @@ from .statespace import (StateSpaceSparse, expand_, deleteat_, get_state_count, 
                          get_statedict, get_state_connectivity, get_sink_connectivity)
 from .fspmatrix import FspMatrixSparse, matvec_, matvecadd_, matvec, get_rowcount, get_colcount
 from .sensmatrix import ForwardSensFspMatrixSparse, sens_matvec_
-from .fspvector import FspVectorSparse, FspOutputSparse, FspOutputSliceSparse
+from .fspvector import FspVectorSparse, FspOutputSparse, FspOutputSliceSparse, get_values, nnz
 from .transientcme import (solve, AdaptiveFspSparse, RStepAdapter, SelectiveRStepAdapter, NativeRK45, NativeBDF, NativeBDFClassic,
                            NativeBDFFused, init_, adapt_)
 from .forwardsenscme import (ForwardSensFspInitialConditionSparse, forwardsens_initial_condition, ForwardSensRStepAdapter,
+                             get_probability, get_sensitivity,
                              AdaptiveForwardSensFspSparse, ForwardSensFspOutputSparse, ForwardSensFspOutputSliceSparse)
 from .parallel import Comm, ShardedVector, shard_bounds
 from . import workloads

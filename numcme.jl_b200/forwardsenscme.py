@@ -41,6 +41,16 @@ def forwardsens_initial_condition(states, probabilities, sensitivity):
     return ForwardSensFspInitialConditionSparse(states, probabilities, sensitivity)
 
 
+def get_probability(ic: ForwardSensFspInitialConditionSparse):
+    """forwardsenscmesparse.jl:52"""
+    return ic.p
+
+
+def get_sensitivity(ic: ForwardSensFspInitialConditionSparse):
+    """forwardsenscmesparse.jl:53"""
+    return ic.S
+
+
 class ForwardSensRStepAdapter:
     """fsspaceadapterssparse.jl:10-14"""
 

@@ -79,6 +79,16 @@ class FspVectorSparse:
         return out
 
 
+def get_values(v: FspVectorSparse):
+    """fspvector.jl:19"""
+    return v.values
+
+
+def nnz(v: FspVectorSparse) -> int:
+    """fspvector.jl:21"""
+    return v.nnz()
+
+
 class FspOutputSliceSparse:
     def __init__(self, t, p, sinks):
         self.t, self.p, self.sinks = t, p, sinks
