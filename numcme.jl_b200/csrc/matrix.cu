@@ -1000,24 +1000,8 @@ __global__ void k_fill_sinks_group(const uint32_t* __restrict__ flags, const uin
     sink_val[k] = G[(int64_t)(r0 + q) * ng + row_lo + i];
 }
 
-__global__ void k_bit_flags(const uint32_t* __restrict__ mask, int64_t n, int r, uint32_t* __restrict__ flags) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = (mask[i] >> r) & 1u;
-}
 
-__global__ void k_pred_flags(const uint32_t* __restrict__ pred, int64_t n, uint32_t* __restrict__ flags) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = pred[i] != NONE32 ? 1u : 0u;
-}
 
-__global__ void k_fill_sinks(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
-                             const double* __restrict__ G_r, uint32_t* __restrict__ sink_row, double* __restrict__ sink_val) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flags[i]) {
-        sink_row[pos[i]] = (uint32_t)i;
-        sink_val[pos[i]] = G_r ? G_r[i] : 0.0;
-    }
-}
 
 // _update_sparsematrix! (:154-166) for one joint reaction: vals[i] = f(t, x_i, theta).
 __global__ void k_set_joint(const double* __restrict__ vals, int64_t n, const uint32_t* __restrict__ col,

@@ -18,10 +18,6 @@ __global__ void k_fill_u32(uint32_t* p, int64_t n, uint32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void k_fill_u64(uint64_t* p, int64_t n, uint64_t v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 
 // insert key -> value i for i in [first, n)
 __global__ void k_table_insert_range(HashView h, const uint64_t* __restrict__ keys, int64_t first, int64_t n) {
