@@ -141,6 +141,138 @@ def cpu_reference_arm(levels, steps, warmup, time_varying=True):
     return nbytes / dt / 1e9, dt, info, (OA, v, out)
 
 
+def cpu_sens_arm(model, x0, levels, steps, warmup, t=2.5):
+    """The reference's CPU sensitivity matvec (sensfspmatrixsparse.jl:97-142) restated with the C port of
+    SparseArrays.mul!: (P+1) full matvec! passes over A's terms, one pass of the summed time-invariant derivative
+    matrix per parameter, two passes per separable (reaction, parameter) entry -- all serial, Int64 indices."""
+    import ctypes
+    from oracle import cbaseline
+    from oracle.sensmatrix import SensFspMatrixOracle
+    from oracle.statespace import StateSpaceOracleFast
+    cm = model.cmemodel
+    osp = StateSpaceOracleFast(cm.stoich_matrix, x0)
+    osp.expand(levels)
+    OS = SensFspMatrixOracle(osp, cm.propensities, model.propensity_gradients, model.gradient_sparsity_patterns, cm.parameters)
+    A = OS.fspmatrix
+    N, P, th = A.rowcount, OS.parameter_count, cm.parameters
+    terms = cbaseline.CscTerms(A.terms_at(t))
+    lib = cbaseline.lib()
+    f64p, i64p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)
+
+    def csc(M):
+        M = M.tocsc()
+        return (np.ascontiguousarray(M.indptr, dtype=np.int64), np.ascontiguousarray(M.indices, dtype=np.int64),
+                np.ascontiguousarray(M.data, dtype=np.float64))
+    dti = [csc(M) for M in OS.timeinvariant_matdiffs]
+    dsep = [(ip, float(A.propensities[r - 1].tfactor(t, th)), float(OS.gradients[r - 1].tfactor_pardiffs[ip](t, th)),
+             csc(dM), csc(A.separabletv_factormatrices[j])) for (ip, r, j, dM) in OS.sep_entries]
+
+    def mul(M, x, alpha, y):
+        lib.ncme_oracle_csc_mul(ctypes.c_int64(N), ctypes.c_int64(N), M[0].ctypes.data_as(i64p), M[1].ctypes.data_as(i64p),
+                                M[2].ctypes.data_as(f64p), x.ctypes.data_as(f64p), ctypes.c_double(alpha),
+                                ctypes.c_double(1.0), y.ctypes.data_as(f64p))
+    rng = np.random.default_rng(0)
+    v = rng.random(N * (P + 1))
+    out = np.empty_like(v)
+    blocks = [v[b * N:(b + 1) * N] for b in range(P + 1)]
+    oblocks = [out[b * N:(b + 1) * N] for b in range(P + 1)]
+
+    def step():
+        terms.matvec(blocks[0], oblocks[0])
+        for ip in range(P):
+            terms.matvec(blocks[ip + 1], oblocks[ip + 1])
+            if dti[ip][2].size:
+                mul(dti[ip], blocks[0], 1.0, oblocks[ip + 1])
+            for (jp, c, dc, dM, FM) in dsep:
+                if jp == ip:
+                    mul(dM, blocks[0], c, oblocks[ip + 1])
+                    mul(FM, blocks[0], dc, oblocks[ip + 1])
+    for _ in range(warmup):
+        step()
+    ref = OS.matvec(t, v)
+    err = float(np.abs(out - ref).max() / np.abs(ref).max())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    # B_sens of this sample from the oracle's own structures (SURVEY 8(d))
+    nb = A.algorithmic_bytes() - 16 * N + 16 * N * (P + 1)
+    for M in OS.timeinvariant_matdiffs:
+        if M.nnz:
+            nb += 8 * M.nnz + 4 * (M.nnz - A.n)
+    for (_, _, _, dM) in OS.sep_entries:
+        nb += 8 * dM.nnz + 4 * (dM.nnz - A.n)
+    return {"kind": "port", "cores": 1, "unit": UNIT, "value": nb / dt / 1e9, "ms_per_matvec": dt * 1e3,
+            "check_vs_oracle_relerr": err,
+            "sample": f"L={levels} (n={A.n}, P={P}, {nb/1e6:.1f} MB B_sens), {steps} sensitivity matvecs as the reference "
+                      f"computes them: (P+1) x (1+n_sep) serial CSC passes over A + one pass per derivative matrix; "
+                      f"host has {os.cpu_count()} cores, the reference path uses 1"}
+
+
+def sens_leg(pkg, ctx, which, levels, steps, warmup, cpu=True, rows=0):
+    """K2 measurement (SURVEY 8(d) "Algorithmic bytes, sensitivity matvec"): one step = one fused block matvec
+    Y = [A p; A s_ip + dA_ip p] over all P + 1 blocks."""
+    import torch
+    if which == "hog1p":
+        th = list(pkg.workloads.HOG1P_THETA)
+        th[2] = 3.2e4
+        model, x0, tt = pkg.workloads.hog1p_sens_model(th), [1, 0, 0, 0, 0, 0], 120.0
+        cpu_levels = min(levels, 400)
+    else:
+        model, x0, tt = pkg.workloads.m3d_sens_model(), [0, 0, 0], 2.5
+        cpu_levels = min(levels, 100)
+    cm = model.cmemodel
+    t0 = time.perf_counter()
+    space = pkg.StateSpaceSparse(cm.stoich_matrix, x0, ctx=ctx)
+    space.expand_(levels)
+    t1 = time.perf_counter()
+    SA = pkg.ForwardSensFspMatrixSparse(model, space)
+    t2 = time.perf_counter()
+    if rows:
+        SA.set_tuning(rows)
+    st = SA.stats()
+    n, N, P = SA.fspmatrix.n, SA.fspmatrix.rowcount, SA.parameter_count
+    rng = np.random.default_rng(0)
+    X = pkg.DeviceVector.from_host(ctx, rng.random(N * (P + 1)))
+    Y = pkg.DeviceVector(ctx, N * (P + 1))
+    for _ in range(max(warmup, 3)):
+        pkg.matvec_(Y, tt, SA, X)
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pkg.matvec_(Y, tt, SA, X)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = ctx.launch_count() - l0
+    peak, peak_src = measured_peak()
+    gbs = st["algorithmic_bytes"] / (ms * 1e-3) / 1e9
+    out = {"metric": "fsp_sens_matvec_hbm_gbs", "value": gbs, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "gpu_launches": int(launches),
+           "config": {"workload": f"{which} forward-sensitivity block matvec, L={levels}", "states": n, "parameters": P,
+                      "entries": len(SA.entries), "slots": SA.fspmatrix.stats()["nterms"], "blocks": P + 1,
+                      "algorithmic_bytes_per_step": st["algorithmic_bytes"], "streamed_bytes_per_step": st["device_bytes"],
+                      "expand_s": round(t1 - t0, 3), "assemble_s": round(t2 - t1, 3),
+                      "l2_policy": "operands larger than the 126 MB L2" if st["device_bytes"] > 4e8 else
+                                   "operands fit the 126 MB L2 (small reference configuration)"},
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": UNIT, "frac": gbs / peak, "traffic": None,
+                        "peak_source": peak_src, "frac_of_nominal_8TBs": gbs / 8000.0, "kernel": "k_sens_matvec",
+                        "streamed_gbs": st["device_bytes"] / (ms * 1e-3) / 1e9,
+                        "note": "achieved = B_sens (SURVEY 8(d)) / CUDA-event time per launch"}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr) and which == "m3d":
+        try:
+            out["roofline"]["traffic"] = json.load(open(tr)).get("k_sens_matvec_dram_bytes_per_launch")
+        except Exception:
+            pass
+    SA.close()
+    if cpu:
+        out["cpu_baseline"] = cpu_sens_arm(model, x0, cpu_levels, 3 if which == "m3d" else 10, 1, tt)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +282,9 @@ def main():
     ap.add_argument("--levels", type=int, default=None, help="expansion depth of the M-3D simplex (default 390)")
     ap.add_argument("--rows", type=int, default=0, help="matvec kernel variant: rows per thread (0 = auto)")
     ap.add_argument("--pipe", default="", help="experiments: ROWS,STAGES of the shared-memory pipelined matvec kernel")
+    ap.add_argument("--workload", default="matvec", choices=["matvec", "sens", "sens-hog1p"],
+                    help="matvec: the headline K1 line (default); sens / sens-hog1p: the K2 line (M-3D P=6 / Hog1p P=14)")
+    ap.add_argument("--sens-rows", type=int, default=0, help="K2 kernel variant: rows per thread (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", action="store_true", help="skip the fixed-space solve leg")
     ap.add_argument("--solve-t", type=float, default=10.0, help="horizon of the solve leg")
@@ -185,6 +320,20 @@ def main():
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
+    if args.workload != "matvec":
+        if rank != 0:
+            return
+        ctx = pkg.Context(local_rank)
+        ctx.use_torch_stream()
+        which = "hog1p" if args.workload == "sens-hog1p" else "m3d"
+        lv = args.levels or (600 if which == "hog1p" else pkg.workloads.M3D_LEVELS)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        line = sens_leg(pkg, ctx, which, lv, K, W, cpu=not args.no_cpu, rows=args.sens_rows)
+        line.update({"n_gpus": 1, "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                     "dtype": "f64", "data": "synthetic", "clocks": sampler.stop()})
+        print(json.dumps(line))
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     ctx = pkg.Context(local_rank)

@@ -42,7 +42,8 @@ typedef enum {
     NCME_ERR_NOMEM = -3,
     NCME_ERR_KEYWIDTH = -4, /* a state component does not fit the 64-bit packed key */
     NCME_ERR_COMM = -5,     /* NCCL failure */
-    NCME_ERR_SOLVER = -6    /* integrator failure (step size underflow, GMRES breakdown ...) */
+    NCME_ERR_SOLVER = -6,   /* integrator failure (step size underflow, GMRES breakdown ...) */
+    NCME_ERR_ABORTED = -7   /* a host callback called ncme_request_abort() (it caught an exception) */
 } ncme_status;
 
 typedef struct ncme_ctx ncme_ctx;
@@ -171,6 +172,14 @@ int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* smat, int entry, const dou
  * [p; s_1; ...; s_P].  One fused launch; A is read once for all P+1 blocks. */
 int ncme_sens_matvec(ncme_sensmatrix* smat, const double* coef, const double* dcoef, const double* X_dev,
                      double* Y_dev);
+/* Structure of the derivative terms as the reference stores them (one summed CSC of the time-invariant derivatives
+ * per parameter, sensfspmatrixsparse.jl:44-58; one CSC per separable / joint entry, :60-93): stored entries per
+ * term (up to 2 * nentries values), B_sens of SURVEY.md 8(d), and the bytes the fused kernel streams.  Any output
+ * pointer may be NULL. */
+/* Experiments: rows per thread of the fused sensitivity kernel (0 = automatic, 1, 2). */
+int ncme_sensmatrix_set_tuning(ncme_sensmatrix* smat, int rows_per_thread);
+int ncme_sensmatrix_stats(ncme_sensmatrix* smat, int* ndterms, int64_t* nnz_per_dterm, int64_t* algorithmic_bytes,
+                          int64_t* device_bytes);
 
 /* ---------------------------------------------------------------- device vector ops (K7) ------ */
 /* The operations an ODE integrator performs on the FSP vector (DiffEq/CVODE internals driven from
@@ -286,6 +295,13 @@ typedef struct ncme_solve_stats {
 
 int ncme_solve_segment(ncme_matrix* mat, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
                        double* u_dev, const ncme_solve_opts* opts, ncme_solve_stats* stats);
+
+/* Callbacks return nothing and exceptions must not unwind through C frames (ctypes swallows them, a Julia @cfunction
+ * would crash): a callback that failed stores its exception on the host side and calls ncme_request_abort(); the
+ * running ncme_[sens_]solve_segment of this thread then stops before using the callback's output and returns
+ * NCME_ERR_ABORTED (the reference propagates the exception out of DE.step!, fspsolve.jl:161).  The flag is
+ * thread-local and cleared at the start of every segment. */
+void ncme_request_abort(void);
 
 /* Forward-sensitivity segment (src/forwardsenscme/sparse/forwardsenscmesparse.jl:142-166): the same integrator on
  * the block vector U = [p; s_1; ...; s_P] ((P+1)*(n+nr) doubles) with ncme_sens_matvec as right-hand side; the event

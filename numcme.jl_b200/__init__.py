@@ -3,7 +3,7 @@
 The directory name contains a dot, so load it with ``__graft_entry__.load_package()`` (registers the
 package as ``numcme_jl_b200``).  Mutating Julia functions ``f!`` are spelled ``f_`` here.
 """
-from ._lib import ArgumentError, NcmeError, LIB_PATH, load as load_library
+from ._lib import ArgumentError, NcmeError, SeparabilityError, LIB_PATH, load as load_library
 from .device import Context, DeviceVector
 from .cmemodel import (CmeModel, CmeModelWithSensitivity, Propensity, StandardTimeInvariantPropensity,
                        SeparableTimeVaryingPropensity, JointTimeVaryingPropensity, propensity, propensitygrad,

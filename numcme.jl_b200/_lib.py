@@ -22,6 +22,36 @@ class ArgumentError(ValueError):
     """Mirror of Julia's ArgumentError / DimensionMismatch raised by the reference."""
 
 
+class SeparabilityError(NcmeError):
+    """A joint propensity that was put on the separable path (rank-1 detection) turned out not to be a product
+    c(t) g(x) at a time actually used.  ``solve`` catches it and repeats the segment on the exact joint path."""
+
+
+class CallbackGuard:
+    """ctypes prints and swallows exceptions raised inside callbacks, so the C integrator would carry on with stale
+    data.  Callbacks run under ``guard.wrap``: the first exception is stored, libncme is told to stop
+    (``ncme_request_abort``) and ``guard.reraise()`` raises it in the caller once the C call has returned."""
+
+    def __init__(self):
+        self.exc = None
+
+    def wrap(self, fn):
+        def guarded(*args):
+            if self.exc is not None:
+                return
+            try:
+                fn(*args)
+            except BaseException as e:          # noqa: BLE001 -- must not unwind through C frames
+                self.exc = e
+                load().ncme_request_abort()
+        return guarded
+
+    def reraise(self):
+        exc, self.exc = self.exc, None
+        if exc is not None:
+            raise exc
+
+
 p_void = C.c_void_p
 p_i64 = C.POINTER(C.c_int64)
 p_i32 = C.POINTER(C.c_int32)
@@ -75,6 +105,8 @@ SIGNATURES = {
     "ncme_sensmatrix_destroy": (cint, [p_void]),
     "ncme_sensmatrix_set_joint_values": (cint, [p_void, cint, p_f64]),
     "ncme_sens_matvec": (cint, [p_void, p_f64, p_f64, p_void, p_void]),
+    "ncme_sensmatrix_set_tuning": (cint, [p_void, cint]),
+    "ncme_sensmatrix_stats": (cint, [p_void, C.POINTER(cint), p_i64, p_i64, p_i64]),
     "ncme_comm_unique_id": (cint, [C.c_char_p]),
     "ncme_comm_create": (cint, [p_void, cint, cint, C.c_char_p, C.POINTER(p_void)]),
     "ncme_comm_destroy": (cint, [p_void]),
@@ -90,6 +122,7 @@ SIGNATURES = {
     "ncme_space_compact_vector": (cint, [p_void, p_void, p_void]),
     "ncme_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),
     "ncme_sens_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),
+    "ncme_request_abort": (None, []),
     "ncme_vec_fill": (cint, [p_void, i64, f64, p_void]),
     "ncme_vec_copy": (cint, [p_void, i64, p_void, p_void]),
     "ncme_vec_scale": (cint, [p_void, i64, f64, p_void]),

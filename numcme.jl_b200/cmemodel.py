@@ -192,20 +192,38 @@ def get_gradient_sparsity_patterns(m: CmeModelWithSensitivity):
 
 
 def eval_over_states(fn, states: np.ndarray, p, t=None) -> np.ndarray:
-    """Evaluate ``fn(x,p)`` (or ``fn(t,x,p)``) at every row of ``states`` (n x NS) -> float64[n]."""
+    """Evaluate ``fn(x,p)`` (or ``fn(t,x,p)``) at every row of ``states`` (n x NS) -> float64[n].
+
+    One vectorised call with ``x[k]`` = the column of species k is tried first.  Its result is only trusted after a
+    spot check against scalar calls on a few states: a callable that reduces over species with numpy (``np.sum(x)``,
+    ``np.max(x)`` ...) returns a 0-d or wrongly shaped value for column arrays, and a broadcast of it would silently
+    assemble a wrong generator.  On any mismatch the per-state loop (the reference's calling convention,
+    fspsparsematrix.jl:129) is used."""
     n = states.shape[0]
+
+    def scalar(i):
+        x = [int(c) for c in states[i]]
+        return float(fn(x, p) if t is None else fn(t, x, p))
+
     cols = [states[:, k].astype(np.float64) for k in range(states.shape[1])]
     try:
         v = fn(cols, p) if t is None else fn(t, cols, p)
         v = np.asarray(v, dtype=np.float64)
         if v.ndim == 0:
-            return np.full(n, float(v))
+            v = np.full(n, float(v))
         if v.shape == (n,):
-            return np.ascontiguousarray(v)
+            ok = True
+            for i in sorted({0, n // 2, n - 1} if n else ()):
+                ref = scalar(i)
+                if not (v[i] == ref or abs(v[i] - ref) <= 1e-12 * max(abs(ref), abs(v[i])) or
+                        (np.isnan(ref) and np.isnan(v[i]))):
+                    ok = False
+                    break
+            if ok:
+                return np.ascontiguousarray(v)
     except Exception:
         pass
     out = np.empty(n, dtype=np.float64)
     for i in range(n):
-        x = [int(c) for c in states[i]]
-        out[i] = fn(x, p) if t is None else fn(t, x, p)
+        out[i] = scalar(i)
     return out

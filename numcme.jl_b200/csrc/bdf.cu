@@ -564,6 +564,7 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     std::vector<double> tails((size_t)(MAX_ORDER + 4) * std::max(R, 1));
 
     while (t < t1) {
+        if (abort_requested()) return abort_status();   // a save callback failed
         if (st->steps + st->rejected >= max_steps) {
             set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)max_steps, t);
             return NCME_ERR_SOLVER;

@@ -941,6 +941,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
 
     // ---- initial step size (Hairer's rule on the WRMS norms of u and f(t0, u)), D_1 = h f(t0, u)
     if (coef_fn) coef_fn(t0, coef, user);
+    if (abort_requested()) return abort_status();
     NCME_TRY(matvec_dist(A, coef, D[0], ynew, 0.0, 0));
     c.rhs_evals++;
     c.h_abs = o->h_init;
@@ -1038,6 +1039,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     };
 
     while (c.t < t1) {
+        if (abort_requested()) return abort_status();   // a save callback failed
         if (!multi) {
             if (c.steps + c.rejected >= c.max_steps) {
                 set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)c.max_steps, c.t);
@@ -1051,6 +1053,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
             bdf_begin_step(c, kc, sa.dyn, ctl_ws);
             if (coef_fn) {
                 coef_fn(c.t_new, coef, user);
+                if (abort_requested()) return abort_status();
                 MatvecArgs ma;
                 matvec_fill_args(A, coef, &ma);
                 for (int q = 0; q < A->nslots; ++q) sa.slot_coef[q] = ma.slot_coef[q];

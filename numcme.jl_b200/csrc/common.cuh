@@ -13,6 +13,9 @@
 namespace ncme {
 
 void set_error(const char* fmt, ...);
+bool abort_requested();   // a host callback called ncme_request_abort() (context.cu)
+void clear_abort();
+int abort_status();        // sets the message, returns NCME_ERR_ABORTED
 
 #define NCME_CUDA(expr)                                                                           \
     do {                                                                                          \

@@ -14,6 +14,14 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local int g_abort = 0;
+bool abort_requested() { return g_abort != 0; }
+void clear_abort() { g_abort = 0; }
+int abort_status() {
+    set_error("solve aborted by a host callback (ncme_request_abort)");
+    return NCME_ERR_ABORTED;
+}
+
 }  // namespace ncme
 
 using namespace ncme;
@@ -21,6 +29,8 @@ using namespace ncme;
 extern "C" {
 
 int ncme_version(void) { return NCME_VERSION; }
+
+void ncme_request_abort(void) { g_abort = 1; }
 
 const char* ncme_last_error(void) { return g_err; }
 

@@ -1381,6 +1381,7 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         for (int r = 0; r < nr; ++r)
             if (kind[r] == pass) A->nnz_term[nt++] = n + npred[r] + (int64_t)nsink_r[(size_t)r];
     A->nterms = nt;
+    for (int r = 0; r < nr; ++r) A->npred_r[r] = npred[r];
     A->algorithmic_bytes = 16 * A->N;
     for (int k = 0; k < nt; ++k) A->algorithmic_bytes += 8 * A->nnz_term[k] + 4 * (A->nnz_term[k] - n);
     // from now on the space tracks where its states were at this build (incremental constructor of the next matrix)

@@ -89,6 +89,7 @@ struct ncme_matrix {
     int nterms = 0;
     int64_t nnz_term[NCME_MAX_REACTIONS + 1] = {0};
     int64_t algorithmic_bytes = 0;
+    int64_t npred_r[NCME_MAX_REACTIONS] = {0};   // rows with a predecessor through reaction r (off-diagonal entries)
 
     // launch tuning (experiments): rows per thread (0 = auto), threads per block
     int tune_rows = 0;

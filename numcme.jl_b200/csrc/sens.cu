@@ -27,6 +27,7 @@ struct ncme_sensmatrix {
     ncme::DevArray<double> dpartial;  // [ntasks][nent]
     unsigned int* counter = nullptr;
     int* meta_dev = nullptr;  // ent_reaction | ent_param | ent_slot | ent_diag | ent_ptr  (device copy)
+    int tune_rows = 0;        // K2 rows per thread (0 = auto)
 };
 
 namespace ncme {
@@ -41,18 +42,20 @@ struct SensArgs {
     const double* dval;
     const double* ddiag;
     const double* dsink;
-    const int* ent_reaction;  // device meta
+    const int* ent_reaction;  // device meta (static per matrix)
     const int* ent_param;
     const int* ent_slot;
     const int* ent_diag;
     const int* ent_ptr;
     const int64_t* dsink_ptr;  // device
-    const double* ent_c;       // device: c_r(t) per entry
-    const double* ent_dc;      // device: d c_r / d theta (t) per entry
     double* partial;
     double* dpartial;
     unsigned int* counter;
+    // time-dependent scalars travel BY VALUE with the launch (no copy, no synchronisation per right-hand side)
+    double ent_c[SMAX_ENT];    // c_r(t) per entry (1 for time-invariant / joint reactions)
+    double ent_dc[SMAX_ENT];   // d c_r / d theta (t) per entry (separable reactions only)
 };
+static_assert(sizeof(SensArgs) <= 4096, "kernel parameter block must stay below 4 KB");
 
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -124,60 +127,137 @@ __device__ void sens_sink_task(const SensArgs& a) {
     }
 }
 
-template <int S>
+// streaming (evict-first) vector loads of ROWS consecutive entries: the once-read matrix must not evict the block
+// vectors, whose gathers live in L1/L2
+template <int ROWS>
+__device__ __forceinline__ void lds(const double* __restrict__ p, double (&v)[ROWS]);
+template <>
+__device__ __forceinline__ void lds<1>(const double* __restrict__ p, double (&v)[1]) {
+    v[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void lds<2>(const double* __restrict__ p, double (&v)[2]) {
+    const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+}
+template <int ROWS>
+__device__ __forceinline__ void ldsc(const uint32_t* __restrict__ p, uint32_t (&v)[ROWS]);
+template <>
+__device__ __forceinline__ void ldsc<1>(const uint32_t* __restrict__ p, uint32_t (&v)[1]) {
+    v[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void ldsc<2>(const uint32_t* __restrict__ p, uint32_t (&v)[2]) {
+    const uint2 t = __ldcs(reinterpret_cast<const uint2*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+}
+
+// K2.  One thread owns ROWS consecutive rows.  The row of A (column indices, values, combined diagonal) is loaded
+// once into registers with vector loads and applied to all P + 1 blocks; per parameter the derivative entries
+// (dval, ddiag: 16 B per row and entry) are streamed once.  All loads of one block iteration are independent and are
+// issued before the first use; the gathered p values a derivative entry needs are re-gathered (an L1 hit: the same
+// addresses were read for block 0) instead of being held in S registers per row.
+template <int S, int ROWS>
 __global__ void __launch_bounds__(SV_THREADS) k_sens_matvec(const __grid_constant__ SensArgs a) {
     const MatvecArgs& m = a.m;
     if ((int)blockIdx.x < m.ntasks) {
         sens_sink_task(a);
         return;
     }
-    const int64_t i = (int64_t)(blockIdx.x - m.ntasks) * SV_THREADS + threadIdx.x;
-    if (i >= m.n) return;
-    uint32_t c[S];
-    double v[S];
+    const int64_t i0 = ((int64_t)(blockIdx.x - m.ntasks) * SV_THREADS + threadIdx.x) * ROWS;
+    if (i0 >= m.n) return;
+    // ---- the row of A: first-level loads, all independent
+    uint32_t c[S][ROWS];
+    double v[S][ROWS];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        c[s] = __ldcs(m.col + (int64_t)s * m.ld + i);
-        v[s] = m.slot_coef[s] * __ldcs(m.val + (int64_t)s * m.ld + i);
+    for (int s = 0; s < S; ++s) ldsc<ROWS>(m.col + (int64_t)s * m.ld + i0, c[s]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) lds<ROWS>(m.val + (int64_t)s * m.ld + i0, v[s]);
+    double pi[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) pi[j] = (i0 + j < m.n) ? __ldg(m.x + i0 + j) : 0.0;
+    double d[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) d[j] = 0.0;
+    for (int k = 0; k < m.ndiag; ++k) {
+        double t[ROWS];
+        lds<ROWS>(m.diag + (int64_t)k * m.ld + i0, t);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) d[j] = fma(m.diag_coef[k], t[j], d[j]);
     }
-    double d = 0.0;
-    for (int k = 0; k < m.ndiag; ++k) d = fma(m.diag_coef[k], __ldcs(m.diag + (int64_t)k * m.ld + i), d);
-    // block 0 (probabilities): keep the gathered p values, the dA terms reuse them
-    double g0[S];
-    const double p_i = __ldg(m.x + i);
+    // padding rows (i0 + j >= n, only inside the last thread) carry col = self, val = 0: their gathers stay in range
+    // ---- block 0: y_0 = A p
     {
-        double acc = d * p_i;
+        double acc[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) acc[j] = d[j] * pi[j];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            g0[s] = __ldg(m.x + c[s]);
-            acc = fma(v[s], g0[s], acc);
+            const double cs = m.slot_coef[s];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) acc[j] = fma(cs * v[s][j], __ldg(m.x + c[s][j]), acc[j]);
         }
-        m.y[i] = acc;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (i0 + j < m.n) m.y[i0 + j] = acc[j];
     }
+    // ---- blocks 1..P: y_ip = A s_ip + sum_e [ c_e (dA_e p) + dc_e (A_r p) ]
     for (int ip = 0; ip < a.npar; ++ip) {
         const double* xb = m.x + (int64_t)(ip + 1) * a.N;
-        double acc = d * __ldg(xb + i);
+        double xs[ROWS], g[S][ROWS];
 #pragma unroll
-        for (int s = 0; s < S; ++s) acc = fma(v[s], __ldg(xb + c[s]), acc);
-        for (int e = a.ent_ptr[ip]; e < a.ent_ptr[ip + 1]; ++e) {
-            const int s = a.ent_slot[e];
-            if (s < 0) continue;
-            double gp = 0.0;
+        for (int j = 0; j < ROWS; ++j) xs[j] = (i0 + j < m.n) ? __ldg(xb + i0 + j) : 0.0;
 #pragma unroll
-            for (int q = 0; q < S; ++q)
-                if (q == s) gp = g0[q];
-            const double dv = __ldcs(a.dval + (int64_t)e * m.ld + i);
-            const double dd = __ldcs(a.ddiag + (int64_t)e * m.ld + i);
-            acc = fma(a.ent_c[e], fma(dv, gp, dd * p_i), acc);
-            const double dc = a.ent_dc[e];
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) g[s][j] = __ldg(xb + c[s][j]);
+        double acc[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) acc[j] = 0.0;
+        const int e0 = a.ent_ptr[ip], e1 = a.ent_ptr[ip + 1];
+        for (int e = e0; e < e1; ++e) {
+            const int se = a.ent_slot[e];
+            if (se < 0) continue;   // zero-stoichiometry reaction: contributes nothing
+            double dv[ROWS], dd[ROWS], gp[ROWS], vr[ROWS];
+            lds<ROWS>(a.dval + (int64_t)e * m.ld + i0, dv);
+            lds<ROWS>(a.ddiag + (int64_t)e * m.ld + i0, dd);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                uint32_t cc = c[0][j];
+                double vv = v[0][j];
+#pragma unroll
+                for (int q = 1; q < S; ++q)
+                    if (q == se) {
+                        cc = c[q][j];
+                        vv = v[q][j];
+                    }
+                gp[j] = __ldg(m.x + cc);   // p at the predecessor through the entry's reaction (L1 hit)
+                vr[j] = vv;
+            }
+            const double ce = a.ent_c[e], dc = a.ent_dc[e];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) acc[j] = fma(ce, fma(dv[j], gp[j], dd[j] * pi[j]), acc[j]);
             if (dc != 0.0) {
-                // (d c_r / d theta) * A_r p : the reaction's own slot and diagonal, without c_r
-                const double wr = __ldcs(m.val + (int64_t)s * m.ld + i);
-                const double gr = __ldcs(m.diag + (int64_t)a.ent_diag[e] * m.ld + i);
-                acc = fma(dc, fma(wr, gp, gr * p_i), acc);
+                // (d c_r / d theta) A_r p: the reaction's own slot (raw values, without c_r) and diagonal array
+                double gr[ROWS];
+                lds<ROWS>(m.diag + (int64_t)a.ent_diag[e] * m.ld + i0, gr);
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) acc[j] = fma(dc, fma(vr[j], gp[j], gr[j] * pi[j]), acc[j]);
             }
         }
-        m.y[(int64_t)(ip + 1) * a.N + i] = acc;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) acc[j] = fma(d[j], xs[j], acc[j]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double cs = m.slot_coef[s];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) acc[j] = fma(cs * v[s][j], g[s][j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+            if (i0 + j < m.n) m.y[(int64_t)(ip + 1) * a.N + i0 + j] = acc[j];
     }
 }
 
@@ -351,6 +431,53 @@ int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t
     return NCME_OK;
 }
 
+// Reference-structure statistics of the derivative terms ("Algorithmic bytes, sensitivity matvec"):
+// the reference holds, per parameter, ONE summed CSC of its time-invariant reactions' derivatives
+// (sensfspmatrixsparse.jl:44-58) and one CSC per separable / joint (reaction, parameter) entry (:60-93).
+//   B_sens = bytes(A) + sum_dterms (8 nnz + 4 nnz_offdiag) + 16 N (P + 1)
+int ncme_sensmatrix_stats(ncme_sensmatrix* SA, int* ndterms, int64_t* nnz_per_dterm, int64_t* algorithmic_bytes,
+                          int64_t* device_bytes) {
+    NCME_REQUIRE(SA, "null sensitivity matrix");
+    ncme_matrix* A = SA->A;
+    const int64_t n = A->n;
+    int nt = 0;
+    int64_t bytes = A->algorithmic_bytes - 16 * A->N;
+    auto add = [&](int64_t nnz) {
+        if (nnz_per_dterm) nnz_per_dterm[nt] = nnz;
+        ++nt;
+        bytes += 8 * nnz + 4 * (nnz - n);
+    };
+    for (int ip = 0; ip < SA->npar; ++ip) {
+        bool any = false, slot_seen[NCME_MAX_REACTIONS] = {false};
+        int64_t nnz = n;
+        for (int e = SA->ent_ptr[ip]; e < SA->ent_ptr[ip + 1]; ++e) {
+            const int r = SA->ent_reaction[e];
+            if (A->kind[r] != NCME_TIME_INVARIANT) continue;
+            any = true;
+            const int s = A->reaction_slot[r];
+            if (s >= 0 && !slot_seen[s]) {   // duplicates (same stoichiometry) are summed by sparse()
+                slot_seen[s] = true;
+                nnz += A->npred_r[r];
+            }
+            nnz += A->sink_ptr[r + 1] - A->sink_ptr[r];
+        }
+        // the reference builds this matrix for every parameter, empty (no stored entry) when no reaction depends on it
+        if (any) add(nnz);
+    }
+    for (int pass = NCME_SEPARABLE_TV; pass <= NCME_JOINT_TV; ++pass)
+        for (int e = 0; e < SA->nent; ++e) {
+            const int r = SA->ent_reaction[e];
+            if (A->kind[r] == pass) add(n + A->npred_r[r] + (A->sink_ptr[r + 1] - A->sink_ptr[r]));
+        }
+    bytes += 16 * A->N * (int64_t)(SA->npar + 1);
+    if (ndterms) *ndterms = nt;
+    if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    if (device_bytes)   // what the fused kernel actually streams: A once, two fp64 arrays per entry, the block vectors
+        *device_bytes = (int64_t)A->ld * (12 * A->nslots + 8 * A->ndiag) + 16 * (int64_t)SA->nent * A->ld +
+                        12 * A->nsink + 8 * SA->dsink_ptr[SA->nent] + 16 * A->N * (int64_t)(SA->npar + 1);
+    return NCME_OK;
+}
+
 int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* SA, int entry, const double* vals) {
     NCME_REQUIRE(SA && vals && entry >= 0 && entry < SA->nent, "bad arguments");
     const int e = SA->user_ent[entry];
@@ -386,39 +513,45 @@ int ncme_sens_matvec(ncme_sensmatrix* SA, const double* coef, const double* dcoe
     a.ent_ptr = SA->meta_dev + 4 * SMAX_ENT;
     char* base = (char*)SA->meta_dev + round_up<size_t>(meta_bytes, 16);
     a.dsink_ptr = (const int64_t*)base;
-    double* cdev = (double*)(base + (SMAX_ENT + 1) * sizeof(int64_t));
-    double hc[2 * SMAX_ENT];
     for (int e = 0; e < SA->nent; ++e) {
         const int r = SA->ent_reaction[e];
         const bool sep = A->kind[r] == NCME_SEPARABLE_TV;
-        hc[e] = sep ? coef[r] : 1.0;
-        hc[SMAX_ENT + e] = sep ? dcoef[SA->ent_user[e]] : 0.0;
+        a.ent_c[e] = sep ? coef[r] : 1.0;
+        a.ent_dc[e] = sep ? dcoef[SA->ent_user[e]] : 0.0;
     }
-    // pageable -> device copy of a few hundred bytes; ordered on the stream before the kernel
-    NCME_CUDA(cudaMemcpyAsync(cdev, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
-    NCME_CUDA(cudaStreamSynchronize(st));
-    a.ent_c = cdev;
-    a.ent_dc = cdev + SMAX_ENT;
     a.partial = SA->partial.p;
     a.dpartial = SA->dpartial.p;
     a.counter = SA->counter;
-    const unsigned grid = (unsigned)(A->ntasks + (A->n + SV_THREADS - 1) / SV_THREADS);
-    switch (A->nslots) {
-#define NCME_SCASE(SS)                                   \
-    case SS:                                             \
-        k_sens_matvec<SS><<<grid, SV_THREADS, 0, st>>>(a); \
+    int rows = SA->tune_rows ? SA->tune_rows : (A->nslots <= 8 ? 2 : 1);
+    const int64_t rpb = (int64_t)SV_THREADS * rows;
+    const unsigned grid = (unsigned)(A->ntasks + (A->n + rpb - 1) / rpb);
+    if (grid == 0) return NCME_OK;
+#define NCME_SCASE(SS)                                                   \
+    case SS:                                                             \
+        if (rows == 2)                                                   \
+            k_sens_matvec<SS, 2><<<grid, SV_THREADS, 0, st>>>(a);        \
+        else                                                             \
+            k_sens_matvec<SS, 1><<<grid, SV_THREADS, 0, st>>>(a);        \
         break;
+    switch (A->nslots) {
         NCME_SCASE(1) NCME_SCASE(2) NCME_SCASE(3) NCME_SCASE(4) NCME_SCASE(5) NCME_SCASE(6) NCME_SCASE(7) NCME_SCASE(8)
         NCME_SCASE(9) NCME_SCASE(10) NCME_SCASE(11) NCME_SCASE(12) NCME_SCASE(13) NCME_SCASE(14) NCME_SCASE(15) NCME_SCASE(16)
         NCME_SCASE(17) NCME_SCASE(18) NCME_SCASE(19) NCME_SCASE(20) NCME_SCASE(21) NCME_SCASE(22) NCME_SCASE(23) NCME_SCASE(24)
         NCME_SCASE(25) NCME_SCASE(26) NCME_SCASE(27) NCME_SCASE(28) NCME_SCASE(29) NCME_SCASE(30) NCME_SCASE(31) NCME_SCASE(32)
-#undef NCME_SCASE
         default:
             set_error("sens matvec: unsupported slot count %d", A->nslots);
             return NCME_ERR_ARG;
     }
+#undef NCME_SCASE
     ctx->launches++;
     NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+// experiments: rows per thread of K2 (0 = auto: 2 up to 8 slots, else 1)
+int ncme_sensmatrix_set_tuning(ncme_sensmatrix* SA, int rows_per_thread) {
+    NCME_REQUIRE(SA && (rows_per_thread == 0 || rows_per_thread == 1 || rows_per_thread == 2), "rows per thread: 0, 1 or 2");
+    SA->tune_rows = rows_per_thread;
     return NCME_OK;
 }
 

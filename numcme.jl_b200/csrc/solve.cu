@@ -357,6 +357,7 @@ int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     const size_t nres = (size_t)(1 + 9 * R);
 
     while (t < t1) {
+        if (abort_requested()) return abort_status();   // a save callback failed
         if (st->steps + st->rejected >= max_steps) {
             set_error("integrator: maximum number of steps (%lld) reached at t = %g", (long long)max_steps, t);
             return NCME_ERR_SOLVER;
@@ -512,6 +513,7 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     for (int r = 0; r < A->nr; ++r) need_coef |= (A->kind[r] != NCME_TIME_INVARIANT);
     NCME_REQUIRE(coef_fn || !need_coef, "the matrix has time-varying reactions: a coefficient callback is required");
     memset(stats, 0, sizeof(*stats));
+    clear_abort();
     double coef[NCME_MAX_REACTIONS];
     for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
     OdeSystem sys;
@@ -528,19 +530,23 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     sys.peers[1] = A->phi;
     sys.rhs = [&](double t, const double* x, double* y) -> int {
         if (coef_fn) coef_fn(t, coef, user);
+        if (abort_requested()) return abort_status();
         return matvec_dist(A, coef, x, y, 0.0, /*no sink reduction, inputs alternate buffers*/ 2);
     };
     sys.rhs_safe = [&](double t, const double* x, double* y) -> int {
         if (coef_fn) coef_fn(t, coef, user);
+        if (abort_requested()) return abort_status();
         return matvec_dist(A, coef, x, y, 0.0, 0);
     };
     sys.n_impl = A->n;
     sys.jac_diag = [&](double t, double* out) -> int {
         if (coef_fn) coef_fn(t, coef, user);
+        if (abort_requested()) return abort_status();
         return matrix_diag(A, coef, out);
     };
     sys.rhs_sinks = [&](double t, const double* x, double* y) -> int {
         if (coef_fn) coef_fn(t, coef, user);
+        if (abort_requested()) return abort_status();
         return matvec_sinks_only(A, coef, x, y);
     };
     if (opts->method == 0) return solve_dp5(sys, save_fn, user, t0, t1, u_dev, opts, stats);
@@ -576,6 +582,7 @@ extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn
     NCME_REQUIRE(t1 >= t0, "solve_segment: t1 < t0");
     NCME_REQUIRE(opts->nsave == 0 || opts->save_t, "save_t is null");
     memset(stats, 0, sizeof(*stats));
+    clear_abort();
     ncme_matrix* A = nullptr;
     int npar = 0, nent = 0;
     NCME_TRY(sens_describe(SA, &A, &npar, &nent));
@@ -590,6 +597,7 @@ extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn
     sys.n_global = A->n;
     sys.rhs = [&](double t, const double* x, double* y) -> int {
         coef_fn(t, cf.data(), user);
+        if (abort_requested()) return abort_status();
         return ncme_sens_matvec(SA, cf.data(), cf.data() + A->nr, x, y);
     };
     // BDF: the whole block vector is implicit; Jacobian = [A 0; dA A] => block-Jacobi diagonal = diag(A) per block
@@ -597,6 +605,7 @@ extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn
     sys.n_impl = sys.len;
     sys.jac_diag = [&](double t, double* out) -> int {
         coef_fn(t, cf.data(), user);
+        if (abort_requested()) return abort_status();
         cudaStream_t st = A->ctx->stream;
         NCME_CUDA(cudaMemsetAsync(out, 0, (size_t)sys.len * sizeof(double), st));
         NCME_TRY(matrix_diag(A, cf.data(), out));

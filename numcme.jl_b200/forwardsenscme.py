@@ -189,7 +189,8 @@ def solve_sens(model: CmeModelWithSensitivity, initial_condition: ForwardSensFsp
         def save_cb(t, ptr, _user, L_=N * (P + 1)):
             saved_t.append(float(t))
             saved_u.append(np.ctypeslib.as_array(ptr, shape=(L_,)).copy())
-        ccb, scb = L.COEF_FN(coef_cb), L.SAVE_FN(save_cb)
+        guard = L.CallbackGuard()
+        ccb, scb = L.COEF_FN(guard.wrap(coef_cb)), L.SAVE_FN(guard.wrap(save_cb))
         opts = L.SolveOpts()
         opts.rtol, opts.atol = float(odertol), float(odeatol)
         opts.check_event, opts.event_slope = 1, float(fsptol / tend)
@@ -198,9 +199,11 @@ def solve_sens(model: CmeModelWithSensitivity, initial_condition: ForwardSensFsp
         opts.nsave, opts.save_t = int(sva.size), sva.ctypes.data_as(C.POINTER(C.c_double))
         opts.h_init, opts.max_steps, opts.method = 0.0, 0, method
         stats = L.SolveStats()
-        L.check(L.load().ncme_sens_solve_segment(SA._h, C.cast(ccb, C.c_void_p), C.cast(scb, C.c_void_p), None,
-                                                 float(tnow), float(tend), C.c_void_p(U.ptr), C.byref(opts),
-                                                 C.byref(stats)))
+        status = L.load().ncme_sens_solve_segment(SA._h, C.cast(ccb, C.c_void_p), C.cast(scb, C.c_void_p), None,
+                                                  float(tnow), float(tend), C.c_void_p(U.ptr), C.byref(opts),
+                                                  C.byref(stats))
+        guard.reraise()                  # exceptions of user closures raised inside the callbacks
+        L.check(status)
         for k in ("steps", "rejected", "rhs_evals", "launches"):
             tot[k] += getattr(stats, k)
         states = space.get_states()

@@ -59,7 +59,10 @@ def _rank1_info(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
     order = np.argsort(-np.abs(g), kind="stable")
     nz = order[: int(np.count_nonzero(g))]
     sent = [int(nz[0])] + [int(nz[k]) for k in (len(nz) // 3, 2 * len(nz) // 3, len(nz) - 1) if 0 < k < len(nz)]
-    return {"g": g, "sent": list(dict.fromkeys(sent)), "t_ref": t_ref, "ratios": ratios, "rtol": rtol}
+    # one more sentinel OUTSIDE the support of g (the state with the largest molecule count): f must stay 0 there
+    off = np.nonzero(g == 0.0)[0]
+    zero_sent = [int(off[np.argmax(states[off].sum(axis=1))])] if off.size else []
+    return {"g": g, "sent": list(dict.fromkeys(sent)), "zero_sent": zero_sent, "t_ref": t_ref, "ratios": ratios, "rtol": rtol}
 
 
 def _rank1_extend(f, info, new_states, parameters):
@@ -155,6 +158,7 @@ class FspMatrixSparse:
                     propvals[r, :n] = g
                     self.kinds[r] = SEPARABLE_TV
                     info["sent_states"] = [[int(v) for v in self.states[i]] for i in info["sent"]]
+                    info["zero_states"] = [[int(v) for v in self.states[i]] for i in info["zero_sent"]]
                     info["sent_g"] = [float(g[i]) for i in info["sent"]]
                     self._rank1[r + 1] = info
                     self._tfactor[r + 1] = self._make_rank1_tfactor(r + 1, a.f, info)
@@ -245,15 +249,17 @@ class FspMatrixSparse:
         L.check(L.load().ncme_matrix_set_tuning(self._h, int(rows_per_thread)))
 
     def _make_rank1_tfactor(self, rid, f, info):
-        xs, gs = info["sent_states"], info["sent_g"]
+        xs, gs, zs = info["sent_states"], info["sent_g"], info.get("zero_states", [])
 
         def tfactor(t):
             c = float(f(t, xs[0], self.parameters)) / gs[0]
+            bad = any(float(f(t, z, self.parameters)) != 0.0 for z in zs)
             for x, gv in zip(xs[1:], gs[1:]):          # sentinels: the product form must hold at every t actually used
                 ck = float(f(t, x, self.parameters)) / gv
-                if abs(ck - c) > 1e-9 * max(abs(c), abs(ck), 1e-300):
-                    raise L.NcmeError(f"propensity {rid} was classified as c(t) g(x) on the probe times but is not "
-                                      f"separable at t = {t!r}; build the matrix with detect_separable=False")
+                bad |= abs(ck - c) > 1e-9 * max(abs(c), abs(ck), 1e-300)
+            if bad:                                    # solve() catches this and repeats the segment on the joint path
+                raise L.SeparabilityError(f"propensity {rid} was classified as c(t) g(x) on the probe times but is not "
+                                          f"separable at t = {t!r}; build the matrix with detect_separable=False")
             return c
         return tfactor
 

@@ -91,6 +91,18 @@ class ForwardSensFspMatrixSparse:
                                      C.c_void_p(dx.ptr), C.c_void_p(dy.ptr)))
         out[:] = dy.to_host()
 
+    def set_tuning(self, rows_per_thread: int):
+        L.check(L.load().ncme_sensmatrix_set_tuning(self._h, int(rows_per_thread)))
+
+    def stats(self) -> dict:
+        """Stored entries per derivative term as the reference holds them, B_sens and the bytes the
+        fused kernel streams per matvec."""
+        nt, ab, db = C.c_int(), C.c_int64(), C.c_int64()
+        nnz = (C.c_int64 * (2 * max(len(self.entries), 1) + 2))()
+        L.check(L.load().ncme_sensmatrix_stats(self._h, C.byref(nt), nnz, C.byref(ab), C.byref(db)))
+        return {"ndterms": nt.value, "nnz_per_dterm": [nnz[k] for k in range(nt.value)],
+                "algorithmic_bytes": ab.value, "device_bytes": db.value}
+
     def close(self):
         if getattr(self, "_h", None):
             L.load().ncme_sensmatrix_destroy(self._h)

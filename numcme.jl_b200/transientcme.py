@@ -134,8 +134,9 @@ class _Segment:
             self.saved_t.append(float(t))
             self.saved_u.append(np.ctypeslib.as_array(u_ptr, shape=(N,)).copy())
 
-        self._coef_cb = L.COEF_FN(coef_cb)
-        self._save_cb = L.SAVE_FN(save_cb)
+        self._guard = L.CallbackGuard()
+        self._coef_cb = L.COEF_FN(self._guard.wrap(coef_cb))
+        self._save_cb = L.SAVE_FN(self._guard.wrap(save_cb))
         self.needs_coef = bool(A.device_separable_ids or A.device_joint_ids)
 
     def run(self, u: DeviceVector, t0, t1, saveat=None, save_every_step=False, event_slope=None):
@@ -153,8 +154,10 @@ class _Segment:
         stats = L.SolveStats()
         self.saved_t, self.saved_u = [], []
         cb = C.cast(self._coef_cb, C.c_void_p) if self.needs_coef else None
-        L.check(L.load().ncme_solve_segment(self.A.handle, cb, C.cast(self._save_cb, C.c_void_p), None, float(t0),
-                                            float(t1), C.c_void_p(u.ptr), C.byref(opts), C.byref(stats)))
+        status = L.load().ncme_solve_segment(self.A.handle, cb, C.cast(self._save_cb, C.c_void_p), None, float(t0),
+                                             float(t1), C.c_void_p(u.ptr), C.byref(opts), C.byref(stats))
+        self._guard.reraise()            # an exception raised inside a callback (the C side stopped: NCME_ERR_ABORTED)
+        L.check(status)
         return stats
 
 
@@ -183,14 +186,19 @@ def _initial(model, initial_distribution):
 
 
 def solve(model: CmeModel, initial_distribution: FspVectorSparse, tspan, algorithm=None, saveat=None, fsptol=1.0e-6,
-          odeatol=None, odertol=1.0e-4, verbose=False, ctx=None, comm=None) -> FspOutputSparse:
+          odeatol=None, odertol=1.0e-4, verbose=False, ctx=None, comm=None, detect_separable=True) -> FspOutputSparse:
     """``solve(model, p0, tspan, ode_method; saveat, odeatol, odertol)``   (fixed space, fspsolve.jl:10-41) when
     ``algorithm`` is None or an ODE method, and
     ``solve(model, p0, tspan, fspalgorithm::AdaptiveFspSparse; saveat, fsptol, odeatol, odertol, verbose)``
     (adaptive, fspsolve.jl:105-197) when it is an ``AdaptiveFspSparse``.
 
     ``comm`` (parallel.Comm, one process per GPU) row-shards the matrix and every FSP vector over the ranks; the
-    state space and the adaptation decisions are replicated, every rank returns the same (gathered) output."""
+    state space and the adaptation decisions are replicated, every rank returns the same (gathered) output.
+
+    ``detect_separable`` (not in the reference): joint time-varying propensities that are numerically a product
+    c(t) g(x) are integrated on the separable path (see ``FspMatrixSparse``).  The classification is re-checked on
+    sentinel states at every time the integrator uses; if it ever fails, the running segment is discarded and
+    repeated with the exact joint path (``_update_sparsematrix!``) -- never a silently wrong generator."""
     if comm is not None and ctx is None:
         ctx = comm.ctx
     from .cmemodel import CmeModelWithSensitivity
@@ -203,8 +211,9 @@ def solve(model: CmeModel, initial_distribution: FspVectorSparse, tspan, algorit
                           odertol=odertol, verbose=verbose, ctx=ctx)
     if isinstance(algorithm, AdaptiveFspSparse):
         return _solve_adaptive(model, initial_distribution, tspan, algorithm, saveat, fsptol, odeatol, odertol, verbose,
-                               ctx, comm)
-    return _solve_fixed(model, initial_distribution, tspan, algorithm, saveat, odeatol, odertol, ctx, comm)
+                               ctx, comm, detect_separable)
+    return _solve_fixed(model, initial_distribution, tspan, algorithm, saveat, odeatol, odertol, ctx, comm,
+                        detect_separable)
 
 
 class _Dist:
@@ -241,7 +250,7 @@ class _Dist:
         return self.u.v.to_host(self.nloc, self.R)
 
 
-def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx, comm=None):
+def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx, comm=None, detect_separable=True):
     states0, vals0 = _initial(model, p0)
     space = StateSpaceSparse(model.stoich_matrix, states0, ctx=ctx)
     R = space.get_sink_count()
@@ -250,13 +259,23 @@ def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx, co
     n = space.get_state_count()
     pv = np.zeros(n)
     pv[idx[idx > 0] - 1] = vals0[idx > 0]
-    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
-    dist = _Dist(A, comm)
-    dist.load(DeviceVector.from_host(space.ctx, pv), np.zeros(R))
     sv = _saveat_array(saveat, tspan)
-    seg = _Segment(A, odertol, odeatol, _method_code(ode_method))
     t_wall = time.perf_counter()
-    stats = seg.run(dist.u.v, tspan[0], tspan[1], saveat=sv, save_every_step=sv is None)
+    p_dev = DeviceVector.from_host(space.ctx, pv)
+    while True:
+        A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm,
+                            detect_separable=detect_separable)
+        dist = _Dist(A, comm)
+        dist.load(p_dev, np.zeros(R))
+        seg = _Segment(A, odertol, odeatol, _method_code(ode_method))
+        try:
+            stats = seg.run(dist.u.v, tspan[0], tspan[1], saveat=sv, save_every_step=sv is None)
+            break
+        except L.SeparabilityError:          # a detected c(t) g(x) form broke down: repeat on the exact joint path
+            if not detect_separable:
+                raise
+            detect_separable = False
+            A.close()
     out = FspOutputSparse()
     states = space.get_states()
     for t, uu in zip(seg.saved_t, seg.saved_u):
@@ -268,7 +287,8 @@ def _solve_fixed(model, p0, tspan, ode_method, saveat, odeatol, odertol, ctx, co
     return out
 
 
-def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, verbose, ctx, comm=None):
+def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, verbose, ctx, comm=None,
+                    detect_separable=True):
     tstart, tend = min(tspan), max(tspan)
     sv = _saveat_array(saveat, tspan)
     adapter = alg.space_adapter
@@ -284,7 +304,8 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
     p = init_(space, adapter, DeviceVector.from_host(ctx, pv), tstart, fsptol)   # all states, replicated
     tnow = tstart
     sinks = np.zeros(R)
-    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm)
+    A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm,
+                        detect_separable=detect_separable)
     out = FspOutputSparse()
     tot = {"steps": 0, "rejected": 0, "rhs_evals": 0, "launches": 0, "adapts": 0, "matrix_builds": 1}
     while tnow < tend:
@@ -292,7 +313,19 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
         dist = _Dist(A, comm)
         dist.load(p, sinks)
         seg = _Segment(A, odertol, odeatol, method)
-        stats = seg.run(dist.u.v, tnow, tend, saveat=sv, save_every_step=sv is None, event_slope=fsptol / tend)
+        try:
+            stats = seg.run(dist.u.v, tnow, tend, saveat=sv, save_every_step=sv is None, event_slope=fsptol / tend)
+        except L.SeparabilityError:
+            # a joint propensity detected as c(t) g(x) broke the product form at a time the integrator used: discard
+            # this segment (p, sinks still hold its initial state) and repeat it on the exact joint path
+            if not detect_separable:
+                raise
+            detect_separable = False
+            A.close()
+            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm, detect_separable=False)
+            tot["matrix_builds"] += 1
+            tot["separability_fallbacks"] = tot.get("separability_fallbacks", 0) + 1
+            continue
         for k in ("steps", "rejected", "rhs_evals", "launches"):
             tot[k] += getattr(stats, k)
         states = space.get_states() if seg.saved_t else None
@@ -310,7 +343,8 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
                 dsinks = du.to_host(dist.nloc, R)
             p = adapt_(space, adapter, dist.gather(), sinks, tnow, tend, fsptol, dsinks=dsinks)
             A_old = A                                    # incremental rebuild: only the new states are evaluated (H8)
-            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm, previous=A_old)
+            A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm, previous=A_old,
+                                detect_separable=detect_separable)
             A_old.close()
             tot["incremental_builds"] = tot.get("incremental_builds", 0) + (1 if A.incremental else 0)
             tot["adapts"] += 1

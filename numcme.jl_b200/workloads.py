@@ -122,3 +122,61 @@ def hog1p_model(theta=HOG1P_THETA, separable=True) -> CmeModel:
         propensity(lambda x, p: p[13] * x[5]),
     ]
     return CmeModel(S, props, list(theta))
+
+
+def _zero_x(x, p):
+    return 0.0 * x[0]
+
+
+def _zero_t(t, p):
+    return 0.0
+
+
+def hog1p_sens_model(theta=HOG1P_THETA):
+    """BASELINE.json config 3: the Hog1p model of examples/hog1p.jl:33-82 as a ``CmeModelWithSensitivity`` (NS = 6,
+    R = 13, P = 14).  Gradient sparsity as src/cmemodel/senstools/sparsity_pattern.jl:19-30 derives it from the rate
+    laws: one parameter per reaction, plus (k10, a) both on reaction 2 (G1 -> G0, rate max(0, k10 - a Hog1p(t))) --
+    15 (reaction, parameter) entries.  Reaction 2 is separable: its time factor carries both parameters."""
+    from .cmemodel import CmeModelWithSensitivity, propensitygrad, propensitygrad_timevarying
+    model = hog1p_model(theta, separable=True)
+    P = 14
+    par_of_reaction = {0: 0, 2: 3, 3: 4, 4: 5, 5: 6, 6: 7, 7: 8, 8: 9, 9: 10, 10: 11, 11: 12, 12: 13}
+    species_of_reaction = {0: 0, 2: 1, 3: 2, 4: 2, 5: 3, 6: 0, 7: 1, 8: 2, 9: 3, 10: 4, 11: 4, 12: 5}
+    pattern = np.zeros((13, P), dtype=bool)
+    grads = []
+    for r in range(13):
+        if r == 1:
+            pattern[r, 1] = pattern[r, 2] = True
+            active = lambda t, p: 1.0 if p[1] - p[2] * hog1p_signal(t) > 0.0 else 0.0
+            dt = [_zero_t] * P
+            dt[1] = active
+            dt[2] = lambda t, p: -hog1p_signal(t) * active(t, p)
+            a = model.propensities[r]
+            grads.append(propensitygrad_timevarying(a.tfactor, a.statefactor, dt, [_zero_x] * P))
+            continue
+        ip, k = par_of_reaction[r], species_of_reaction[r]
+        pattern[r, ip] = True
+        d = [_zero_x] * P
+        d[ip] = (lambda x, p, k=k: 1.0 * x[k])
+        grads.append(propensitygrad(d))
+    return CmeModelWithSensitivity(model, pattern, grads)
+
+
+def m3d_sens_model(time_varying=True):
+    """M-3D (BASELINE.json config 5) with its P = 6 rate constants as sensitivity parameters: reaction r depends on
+    parameter r only (6 derivative matrices); the separable time factor of death-3 carries no parameter."""
+    from .cmemodel import CmeModelWithSensitivity, propensitygrad, propensitygrad_timevarying
+    model = m3d_model(time_varying=time_varying)
+    P = 6
+    dstate = [lambda x, p: 1.0 + 0.0 * x[0], lambda x, p: 1.0 * x[0], lambda x, p: 1.0 + 0.0 * x[0],
+              lambda x, p: 1.0 * x[1], lambda x, p: 1.0 + 0.0 * x[0], lambda x, p: 1.0 * x[2]]
+    grads = []
+    for r in range(6):
+        d = [_zero_x] * P
+        d[r] = dstate[r]
+        a = model.propensities[r]
+        if a.kind == "sep":
+            grads.append(propensitygrad_timevarying(a.tfactor, a.statefactor, [_zero_t] * P, d))
+        else:
+            grads.append(propensitygrad(d))
+    return CmeModelWithSensitivity(model, np.eye(6, dtype=bool), grads)

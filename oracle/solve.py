@@ -24,6 +24,17 @@ from .statespace import StateSpaceOracleFast
 EPS = np.finfo(np.float64).eps
 
 
+def _sparse_jac(A):
+    """Exact Jacobian A(t) = sum of the reference's per-term CSC matrices (the ODE is linear): lets scipy's implicit
+    methods factorise a sparse matrix instead of estimating a dense one column by column."""
+    def jac(t, u):
+        J = None
+        for c, M in A.terms_at(t):
+            J = c * M if J is None else J + c * M
+        return J.tocsc()
+    return jac
+
+
 class RStepAdapterOracle:
     selective = False
 
@@ -68,21 +79,22 @@ class SelectiveRStepAdapterOracle(RStepAdapterOracle):
 
 
 def solve_fixed(stoich, propensities, parameters, states, p0, tspan, saveat=None,
-                odeatol=1e-6, odertol=1e-4, method="BDF"):
+                odeatol=1e-6, odertol=1e-4, method="BDF", sparse_jac=False):
     """fspsolve.jl:10-41 on a fixed state space given by ``states`` (rows)."""
     space = StateSpaceOracleFast(stoich, states)
     A = FspMatrixOracle(space, propensities, parameters)
     R = space.get_sink_count()
     u0 = np.concatenate([p0, np.zeros(R)])
+    kw = {"jac": _sparse_jac(A)} if sparse_jac and method in ("BDF", "Radau") else {}
     sol = solve_ivp(lambda t, u: A.matvec(t, u), tspan, u0, method=method, atol=odeatol, rtol=odertol,
-                    t_eval=saveat)
+                    t_eval=saveat, **kw)
     n = space.get_state_count()
     return {"t": sol.t, "states": space.states_array(), "p": [sol.y[:n, k] for k in range(sol.t.size)],
             "sinks": [sol.y[n:, k] for k in range(sol.t.size)]}
 
 
 def solve_adaptive(stoich, propensities, parameters, states0, p0, tspan, adapter, saveat=None,
-                   fsptol=1e-6, odeatol=1e-6, odertol=1e-4, method="BDF", verbose=False):
+                   fsptol=1e-6, odeatol=1e-6, odertol=1e-4, method="BDF", verbose=False, sparse_jac=False):
     """fspsolve.jl:105-197.  Returns dict(t, states[k], p[k], sinks[k])."""
     tstart, tend = min(tspan), max(tspan)
     saveat = None if saveat is None else np.asarray(saveat, dtype=np.float64)
@@ -109,8 +121,9 @@ def solve_adaptive(stoich, propensities, parameters, states0, p0, tspan, adapter
         te = None
         if saveat is not None:
             te = saveat[(saveat >= tnow) & (saveat <= tend)]
+        kw = {"jac": _sparse_jac(A)} if sparse_jac and method in ("BDF", "Radau") else {}
         sol = solve_ivp(rhs, (tnow, tend), unow, method=method, atol=odeatol, rtol=odertol,
-                        events=event, t_eval=te, dense_output=False)
+                        events=event, t_eval=te, dense_output=False, **kw)
         hit = sol.status == 1
         sol.t = np.asarray(sol.t, dtype=np.float64)
         sol.y = np.asarray(sol.y, dtype=np.float64).reshape(unow.size, -1)
@@ -124,7 +137,7 @@ def solve_adaptive(stoich, propensities, parameters, states0, p0, tspan, adapter
                 out["p"].append(sol.y[:n, k].copy())
                 out["sinks"].append(sol.y[n:, k].copy())
         if u_stop is None:                       # reached tend with t_eval: integrate state at tend
-            s2 = solve_ivp(rhs, (tnow, tend), unow, method=method, atol=odeatol, rtol=odertol)
+            s2 = solve_ivp(rhs, (tnow, tend), unow, method=method, atol=odeatol, rtol=odertol, **kw)
             u_stop = s2.y[:, -1]
         tnow = t_stop
         if tnow < tend:

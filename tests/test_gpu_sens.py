@@ -155,3 +155,94 @@ def test_sens_solve_bdf_matches_explicit(pkg):
     for ip in range(5):
         sb = b.S[0][ip].values
         assert np.abs(on(a.S[0][ip], st) - sb).max() <= 2e-5 * max(np.abs(sb).max(), 1e-2), ip
+
+
+def test_sens_hog1p_matrix_vs_oracle(pkg, ctx):
+    """BASELINE.json config 3: Hog1p (examples/hog1p.jl:33-82, NS=6, R=13, P=14) with the forward-sensitivity matrix
+    (sensfspmatrixsparse.jl:31-142): 15 (reaction, parameter) entries, separable reaction 2 carrying two parameters in
+    its time factor.  >= 10^4 states, 1e-12 relative, device-resident and host-buffer entry points."""
+    th = list(pkg.workloads.HOG1P_THETA)
+    th[2] = 3.2e4                                     # a: signal on, so d c / d(k10, a) are non-trivial
+    model = pkg.workloads.hog1p_sens_model(th)
+    cm = model.cmemodel
+    sp = pkg.StateSpaceSparse(cm.stoich_matrix, [1, 0, 0, 0, 0, 0], ctx=ctx)
+    sp.expand_(105)                                   # gene states x (nuclear, cytoplasmic) RNA counts: ~4 L^2 / 2 states
+    osp = StateSpaceOracleFast(cm.stoich_matrix, [1, 0, 0, 0, 0, 0])
+    osp.expand(105)
+    n = sp.get_state_count()
+    assert n >= 10000 and np.array_equal(sp.get_states(), osp.states_array())
+    SA = pkg.ForwardSensFspMatrixSparse(model, sp)
+    assert len(SA.entries) == 15 and SA.parameter_count == 14
+    OS = SensFspMatrixOracle(osp, cm.propensities, model.propensity_gradients, model.gradient_sparsity_patterns, th)
+    N = SA.fspmatrix.rowcount
+    rng = np.random.default_rng(5)
+    v = rng.random(15 * N)
+    dv, do = pkg.DeviceVector.from_host(ctx, v), pkg.DeviceVector(ctx, 15 * N)
+    out = np.empty_like(v)
+    for t in (0.0, 45.0, 120.0, 900.0):               # k10 - a Hog1p(t) changes sign between these times
+        ref = OS.matvec(t, v)
+        pkg.matvec_(do, t, SA, dv)
+        got = do.to_host()
+        for b in range(15):                           # per block: every sensitivity block to 1e-12 of its own scale
+            sl = slice(b * N, (b + 1) * N)
+            assert _relerr(got[sl], ref[sl]) <= 1e-12, (t, b)
+        pkg.matvec_(out, t, SA, v)                    # host-buffer entry point
+        assert np.array_equal(out, got)
+    ones = np.ones(15 * N)
+    pkg.matvec_(out, 120.0, SA, ones)                 # column sums of A and of every dA vanish (telegraph.jl:34-43)
+    assert abs(out.sum()) <= 1e-9 * np.abs(out).sum()
+
+
+def test_sens_m3d_matrix_vs_oracle(pkg, ctx):
+    """The bench's sensitivity workload (M-3D, P = 6, separable death-3) at 1.8e5 states vs the oracle."""
+    model = pkg.workloads.m3d_sens_model()
+    cm = model.cmemodel
+    sp = pkg.StateSpaceSparse(cm.stoich_matrix, [0, 0, 0], ctx=ctx)
+    sp.expand_(100)
+    osp = StateSpaceOracleFast(cm.stoich_matrix, [0, 0, 0])
+    osp.expand(100)
+    SA = pkg.ForwardSensFspMatrixSparse(model, sp)
+    OS = SensFspMatrixOracle(osp, cm.propensities, model.propensity_gradients, model.gradient_sparsity_patterns, cm.parameters)
+    N = SA.fspmatrix.rowcount
+    v = np.random.default_rng(9).random(7 * N)
+    dv, do = pkg.DeviceVector.from_host(ctx, v), pkg.DeviceVector(ctx, 7 * N)
+    for t in (0.0, 2.5):
+        pkg.matvec_(do, t, SA, dv)
+        got, ref = do.to_host(), OS.matvec(t, v)
+        for b in range(7):
+            assert _relerr(got[b * N:(b + 1) * N], ref[b * N:(b + 1) * N]) <= 1e-12, (t, b)
+
+
+def _on_states(states_from, values, states_to):
+    d = {tuple(s): v for s, v in zip(states_from.tolist(), values)}
+    return np.array([d.get(tuple(s), 0.0) for s in states_to.tolist()])
+
+
+@pytest.mark.parametrize("method", ["bdf", "rk45"])
+def test_sens_solve_vs_oracle(pkg, method):
+    """The forward-sensitivity solve loop against its ORACLE (oracle/senssolve.py, restating
+    forwardsenscmesparse.jl:99-215 and pinned by analytic birth-death sensitivities) on the reference's own telegraph
+    sensitivity fixture (test/test_sensfsp.jl, test/sensmat/telegraph.jl): probabilities, all five sensitivity blocks,
+    sinks and d(sinks)/d(theta)."""
+    from oracle.senssolve import ForwardSensRStepAdapterOracle, solve_sens
+    props, grads, pattern, _ = sens_telegraph()
+    model = _sensmodel(pkg, TELEGRAPH_S, props, grads, pattern, SENS_THETA)
+    ic = pkg.forwardsens_initial_condition([[1, 0, 0]], [1.0], [[0.0] for _ in range(5)])
+    ode = None if method == "bdf" else pkg.NativeRK45()
+    alg = pkg.AdaptiveForwardSensFspSparse(ode_method=ode, space_adapter=pkg.ForwardSensRStepAdapter(10, 10, True))
+    touts = [5.0, 20.0, 40.0]
+    rt = 1e-7 if method == "bdf" else 1e-8
+    sol = pkg.solve(model, ic, (0.0, 40.0), alg, saveat=touts, fsptol=1e-8, odeatol=1e-13, odertol=rt)
+    ref = solve_sens(TELEGRAPH_S, props, grads, pattern, SENS_THETA, [[1, 0, 0]], [1.0], [[0.0]] * 5, (0.0, 40.0),
+                     ForwardSensRStepAdapterOracle(10, 10, True), saveat=touts, fsptol=1e-8, odeatol=1e-13, odertol=1e-9)
+    assert len(sol) == len(ref["t"]) == len(touts) + 1
+    tol = 2e-5 if method == "bdf" else 2e-6
+    for k in range(len(touts)):
+        st = ref["states"][k]
+        assert np.abs(_on_states(sol.p[k].states, sol.p[k].values, st) - ref["p"][k]).max() < tol
+        assert np.abs(sol.sinks[k] - ref["sinks"][k]).max() < tol
+        for ip in range(5):
+            s_ref = ref["S"][k][ip]
+            scale = max(np.abs(s_ref).max(), 1e-2)
+            assert np.abs(_on_states(sol.S[k][ip].states, sol.S[k][ip].values, st) - s_ref).max() <= tol * scale, (k, ip)
+            assert np.abs(sol.dsinks[k][ip] - ref["dsinks"][k][ip]).max() <= tol * scale, (k, ip)

@@ -363,3 +363,84 @@ def test_bdf_fused_multistep_launches(pkg):
     assert f1.stats["launches"] < 0.1 * f1.stats["steps"] + 10
     assert np.abs(f1.p[-1].values - rk.p[0].values).max() < 5e-7
     assert np.abs(f1.sinks[-1] - rk.sinks[0]).max() < 5e-7
+
+
+def test_callback_exceptions_propagate(pkg):
+    """an exception raised by a user time factor / propensity inside the integrator's host callback
+    must stop the C integrator (NCME_ERR_ABORTED) and surface in the caller."""
+    class Boom(RuntimeError):
+        pass
+
+    def tfac(t, p):
+        if t > 3.0:
+            raise Boom(f"time factor failed at t = {t}")
+        return 1.0
+    props = [pkg.propensity(lambda x, p: 0.05 * x[0]), pkg.propensity(lambda x, p: 0.1 * x[1], tfac),
+             pkg.propensity(lambda x, p: 5.0 * x[1]), pkg.propensity(lambda x, p: 1.0 * x[2])]
+    model = pkg.CmeModel(TELEGRAPH_S, props, [])
+    p0 = pkg.FspVectorSparse([[1, 0, 0]], [1.0])
+    for ode in (None, pkg.NativeRK45(), pkg.NativeBDFClassic()):
+        alg = pkg.AdaptiveFspSparse(ode_method=ode, space_adapter=pkg.RStepAdapter(10, 10, True))
+        with pytest.raises(Boom):
+            pkg.solve(model, p0, (0.0, 50.0), alg)
+    # the library is usable afterwards (the abort flag is cleared at the next segment)
+    ok = pkg.CmeModel(TELEGRAPH_S, _to_pkg_props(pkg, fspmat_propensities("tv")), FSPMAT_THETA)
+    alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=pkg.RStepAdapter(10, 10, True))
+    sol = pkg.solve(ok, p0, (0.0, 10.0), alg)
+    assert sol.p[-1].sum() + sol.sinks[-1].sum() == pytest.approx(1.0, abs=1e-6)
+
+
+def test_separability_fallback_in_solve(pkg):
+    """f = c1 x0 + 1{5<t<10} c2 x1 is classified as separable from the probe times; the run-time
+    sentinels must catch it and solve() must repeat the segment on the exact joint path -- same answer as
+    detect_separable=False, and different from the (wrong) separable generator."""
+    S = np.array([[1, 0], [-1, 0], [0, 1], [0, -1]]).T
+    f = lambda t, x, p: 0.3 * x[0] + (2.0 * x[1] if 5.0 < t < 10.0 else 0.0 * x[1])
+    props = [pkg.propensity(lambda x, p: 4.0 + 0.0 * x[0]), pkg.propensity(lambda x, p: 0.2 * x[0]),
+             pkg.propensity(f), pkg.propensity(lambda x, p: 0.5 * x[1])]
+    model = pkg.CmeModel(S, props, [])
+    p0 = pkg.FspVectorSparse([[3, 2]], [1.0])
+    alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=pkg.RStepAdapter(15, 10, True))
+    kw = dict(saveat=[4.0, 8.0, 12.0], fsptol=1e-6, odertol=1e-7, odeatol=1e-12)
+    auto = pkg.solve(model, p0, (0.0, 12.0), alg, **kw)
+    exact = pkg.solve(model, p0, (0.0, 12.0), alg, detect_separable=False, **kw)
+    assert auto.stats.get("separability_fallbacks", 0) == 1
+    for k in range(len(exact)):
+        a, b = _align(auto.p[k].states, auto.p[k].values, exact.p[k].states, exact.p[k].values)
+        assert np.abs(a - b).max() < 1e-6
+    # sanity: the window matters (mean of species 2 at t = 12 differs visibly from a run that ignores it)
+    g = lambda t, x, p: 0.3 * x[0]
+    m2 = pkg.CmeModel(S, props[:2] + [pkg.propensity(g), props[3]], [])
+    wrong = pkg.solve(m2, p0, (0.0, 12.0), alg, **kw)
+    mean = lambda sol: float((sol.p[-1].values * sol.p[-1].states[:, 1]).sum())
+    assert abs(mean(exact) - mean(wrong)) > 0.1
+
+
+@pytest.mark.parametrize("variant", ["full_sep", "sel_sep", "full_joint"])
+def test_toggle_full_horizon_vs_oracle(pkg, variant):
+    """BASELINE.json config 2 at the example's FULL horizon (examples/toggleswitch_fsp_variants.jl:62-75: t in
+    [0, 8 h], saveat every 60 s = 481 slices + the final one, RStepAdapter / SelectiveRStepAdapter (20, 5, true),
+    odertol 1e-4, odeatol 1e-14) against oracle.solve.solve_adaptive (scipy BDF with the exact sparse Jacobian at
+    odertol 1e-8).  Tolerance = the solver tolerance: |p_gpu - p_oracle| <= 1e-4 * max p per slice at the example's
+    odertol = 1e-4, and 2e-6 at odertol = 1e-7."""
+    sep = variant != "full_joint"
+    selective = variant == "sel_sep"
+    model = pkg.workloads.toggle_model(separable=sep)
+    tend = 8 * 3600.0
+    touts = np.arange(0.0, tend + 1.0, 60.0)
+    ada = (pkg.SelectiveRStepAdapter if selective else pkg.RStepAdapter)(20, 5, True)
+    oada = (SelectiveRStepAdapterOracle if selective else RStepAdapterOracle)(20, 5, True)
+    ref = solve_adaptive(model.stoich_matrix, model.propensities, model.parameters, [[0, 0]], [1.0], (0.0, tend), oada,
+                         saveat=touts, fsptol=1e-6, odeatol=1e-14, odertol=1e-8, method="BDF", sparse_jac=True)
+    assert len(ref["t"]) == 482
+    p0 = pkg.FspVectorSparse([[0, 0]], [1.0])
+    for rt, tol in ((1e-4, 1e-4), (1e-7, 2e-6)):
+        sol = pkg.solve(model, p0, (0.0, tend), pkg.AdaptiveFspSparse(None, ada), saveat=touts, odertol=rt, odeatol=1e-14)
+        assert len(sol) == 482 and np.allclose(sol.t, ref["t"])
+        worst = 0.0
+        for k in range(0, 482, 13):
+            a, b = _align(sol.p[k].states, sol.p[k].values, ref["states"][k], ref["p"][k])
+            worst = max(worst, np.abs(a - b).max() / b.max())
+            assert sol.p[k].sum() + sol.sinks[k].sum() == pytest.approx(1.0, abs=1e-6)
+        print(f"toggle {variant} odertol={rt:g}: worst slice error {worst:.2e} of max p; {sol.stats}")
+        assert worst <= tol

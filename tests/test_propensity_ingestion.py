@@ -36,3 +36,59 @@ def test_detect_rank1_host(pkg):
     assert FM.detect_rank1(lambda t, x, p: 0.0 * x[0], st, []) is None
     # support that moves in time is not separable
     assert FM.detect_rank1(lambda t, x, p: np.where(x[0] > t, 1.0, 0.0) * (1.0 + x[1]), st, []) is None
+
+
+def test_eval_over_states_rejects_species_reductions(pkg):
+    """a propensity that reduces over species with numpy must not be broadcast as a constant."""
+    from numcme_jl_b200.cmemodel import eval_over_states
+    st = np.array([[0, 1], [2, 3], [4, 5]], dtype=np.int64)
+    assert eval_over_states(lambda x, p: p[0] * np.sum(x), st, [2.0]).tolist() == [2.0, 10.0, 18.0]
+    assert eval_over_states(lambda x, p: float(np.max(x)), st, []).tolist() == [1.0, 3.0, 5.0]
+    assert eval_over_states(lambda x, p: np.prod(x), st, []).tolist() == [0.0, 6.0, 20.0]
+    # genuinely constant and properly vectorised callables keep the one-call path
+    assert eval_over_states(lambda x, p: 3.0, st, []).tolist() == [3.0, 3.0, 3.0]
+    assert eval_over_states(lambda x, p: p[0] * x[0] * x[1], st, [0.5]).tolist() == [0.0, 3.0, 10.0]
+    assert eval_over_states(lambda t, x, p: t * x[1], st, [], t=2.0).tolist() == [2.0, 6.0, 10.0]
+    assert eval_over_states(lambda x, p: 1.0, st[:0], []).shape == (0,)
+
+
+def test_rank1_probe_miss_is_caught_by_sentinels(pkg):
+    """f = x0 + 1{5<t<10} 2 x1 passes the six probe times; the run-time sentinels must refuse it."""
+    import numcme_jl_b200.fspmatrix as FM
+    import numcme_jl_b200._lib as L
+    st = _states()
+    f = lambda t, x, p: 1.0 * x[0] + (2.0 * x[1] if 5.0 < t < 10.0 else 0.0 * x[1])
+    info = FM._rank1_info(f, st, [])
+    assert info is not None                      # the probe times miss the window: classified as separable
+    g = info["g"]
+    info["sent_states"] = [[int(v) for v in st[i]] for i in info["sent"]]
+    info["sent_g"] = [float(g[i]) for i in info["sent"]]
+    info["zero_states"] = [[int(v) for v in st[i]] for i in info["zero_sent"]]
+    assert info["zero_states"] and info["zero_states"][0][0] == 0       # a state outside the support of g = x0
+
+    class Holder:
+        parameters = []
+    tf = FM.FspMatrixSparse._make_rank1_tfactor(Holder(), 1, f, info)
+    assert tf(1.0) == 1.0 and tf(12.0) == 1.0
+    import pytest
+    with pytest.raises(L.SeparabilityError):
+        tf(7.0)
+
+
+def test_callback_guard_stores_first_exception(pkg):
+    """exceptions inside ctypes callbacks are stored and re-raised, never swallowed."""
+    import numcme_jl_b200._lib as L
+    import pytest
+    calls = []
+    guard = L.CallbackGuard()
+
+    def boom(t):
+        calls.append(t)
+        raise KeyError("user tfactor failed")
+    cb = guard.wrap(boom)
+    cb(1.0)              # must not raise here (we would be inside a C frame)
+    cb(2.0)              # after a failure the callback is not entered again
+    assert calls == [1.0]
+    with pytest.raises(KeyError):
+        guard.reraise()
+    guard.reraise()      # cleared
