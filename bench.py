@@ -119,6 +119,8 @@ def cpu_reference_arm(levels, steps, warmup, time_varying=True):
     # threads OpenMP gives this process (torchrun pins OMP_NUM_THREADS=1; the plain N=1 run gets every core)
     best_omp = None
     try:
+        if levels > 200:       # the extra line is for the bounded sample only (summing 70 M-entry scipy matrices is slow)
+            raise RuntimeError("skipped at full size")
         fused = None
         for c, m in OA.terms_at(2.5):
             fused = c * m if fused is None else fused + c * m
@@ -135,10 +137,41 @@ def cpu_reference_arm(levels, steps, warmup, time_varying=True):
     except Exception as exc:   # the baseline arm must not fail the bench
         best_omp = {"error": repr(exc)}
     info = {"kind": "port", "cores": 1, "unit": UNIT, "value": nbytes / dt / 1e9, "best_omp": best_omp,
+            "states": osp.get_state_count(), "algorithmic_bytes": nbytes,
             "sample": f"M-3D TV at L={levels} (n={osp.get_state_count()}, {nbytes/1e6:.1f} MB algorithmic bytes per matvec), "
                       f"{steps} serial CSC matvecs (one pass per term, Int64 indices) = SparseArrays.mul! restated in C; "
                       f"{dt*1e3:.2f} ms per matvec; host has {os.cpu_count()} cores, the reference path uses 1"}
     return nbytes / dt / 1e9, dt, info, (OA, v, out)
+
+
+CPU_SOLVE_LEVELS = 120           # M-3D at L=120: 302 621 states; holds all but ~1e-8 of the mass at t = 10
+
+
+def cpu_solve_arm(pkg, t_end, n_full):
+    """MEASURED CPU baseline of the fixed-space solve (BASELINE.md section 2 `cpu_solve`): the structure of the
+    reference's CVODE_BDF(linear_solver=:GMRES) run (variable-order BDF, matrix-free Jacobi-GMRES, one serial per-term
+    CSC matvec per right-hand side) on a bounded sample of the workload -- oracle/cpu_solve.py."""
+    from oracle.cpu_solve import bdf_gmres_fixed
+    from oracle.fspmatrix import FspMatrixOracle
+    from oracle.statespace import StateSpaceOracleFast
+    model = pkg.workloads.m3d_model(time_varying=True)
+    osp = StateSpaceOracleFast(model.stoich_matrix, [0, 0, 0])
+    osp.expand(CPU_SOLVE_LEVELS)
+    OA = FspMatrixOracle(osp, model.propensities, model.parameters)
+    ns = osp.get_state_count()
+    u0 = np.zeros(OA.rowcount)
+    u0[0] = 1.0
+    u, st = bdf_gmres_fixed(OA, u0, (0.0, t_end), rtol=1e-4, atol=1e-8)
+    X = osp.states_array()
+    return {"kind": "port", "cores": 1, "unit": "s", "value": st["wall_s"], "steps": st["steps"],
+            "rhs_evals": st["rhs_evals"], "krylov_matvecs": st["krylov_matvecs"], "mass": float(u.sum()),
+            "mean_x": [float((u[:ns] * X[:, k]).sum()) for k in range(3)],
+            "scaled_to_full_size_s": st["wall_s"] * n_full / ns,
+            "sample": f"M-3D TV at L={CPU_SOLVE_LEVELS} (n={ns} of the {n_full} states; the same initial condition, horizon and "
+                      f"tolerances; the truncated tail holds < 1e-7 of the mass, see mean_x), scipy BDF (NDF) stepping with "
+                      f"matrix-free Jacobi-GMRES(24) linear solves and the C restatement of the serial per-term CSC matvec "
+                      f"as right-hand side = the structure of the reference's CVODE_BDF(GMRES) path; measured wall time on "
+                      f"1 of {os.cpu_count()} host cores; scaled_to_full_size_s = value x n_full / n (cost per step is linear in n)"}
 
 
 def cpu_sens_arm(model, x0, levels, steps, warmup, t=2.5):
@@ -207,6 +240,21 @@ def cpu_sens_arm(model, x0, levels, steps, warmup, t=2.5):
             "sample": f"L={levels} (n={A.n}, P={P}, {nb/1e6:.1f} MB B_sens), {steps} sensitivity matvecs as the reference "
                       f"computes them: (P+1) x (1+n_sep) serial CSC passes over A + one pass per derivative matrix; "
                       f"host has {os.cpu_count()} cores, the reference path uses 1"}
+
+
+def telegraph_cpu_ms(pkg):
+    from oracle.solve import RStepAdapterOracle, solve_adaptive
+    tm = pkg.workloads.telegraph_model()
+    res = {}
+    for m in ("BDF", "LSODA"):
+        tt = []
+        for _ in range(3):
+            tq = time.perf_counter()
+            solve_adaptive(tm.stoich_matrix, tm.propensities, tm.parameters, [[1, 0, 0]], [1.0], (0.0, 300.0),
+                           RStepAdapterOracle(5, 10, True), method=m)
+            tt.append(time.perf_counter() - tq)
+        res[m] = min(tt) * 1e3
+    return res
 
 
 def sens_leg(pkg, ctx, which, levels, steps, warmup, cpu=True, rows=0):
@@ -307,9 +355,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        gbs, dt, info, _ = cpu_reference_arm(CPU_SAMPLE_LEVELS, max(1, min(K, 40)), min(W, 3))
+        # the SAME configuration as our arm (M-3D TV at the full L): building it through the oracle's numpy expand!
+        # takes ~1.5 min and ~9 GB of host memory; every timed step is one full-size serial matvec (~0.1-0.2 s)
+        gbs, dt, info, _ = cpu_reference_arm(levels, K, W)
+        config.update({"states": info.pop("states"), "algorithmic_bytes_per_step": info.pop("algorithmic_bytes")})
         line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": max(1, min(K, 40)), "warmup": min(W, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "steps": K, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
                 "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "cpu_baseline": info,
                 "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -381,20 +432,31 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing: one step = one fused matvec over the whole (sharded) state space
+    # The clock sampler (a fork + exec of nvidia-smi: milliseconds, different on every rank) starts BEFORE the barrier.
+    # Ranks are then aligned on the DEVICE: an NCCL all-reduce on the compute stream followed by a few untimed pre-roll
+    # matvecs, so that every GPU's queue already holds work when e0 is reached and host-side launch skew between the
+    # ranks (which the boundary rows' flag wait would otherwise charge to the faster rank) stays outside the timed region.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         A.matvec_local_(y, tt, x.v)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    if world > 1:
+        dist.all_reduce(torch.zeros(1, device=f"cuda:{local_rank}"))
+    PRE = 8 if world > 1 else 0
+    for _ in range(PRE):
         A.matvec_local_(y, tt, x.v)
-    e1.record()
+    l0 = ctx.launch_count()
+    ev[0].record()
+    for i in range(K):
+        A.matvec_local_(y, tt, x.v)
+        ev[i + 1].record()
     barrier()
     launches = ctx.launch_count() - l0
-    ms = e0.elapsed_time(e1) / K
+    ms = ev[0].elapsed_time(ev[K]) / K
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
+    step_stats = {"median_ms": per_step[K // 2], "min_ms": per_step[0], "max_ms": per_step[-1]}
     # nvidia-smi delivers a sample every ~100 ms and the timed region may be shorter: keep issuing the SAME kernel
     # (untimed) until at least 5 samples under this load are in, so that clocks / throttle reasons are observed
     ms_hold = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -464,7 +526,43 @@ def main():
                            "method": {"dp5": "native Dormand-Prince 5(4)", "bdf": "native BDF/NDF + Jacobi-GMRES"}[best] +
                                      ", device-resident", "all_methods": runs})
 
+    # ---- the same solve through the PUBLIC API, end to end (SURVEY 8(d) "solve metric": wall time of `solve` incl. the
+    # state-space build, propensity evaluation, matrix assembly, the adaptive loop and the output download; only
+    # context / NCCL init excluded): solve(model, p0, tspan, AdaptiveFspSparse(RStepAdapter(L, 10, false)); saveat)
+    if solve_info is not None:
+        try:
+            p0 = pkg.FspVectorSparse([[0, 0, 0]], [1.0])
+            alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=pkg.RStepAdapter(levels, 10, False))
+            barrier()
+            tw = time.perf_counter()
+            sol = pkg.solve(model, p0, (0.0, args.solve_t), alg, saveat=[args.solve_t], ctx=ctx, comm=comm)
+            barrier()
+            api_wall = time.perf_counter() - tw
+            if world > 1:
+                tw_t = torch.tensor([api_wall], dtype=torch.float64, device=f"cuda:{local_rank}")
+                dist.all_reduce(tw_t, op=dist.ReduceOp.MAX)
+                api_wall = float(tw_t)
+            pl = sol.p[-1]
+            solve_info["solve_api_wall_s"] = api_wall
+            solve_info["solve_api"] = {"call": f"solve(model, p0, (0, {args.solve_t}), AdaptiveFspSparse(nothing, RStepAdapter({levels}, 10, false)); saveat=[{args.solve_t}])",
+                                       "steps": int(sol.stats["steps"]), "rhs_evals": int(sol.stats["rhs_evals"]),
+                                       "adapts": int(sol.stats["adapts"]), "final_states": int(sol.stats["final_states"]),
+                                       "breakdown_s": sol.stats.get("breakdown_s"),
+                                       "mass": float(pl.values.sum() + sol.sinks[-1].sum()),
+                                       "mean_x": [float((pl.values * pl.states[:, k]).sum()) for k in range(3)],
+                                       "includes": "expand! of the simplex, host propensity evaluation, matrix assembly, "
+                                                   "the integration, download of the final distribution and its states"}
+            del sol, pl
+        except Exception as exc:
+            solve_info["solve_api"] = {"error": repr(exc)}
+
+    per_rank_ms = [ms]
     if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"ms": ms, **step_stats})
+        per_rank_ms = [g_["ms"] for g_ in gathered]
+        step_stats = {"median_ms": max(g_["median_ms"] for g_ in gathered), "min_ms": max(g_["min_ms"] for g_ in gathered),
+                      "max_ms": max(g_["max_ms"] for g_ in gathered)}
         tms = torch.tensor([ms, ms_e2e, solve_info["wall_s"] if solve_info else 0.0], dtype=torch.float64,
                            device=f"cuda:{local_rank}")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -483,6 +581,9 @@ def main():
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "per_step": {**step_stats, "per_rank_ms_per_step": per_rank_ms,
+                         "note": "ms_per_step = (event after step K - event before step 1) / K, max over ranks; "
+                                 "median/min/max of the K per-step event intervals (max over ranks of each)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (nloc + R) * world,
                     "d2h_bytes_per_step": 8 * (nloc + R) * world, "ms_per_step": ms_e2e, "checksum_sum_y_states": checksum},
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": UNIT, "frac": per_gpu / peak,
@@ -503,9 +604,10 @@ def main():
         gbs, dt, info_cpu, _ = cpu_reference_arm(CPU_SAMPLE_LEVELS, 20, 2)
         line["cpu_baseline"] = info_cpu
         if solve_info:
-            # estimate: the reference spends (at least) one serial CPU matvec per RHS evaluation
-            line["solve"]["cpu_est_s"] = solve_info["rhs_evals"] * (nbytes / (gbs * 1e9))
-            line["solve"]["cpu_est_note"] = "rhs_evals x full-size matvec time at the measured 1-core CPU GB/s (lower bound: no integrator vector ops)"
+            try:
+                solve_info["cpu_baseline"] = cpu_solve_arm(pkg, args.solve_t, n)
+            except Exception as exc:   # the baseline leg must not fail the bench
+                solve_info["cpu_baseline"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_solve:
         # BASELINE.json configs[0] (the reference's own CPU-runnable case and its only published number):
         # examples/telegraph_cme.jl, adaptive FSP solve over t in [0, 300], defaults
@@ -523,6 +625,8 @@ def main():
             line["parity_configs"] = {"telegraph_adaptive_solve_ms": {
                 "best": min(tt_) * 1e3, "median": sorted(tt_)[len(tt_) // 2] * 1e3, "steps": sol.stats["steps"],
                 "launches": sol.stats["launches"], "adapts": sol.stats["adapts"], "final_states": sol.stats["final_states"],
+                "cpu_oracle_ms": telegraph_cpu_ms(pkg),
+                "cpu_oracle_note": "oracle.solve.solve_adaptive (scipy BDF / LSODA restatement of fspsolve.jl:105-197), best of 3 each, on this host, 1 core",
                 "reference_published_ms": 5.454, "reference_hardware": "Apple M1, Julia, docs/src/examples/telegraph.md:84-90",
                 "note": "through the Python mirror of solve(); fused-step BDF, one kernel launch per step"}}
         except Exception as exc:

@@ -99,6 +99,9 @@ int ncme_space_state_count(ncme_space* space, int64_t* n);
 int ncme_space_sink_count(ncme_space* space, int64_t* r);
 /* get_states (rows [first, first+count), 0-based range)   sparsestatespace.jl:69 */
 int ncme_space_download_states(ncme_space* space, int64_t first, int64_t count, int64_t* states_out);
+/* The same states species-major as doubles, cols_out[s * count + i] = x_{first+i}[s]: the layout a vectorised host
+ * evaluation of the propensities over many states wants (one contiguous column per species, no strided gathers). */
+int ncme_space_download_state_columns(ncme_space* space, int64_t first, int64_t count, double* cols_out);
 /* get_state_connectivity / get_sink_connectivity   sparsestatespace.jl:78-80.  Row-major count x nr. */
 int ncme_space_download_connectivity(ncme_space* space, int64_t first, int64_t count, uint32_t* state_conn_out,
                                      uint32_t* sink_conn_out);
@@ -219,6 +222,15 @@ int ncme_comm_allgatherv(ncme_comm* comm, const double* send_dev, double* recv_d
  * ncme_matvec on a sharded matrix returns globally reduced sink entries on every rank. */
 int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
                                ncme_matrix** out);
+/* Sharded BUILD (SURVEY.md 8(e) "State-space ops"; the reference's constructor evaluates every propensity at every
+ * state, src/fspmatrix/sparse/fspsparsematrix.jl:47-108): ncme_matrix_shard_window returns this rank's row block and
+ * the predecessor window of its rows, out = {row_lo, row_hi, ext_lo, ext_hi}, before any propensity is evaluated; the
+ * host then evaluates the state factors of the states [ext_lo, ext_hi) only and passes them (reaction-major,
+ * (win_hi - win_lo) x nr) to ncme_matrix_create_window.  Host evaluation and upload shrink with the number of ranks.
+ * The result is the matrix ncme_matrix_create_sharded builds; it cannot seed ncme_matrix_create_incremental. */
+int ncme_matrix_shard_window(ncme_space* space, ncme_comm* comm, int64_t out[4]);
+int ncme_matrix_create_window(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals_window,
+                              int64_t win_lo, int64_t win_hi, ncme_matrix** out);
 /* Incremental constructor for the matrix that follows an adapt! (the reference rebuilds from scratch and re-evaluates
  * every propensity at every state, src/transientcme/sparse/fspsolve.jl:176).  `prev` must be the matrix
  * this space was last assembled into.  States that survived the prunes since then (always a prefix of the state list,

@@ -85,6 +85,7 @@ SIGNATURES = {
     "ncme_space_state_count": (cint, [p_void, p_i64]),
     "ncme_space_sink_count": (cint, [p_void, p_i64]),
     "ncme_space_download_states": (cint, [p_void, i64, i64, p_i64]),
+    "ncme_space_download_state_columns": (cint, [p_void, i64, i64, p_f64]),
     "ncme_space_download_connectivity": (cint, [p_void, i64, i64, p_u32, p_u32]),
     "ncme_space_lookup": (cint, [p_void, i64, p_i64, p_u32]),
     "ncme_space_marginal": (cint, [p_void, p_void, cint, p_i32, i64, p_i64, p_i64, p_f64]),
@@ -118,6 +119,8 @@ SIGNATURES = {
     "ncme_comm_info": (cint, [p_void, p_i64]),
     "ncme_matrix_create_sharded": (cint, [p_void, p_void, p_i32, p_f64, C.POINTER(p_void)]),
     "ncme_matrix_shard_info": (cint, [p_void, p_i64]),
+    "ncme_matrix_shard_window": (cint, [p_void, p_void, p_i64]),
+    "ncme_matrix_create_window": (cint, [p_void, p_void, p_i32, p_f64, i64, i64, C.POINTER(p_void)]),
     "ncme_space_prune_by_mass": (cint, [p_void, p_void, f64, cint, p_i64]),
     "ncme_space_compact_vector": (cint, [p_void, p_void, p_void]),
     "ncme_solve_segment": (cint, [p_void, p_void, p_void, p_void, f64, f64, p_void, p_void, p_void]),

@@ -191,21 +191,19 @@ def get_gradient_sparsity_patterns(m: CmeModelWithSensitivity):
     return m.gradient_sparsity_patterns
 
 
-def eval_over_states(fn, states: np.ndarray, p, t=None) -> np.ndarray:
-    """Evaluate ``fn(x,p)`` (or ``fn(t,x,p)``) at every row of ``states`` (n x NS) -> float64[n].
+def eval_over_columns(fn, cols, p, t=None) -> np.ndarray:
+    """Evaluate ``fn(x,p)`` (or ``fn(t,x,p)``) over n states given species-major: ``cols[k]`` = float64[n] of species k.
 
-    One vectorised call with ``x[k]`` = the column of species k is tried first.  Its result is only trusted after a
-    spot check against scalar calls on a few states: a callable that reduces over species with numpy (``np.sum(x)``,
-    ``np.max(x)`` ...) returns a 0-d or wrongly shaped value for column arrays, and a broadcast of it would silently
-    assemble a wrong generator.  On any mismatch the per-state loop (the reference's calling convention,
-    fspsparsematrix.jl:129) is used."""
-    n = states.shape[0]
+    One vectorised call with ``x[k] = cols[k]`` is tried first.  Its result is only trusted after a spot check against
+    scalar calls on a few states: a callable that reduces over species with numpy (``np.sum(x)``, ``np.max(x)`` ...)
+    returns a 0-d or wrongly shaped value for column arrays, and a broadcast of it would silently assemble a wrong
+    generator.  On any mismatch the per-state loop (the reference's calling convention, fspsparsematrix.jl:129) is used."""
+    n = cols[0].shape[0] if len(cols) else 0
 
     def scalar(i):
-        x = [int(c) for c in states[i]]
+        x = [int(c[i]) for c in cols]
         return float(fn(x, p) if t is None else fn(t, x, p))
 
-    cols = [states[:, k].astype(np.float64) for k in range(states.shape[1])]
     try:
         v = fn(cols, p) if t is None else fn(t, cols, p)
         v = np.asarray(v, dtype=np.float64)
@@ -227,3 +225,8 @@ def eval_over_states(fn, states: np.ndarray, p, t=None) -> np.ndarray:
     for i in range(n):
         out[i] = scalar(i)
     return out
+
+
+def eval_over_states(fn, states: np.ndarray, p, t=None) -> np.ndarray:
+    """``eval_over_columns`` for states given row-major (n x NS integers) -> float64[n]."""
+    return eval_over_columns(fn, [states[:, k].astype(np.float64) for k in range(states.shape[1])], p, t)

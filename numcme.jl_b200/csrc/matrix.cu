@@ -69,10 +69,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // y[n+r] = c_r * sum over the sink entries of reaction r.  One CTA per (reaction, <=SINK_CHUNK
 // entries) task writes a partial; the last CTA to finish adds the partials of each reaction in task
 // order, so the result is deterministic (no floating-point atomics).
-__device__ __forceinline__ void sink_task(const MatvecArgs& a) {
+__device__ __forceinline__ void sink_task(const MatvecArgs& a, const int task) {
     __shared__ double wsum[MV_THREADS / 32];
     __shared__ bool is_last;
-    const int4 t = a.tasks[blockIdx.x];
+    const int4 t = a.tasks[task];
     double s = 0.0;
     for (int k = t.y + (int)threadIdx.x; k < t.z; k += MV_THREADS) s += __ldcs(a.sink_val + k) * __ldg(a.xd + __ldcs(a.sink_row + k));
     s = warp_sum(s);
@@ -82,7 +82,7 @@ __device__ __forceinline__ void sink_task(const MatvecArgs& a) {
         double tot = 0.0;
 #pragma unroll
         for (int w = 0; w < MV_THREADS / 32; ++w) tot += wsum[w];
-        a.sink_partial[blockIdx.x] = tot;
+        a.sink_partial[task] = tot;
         __threadfence();
         const unsigned prev = atomicAdd(a.sink_counter, 1u);
         is_last = (prev == (unsigned)a.ntasks - 1u);
@@ -150,44 +150,9 @@ __device__ __forceinline__ void decode_cols(const MatvecArgs& a, int s, int64_t 
     }
 }
 
-template <int S, int ROWS, bool C8, bool P2P = false>
-__global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
-    if (a.nsig && blockIdx.x == 0 && threadIdx.x == 0) {
-        // everything enqueued before this kernel has completed: the input vector is final -> tell the readers
-        __threadfence_system();
-        for (int k = 0; k < a.nsig; ++k) *((volatile unsigned int*)a.sig_flag[k]) = a.epoch;
-    }
-    const int nt = a.do_sinks ? a.ntasks : 0;
-    if ((int)blockIdx.x < nt) {
-        sink_task(a);
-        return;
-    }
-    int64_t i0 = a.row_begin + ((int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x) * ROWS;
-    int64_t row_end = a.row_end;
-    if (P2P) {
-        // boundary rows of a sharded matrix: wait (bounded) until the neighbours have published this matvec's input
-        if (a.nwait) {
-            if (threadIdx.x == 0) {
-                const unsigned long long t0 = global_ns();
-                for (int k = 0; k < a.nwait; ++k) {
-                    const volatile unsigned int* f = a.wait_flag[k];
-                    while ((int)(*f - a.epoch) < 0) {
-                        if (global_ns() - t0 > 2000000000ull) {
-                            atomicExch(a.err_flag, 1u);
-                            break;
-                        }
-                    }
-                }
-                __threadfence_system();
-            }
-            __syncthreads();
-        }
-        const int64_t nb1 = (a.row_end - a.row_begin + MV_THREADS * ROWS - 1) / (MV_THREADS * ROWS);
-        if ((int64_t)(blockIdx.x - nt) >= nb1) {   // second range
-            i0 = a.row_begin2 + ((int64_t)(blockIdx.x - nt - nb1) * MV_THREADS + threadIdx.x) * ROWS;
-            row_end = a.row_end2;
-        }
-    }
+// rows [i0, i0 + ROWS) of y (clipped to row_end): the whole per-thread work of K1
+template <int S, int ROWS, bool C8, bool P2P>
+__device__ __forceinline__ void mv_rows(const MatvecArgs& a, const int64_t i0, const int64_t row_end) {
     if (i0 >= row_end) return;
 
     // ---- first-level loads: all independent, all issued before the first use (one exposed DRAM latency)
@@ -277,6 +242,147 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant
 }
 
 
+template <int S, int ROWS, bool C8, bool P2P = false>
+__global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec(const __grid_constant__ MatvecArgs a) {
+    if (a.nsig && blockIdx.x == 0 && threadIdx.x == 0) {
+        // everything enqueued before this kernel has completed: the input vector is final -> tell the readers
+        __threadfence_system();
+        for (int k = 0; k < a.nsig; ++k) *((volatile unsigned int*)a.sig_flag[k]) = a.epoch;
+    }
+    const int nt = a.do_sinks ? a.ntasks : 0;
+    if ((int)blockIdx.x < nt) {
+        sink_task(a, (int)blockIdx.x);
+        return;
+    }
+    int64_t i0 = a.row_begin + ((int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x) * ROWS;
+    int64_t row_end = a.row_end;
+    if (P2P) {
+        // boundary rows of a sharded matrix: wait (bounded) until the neighbours have published this matvec's input
+        if (a.nwait) {
+            if (threadIdx.x == 0) {
+                const unsigned long long t0 = global_ns();
+                for (int k = 0; k < a.nwait; ++k) {
+                    const volatile unsigned int* f = a.wait_flag[k];
+                    while ((int)(*f - a.epoch) < 0) {
+                        if (global_ns() - t0 > 2000000000ull) {
+                            atomicExch(a.err_flag, 1u);
+                            break;
+                        }
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+        const int64_t nb1 = (a.row_end - a.row_begin + MV_THREADS * ROWS - 1) / (MV_THREADS * ROWS);
+        if ((int64_t)(blockIdx.x - nt) >= nb1) {   // second range
+            i0 = a.row_begin2 + ((int64_t)(blockIdx.x - nt - nb1) * MV_THREADS + threadIdx.x) * ROWS;
+            row_end = a.row_end2;
+        }
+    }
+    mv_rows<S, ROWS, C8, P2P>(a, i0, row_end);
+}
+
+// ------------------------------------------------------------------------------ K1, sharded, one launch --
+// The whole matvec of a row shard in ONE launch on ONE stream (K8): CTA 0 publishes ready(e) ("my x is final"),
+// the halo-free rows run exactly like the single-GPU kernel (ROWS rows per thread), the boundary rows (one row per
+// thread) wait -- bounded -- for ready(e) of the owners of their halo and gather it straight from the neighbours'
+// HBM over NVLink.  The optional "done" handshake (the caller overwrites x right after this matvec) is folded in:
+// the last boundary CTA to finish publishes done(e) to the owners and waits for done(e) of its readers.
+// Replaces two launches on two streams + two event record/wait pairs + a third launch for the handshake.
+__device__ __forceinline__ void flag_wait(const volatile unsigned int* f, unsigned int epoch, unsigned int* err,
+                                          unsigned long long t0) {
+    while ((int)(*f - epoch) < 0) {
+        if (global_ns() - t0 > 2000000000ull) {
+            atomicExch(err, 1u);
+            break;
+        }
+    }
+}
+
+template <int S, int ROWS, int MINB>
+__global__ void __launch_bounds__(MV_THREADS, MINB) k_fsp_matvec_sharded(const __grid_constant__ MatvecArgs a) {
+    if (a.nsig && blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int k = 0; k < a.nsig; ++k) *((volatile unsigned int*)a.sig_flag[k]) = a.epoch;
+    }
+    const int nt = a.ntasks;
+    int b = (int)blockIdx.x;
+    bool boundary;
+    if (a.bd_first) {
+        boundary = b < a.nb_bd;
+        if (!boundary) {
+            b -= a.nb_bd;
+            if (b < nt) {
+                sink_task(a, b);
+                return;
+            }
+            b -= nt;
+        }
+    } else {
+        if (b < nt) {
+            sink_task(a, b);
+            return;
+        }
+        b -= nt;
+        boundary = b >= a.nb_int;
+        if (boundary) b -= a.nb_int;
+    }
+    if (!boundary) {
+        mv_rows<S, ROWS, false, false>(a, a.int_begin + ((int64_t)b * MV_THREADS + threadIdx.x) * ROWS, a.int_end);
+        return;
+    }
+    if (a.nwait) {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = global_ns();
+            for (int k = 0; k < a.nwait; ++k) flag_wait(a.wait_flag[k], a.epoch, a.err_flag, t0);
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    const int nb1 = (int)((a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS);
+    if (b < nb1)
+        mv_rows<S, 1, false, true>(a, a.row_begin + (int64_t)b * MV_THREADS + threadIdx.x, a.row_end);
+    else
+        mv_rows<S, 1, false, true>(a, a.row_begin2 + (int64_t)(b - nb1) * MV_THREADS + threadIdx.x, a.row_end2);
+    if (a.ndone_sig || a.ndone_wait) {
+        __syncthreads();                      // every gather of this CTA has been consumed
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(a.bd_counter, 1u) == (unsigned)a.nb_bd - 1u) {
+                *a.bd_counter = 0u;
+                __threadfence_system();
+                for (int k = 0; k < a.ndone_sig; ++k) *((volatile unsigned int*)a.done_sig[k]) = a.epoch;
+                const unsigned long long t0 = global_ns();
+                for (int k = 0; k < a.ndone_wait; ++k) flag_wait(a.done_wait[k], a.epoch, a.err_flag, t0);
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+template <int ROWS, int MINB>
+static int launch_sharded(ncme_matrix* A, MatvecArgs& a) {
+    a.nb_int = (int)((a.int_end - a.int_begin + (int64_t)MV_THREADS * ROWS - 1) / ((int64_t)MV_THREADS * ROWS));
+    a.nb_bd = (int)((a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS + (a.row_end2 - a.row_begin2 + MV_THREADS - 1) / MV_THREADS);
+    const unsigned grid = (unsigned)(a.ntasks + a.nb_int + a.nb_bd);
+    cudaStream_t st = A->ctx->stream;
+    switch (a.nslots) {
+#define NCME_CASE(SS)                                                   \
+    case SS:                                                            \
+        k_fsp_matvec_sharded<SS, ROWS, MINB><<<grid, MV_THREADS, 0, st>>>(a); \
+        break;
+        NCME_CASE(1) NCME_CASE(2) NCME_CASE(3) NCME_CASE(4) NCME_CASE(5) NCME_CASE(6) NCME_CASE(7) NCME_CASE(8)
+        NCME_CASE(9) NCME_CASE(10) NCME_CASE(11) NCME_CASE(12) NCME_CASE(13) NCME_CASE(14) NCME_CASE(15) NCME_CASE(16)
+#undef NCME_CASE
+        default:
+            return -1;
+    }
+    A->ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
 // ------------------------------------------------------------------------------ K1, pipelined --
 // Same arithmetic as k_fsp_matvec, different data movement: the once-read matrix streams (values, diagonals,
 // byte-compressed column indices, chunk descriptors) are staged through shared memory with a 4-stage cp.async
@@ -311,7 +417,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_pipe(const __grid_con
     extern __shared__ __align__(16) unsigned char smem[];
     const int nt = a.do_sinks ? a.ntasks : 0;
     if ((int)blockIdx.x < nt) {
-        sink_task(a);
+        sink_task(a, (int)blockIdx.x);
         return;
     }
     const int64_t G = (int64_t)gridDim.x - nt;
@@ -453,7 +559,7 @@ static int launch_pipe(ncme_matrix* A, const MatvecArgs& a) {
 __global__ void __launch_bounds__(MV_THREADS) k_fsp_matvec_generic(const __grid_constant__ MatvecArgs a) {
     const int nt = a.do_sinks ? a.ntasks : 0;
     if ((int)blockIdx.x < nt) {
-        sink_task(a);
+        sink_task(a, (int)blockIdx.x);
         return;
     }
     const int64_t i = a.row_begin + (int64_t)(blockIdx.x - nt) * MV_THREADS + threadIdx.x;
@@ -685,8 +791,36 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
     a.hi_begin = (uint32_t)(A->hl + A->n + A->nr);
     a.x_lo = xlo ? xlo + (A->ext_lo - A->plo_row_lo) : a.x;
     a.x_hi = xhi ? xhi + (A->row_hi - A->phi_row_lo) - (int64_t)a.hi_begin : a.x;
-    if (!sig_in_kernel) NCME_TRY(p2p_sync(A, ready_sig));
     const bool interior = A->b1 > A->b0;
+    static const bool two_launch = getenv("NCME_P2P_TWO_LAUNCH") != nullptr;   // experiments: the round-1 control path
+    static const bool bd_last = getenv("NCME_P2P_BD_LAST") != nullptr;
+    const bool handshake = !(flags & 2);
+    if (!two_launch && sig_in_kernel && a.nslots <= 16 && done.nsig <= 4 && done.nwait <= 4 && a.nwait > 0) {
+        MatvecArgs f = a;
+        f.int_begin = interior ? A->b0 : 0;
+        f.int_end = interior ? A->b1 : 0;
+        f.row_begin = 0;
+        f.row_end = interior ? A->b0 : A->n;
+        f.row_begin2 = interior ? A->b1 : 0;
+        f.row_end2 = interior ? A->n : 0;
+        f.bd_first = bd_last ? 0 : 1;
+        f.ndone_sig = handshake ? done.nsig : 0;
+        f.ndone_wait = handshake ? done.nwait : 0;
+        for (int k = 0; k < f.ndone_sig; ++k) f.done_sig[k] = done.sig[k];
+        for (int k = 0; k < f.ndone_wait; ++k) f.done_wait[k] = done.wait[k];
+        f.bd_counter = A->sink_counter + 1;
+        if (f.row_end - f.row_begin + f.row_end2 - f.row_begin2 > 0) {
+            static const bool minb3 = getenv("NCME_SHARDED_MINB3") != nullptr;   // experiments: 3 CTAs/SM, no spills
+            if (minb3)
+                NCME_TRY(a.nslots <= 8 ? (launch_sharded<2, 3>(A, f)) : (launch_sharded<1, 3>(A, f)));
+            else
+                NCME_TRY(a.nslots <= 8 ? (launch_sharded<2, 4>(A, f)) : (launch_sharded<1, 4>(A, f)));
+            c->p2p_matvecs++;
+            if (flags & 1) NCME_TRY(comm_allreduce_sum(c, a.y + A->n, (size_t)A->nr, A->ctx->stream));
+            return NCME_OK;
+        }
+    }
+    if (!sig_in_kernel) NCME_TRY(p2p_sync(A, ready_sig));
     if (interior) {
         // boundary rows (peer loads over NVLink, waiting for the neighbours inside the kernel) run on the
         // high-priority stream CONCURRENTLY with the interior rows; they write disjoint rows of y
@@ -1071,8 +1205,10 @@ __global__ void k_carry_factors(const double* __restrict__ Gprev, int64_t ngprev
 
 // prev != nullptr: incremental build -- `propvals` then holds the factors of the nnew = n - nkept states appended since
 // prev was built (reaction-major nnew x nr), everything else is carried over on the device.
+// win_lo >= 0: windowed build of a row shard -- `propvals` holds the factors of the states [win_lo, win_hi) only
+// (reaction-major, stride win_hi - win_lo); the window must cover this rank's rows and their predecessor window.
 static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propvals, ncme_matrix* A, ncme_comm* comm,
-                        const ncme_matrix* prev = nullptr, int64_t nkept = 0) {
+                        const ncme_matrix* prev = nullptr, int64_t nkept = 0, int64_t win_lo = -1, int64_t win_hi = -1) {
     ncme_ctx* ctx = sp->ctx;
     cudaStream_t st = ctx->stream;
     const int nr = sp->nr;
@@ -1162,6 +1298,16 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
         ctx->launches++;
         NCME_CUDA(cudaGetLastError());
         tail.release();
+    } else if (win_lo >= 0) {
+        NCME_REQUIRE(win_lo <= row_lo && row_hi <= win_hi && win_hi <= ng, "state-factor window does not cover this rank's rows");
+        const int64_t nw = win_hi - win_lo;
+        A->g_window = true;     // G is only valid inside the window: no incremental rebuild from this matrix
+        for (int r = 0; r < nr && nw > 0; ++r) {
+            if (kind[r] == NCME_JOINT_TV || !propvals)
+                NCME_CUDA(cudaMemsetAsync(G.p + (size_t)r * ng + win_lo, 0, (size_t)nw * 8, st));
+            else
+                NCME_CUDA(cudaMemcpyAsync(G.p + (size_t)r * ng + win_lo, propvals + (size_t)r * nw, (size_t)nw * 8, cudaMemcpyHostToDevice, st));
+        }
     } else {
         for (int r = 0; r < nr && ng > 0; ++r) {
             if (kind[r] == NCME_JOINT_TV || !propvals)
@@ -1196,6 +1342,8 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     }
     A->hl = row_lo - A->ext_lo;
     A->hh = A->ext_hi - row_hi;
+    NCME_REQUIRE(win_lo < 0 || (win_lo <= A->ext_lo && A->ext_hi <= win_hi),
+                 "state-factor window does not cover the predecessor window of this rank's rows (see ncme_matrix_shard_window)");
     geom.ext_lo = A->ext_lo;
     NCME_REQUIRE(A->ext_hi - A->ext_lo + nr < 0xFFFFFFF0ll, "padded window exceeds the 32-bit index range");
     NCME_TRY(A->col.reserve((size_t)A->ld * (nslots > 0 ? nslots : 1), st, false));
@@ -1362,9 +1510,9 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     NCME_TRY(A->tasks.reserve(tasks.size(), st, false));
     NCME_TRY(A->sink_partial.reserve(tasks.size(), st, false));
     NCME_CUDA(cudaMemcpyAsync(A->tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-    NCME_TRY(A->sink_counter_mem.reserve(1, st, false));
+    NCME_TRY(A->sink_counter_mem.reserve(2, st, false));   // [0] sink tasks, [1] boundary CTAs of the sharded launch
     A->sink_counter = A->sink_counter_mem.p;
-    NCME_CUDA(cudaMemsetAsync(A->sink_counter, 0, sizeof(unsigned), st));
+    NCME_CUDA(cudaMemsetAsync(A->sink_counter, 0, 2 * sizeof(unsigned), st));
     NCME_CUDA(cudaStreamSynchronize(st));
 
     // ---- reference-structure statistics
@@ -1417,6 +1565,60 @@ int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t
     return NCME_OK;
 }
 
+// Rows and predecessor window of this rank's shard, BEFORE any propensity is evaluated: the host then evaluates the
+// state factors of the states [ext_lo, ext_hi) only and builds with ncme_matrix_create_window (sharded build: host
+// evaluation and upload shrink with the number of ranks).  out = {row_lo, row_hi, ext_lo, ext_hi}.
+int ncme_matrix_shard_window(ncme_space* sp, ncme_comm* comm, int64_t out[4]) {
+    NCME_REQUIRE(sp && out, "null argument");
+    ncme_ctx* ctx = sp->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t ng = sp->n;
+    const int P = comm ? comm->nranks : 1, me = comm ? comm->rank : 0;
+    auto cut = [&](int r) -> int64_t {
+        if (r <= 0) return 0;
+        if (r >= P) return ng;
+        return std::min<int64_t>(ng, round_up<int64_t>((int64_t)((__int128)ng * r / P), 64));
+    };
+    const int64_t row_lo = cut(me), row_hi = cut(me + 1), n = row_hi - row_lo;
+    out[0] = out[2] = row_lo;
+    out[1] = out[3] = row_hi;
+    if (P == 1 || n <= 0) return NCME_OK;
+    ShardGeom geom{ng, row_lo, row_hi, row_lo, n, sp->nr};
+    unsigned int h_mm[4] = {0xFFFFFFFFu, 0u, 0u, (unsigned int)n};
+    unsigned int* d_mm = nullptr;
+    NCME_CUDA(cudaMalloc(&d_mm, sizeof(h_mm)));
+    NCME_CUDA(cudaMemcpyAsync(d_mm, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, st));
+    for (int r = 0; r < sp->nr; ++r) {
+        if (zero_stoich(sp, r)) continue;
+        k_pred_window<<<nblk(n), 256, 0, st>>>(sp->pred.p + (size_t)r * sp->ld, geom, d_mm);
+        ctx->launches++;
+    }
+    NCME_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    NCME_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_mm);
+    if (h_mm[0] != 0xFFFFFFFFu) out[2] = std::min<int64_t>(row_lo, (int64_t)h_mm[0]);
+    if (h_mm[1] != 0u) out[3] = std::max<int64_t>(row_hi, (int64_t)h_mm[1] + 1);
+    return NCME_OK;
+}
+
+int ncme_matrix_create_window(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals_window,
+                              int64_t win_lo, int64_t win_hi, ncme_matrix** out) {
+    NCME_REQUIRE(space && kind && out, "null argument");
+    NCME_REQUIRE(win_lo >= 0 && win_lo <= win_hi && win_hi <= space->n, "bad window");
+    NCME_REQUIRE(propvals_window || win_hi == win_lo, "propvals is null");
+    if (comm && comm->nranks > 1)
+        for (int r = 0; r < space->nr; ++r)
+            NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
+    ncme_matrix* A = new ncme_matrix();
+    int st = matrix_build(space, kind, propvals_window, A, comm, nullptr, 0, win_lo, win_hi);
+    if (st != NCME_OK) {
+        ncme_matrix_destroy(A);
+        return st;
+    }
+    *out = A;
+    return NCME_OK;
+}
+
 int ncme_space_new_count(ncme_space* space, int64_t* n_kept, int64_t* n_new) {
     NCME_REQUIRE(space && n_kept && n_new, "null argument");
     if (space->mark_n < 0) {   // never marked: everything is new
@@ -1434,6 +1636,7 @@ int ncme_matrix_create_incremental(ncme_space* space, ncme_comm* comm, ncme_matr
     NCME_REQUIRE(space && prev && kind && out, "null argument");
     NCME_REQUIRE(prev->space_mark == space->mark_id && space->mark_n >= 0 && prev->G.p,
                  "incremental build: `prev` is not the matrix this space was last assembled into");
+    NCME_REQUIRE(!prev->g_window, "incremental build: `prev` was built from a state-factor window (sharded build)");
     NCME_REQUIRE(prev->nr == space->nr, "incremental build: reaction count changed");
     for (int r = 0; r < space->nr; ++r) NCME_REQUIRE(prev->kind[r] == kind[r], "incremental build: reaction kinds changed");
     if (comm && comm->nranks > 1)

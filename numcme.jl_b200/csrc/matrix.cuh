@@ -57,6 +57,7 @@ struct ncme_matrix {
     // state factors G[r][i] of ALL states (reaction-major, stride n_global), kept for the incremental constructor of the
     // matrix that follows an adapt! (H8): only the states added since are evaluated on the host
     ncme::DevArray<double> G;
+    bool g_window = false;          // G only holds the factors of this rank's rows + halo window (ncme_matrix_create_window)
     uint64_t space_mark = 0;        // mark of the space this matrix was built at
     // compressed column indices (K1 fast path): one byte per (slot,row) relative to a per-(slot, 64-row chunk)
     // descriptor {base:i32, mode:u32}; mode 0 = chunk stays on the 32-bit array (range does not fit)
@@ -134,6 +135,15 @@ struct MatvecArgs {
     int64_t row_begin2, row_end2;      // P2P launches: optional second row range (high boundary rows)
     int64_t row_begin, row_end;  // rows handled by this launch
     int do_sinks;                // 1: the sink-task CTAs run in this launch
+    // one-launch sharded matvec (k_fsp_matvec_sharded): halo-free rows [int_begin, int_end) + both boundary ranges
+    int64_t int_begin, int_end;
+    int nb_int, nb_bd;                 // CTAs of the halo-free rows / of the boundary rows
+    int bd_first;                      // 1: the boundary CTAs take the lowest block indices (scheduled first)
+    int ndone_sig;                     // "done" handshake folded into the launch: the last boundary CTA publishes
+    unsigned int* done_sig[4];         // `epoch` into these peer flags ("I no longer read your x") and then waits
+    int ndone_wait;                    // until these local flags reach `epoch` ("nobody reads my x any more")
+    const unsigned int* done_wait[4];
+    unsigned int* bd_counter;
 };
 
 int matvec_fill_args(const ncme_matrix* A, const double* coef, MatvecArgs* a);

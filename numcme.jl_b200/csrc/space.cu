@@ -1081,6 +1081,21 @@ int ncme_space_download_states(ncme_space* sp, int64_t first, int64_t count, int
     return NCME_OK;
 }
 
+int ncme_space_download_state_columns(ncme_space* sp, int64_t first, int64_t count, double* out) {
+    NCME_REQUIRE(sp && first >= 0 && count >= 0 && first + count <= sp->n && (count == 0 || out), "bad range");
+    if (count == 0) return NCME_OK;
+    std::vector<uint64_t> hk((size_t)count);
+    NCME_CUDA(cudaMemcpyAsync(hk.data(), sp->keys.p + first, (size_t)count * 8, cudaMemcpyDeviceToHost, sp->ctx->stream));
+    NCME_CUDA(cudaStreamSynchronize(sp->ctx->stream));
+    for (int s = 0; s < sp->ns; ++s) {
+        const int sh = sp->layout.shift[s];
+        const uint64_t mk = sp->layout.mask[s];
+        double* col = out + (size_t)s * count;
+        for (int64_t i = 0; i < count; ++i) col[i] = (double)((hk[(size_t)i] >> sh) & mk);
+    }
+    return NCME_OK;
+}
+
 int ncme_space_download_connectivity(ncme_space* sp, int64_t first, int64_t count, uint32_t* sc_out, uint32_t* kc_out) {
     NCME_REQUIRE(sp && first >= 0 && count >= 0 && first + count <= sp->n, "bad range");
     if (count == 0) return NCME_OK;

@@ -11,11 +11,12 @@ kernel only, asynchronous on the context's stream).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _lib as L
-from .cmemodel import JOINT_TV, SEPARABLE_TV, Propensity, eval_over_states
+from .cmemodel import JOINT_TV, SEPARABLE_TV, Propensity, eval_over_columns, eval_over_states
 from .device import DeviceVector, device_ptr, is_device, vec_len
 from .statespace import StateSpaceSparse
 
@@ -27,6 +28,10 @@ _PROBE_TIMES = (0.0, 0.7310585786300049, 19.098300562505255, 738.90560989306495,
 
 # below this many states the incremental rebuild (one more kernel + host round trip) costs more than it saves
 INCREMENTAL_MIN_STATES = 2048
+# up to this many states a matrix keeps an eager host copy of the state list (the reference's deepcopy, :97)
+EAGER_STATES_MAX = 1 << 21
+# from this many states on, the reactions' state factors are evaluated concurrently on host threads
+PARALLEL_EVAL_MIN_STATES = 1 << 20
 
 
 def _rank1_info(f, states, parameters, probe_times=_PROBE_TIMES, rtol=1e-12):
@@ -115,15 +120,18 @@ class FspMatrixSparse:
         for a in self.propensities:
             if not isinstance(a, Propensity):
                 raise L.ArgumentError("propensities must be Propensity instances (see propensity())")
-        self.states = space.get_states()          # host copy, like `deepcopy(space.states)` (:97)
-        n = self.states.shape[0]
+        n = space.get_state_count()
         self.n = n
+        self._space, self._space_version, self._states = space, space.version, None
+        if n <= EAGER_STATES_MAX:                 # host copy, like `deepcopy(space.states)` (:97); lazy for huge spaces
+            self._states = space.get_states()
         self.nr = space.nr
         self.rowcount = self.colcount = n + space.get_sink_count()   # global size, as size(A) in the reference
         self.timeinvariant_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "ti"]
         self.separabletv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "sep"]
         self.jointtv_propensity_ids = [i + 1 for i, a in enumerate(self.propensities) if a.kind == "joint"]
         self.incremental = False
+        self.build_window = None
         h = None
         if previous is not None and getattr(previous, "_h", None) and n >= max(1, INCREMENTAL_MIN_STATES):
             h = self._build_incremental(space, previous, comm)
@@ -137,6 +145,17 @@ class FspMatrixSparse:
         self.t_cache = -np.inf
         self._coef = np.ones(self.nr, dtype=np.float64)
 
+    @property
+    def states(self) -> np.ndarray:
+        """The states this matrix was built on (n x NS).  Above EAGER_STATES_MAX states the copy is made on first use
+        (the matrix itself only needs the species columns of its own rows); it is an error to ask for it after the
+        space has been mutated."""
+        if self._states is None:
+            if self._space.version != self._space_version:
+                raise L.NcmeError("the state space was modified after this matrix was built; its state list is gone")
+            self._states = self._space.get_states()
+        return self._states
+
     def _build_full(self, space, comm, detect_separable):
         n, parameters = self.n, self.parameters
         self.kinds = np.array([a.kind_code for a in self.propensities], dtype=np.int32)
@@ -144,14 +163,41 @@ class FspMatrixSparse:
         # propensities found to be rank-1 separable)
         self._tfactor = {}                 # 1-based reaction id -> callable t -> c(t)
         self._rank1 = {}                   # 1-based reaction id -> factorisation info of detected reactions
-        propvals = np.zeros((self.nr, max(n, 1)), dtype=np.float64)
-        for r, a in enumerate(self.propensities):
+        lib = L.load()
+        # Row-sharded build: without joint propensities every rank evaluates the state factors of its own
+        # rows + predecessor window only -- host evaluation and upload shrink with the number of ranks.
+        lo, hi = 0, n
+        windowed = comm is not None and comm.nranks > 1 and n > 0 and all(a.kind != "joint" for a in self.propensities)
+        if windowed:
+            w = (C.c_int64 * 4)()
+            L.check(lib.ncme_matrix_shard_window(space.handle, comm.handle, w))
+            lo, hi = int(w[2]), int(w[3])
+            self.build_window = (lo, hi)
+        nw = hi - lo
+        # species columns of the window straight from the device keys: one contiguous float64 array per species
+        cols = space.get_state_columns(lo, nw) if nw else [np.zeros(0) for _ in range(space.ns)]
+        propvals = np.empty((self.nr, max(nw, 1)), dtype=np.float64)
+
+        def fill(r):
+            a = self.propensities[r]
             if a.kind == "ti":
-                propvals[r, :n] = eval_over_states(a.f, self.states, parameters)
+                propvals[r, :nw] = eval_over_columns(a.f, cols, parameters)
             elif a.kind == "sep":
-                propvals[r, :n] = eval_over_states(a.statefactor, self.states, parameters)
+                propvals[r, :nw] = eval_over_columns(a.statefactor, cols, parameters)
+            else:
+                propvals[r, :nw] = 0.0
+        if nw >= PARALLEL_EVAL_MIN_STATES and self.nr > 1:
+            # numpy releases the GIL inside its loops: the reactions are evaluated concurrently on the host cores
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(self.nr, os.cpu_count() or 1, 16)) as pool:
+                list(pool.map(fill, range(self.nr)))
+        else:
+            for r in range(self.nr):
+                fill(r)
+        for r, a in enumerate(self.propensities):
+            if a.kind == "sep":
                 self._tfactor[r + 1] = (lambda t, a=a: float(a.tfactor(t, self.parameters)))
-            elif detect_separable:
+            elif a.kind == "joint" and detect_separable:
                 info = _rank1_info(a.f, self.states, parameters)
                 if info is not None:
                     g = info.pop("g")
@@ -162,10 +208,14 @@ class FspMatrixSparse:
                     info["sent_g"] = [float(g[i]) for i in info["sent"]]
                     self._rank1[r + 1] = info
                     self._tfactor[r + 1] = self._make_rank1_tfactor(r + 1, a.f, info)
-        propvals = np.ascontiguousarray(propvals[:, :n]) if n else propvals
+        propvals = np.ascontiguousarray(propvals[:, :nw]) if nw else propvals
         h = L.p_void()
-        L.check(L.load().ncme_matrix_create_sharded(space.handle, comm.handle if comm is not None else None,
-                                                    L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double), C.byref(h)))
+        if windowed:
+            L.check(lib.ncme_matrix_create_window(space.handle, comm.handle, L.ptr(self.kinds, C.c_int32),
+                                                  L.ptr(propvals, C.c_double), lo, hi, C.byref(h)))
+        else:
+            L.check(lib.ncme_matrix_create_sharded(space.handle, comm.handle if comm is not None else None,
+                                                   L.ptr(self.kinds, C.c_int32), L.ptr(propvals, C.c_double), C.byref(h)))
         return h
 
     def _build_incremental(self, space, previous, comm):
@@ -179,7 +229,7 @@ class FspMatrixSparse:
         n_kept, n_new = nk.value, nn.value
         if n_kept == 0:
             return None
-        new_states = self.states[n_kept:]
+        new_states = space.get_states(n_kept, n_new) if self._states is None else self._states[n_kept:]
         th = self.parameters
         propvals = np.zeros((self.nr, max(n_new, 1)), dtype=np.float64)
         for r, a in enumerate(self.propensities):

@@ -24,6 +24,7 @@ class StateSpaceSparse:
         self.ns, self.nr = self.stoich_matrix.shape
         self._states_cache = None
         self._states_cache_n = 0
+        self.version = 0                         # bumped by every mutation (expand_, deleteat_, prune_by_mass_)
         if _handle is not None:
             self._h = _handle
             return
@@ -92,6 +93,16 @@ class StateSpaceSparse:
             self._states_cache, self._states_cache_n = out, n
         return out
 
+    def get_state_columns(self, first: int = 0, count: int | None = None) -> list:
+        """The states [first, first + count) species-major as float64 columns (one contiguous array per species): what
+        a vectorised propensity evaluation over many states reads."""
+        n = self.get_state_count()
+        count = n - first if count is None else count
+        buf = np.empty((self.ns, max(count, 0)), dtype=np.float64)
+        if count:
+            L.check(L.load().ncme_space_download_state_columns(self._h, first, count, L.ptr(buf, C.c_double)))
+        return [buf[k] for k in range(self.ns)]
+
     @property
     def states(self):
         return self.get_states()
@@ -151,12 +162,14 @@ class StateSpaceSparse:
     # -- mutation
     def expand_(self, expansionlevel: int, onlyreactions=()):
         self._states_cache = None
+        self.version += 1
         only = np.ascontiguousarray(list(onlyreactions), dtype=np.int32)
         L.check(L.load().ncme_space_expand(self._h, int(expansionlevel), only.size,
                                            L.ptr(only, C.c_int32) if only.size else None))
 
     def deleteat_(self, ids):
         self._states_cache = None
+        self.version += 1
         ids = np.ascontiguousarray(np.asarray(ids, dtype=np.int64).reshape(-1))
         if ids.size:
             L.check(L.load().ncme_space_delete(self._h, ids.size, L.ptr(ids, C.c_int64)))
@@ -166,6 +179,7 @@ class StateSpaceSparse:
         ``dropcount`` least probable states; returns dropcount.  Follow with ``compact_vector``."""
         from .device import device_ptr
         self._states_cache = None
+        self.version += 1
         dc = C.c_int64()
         L.check(L.load().ncme_space_prune_by_mass(self._h, C.c_void_p(device_ptr(p_dev)), float(threshold),
                                                   1 if strict else 0, C.byref(dc)))

@@ -301,11 +301,15 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
     pv = np.zeros(space.get_state_count())
     pv[idx[idx > 0] - 1] = vals0[idx > 0]
     t_wall = time.perf_counter()
+    br = {"expand": 0.0, "matrix": 0.0, "integrate": 0.0, "output": 0.0}      # wall-time breakdown (seconds)
     p = init_(space, adapter, DeviceVector.from_host(ctx, pv), tstart, fsptol)   # all states, replicated
+    br["expand"] += time.perf_counter() - t_wall
     tnow = tstart
     sinks = np.zeros(R)
+    tq = time.perf_counter()
     A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm,
                         detect_separable=detect_separable)
+    br["matrix"] += time.perf_counter() - tq
     out = FspOutputSparse()
     tot = {"steps": 0, "rejected": 0, "rhs_evals": 0, "launches": 0, "adapts": 0, "matrix_builds": 1}
     while tnow < tend:
@@ -313,8 +317,10 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
         dist = _Dist(A, comm)
         dist.load(p, sinks)
         seg = _Segment(A, odertol, odeatol, method)
+        tq = time.perf_counter()
         try:
             stats = seg.run(dist.u.v, tnow, tend, saveat=sv, save_every_step=sv is None, event_slope=fsptol / tend)
+            br["integrate"] += time.perf_counter() - tq
         except L.SeparabilityError:
             # a joint propensity detected as c(t) g(x) broke the product form at a time the integrator used: discard
             # this segment (p, sinks still hold its initial state) and repeat it on the exact joint path
@@ -328,11 +334,13 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
             continue
         for k in ("steps", "rejected", "rhs_evals", "launches"):
             tot[k] += getattr(stats, k)
+        tq = time.perf_counter()
         states = space.get_states() if seg.saved_t else None
         for t, uu in zip(seg.saved_t, seg.saved_u):
             out.t.append(t)
             out.p.append(FspVectorSparse(states, uu[:n]))
             out.sinks.append(uu[n:].copy())
+        br["output"] += time.perf_counter() - tq
         tnow = stats.t_final
         sinks = dist.sinks()
         if stats.event_hit and tnow < tend:
@@ -341,11 +349,15 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
                 du = DeviceVector(ctx, dist.nloc + R)
                 matvec_(du, tnow, A, dist.u.v)
                 dsinks = du.to_host(dist.nloc, R)
+            tq = time.perf_counter()
             p = adapt_(space, adapter, dist.gather(), sinks, tnow, tend, fsptol, dsinks=dsinks)
+            br["expand"] += time.perf_counter() - tq
+            tq = time.perf_counter()
             A_old = A                                    # incremental rebuild: only the new states are evaluated (H8)
             A = FspMatrixSparse(space, model.propensities, parameters=model.parameters, comm=comm, previous=A_old,
                                 detect_separable=detect_separable)
             A_old.close()
+            br["matrix"] += time.perf_counter() - tq
             tot["incremental_builds"] = tot.get("incremental_builds", 0) + (1 if A.incremental else 0)
             tot["adapts"] += 1
             tot["matrix_builds"] += 1
@@ -354,11 +366,14 @@ def _solve_adaptive(model, p0, tspan, alg, saveat, fsptol, odeatol, odertol, ver
             if verbose:
                 print(f"t = {tnow:.2f}. Update state space. New size: {space.get_state_count()}.")
         else:
+            tq = time.perf_counter()
             out.t.append(tnow)                           # final slice (duplicates the last saveat point when
             out.p.append(FspVectorSparse(space.get_states(), dist.gather().to_host()))   # tend is in saveat, Q3)
             out.sinks.append(sinks.copy())
+            br["output"] += time.perf_counter() - tq
             tnow = tend
     tot["wall_s"] = time.perf_counter() - t_wall
+    tot["breakdown_s"] = {k: round(v, 4) for k, v in br.items()}
     tot["final_states"] = space.get_state_count()
     out.stats = tot
     return out

@@ -136,7 +136,7 @@ def hog1p_sens_model(theta=HOG1P_THETA):
     """BASELINE.json config 3: the Hog1p model of examples/hog1p.jl:33-82 as a ``CmeModelWithSensitivity`` (NS = 6,
     R = 13, P = 14).  Gradient sparsity as src/cmemodel/senstools/sparsity_pattern.jl:19-30 derives it from the rate
     laws: one parameter per reaction, plus (k10, a) both on reaction 2 (G1 -> G0, rate max(0, k10 - a Hog1p(t))) --
-    15 (reaction, parameter) entries.  Reaction 2 is separable: its time factor carries both parameters."""
+    14 (reaction, parameter) entries (12 + 2).  Reaction 2 is separable: its time factor carries both parameters."""
     from .cmemodel import CmeModelWithSensitivity, propensitygrad, propensitygrad_timevarying
     model = hog1p_model(theta, separable=True)
     P = 14

@@ -158,31 +158,45 @@ class StateSpaceOracle:
 # Vectorised variant (same insertion order, same connectivity), for large parity fixtures.
 # ----------------------------------------------------------------------------------------------
 class _SortedKeyIndex:
-    """Sorted int64 keys -> 1-based state index, with O(n) merge per insert batch."""
+    """Sorted int64 keys -> 1-based state index.  Two sorted runs (a large one and a small recent one that is
+    merged into it when it reaches 1/16 of its size), so that an insert batch costs O(batch) amortised."""
 
     def __init__(self):
         self.keys = np.empty(0, dtype=np.int64)
         self.idx = np.empty(0, dtype=np.int64)
+        self.rkeys = np.empty(0, dtype=np.int64)
+        self.ridx = np.empty(0, dtype=np.int64)
+
+    @staticmethod
+    def _find(keys, idx, q):
+        if keys.size == 0:
+            return np.zeros(q.shape, dtype=np.int64)
+        pos_c = np.minimum(np.searchsorted(keys, q), keys.size - 1)
+        return np.where(keys[pos_c] == q, idx[pos_c], 0)
 
     def lookup(self, q: np.ndarray) -> np.ndarray:
         """Return 1-based indices, 0 where absent."""
-        if self.keys.size == 0:
-            return np.zeros(q.shape, dtype=np.int64)
-        pos = np.searchsorted(self.keys, q)
-        pos_c = np.minimum(pos, self.keys.size - 1)
-        hit = self.keys[pos_c] == q
-        return np.where(hit, self.idx[pos_c], 0)
+        out = self._find(self.keys, self.idx, q)
+        if self.rkeys.size:
+            out = np.maximum(out, self._find(self.rkeys, self.ridx, q))      # a key lives in one run only
+        return out
+
+    @staticmethod
+    def _merge(ka, ia, kb, ib):
+        pos = np.searchsorted(ka, kb)
+        return np.insert(ka, pos, kb), np.insert(ia, pos, ib)
 
     def insert(self, k: np.ndarray, idx: np.ndarray):
         order = np.argsort(k, kind="stable")
-        k, idx = k[order], idx[order]
-        pos = np.searchsorted(self.keys, k)
-        self.keys = np.insert(self.keys, pos, k)
-        self.idx = np.insert(self.idx, pos, idx)
+        self.rkeys, self.ridx = self._merge(self.rkeys, self.ridx, k[order], idx[order])
+        if self.rkeys.size > max(4096, self.keys.size // 16):
+            self.keys, self.idx = self._merge(self.keys, self.idx, self.rkeys, self.ridx)
+            self.rkeys, self.ridx = np.empty(0, dtype=np.int64), np.empty(0, dtype=np.int64)
 
     def rebuild(self, k: np.ndarray, idx: np.ndarray):
         order = np.argsort(k, kind="stable")
         self.keys, self.idx = k[order], idx[order]
+        self.rkeys, self.ridx = np.empty(0, dtype=np.int64), np.empty(0, dtype=np.int64)
 
 
 class StateSpaceOracleFast:
@@ -199,14 +213,33 @@ class StateSpaceOracleFast:
         self.bits = np.asarray(bits_per_species, dtype=np.int64)
         assert self.bits.sum() <= 63
         self.shifts = np.concatenate(([0], np.cumsum(self.bits)[:-1])).astype(np.int64)
-        self.states = np.empty((0, self.ns), dtype=np.int64)
-        self.state_connectivity = np.empty((0, self.nr), dtype=np.int64)
-        self.sink_connectivity = np.empty((0, self.nr), dtype=np.int64)
+        self._n = 0                                             # growable buffers (capacity doubling): rows [0, _n) are live
+        self._states = np.empty((0, self.ns), dtype=np.int64)
+        self._sc = np.empty((0, self.nr), dtype=np.int64)
+        self._kc = np.empty((0, self.nr), dtype=np.int64)
         self._index = _SortedKeyIndex()
         initstates = np.asarray(initstates, dtype=np.int64)
         if initstates.ndim == 1:
             initstates = initstates[None, :]
         self._addstates(initstates.reshape(-1, self.ns))
+
+    states = property(lambda self: self._states[:self._n])
+    state_connectivity = property(lambda self: self._sc[:self._n])
+    sink_connectivity = property(lambda self: self._kc[:self._n])
+
+    def _append(self, newstates: np.ndarray):
+        m, n = newstates.shape[0], self._n
+        if n + m > self._states.shape[0]:
+            cap = max(1024, 2 * (n + m))
+            for name in ("_states", "_sc", "_kc"):
+                buf = getattr(self, name)
+                grown = np.empty((cap, buf.shape[1]), dtype=np.int64)
+                grown[:n] = buf[:n]
+                setattr(self, name, grown)
+        self._states[n:n + m] = newstates
+        self._sc[n:n + m] = 0
+        self._kc[n:n + m] = 0
+        self._n = n + m
 
     def _pack(self, X: np.ndarray) -> np.ndarray:
         """Pack non-negative rows into int64 keys; rows with a negative entry get key -1."""
@@ -217,7 +250,7 @@ class StateSpaceOracleFast:
         return np.where(neg, np.int64(-1), k)
 
     def get_state_count(self):
-        return self.states.shape[0]
+        return self._n
 
     def get_sink_count(self):
         return self.sink_count
@@ -259,9 +292,7 @@ class StateSpaceOracleFast:
         newkeys = ck[first]
         m = newstates.shape[0]
         newidx = np.arange(old + 1, old + m + 1, dtype=np.int64)
-        self.states = np.concatenate([self.states, newstates])
-        self.state_connectivity = np.concatenate([self.state_connectivity, np.zeros((m, R), np.int64)])
-        self.sink_connectivity = np.concatenate([self.sink_connectivity, np.zeros((m, R), np.int64)])
+        self._append(newstates)
         if m == 0:
             return
         self._index.insert(newkeys, newidx)
@@ -289,15 +320,14 @@ class StateSpaceOracleFast:
         keep = np.ones(nold, dtype=bool)
         keep[ids - 1] = False
         newidxs = np.where(keep, np.cumsum(keep), 0).astype(np.int64)
-        self.states = self.states[keep]
         sc = self.state_connectivity[keep]
-        self.sink_connectivity = self.sink_connectivity[keep]
-        n = self.states.shape[0]
+        self._states, self._kc = self.states[keep], self.sink_connectivity[keep]
+        n = self._n = self._states.shape[0]
         if n == 0:
-            self.state_connectivity = sc
+            self._sc = sc
             self._index.rebuild(np.empty(0, np.int64), np.empty(0, np.int64))
             return
-        self.state_connectivity = np.where(sc != 0, newidxs[np.maximum(sc, 1) - 1], 0)
+        self._sc = np.where(sc != 0, newidxs[np.maximum(sc, 1) - 1], 0)
         self._index.rebuild(self._pack(self.states), np.arange(1, n + 1, dtype=np.int64))
         for ir in range(self.nr):
             s = self.stoich[:, ir][None, :]

@@ -159,7 +159,7 @@ def test_sens_solve_bdf_matches_explicit(pkg):
 
 def test_sens_hog1p_matrix_vs_oracle(pkg, ctx):
     """BASELINE.json config 3: Hog1p (examples/hog1p.jl:33-82, NS=6, R=13, P=14) with the forward-sensitivity matrix
-    (sensfspmatrixsparse.jl:31-142): 15 (reaction, parameter) entries, separable reaction 2 carrying two parameters in
+    (sensfspmatrixsparse.jl:31-142): 14 (reaction, parameter) entries, separable reaction 2 carrying two parameters in
     its time factor.  >= 10^4 states, 1e-12 relative, device-resident and host-buffer entry points."""
     th = list(pkg.workloads.HOG1P_THETA)
     th[2] = 3.2e4                                     # a: signal on, so d c / d(k10, a) are non-trivial
@@ -172,7 +172,7 @@ def test_sens_hog1p_matrix_vs_oracle(pkg, ctx):
     n = sp.get_state_count()
     assert n >= 10000 and np.array_equal(sp.get_states(), osp.states_array())
     SA = pkg.ForwardSensFspMatrixSparse(model, sp)
-    assert len(SA.entries) == 15 and SA.parameter_count == 14
+    assert len(SA.entries) == 14 and SA.parameter_count == 14
     OS = SensFspMatrixOracle(osp, cm.propensities, model.propensity_gradients, model.gradient_sparsity_patterns, th)
     N = SA.fspmatrix.rowcount
     rng = np.random.default_rng(5)
