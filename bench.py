@@ -535,7 +535,8 @@ def main():
             alg = pkg.AdaptiveFspSparse(ode_method=None, space_adapter=pkg.RStepAdapter(levels, 10, False))
             barrier()
             tw = time.perf_counter()
-            sol = pkg.solve(model, p0, (0.0, args.solve_t), alg, saveat=[args.solve_t], ctx=ctx, comm=comm)
+            sol = pkg.solve(model, p0, (0.0, args.solve_t), alg, saveat=[args.solve_t], odertol=1e-4, odeatol=1e-8,
+                            ctx=ctx, comm=comm)
             barrier()
             api_wall = time.perf_counter() - tw
             if world > 1:
@@ -544,7 +545,7 @@ def main():
                 api_wall = float(tw_t)
             pl = sol.p[-1]
             solve_info["solve_api_wall_s"] = api_wall
-            solve_info["solve_api"] = {"call": f"solve(model, p0, (0, {args.solve_t}), AdaptiveFspSparse(nothing, RStepAdapter({levels}, 10, false)); saveat=[{args.solve_t}])",
+            solve_info["solve_api"] = {"call": f"solve(model, p0, (0, {args.solve_t}), AdaptiveFspSparse(nothing, RStepAdapter({levels}, 10, false)); saveat=[{args.solve_t}], odertol=1e-4, odeatol=1e-8)",
                                        "steps": int(sol.stats["steps"]), "rhs_evals": int(sol.stats["rhs_evals"]),
                                        "adapts": int(sol.stats["adapts"]), "final_states": int(sol.stats["final_states"]),
                                        "breakdown_s": sol.stats.get("breakdown_s"),

@@ -200,6 +200,12 @@ int ncme_vec_dot(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* y_
 int ncme_vec_wrms(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* u0_dev, const double* u1_dev,
                   double atol, double rtol, double* out);
 int ncme_vec_any_nonfinite(ncme_ctx* ctx, int64_t n, const double* x_dev, int* out);
+/* out_i = x_i / (atol + rtol*max(|u0_i|,|u1_i|)): the elementwise form of OrdinaryDiffEq's calculate_residuals!, what
+ * a DifferentialEquations.jl algorithm broadcasts before it takes its error norm (Julia glue: Broadcast surface) */
+int ncme_vec_residuals(ncme_ctx* ctx, int64_t n, const double* x_dev, const double* u0_dev, const double* u1_dev,
+                       double atol, double rtol, double* out_dev);
+/* x_i += a (the constant term of a broadcast linear expression) */
+int ncme_vec_shift(ncme_ctx* ctx, int64_t n, double a, double* x_dev);
 
 /* ---------------------------------------------------------------- multi-GPU (K8) --------------- */
 /* One process per GPU.  The reference is single-process (no collective call site exists in it); large state

@@ -135,6 +135,8 @@ SIGNATURES = {
     "ncme_vec_dot": (cint, [p_void, i64, p_void, p_void, p_f64]),
     "ncme_vec_wrms": (cint, [p_void, i64, p_void, p_void, p_void, f64, f64, p_f64]),
     "ncme_vec_any_nonfinite": (cint, [p_void, i64, p_void, C.POINTER(cint)]),
+    "ncme_vec_residuals": (cint, [p_void, i64, p_void, p_void, p_void, f64, f64, p_void]),
+    "ncme_vec_shift": (cint, [p_void, i64, f64, p_void]),
 }
 
 COEF_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_void_p)

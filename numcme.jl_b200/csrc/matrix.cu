@@ -309,27 +309,30 @@ __global__ void __launch_bounds__(MV_THREADS, MINB) k_fsp_matvec_sharded(const _
     const int nt = a.ntasks;
     int b = (int)blockIdx.x;
     bool boundary;
-    if (a.bd_first) {
-        boundary = b < a.nb_bd;
-        if (!boundary) {
+    if (a.bd_first >= 2) {
+        // interleaved: among the first nb_bd * bd_first blocks every bd_first-th one is a boundary CTA, so the
+        // latency-bound NVLink gathers share their SM with bandwidth-bound halo-free rows instead of filling a wave
+        const int stride = a.bd_first, span = a.nb_bd * stride;
+        if (b < span) {
+            boundary = (b % stride) == 0;
+            b = boundary ? b / stride : b - b / stride - 1;
+        } else {
+            boundary = false;
             b -= a.nb_bd;
-            if (b < nt) {
-                sink_task(a, b);
-                return;
-            }
-            b -= nt;
         }
+    } else if (a.bd_first) {
+        boundary = b < a.nb_bd;
+        if (!boundary) b -= a.nb_bd;
     } else {
+        boundary = b >= nt + a.nb_int;
+        if (boundary) b -= nt + a.nb_int;
+    }
+    if (!boundary) {   // b indexes [sink tasks | halo-free row tiles]
         if (b < nt) {
             sink_task(a, b);
             return;
         }
-        b -= nt;
-        boundary = b >= a.nb_int;
-        if (boundary) b -= a.nb_int;
-    }
-    if (!boundary) {
-        mv_rows<S, ROWS, false, false>(a, a.int_begin + ((int64_t)b * MV_THREADS + threadIdx.x) * ROWS, a.int_end);
+        mv_rows<S, ROWS, false, false>(a, a.int_begin + ((int64_t)(b - nt) * MV_THREADS + threadIdx.x) * ROWS, a.int_end);
         return;
     }
     if (a.nwait) {
@@ -340,11 +343,12 @@ __global__ void __launch_bounds__(MV_THREADS, MINB) k_fsp_matvec_sharded(const _
         }
         __syncthreads();
     }
-    const int nb1 = (int)((a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS);
-    if (b < nb1)
-        mv_rows<S, 1, false, true>(a, a.row_begin + (int64_t)b * MV_THREADS + threadIdx.x, a.row_end);
-    else
-        mv_rows<S, 1, false, true>(a, a.row_begin2 + (int64_t)(b - nb1) * MV_THREADS + threadIdx.x, a.row_end2);
+    {
+        const int nb1 = (int)((a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS);
+        const bool second = b >= nb1;
+        const int64_t i0 = (second ? a.row_begin2 + (int64_t)(b - nb1) * MV_THREADS : a.row_begin + (int64_t)b * MV_THREADS) + threadIdx.x;
+        mv_rows<S, 1, false, true>(a, i0, second ? a.row_end2 : a.row_end);
+    }
     if (a.ndone_sig || a.ndone_wait) {
         __syncthreads();                      // every gather of this CTA has been consumed
         if (threadIdx.x == 0) {
@@ -366,6 +370,10 @@ static int launch_sharded(ncme_matrix* A, MatvecArgs& a) {
     a.nb_int = (int)((a.int_end - a.int_begin + (int64_t)MV_THREADS * ROWS - 1) / ((int64_t)MV_THREADS * ROWS));
     a.nb_bd = (int)((a.row_end - a.row_begin + MV_THREADS - 1) / MV_THREADS + (a.row_end2 - a.row_begin2 + MV_THREADS - 1) / MV_THREADS);
     const unsigned grid = (unsigned)(a.ntasks + a.nb_int + a.nb_bd);
+    if (a.bd_first >= 2) {   // the interleaved span nb_bd * stride must fit the grid
+        a.bd_first = (int)std::min<unsigned>((unsigned)a.bd_first, a.nb_bd > 0 ? grid / (unsigned)a.nb_bd : 1u);
+        if (a.bd_first < 2) a.bd_first = 1;
+    }
     cudaStream_t st = A->ctx->stream;
     switch (a.nslots) {
 #define NCME_CASE(SS)                                                   \
@@ -611,6 +619,17 @@ static int matvec_launch_p2p(ncme_matrix* A, const MatvecArgs& a) {
 
 int matvec_launch(ncme_matrix* A, const MatvecArgs& a) {
     ncme_ctx* ctx = A->ctx;
+    static const bool force_sharded = getenv("NCME_FORCE_SHARDED_KERNEL") != nullptr;   // experiments: code-quality check
+    if (force_sharded && a.do_sinks && a.nslots <= 8 && a.row_begin == 0 && a.row_end == A->n && !A->comm) {
+        MatvecArgs f = a;
+        f.int_begin = 0;
+        f.int_end = A->n;
+        f.row_begin = f.row_end = f.row_begin2 = f.row_end2 = 0;
+        f.bd_first = 1;
+        f.ndone_sig = f.ndone_wait = 0;
+        f.bd_counter = A->sink_counter + 1;
+        return launch_sharded<2, 4>(A, f);
+    }
     int rows = A->tune_rows;
     if (rows == 0) rows = (a.nslots <= 8) ? 2 : 1;
     // vector loads of x[i0..] / y are not used (scalar), but the matrix streams need i0 % ROWS == 0 only.
@@ -793,7 +812,7 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
     a.x_hi = xhi ? xhi + (A->row_hi - A->phi_row_lo) - (int64_t)a.hi_begin : a.x;
     const bool interior = A->b1 > A->b0;
     static const bool two_launch = getenv("NCME_P2P_TWO_LAUNCH") != nullptr;   // experiments: the round-1 control path
-    static const bool bd_last = getenv("NCME_P2P_BD_LAST") != nullptr;
+    static const int bd_mode = getenv("NCME_P2P_BD_MODE") ? atoi(getenv("NCME_P2P_BD_MODE")) : 4;   // 0 last, 1 first, >= 2 interleave stride
     const bool handshake = !(flags & 2);
     if (!two_launch && sig_in_kernel && a.nslots <= 16 && done.nsig <= 4 && done.nwait <= 4 && a.nwait > 0) {
         MatvecArgs f = a;
@@ -803,7 +822,7 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
         f.row_end = interior ? A->b0 : A->n;
         f.row_begin2 = interior ? A->b1 : 0;
         f.row_end2 = interior ? A->n : 0;
-        f.bd_first = bd_last ? 0 : 1;
+        f.bd_first = bd_mode;
         f.ndone_sig = handshake ? done.nsig : 0;
         f.ndone_wait = handshake ? done.nwait : 0;
         for (int k = 0; k < f.ndone_sig; ++k) f.done_sig[k] = done.sig[k];

@@ -169,6 +169,36 @@ int ncme_vec_scale(ncme_ctx* ctx, int64_t n, double a, double* x) {
     return NCME_OK;
 }
 
+// out_i = x_i / (atol + rtol max(|u0_i|, |u1_i|)) : OrdinaryDiffEq's calculate_residuals!(out, x, u0, u1, atol, rtol, ...)
+__global__ void k_residuals(int64_t n, const double* __restrict__ x, const double* __restrict__ u0,
+                            const double* __restrict__ u1, double atol, double rtol, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = x[i] / (atol + rtol * fmax(fabs(u0[i]), fabs(u1[i])));
+}
+// x_i += a  (the constant term of a broadcast expression)
+__global__ void k_shift(int64_t n, double a, double* __restrict__ x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += a;
+}
+
+int ncme_vec_residuals(ncme_ctx* ctx, int64_t n, const double* x, const double* u0, const double* u1, double atol,
+                       double rtol, double* out) {
+    NCME_REQUIRE(ctx && n >= 0 && (n == 0 || (x && u0 && u1 && out)), "bad arguments");
+    if (n == 0) return NCME_OK;
+    k_residuals<<<ew_grid(n, 1), VT, 0, ctx->stream>>>(n, x, u0, u1, atol, rtol, out);
+    ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
+int ncme_vec_shift(ncme_ctx* ctx, int64_t n, double a, double* x) {
+    NCME_REQUIRE(ctx && n >= 0 && (n == 0 || x), "bad arguments");
+    if (n == 0) return NCME_OK;
+    k_shift<<<ew_grid(n, 1), VT, 0, ctx->stream>>>(n, a, x);
+    ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
 int ncme_vec_axpy(ncme_ctx* ctx, int64_t n, double a, const double* x, double* y) {
     NCME_REQUIRE(ctx && n >= 0 && (n == 0 || (x && y)), "bad arguments");
     if (n == 0) return NCME_OK;

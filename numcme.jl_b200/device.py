@@ -212,6 +212,17 @@ class DeviceVector:
                                        C.c_void_p(device_ptr(u1)), float(atol), float(rtol), C.byref(out)))
         return out.value
 
+    def residuals(self, x, u0, u1, atol: float, rtol: float):
+        """self_i = x_i / (atol + rtol max(|u0_i|, |u1_i|))   (OrdinaryDiffEq's calculate_residuals!)"""
+        L.check(L.load().ncme_vec_residuals(self.ctx.handle, self.n, C.c_void_p(device_ptr(x)), C.c_void_p(device_ptr(u0)),
+                                            C.c_void_p(device_ptr(u1)), float(atol), float(rtol), C.c_void_p(self.ptr)))
+        return self
+
+    def shift(self, a: float):
+        """self += a (elementwise)"""
+        L.check(L.load().ncme_vec_shift(self.ctx.handle, self.n, float(a), C.c_void_p(self.ptr)))
+        return self
+
     def any_nonfinite(self) -> bool:
         out = C.c_int()
         L.check(L.load().ncme_vec_any_nonfinite(self.ctx.handle, self.n, C.c_void_p(self.ptr), C.byref(out)))

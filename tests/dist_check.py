@@ -44,6 +44,18 @@ def main():
         pkg.matvec_(ys, 2.5, A_sh, xs.v)
     y = ys.to_host()
     assert np.array_equal(y[:hi - lo], y_ref[lo:hi]), "state rows differ from the single-GPU result"
+    # ... and against the ORACLE (numpy restatement of the reference's per-term CSC matvec), 1e-12 relative
+    from oracle.fspmatrix import FspMatrixOracle
+    from oracle.statespace import StateSpaceOracleFast
+    osp = StateSpaceOracleFast(model.stoich_matrix, [0, 0, 0])
+    osp.expand(levels)
+    assert np.array_equal(space.get_states(), osp.states_array())
+    y_or = FspMatrixOracle(osp, model.propensities, model.parameters).matvec(2.5, x)
+    scale = np.abs(y_or).max()
+    assert np.abs(y[:hi - lo] - y_or[lo:hi]).max() <= 1e-12 * scale, "sharded state rows differ from the oracle"
+    assert np.abs(y[hi - lo:] - y_or[n:]).max() <= 1e-12 * scale, "sharded sink rows differ from the oracle"
+    assert A_sh.build_window is not None and A_sh.build_window[0] <= lo and hi <= A_sh.build_window[1] and (
+        world == 1 or A_sh.build_window[1] - A_sh.build_window[0] < n), "sharded build did not use a state-factor window"
     assert np.abs(y[hi - lo:] - y_ref[n:]).max() <= 1e-12 * np.abs(y_ref[n:]).max(), "sink rows differ"
     # same through the peer-memory halo (CUDA IPC): registered input buffer, no NCCL in the matvec
     before = comm.info()

@@ -169,6 +169,10 @@ def test_vector_ops(pkg, ctx):
     assert np.allclose(out.to_host(), 0.5 * (5 * a - b + 0.5 * c), rtol=1e-14, atol=1e-14)
     w = da.wrms(db, dc, 1e-6, 1e-3)
     assert w == pytest.approx(np.sqrt(np.mean((a / (1e-6 + 1e-3 * np.maximum(np.abs(b), np.abs(c)))) ** 2)), rel=1e-12)
+    out.residuals(da, db, dc, 1e-6, 1e-3)                         # calculate_residuals! (Julia Broadcast surface)
+    assert np.array_equal(out.to_host(), a / (1e-6 + 1e-3 * np.maximum(np.abs(b), np.abs(c))))
+    out.shift(0.25)
+    assert np.array_equal(out.to_host(), a / (1e-6 + 1e-3 * np.maximum(np.abs(b), np.abs(c))) + 0.25)
     assert not da.any_nonfinite()
     a2 = a.copy()
     a2[5] = np.nan
