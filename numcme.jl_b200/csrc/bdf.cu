@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "comm.cuh"
 #include "matrix.cuh"
 #include "ode.cuh"
 #include "vec.cuh"
@@ -70,6 +71,79 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NS], int nslot, d
         result[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *counter = 0u;
+}
+
+// Same two-stage block reduction, followed -- inside the SAME kernel, by the CTA that finished last -- by the all-reduce
+// over the ranks through peer memory (NVLink stores into every rank's PeerFlags::red_slot, one flag per source rank,
+// summation in rank order => identical bits everywhere).  The reduced values land in device memory `result`, where
+// the next kernel of the Krylov iteration reads them: no host round trip, no NCCL launch in the iteration.
+__device__ __forceinline__ unsigned long long bdf_global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+template <int NS>
+__device__ __forceinline__ void block_reduce_allreduce(double (&v)[NS], double* partials, unsigned int* counter,
+                                                       double* result, const DevAllreduce& ar) {
+    static_assert(NS <= NCME_RED_VALS, "too many values for the in-kernel all-reduce");
+    __shared__ double sh[BT / 32][NS];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double x = v[s];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0) sh[wid][s] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < BT / 32; ++w) t += sh[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * NS + threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t = 0.0;
+    if (threadIdx.x < NS) {
+        const volatile double* p = partials;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += p[(size_t)b * NS + threadIdx.x];
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+    if (ar.nranks > 1) {
+        const int buf = (int)(ar.epoch % NCME_RED_BUFS);
+        if (threadIdx.x < NS)
+            for (int q = 0; q < ar.nranks; ++q) ar.flags[q]->red_slot[buf][ar.me][threadIdx.x] = t;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < ar.nranks)
+            *((volatile unsigned int*)&ar.flags[threadIdx.x]->red_flag[buf][ar.me]) = ar.epoch;
+        if (threadIdx.x < ar.nranks) {   // wait (bounded) for the partial sums of every rank
+            const volatile unsigned int* f = &ar.flags[ar.me]->red_flag[buf][threadIdx.x];
+            const unsigned long long t0 = bdf_global_ns();
+            while ((int)(*f - ar.epoch) < 0) {
+                if (bdf_global_ns() - t0 > 2000000000ull) {
+                    atomicExch(&ar.flags[ar.me]->error, 1u);
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < NS) {
+            const volatile double* sl = &ar.flags[ar.me]->red_slot[buf][0][0];
+            t = 0.0;
+            for (int q = 0; q < ar.nranks; ++q) t += sl[q * NCME_RED_VALS + threadIdx.x];
+        }
+    }
+    if (threadIdx.x < NS) result[threadIdx.x] = t;
 }
 
 // y_pred = sum_{j<=k} D_j ;  psi = (sum_{1<=j<=k} gamma_j D_j) / alpha_k
@@ -141,7 +215,8 @@ struct ApplyArgs {
     double* w;
     double* partials;
     unsigned int* counter;
-    double* result;
+    double* result;      // device: column k of the Hessenberg data, [0..k] dots, [RED_SLOTS-1] = <w,w>, summed over the ranks
+    DevAllreduce ar;
 };
 // KB = number of basis vectors dotted (k+1 rounded up to a multiple of 4; the surplus pointers alias V_0 and their
 // results are ignored): fully unrolled, no predication, all loads of an element independent.
@@ -167,7 +242,7 @@ __global__ void __launch_bounds__(BT) k_gm_apply_dots(const __grid_constant__ Ap
 #pragma unroll
     for (int j = 0; j < KB; ++j) full[j] = v[j];
     full[RED_SLOTS - 1] = v[KB];
-    block_reduce_store<RED_SLOTS>(full, RED_SLOTS, a.partials, a.counter, a.result);
+    block_reduce_allreduce<RED_SLOTS>(full, a.partials, a.counter, a.result, a.ar);
 }
 
 static int launch_apply_dots(ncme_ctx* ctx, const ApplyArgs& aa, unsigned grid) {
@@ -188,23 +263,38 @@ static int launch_apply_dots(ncme_ctx* ctx, const ApplyArgs& aa, unsigned grid) 
 }
 
 // v_{k+1} = (w - sum_j h_j V_j) * inv ;  z = v_{k+1} * scale
+// The coefficients h_j = <w, V_j> and |w|^2 are read from DEVICE memory (column k written by k_gm_apply_dots, already
+// summed over the ranks): the host is not needed between the inner products and the orthogonalisation, so several
+// Krylov iterations can be enqueued back to back.  |w - sum h_j v_j| by Pythagoras, exactly as the host recomputes it.
 struct OrthoArgs {
     int64_t n;
     int k;
     const double* w;
     PtrList V;
-    double h[GM_M + 1];
-    double inv;
+    const double* hcol;   // device: [0..k] = h_j, [RED_SLOTS-1] = <w,w>
     const double* scale;
     double* vout;
     double* z;
 };
+__host__ __device__ __forceinline__ double gm_hk1(const double* hh, int k) {
+    const double ww = hh[RED_SLOTS - 1];
+    double hsq = 0.0;
+    for (int j = 0; j <= k; ++j) hsq += hh[j] * hh[j];
+    double hk1sq = ww - hsq;
+    if (!(hk1sq > 1e-10 * ww)) hk1sq = hk1sq > 0.0 ? hk1sq : 0.0;
+    return sqrt(hk1sq > 0.0 ? hk1sq : 0.0);
+}
 __global__ void __launch_bounds__(BT) k_gm_ortho(const __grid_constant__ OrthoArgs a) {
+    __shared__ double sh[RED_SLOTS + 1];
+    if (threadIdx.x < RED_SLOTS) sh[threadIdx.x] = a.hcol[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) sh[RED_SLOTS] = 1.0 / gm_hk1(sh, a.k);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
     if (i >= a.n) return;
     double x = a.w[i];
-    for (int j = 0; j <= a.k; ++j) x = fma(-a.h[j], a.V.p[j][i], x);
-    x *= a.inv;
+    for (int j = 0; j <= a.k; ++j) x = fma(-sh[j], a.V.p[j][i], x);
+    x *= sh[RED_SLOTS];
     a.vout[i] = x;
     a.z[i] = x * a.scale[i];
 }
@@ -557,11 +647,19 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     double t = t0;
     double g_prev = 0.0;
     bool have_g = false;
-    const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+    // smallest resolvable step: relative to where the segment STARTS (a long horizon must not forbid the tiny first
+    // steps a tight absolute tolerance asks for: toggle example, odeatol = 1e-14 over 8 h)
+    const double hmin = std::max(1e-14 * fabs(t0), 1e-20 * fabs(t1 - t0));
     // weighted-RMS residual of the linear solve = CVODE's 0.05 x Newton tolerance 0.1.  The residual of the inexact
     // solve is the only source of total-mass drift (1^T A = 0); it is removed by the invariant projection below.
     const double lin_tol = 5e-3;
     std::vector<double> tails((size_t)(MAX_ORDER + 4) * std::max(R, 1));
+    // Hessenberg columns of the running Krylov cycle: device scalars (written by k_gm_apply_dots) and their host image
+    constexpr int HCOL_LD = 32, HCOL_OFF = 32;
+    static_assert(HCOL_OFF + HCOL_LD * (GM_M + 1) <= 1000 && RED_SLOTS <= HCOL_LD, "Hessenberg columns must fit the scalar buffers");
+    auto hcol_dev = [&](int k) { return ctx->red_result_dev + HCOL_OFF + (size_t)HCOL_LD * k; };
+    auto hcol_host = [&](int k) { return ctx->red_result_host + HCOL_OFF + (size_t)HCOL_LD * k; };
+    int k_pred = 2;   // Krylov iterations of the previous linear solve (batch size of the next one)
 
     while (t < t1) {
         if (abort_requested()) return abort_status();   // a save callback failed
@@ -618,71 +716,81 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
                 ctx->launches++;
                 int k = 0;
                 double resid = beta;
-                for (; k < GM_M; ++k) {
-                    NCME_TRY(rhs(t_new, z, Ay));
-                    ApplyArgs aa{};
-                    aa.n = n;
-                    aa.k = k;
-                    aa.z = z;
-                    aa.Az = Ay;
-                    aa.ps = ps;
-                    aa.c = c;
-                    for (int j = 0; j <= k; ++j) aa.V.p[j] = V[j];
-                    for (int j = k + 1; j < GM_M + 2; ++j) aa.V.p[j] = V[0];
-                    aa.w = w;
-                    aa.partials = gm_partials;
-                    aa.counter = ctx->red_counter;
-                    aa.result = ctx->red_result_dev;
-                    NCME_TRY(launch_apply_dots(ctx, aa, gm_grid));
-                    NCME_TRY(fetch(RED_SLOTS));
-                    const double* hh = ctx->red_result_host;
-                    double ww = hh[RED_SLOTS - 1], hsq = 0.0;
-                    for (int j = 0; j <= k; ++j) {
-                        H[j][k] = hh[j];
-                        hsq += hh[j] * hh[j];
+                // Krylov iterations are enqueued in BATCHES: the inner products stay on the device (summed over the
+                // ranks inside k_gm_apply_dots), k_gm_ortho reads them there, and the host fetches the Hessenberg
+                // columns of a whole batch with one copy.  The first batch of a cycle speculates on one iteration
+                // fewer than the previous linear solve needed, then single iterations follow: (almost) no wasted
+                // matvec, 2-3 host round trips per solve instead of one per iteration.
+                bool cycle_done = false;
+                bool first_batch = true;
+                while (!cycle_done && lin_ok) {
+                    const int nb = first_batch ? std::max(1, std::min(k_pred - 1, GM_M - k)) : 1;
+                    first_batch = false;
+                    for (int b = 0; b < nb; ++b) {
+                        const int kk = k + b;
+                        if (kk > 0) {   // v_kk, z from column kk-1 (device-resident coefficients)
+                            OrthoArgs oa{};
+                            oa.n = n;
+                            oa.k = kk - 1;
+                            oa.w = w;
+                            for (int j = 0; j <= kk - 1; ++j) oa.V.p[j] = V[j];
+                            oa.hcol = hcol_dev(kk - 1);
+                            oa.scale = scale;
+                            oa.vout = V[kk];
+                            oa.z = z;
+                            k_gm_ortho<<<grid_for(n), BT, 0, s>>>(oa);
+                            ctx->launches++;
+                        }
+                        NCME_TRY(rhs(t_new, z, Ay));
+                        ApplyArgs aa{};
+                        aa.n = n;
+                        aa.k = kk;
+                        aa.z = z;
+                        aa.Az = Ay;
+                        aa.ps = ps;
+                        aa.c = c;
+                        for (int j = 0; j <= kk; ++j) aa.V.p[j] = V[j];
+                        for (int j = kk + 1; j < GM_M + 2; ++j) aa.V.p[j] = V[0];
+                        aa.w = w;
+                        aa.partials = gm_partials;
+                        aa.counter = ctx->red_counter;
+                        aa.result = hcol_dev(kk);
+                        const bool in_kernel = comm_dev_allreduce(comm, &aa.ar);
+                        NCME_TRY(launch_apply_dots(ctx, aa, gm_grid));
+                        if (!in_kernel) NCME_TRY(comm_allreduce_sum(comm, hcol_dev(kk), RED_SLOTS, s));
                     }
-                    double hk1sq = ww - hsq;                    // |w - sum h_j v_j|^2 by Pythagoras
-                    if (!(hk1sq > 1e-10 * ww)) hk1sq = std::max(hk1sq, 0.0);
-                    const double hk1 = sqrt(std::max(hk1sq, 0.0));
-                    H[k + 1][k] = hk1;
-                    // Givens rotations on column k
-                    for (int j = 0; j < k; ++j) {
-                        const double tmp = cs_[j] * H[j][k] + sn_[j] * H[j + 1][k];
-                        H[j + 1][k] = -sn_[j] * H[j][k] + cs_[j] * H[j + 1][k];
-                        H[j][k] = tmp;
+                    NCME_CUDA(cudaMemcpyAsync(hcol_host(k), hcol_dev(k), sizeof(double) * HCOL_LD * nb, cudaMemcpyDeviceToHost, s));
+                    NCME_CUDA(cudaStreamSynchronize(s));
+                    if (abort_requested()) return abort_status();
+                    for (int b = 0; b < nb && !cycle_done; ++b, ++k) {
+                        const double* hh = hcol_host(k);
+                        const double ww = hh[RED_SLOTS - 1];
+                        for (int j = 0; j <= k; ++j) H[j][k] = hh[j];
+                        const double hk1 = gm_hk1(hh, k);
+                        H[k + 1][k] = hk1;
+                        // Givens rotations on column k
+                        for (int j = 0; j < k; ++j) {
+                            const double tmp = cs_[j] * H[j][k] + sn_[j] * H[j + 1][k];
+                            H[j + 1][k] = -sn_[j] * H[j][k] + cs_[j] * H[j + 1][k];
+                            H[j][k] = tmp;
+                        }
+                        const double den = hypot(H[k][k], H[k + 1][k]);
+                        if (!(den > 0.0) || !(ww == ww)) {
+                            lin_ok = false;
+                            break;
+                        }
+                        cs_[k] = H[k][k] / den;
+                        sn_[k] = H[k + 1][k] / den;
+                        H[k][k] = den;
+                        H[k + 1][k] = 0.0;
+                        gvec[k + 1] = -sn_[k] * gvec[k];
+                        gvec[k] = cs_[k] * gvec[k];
+                        resid = fabs(gvec[k + 1]);
+                        const bool happy = hk1 <= 1e-14 * sqrt(std::max(ww, 1e-300));
+                        if (resid / sqrtn <= lin_tol || happy || k + 1 == GM_M) cycle_done = true;   // k is advanced by the loop
                     }
-                    const double den = hypot(H[k][k], H[k + 1][k]);
-                    if (!(den > 0.0) || !(ww == ww)) {
-                        lin_ok = false;
-                        break;
-                    }
-                    cs_[k] = H[k][k] / den;
-                    sn_[k] = H[k + 1][k] / den;
-                    H[k][k] = den;
-                    H[k + 1][k] = 0.0;
-                    gvec[k + 1] = -sn_[k] * gvec[k];
-                    gvec[k] = cs_[k] * gvec[k];
-                    resid = fabs(gvec[k + 1]);
-                    const bool happy = hk1 <= 1e-14 * sqrt(std::max(ww, 1e-300));
-                    if (resid / sqrtn <= lin_tol || happy || k + 1 == GM_M) {
-                        ++k;
-                        break;
-                    }
-                    OrthoArgs oa{};
-                    oa.n = n;
-                    oa.k = k;
-                    oa.w = w;
-                    for (int j = 0; j <= k; ++j) {
-                        oa.V.p[j] = V[j];
-                        oa.h[j] = hh[j];
-                    }
-                    oa.inv = 1.0 / hk1;
-                    oa.scale = scale;
-                    oa.vout = V[k + 1];
-                    oa.z = z;
-                    k_gm_ortho<<<grid_for(n), BT, 0, s>>>(oa);
-                    ctx->launches++;
                 }
+                if (lin_ok && restarts == 0) k_pred = k;
                 if (!lin_ok) break;
                 // back substitution H y = g
                 double yk[GM_M + 1] = {};

@@ -920,7 +920,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     c.t = t0;
     c.t1 = t1;
     c.tspan = tspan;
-    c.hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+    c.hmin = std::max(1e-14 * fabs(t0), 1e-20 * fabs(t1 - t0));   // see bdf.cu
     c.order = 1;
     c.max_steps = o->max_steps > 0 ? o->max_steps : 100000000;
     c.check_event = (o->check_event && R > 0) ? 1 : 0;

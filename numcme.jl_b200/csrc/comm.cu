@@ -275,6 +275,21 @@ int comm_hostreduce_sum(ncme_comm* c, double* vals, size_t count) {
     return NCME_OK;
 }
 
+bool comm_dev_allreduce(ncme_comm* c, DevAllreduce* ar) {
+    ar->nranks = 1;
+    ar->me = 0;
+    ar->epoch = 0;
+    for (int q = 0; q < NCME_RED_RANKS; ++q) ar->flags[q] = nullptr;
+    if (!c || c->nranks == 1) return true;
+    static const bool off = getenv("NCME_NO_DEV_ALLREDUCE") != nullptr;
+    if (off || !c->p2p_ok || c->nranks > NCME_RED_RANKS || !c->my_flags) return false;
+    ar->nranks = c->nranks;
+    ar->me = c->rank;
+    ar->epoch = ++c->red_epoch;
+    for (int q = 0; q < c->nranks; ++q) ar->flags[q] = (q == c->rank) ? c->my_flags : c->peer_flags[q];
+    return true;
+}
+
 // Flags: every rank exports its PeerFlags block and maps everybody else's.
 static int comm_setup_p2p(ncme_comm* c) {
     c->p2p_ok = false;

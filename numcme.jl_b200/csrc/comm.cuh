@@ -9,11 +9,26 @@
 constexpr int NCME_MAX_RANKS = 64;
 constexpr int NCME_HOSTREDUCE_MAX = 320;   // doubles per host-side all-reduce (1 + 9 R sink tails, R <= 32)
 
+constexpr int NCME_RED_RANKS = 16;         // device-side all-reduce of small scalar sets: ranks, buffers, values
+constexpr int NCME_RED_BUFS = 4;
+constexpr int NCME_RED_VALS = 32;
+
 // Flags each rank exposes to its peers through CUDA IPC (peer GPUs store into them over NVLink).
 struct PeerFlags {
     unsigned int ready[NCME_MAX_RANKS];   // ready[q] = e: rank q's input vector of matvec #e is complete
     unsigned int done[NCME_MAX_RANKS];    // done[q]  = e: rank q has finished reading my vector in matvec #e
     unsigned int error;                   // a wait timed out
+    // in-kernel all-reduce (Krylov inner products): rank q stores its partial sums of reduction #e into
+    // red_slot[e % BUFS][q][..] of EVERY rank and then publishes red_flag[e % BUFS][q] = e there
+    unsigned int red_flag[NCME_RED_BUFS][NCME_RED_RANKS];
+    double red_slot[NCME_RED_BUFS][NCME_RED_RANKS][NCME_RED_VALS];
+};
+
+// By-value kernel argument of the in-kernel all-reduce.  nranks == 1: no exchange.
+struct DevAllreduce {
+    int nranks, me;
+    unsigned int epoch;                   // sequence number of this reduction (same on every rank)
+    PeerFlags* flags[NCME_RED_RANKS];     // flags[q] = rank q's PeerFlags as mapped into this process (flags[me] = my own)
 };
 
 // A device allocation whose vectors the neighbouring ranks may read directly (halo pull over NVLink).
@@ -44,6 +59,7 @@ struct ncme_comm {
     PeerFlags* my_flags = nullptr;
     PeerFlags* peer_flags[NCME_MAX_RANKS] = {nullptr};
     unsigned int epoch = 0;
+    unsigned int red_epoch = 0;           // sequence number of the in-kernel all-reduces
     std::vector<RegBuf> regs;
     int64_t p2p_matvecs = 0, nccl_matvecs = 0;
     // host-side all-reduce of step-control scalars through POSIX shared memory (all ranks live on one node)
@@ -101,6 +117,10 @@ const double* comm_peer_vector(const ncme_comm* c, const double* x_local, int q)
 // Returns false when the shared segment is unavailable (the caller then uses comm_allreduce_sum on the device).
 bool comm_hostreduce_available(const ncme_comm* c);
 int comm_hostreduce_sum(ncme_comm* c, double* host_vals, size_t count);
+
+// Descriptor of the next in-kernel all-reduce (advances the sequence number).  Returns false when the peer-memory
+// transport is unavailable or there are more than NCME_RED_RANKS ranks: the caller then reduces with NCCL.
+bool comm_dev_allreduce(ncme_comm* c, DevAllreduce* ar);
 
 // in-place sum over ranks of `count` doubles on the device (stream-ordered on `st`)
 int comm_allreduce_sum(ncme_comm* c, double* buf_dev, size_t count, cudaStream_t st);

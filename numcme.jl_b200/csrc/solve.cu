@@ -353,7 +353,9 @@ int solve_dp5(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     ea.result = ctx->red_result_dev;
     int64_t nb = (N + (int64_t)ST * 8 - 1) / ((int64_t)ST * 8);
     nb = std::max<int64_t>(1, std::min<int64_t>(nb, 4096));
-    const double hmin = 1e-14 * std::max(fabs(t0), fabs(t1));
+    // smallest resolvable step: relative to where the segment STARTS (a long horizon must not forbid the tiny first
+    // steps a tight absolute tolerance asks for: toggle example, odeatol = 1e-14 over 8 h)
+    const double hmin = std::max(1e-14 * fabs(t0), 1e-20 * fabs(t1 - t0));
     const size_t nres = (size_t)(1 + 9 * R);
 
     while (t < t1) {

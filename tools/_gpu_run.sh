@@ -1,9 +1,17 @@
 set -x
-for v in k1 forced; do
-  if [ $v = forced ]; then export NCME_FORCE_SHARDED_KERNEL=1; fi
-  timeout 300 python bench.py --steps 200 --warmup 10 --no-solve --no-cpu > gpurun_out/r2d_n1_$v.json 2> gpurun_out/r2d_n1_$v.err
-  python -c "
-import json; d=json.loads(open('gpurun_out/r2d_n1_$v.json').read().strip().splitlines()[-1]); print('$v', d['ms_per_step'], d['value'], d['per_step']['median_ms'], d['config']['assemble_s'], d['config']['expand_s'])"
-done
-unset NCME_FORCE_SHARDED_KERNEL
-timeout 2700 python -m pytest tests -v -m gpu --durations=60 --timeout=900 -p no:cacheprovider > gpurun_out/r2d_pytest.log 2>&1; echo "pytest exit $?"; grep -E "PASSED|FAILED|ERROR|SKIPPED" gpurun_out/r2d_pytest.log | grep -v PASSED | head -20; tail -75 gpurun_out/r2d_pytest.log
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -15
+run() { name=$1; n=$2; shift; shift; env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $n --steps 20 --warmup 5 --solve-method bdf > gpurun_out/r2f_$name.json 2> gpurun_out/r2f_$name.err; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r2f_$name.json").read().strip().splitlines()[-1])
+    s=d.get("solve") or {}
+    print("$name", round(d["ms_per_step"],5), round(d["value"]), {k:(round(v,5) if isinstance(v,float) else v) for k,v in d["per_step"].items() if k!="note"}, d["gpu_launches"], "assemble", d["config"]["assemble_s"], "solve", s.get("wall_s"), s.get("rhs_evals"), s.get("launches"), "api", s.get("solve_api_wall_s"), (s.get("solve_api") or {}).get("breakdown_s"))
+except Exception as e:
+    print("$name FAILED", e); print(open("gpurun_out/r2f_$name.err").read()[-2500:])
+PY
+}
+run n4_one 4 NCME_X=1
+run n4_two 4 NCME_P2P_TWO_LAUNCH=1
+run n4_one_hostred 4 NCME_NO_DEV_ALLREDUCE=1
+run n2_one 2 NCME_X=1
+run n2_two 2 NCME_P2P_TWO_LAUNCH=1
