@@ -550,16 +550,34 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
     error_const[MAX_ORDER + 1] = 1.0 / (MAX_ORDER + 2);
 
     const bool host_reduce = comm_hostreduce_available(comm);
+    // NCME_BDF_PROFILE=1: where the wall time of a segment goes (host blocked on the stream = the GPU was busy;
+    // the rest = the GPU waited for the host) -- printed to stderr by rank 0 at the end of the segment
+    static const bool profile = getenv("NCME_BDF_PROFILE") != nullptr;
+    double prof_sync = 0.0, prof_hostred = 0.0;
+    long long prof_nsync = 0;
+    const double prof_t0 = profile ? wall_seconds() : 0.0;
+    auto sync_stream = [&]() -> int {
+        const double ta = profile ? wall_seconds() : 0.0;
+        NCME_CUDA(cudaStreamSynchronize(s));
+        if (profile) {
+            prof_sync += wall_seconds() - ta;
+            ++prof_nsync;
+        }
+        return NCME_OK;
+    };
     auto fetch = [&](size_t count) -> int {   // reduced scalars -> pinned host
         if (host_reduce && count <= (size_t)NCME_HOSTREDUCE_MAX) {
             // sharded: this rank's partial sums go to the host, the ranks combine them through shared memory
             NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
-            NCME_CUDA(cudaStreamSynchronize(s));
-            return comm_hostreduce_sum(comm, ctx->red_result_host, count);
+            NCME_TRY(sync_stream());
+            const double ta = profile ? wall_seconds() : 0.0;
+            const int rc = comm_hostreduce_sum(comm, ctx->red_result_host, count);
+            if (profile) prof_hostred += wall_seconds() - ta;
+            return rc;
         }
         NCME_TRY(comm_allreduce_sum(comm, ctx->red_result_dev, count, s));
         NCME_CUDA(cudaMemcpyAsync(ctx->red_result_host, ctx->red_result_dev, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
-        NCME_CUDA(cudaStreamSynchronize(s));
+        NCME_TRY(sync_stream());
         return NCME_OK;
     };
     auto rhs = [&](double t, const double* x, double* y) -> int {
@@ -591,6 +609,10 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
         if (sinks_explicit) NCME_TRY(comm_allreduce_sum(comm, u + off, (size_t)R, s));
         NCME_CUDA(cudaStreamSynchronize(s));
         st->launches = ctx->launches - launches0;
+        if (profile && (!comm || comm->rank == 0))
+            fprintf(stderr, "[ncme bdf profile] wall %.4f s, blocked on the stream %.4f s in %lld syncs, host all-reduce %.4f s, "
+                            "%lld launches, %lld rhs, %lld steps\n", wall_seconds() - prof_t0, prof_sync, prof_nsync, prof_hostred,
+                    (long long)st->launches, (long long)st->rhs_evals, (long long)st->steps);
         if (comm && comm->my_flags) {
             unsigned int perr = 0;
             NCME_CUDA(cudaMemcpy(&perr, &comm->my_flags->error, sizeof(perr), cudaMemcpyDeviceToHost));
@@ -760,7 +782,7 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
                         if (!in_kernel) NCME_TRY(comm_allreduce_sum(comm, hcol_dev(kk), RED_SLOTS, s));
                     }
                     NCME_CUDA(cudaMemcpyAsync(hcol_host(k), hcol_dev(k), sizeof(double) * HCOL_LD * nb, cudaMemcpyDeviceToHost, s));
-                    NCME_CUDA(cudaStreamSynchronize(s));
+                    NCME_TRY(sync_stream());
                     if (abort_requested()) return abort_status();
                     for (int b = 0; b < nb && !cycle_done; ++b, ++k) {
                         const double* hh = hcol_host(k);

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "bdf_ctl.h"
+#include "comm.cuh"
 #include "matrix.cuh"
 #include "ode.cuh"
 #include "vec.cuh"
@@ -47,7 +48,7 @@ constexpr int MAXO = BDF_MAXO;        // maximum BDF order
 constexpr int GM = 24;                // Krylov dimension before restart
 constexpr int NSLOT = GM + 2;         // widest reduction (k+1 inner products + <w,w>)
 constexpr int MAXR = NCME_MAX_REACTIONS;
-constexpr int SMEM_MAX_BYTES = 212 * 1024;   // dynamic shared memory of the SMEMV variant (+ ~12 KB static <= 227 KB)
+constexpr int SMEM_MAX_BYTES = 211 * 1024;   // dynamic shared memory of the SMEMV variant (+ ~15 KB static <= 227 KB)
 
 struct StepResult {                   // written by CTA 0 straight into pinned (device-mapped) host memory
     double error_sumsq;               // sum over ALL entries (states + sinks) of (d / (atol + rtol |ynew|))^2
@@ -90,6 +91,13 @@ struct StepArgs {
     BdfConst kc;
     double* ring;                     // [BDF_RING][stride] every-step output slices
     int max_attempts;
+    // row sharding (P > 1, cooperative launches only): column indices are positions in the halo-padded window
+    // [halo_lo | local rows | R sinks | halo_hi]; halo entries are read from the neighbours' HBM (NVLink), the ranks'
+    // grids meet in barriers / all-reduces through PeerFlags::fz_flag / fz_slot
+    int P, me;
+    uint32_t self_off, lo_end, hi_begin;
+    const double *ypred_lo, *ypred_hi, *z_lo, *z_hi, *ynew_lo, *ynew_hi;   // peer views, indexed by padded position
+    PeerFlags* flags[NCME_RED_RANKS];
     // scratch
     double* partials;                 // [2][G][NSLOT]
     double* sinkbuf;                  // [2][MAXR]: sum val*x, sum val*|x|
@@ -103,6 +111,11 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
+struct SyncState {          // identical in every thread of the grid
+    int parity;             // which half of the partials buffer the next reduction uses
+    unsigned int xe;        // sequence number of the cross-GPU exchanges (sharded mode)
+};
+
 struct Shared {
     double w[FW][NSLOT];
     double res[NSLOT];
@@ -112,6 +125,7 @@ struct Shared {
     int stop, ok;
     double sink_d[MAXR];
     double sinkS[MAXR], sinkA[MAXR];   // sink rows of A x and of A |x| (every CTA keeps a copy)
+    double xg[NCME_FZ_VALS];           // staging of a cross-GPU all-reduce
 };
 
 template <bool MULTI>
@@ -122,10 +136,69 @@ __device__ __forceinline__ void grid_barrier() {
         __syncthreads();
 }
 
+// ---- sharded mode: exchanges between the ranks' cooperative grids (all CTAs of all ranks are resident) ------------
+// Every rank executes the same sequence of exchanges (all control flow derives from all-reduced values), numbered by
+// sy.xe.  Slot / flag buffers are reused every NCME_RED_BUFS exchanges; every exchange is preceded by a grid-wide
+// barrier on each rank, so a rank can be at most one exchange ahead of any CTA of any other rank.  Waits are bounded
+// (2 s): a lost peer raises PeerFlags::error instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long fz_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void xg_wait_all(const StepArgs& a, int buf, unsigned int e) {
+    if ((int)threadIdx.x < a.P) {
+        const volatile unsigned int* f = &a.flags[a.me]->fz_flag[buf][threadIdx.x];
+        const volatile unsigned int* err = &a.flags[a.me]->error;
+        const unsigned long long t0 = fz_ns();
+        while ((int)(*f - e) < 0) {
+            if (*err) break;   // an exchange already timed out: the step is lost, do not wait 2 s at every exchange
+            if (fz_ns() - t0 > 2000000000ull) {
+                atomicExch(&a.flags[a.me]->error, 1u);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+// Barrier over all ranks.  Precondition: a grid-wide barrier on this rank since its last writes that peers will read
+// (those writes are then in this GPU's L2, where peer loads are served).
+__device__ __forceinline__ void xg_barrier(const StepArgs& a, SyncState& sy) {
+    const unsigned int e = ++sy.xe;
+    const int buf = (int)(e % NCME_RED_BUFS);
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.P) {
+        __threadfence_system();
+        *((volatile unsigned int*)&a.flags[threadIdx.x]->fz_flag[buf][a.me]) = e;
+    }
+    xg_wait_all(a, buf, e);
+}
+// In-place sum over the ranks of vals[0..nv) (shared memory, identical in every CTA of a rank on entry); summation in
+// rank order => identical bits on every rank.  Precondition as xg_barrier.  Ends with __syncthreads.
+__device__ __forceinline__ void xg_allreduce(const StepArgs& a, SyncState& sy, double* vals, int nv) {
+    const unsigned int e = ++sy.xe;
+    const int buf = (int)(e % NCME_RED_BUFS);
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < nv)
+            for (int q = 0; q < a.P; ++q) a.flags[q]->fz_slot[buf][a.me][threadIdx.x] = vals[threadIdx.x];
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < a.P) *((volatile unsigned int*)&a.flags[threadIdx.x]->fz_flag[buf][a.me]) = e;
+    }
+    xg_wait_all(a, buf, e);
+    if ((int)threadIdx.x < nv) {
+        const volatile double* sl = &a.flags[a.me]->fz_slot[buf][0][0];
+        double t = 0.0;
+        for (int q = 0; q < a.P; ++q) t += sl[q * NCME_FZ_VALS + threadIdx.x];
+        vals[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
 // Ordered two-stage reduction of nv <= NV values; afterwards sh.res[0..nv) holds the totals in EVERY CTA (identical
 // bits everywhere: same partials, same summation order).  Contains a grid-wide barrier when MULTI.
 template <int NV, bool MULTI>
-__device__ __forceinline__ void reduce_all(double (&v)[NV], int nv, const StepArgs& a, int& parity, Shared& sh) {
+__device__ __forceinline__ void reduce_all(double (&v)[NV], int nv, const StepArgs& a, SyncState& sy, Shared& sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // single CTA: row i is handled by thread i % FBT, so warps beyond ceil(N / 32) only ever hold zeros -- they skip the
     // shuffles and the second stage skips their slots (a 100-state system keeps 4 of 16 warps busy)
@@ -144,49 +217,62 @@ __device__ __forceinline__ void reduce_all(double (&v)[NV], int nv, const StepAr
         double t = 0.0;
         for (int w = 0; w < nw; ++w) t += sh.w[w][threadIdx.x];
         if (MULTI)
-            a.partials[((size_t)parity * a.G + blockIdx.x) * NSLOT + threadIdx.x] = t;
+            a.partials[((size_t)sy.parity * a.G + blockIdx.x) * NSLOT + threadIdx.x] = t;
         else
             sh.res[threadIdx.x] = t;
     }
     if (MULTI) {
         cg::this_grid().sync();
-        const double* P = a.partials + (size_t)parity * a.G * NSLOT;
+        const double* P = a.partials + (size_t)sy.parity * a.G * NSLOT;
         for (int s = wid; s < nv; s += FW) {
             double t = 0.0;
             for (int b = lane; b < a.G; b += 32) t += __ldcg(P + (size_t)b * NSLOT + s);
             t = warp_sum(t);
             if (lane == 0) sh.res[s] = t;
         }
-        parity ^= 1;
+        sy.parity ^= 1;
     }
     __syncthreads();
+    if (MULTI && a.P > 1) xg_allreduce(a, sy, sh.res, nv);
 }
 
 struct Vecs {   // where the per-step work vectors live (global workspace or shared memory)
     double *ypred, *ynew, *z, *psi, *scale, *ps, *w, *d, *V;
     int64_t vs;   // stride between Krylov vectors
 };
+struct XView {   // a matvec input: local rows + (sharded) the neighbours' copies, indexed by padded position
+    const double *x, *lo, *hi;
+};
 
-// (A x)_i and diag(A)_i for one state row
-__device__ __forceinline__ double row_apply(const StepArgs& a, const double* x, int64_t i, double& jd) {
+// (A x)_i and diag(A)_i for one state row.  Sharded: the column index is a position in the halo-padded window; halo
+// entries come from the neighbour's HBM over NVLink (L1 bypassed: the same addresses are rewritten every iteration).
+__device__ __forceinline__ double row_apply(const StepArgs& a, const XView& xv, int64_t i, double& jd) {
     double acc = 0.0;
     const uint32_t* cp = a.col + i;
     const double* vp = a.val + i;
+    const double* xb = xv.x - a.self_off;
 #pragma unroll 4
     for (int s = 0; s < a.nslots; ++s) {
         const uint32_t c = __ldg(cp + (size_t)s * a.ld);
         const double v = __ldg(vp + (size_t)s * a.ld);
-        acc = fma(a.slot_coef[s] * v, x[c], acc);
+        double xc;
+        if (a.P > 1 && c < a.lo_end)
+            xc = __ldcg(xv.lo + c);
+        else if (a.P > 1 && c >= a.hi_begin)
+            xc = __ldcg(xv.hi + c);
+        else
+            xc = xb[c];
+        acc = fma(a.slot_coef[s] * v, xc, acc);
     }
     double dg = 0.0;
     for (int d = 0; d < a.ndiag; ++d) dg = fma(a.diag_coef[d], __ldg(a.diag + (size_t)d * a.ld + i), dg);
     jd = dg;
-    return fma(dg, x[i], acc);
+    return fma(dg, xv.x[i], acc);
 }
 
 // sh.sinkS[r] = c_r * sum_k sink_val[k] x[sink_row[k]], sh.sinkA[r] = same with |x|, in every CTA; ends with a barrier
 template <bool MULTI>
-__device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Shared& sh) {
+__device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Shared& sh, SyncState& sy) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (!MULTI) {
         for (int r = wid; r < a.R; r += FW) {
@@ -233,19 +319,32 @@ __device__ __forceinline__ void sink_rows(const StepArgs& a, const double* x, Sh
             sh.sinkA[threadIdx.x] = __ldcg(a.sinkbuf + MAXR + threadIdx.x);
         }
         __syncthreads();
+        if (a.P > 1) {   // sink rows are sums over ALL states: combine the ranks' parts (every rank keeps the totals)
+            if ((int)threadIdx.x < a.R) {
+                sh.xg[threadIdx.x] = sh.sinkS[threadIdx.x];
+                sh.xg[a.R + threadIdx.x] = sh.sinkA[threadIdx.x];
+            }
+            __syncthreads();
+            xg_allreduce(a, sy, sh.xg, 2 * a.R);
+            if ((int)threadIdx.x < a.R) {
+                sh.sinkS[threadIdx.x] = sh.xg[threadIdx.x];
+                sh.sinkA[threadIdx.x] = sh.xg[a.R + threadIdx.x];
+            }
+            __syncthreads();
+        }
     }
 }
 
 // Krylov iteration k: w = (z - c A z) ps, inner products with V_0..V_k (KB = k+1 rounded up to a multiple of 4; the
 // surplus products are garbage-free duplicates of V_0 and ignored), <w,w> in slot KB.
 template <int KB, bool MULTI>
-__device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, const StepDyn& dyn, int k, int& parity, Shared& sh) {
+__device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, const StepDyn& dyn, int k, SyncState& sy, Shared& sh) {
     double acc[KB + 1];
 #pragma unroll
     for (int s = 0; s <= KB; ++s) acc[s] = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * FBT + threadIdx.x; i < a.n; i += (int64_t)a.G * FBT) {
         double jd;
-        const double Az = row_apply(a, v.z, i, jd);
+        const double Az = row_apply(a, XView{v.z, a.z_lo, a.z_hi}, i, jd);
         const double w = (v.z[i] - dyn.c * Az) * v.ps[i];
         v.w[i] = w;
 #pragma unroll
@@ -255,7 +354,7 @@ __device__ __forceinline__ void krylov_apply(const StepArgs& a, const Vecs& v, c
         }
         acc[KB] = fma(w, w, acc[KB]);
     }
-    reduce_all<KB + 1, MULTI>(acc, KB + 1, a, parity, sh);
+    reduce_all<KB + 1, MULTI>(acc, KB + 1, a, sy, sh);
     // results: sh.res[0..k] = h_j, sh.res[KB] = <w,w>.  Thread 0 runs the Hessenberg/Givens recurrence: a serial chain, so
     // the rotation coefficients are prefetched, and sqrt/one reciprocal replace hypot and the divisions
     if (threadIdx.x == 0) {
@@ -304,7 +403,7 @@ struct StepOut {   // identical in every thread of the grid
 
 // One BDF step attempt described by `dyn` (see the file header); `publish`: write the sequence number of the result record
 template <bool MULTI>
-__device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, const StepDyn& dyn, Shared& sh, int& parity,
+__device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, const StepDyn& dyn, Shared& sh, SyncState& sy,
                                              const bool publish) {
     // publish: single-step launch -- the result record goes to pinned host memory and its sequence number is published.
     // In multi-step mode the in-kernel controller consumes StepOut and writes the record only for the step it leaves
@@ -352,12 +451,13 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
     }
     if (publish && blockIdx.x == 0 && (int)threadIdx.x < a.R) a.res->sink_old0[threadIdx.x] = D[a.n + threadIdx.x];
     grid_barrier<MULTI>();
+    if (MULTI && a.P > 1) xg_barrier(a, sy);   // the neighbours' y_pred is complete before P1 gathers its halo
 
     // ---- P1: A y_pred, Jacobi preconditioner and error weights, right-hand side w0, beta^2 = |w0|^2
     double v1[1] = {0.0};
     for (int64_t i = gtid; i < a.n; i += gstride) {
         double jd;
-        const double Ay = row_apply(a, v.ypred, i, jd);
+        const double Ay = row_apply(a, XView{v.ypred, a.ypred_lo, a.ypred_hi}, i, jd);
         const double sc = a.atol + a.rtol * fabs(v.ypred[i]);
         const double p = 1.0 / ((1.0 - dyn.c * jd) * sc);
         const double w = (dyn.c * Ay - v.psi[i]) * p;
@@ -367,7 +467,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
         v1[0] = fma(w, w, v1[0]);
     }
     rhs_evals++;
-    reduce_all<1, MULTI>(v1, 1, a, parity, sh);
+    reduce_all<1, MULTI>(v1, 1, a, sy, sh);
     double beta = sqrt(fmax(sh.res[0], 0.0));
     const double beta0 = beta;
     bool lin_ok = (beta == beta);
@@ -384,7 +484,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
             v2[0] += v.psi[i];
             v2[1] += fabs(yn);
         }
-        reduce_all<2, MULTI>(v2, 2, a, parity, sh);
+        reduce_all<2, MULTI>(v2, 2, a, sy, sh);
         ms0 = sh.res[0];
         ms1 = sh.res[1];
     } else {
@@ -407,17 +507,19 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
                 }
             }
             grid_barrier<MULTI>();
+            if (MULTI && a.P > 1) xg_barrier(a, sy);   // z complete on the neighbours (they finished READING the old z
+                                                       // before the all-reduce that precedes this phase)
             int k = 0;
             for (; k < GM; ++k) {
                 // ---- P3: fused matvec + Gram-Schmidt inner products + Givens update
                 const int kb = ((k + 1 + 3) / 4) * 4;
                 switch (kb) {
-                    case 4: krylov_apply<4, MULTI>(a, v, dyn, k, parity, sh); break;
-                    case 8: krylov_apply<8, MULTI>(a, v, dyn, k, parity, sh); break;
-                    case 12: krylov_apply<12, MULTI>(a, v, dyn, k, parity, sh); break;
-                    case 16: krylov_apply<16, MULTI>(a, v, dyn, k, parity, sh); break;
-                    case 20: krylov_apply<20, MULTI>(a, v, dyn, k, parity, sh); break;
-                    default: krylov_apply<24, MULTI>(a, v, dyn, k, parity, sh); break;
+                    case 4: krylov_apply<4, MULTI>(a, v, dyn, k, sy, sh); break;
+                    case 8: krylov_apply<8, MULTI>(a, v, dyn, k, sy, sh); break;
+                    case 12: krylov_apply<12, MULTI>(a, v, dyn, k, sy, sh); break;
+                    case 16: krylov_apply<16, MULTI>(a, v, dyn, k, sy, sh); break;
+                    case 20: krylov_apply<20, MULTI>(a, v, dyn, k, sy, sh); break;
+                    default: krylov_apply<24, MULTI>(a, v, dyn, k, sy, sh); break;
                 }
                 rhs_evals++;
                 kiters++;
@@ -437,6 +539,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
                     }
                 }
                 grid_barrier<MULTI>();
+                if (MULTI && a.P > 1) xg_barrier(a, sy);
             }
             if (!sh.ok) {
                 lin_ok = false;
@@ -465,7 +568,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
                 v2[1] += fabs(yn);
             }
             have_d = true;
-            reduce_all<2, MULTI>(v2, 2, a, parity, sh);
+            reduce_all<2, MULTI>(v2, 2, a, sy, sh);
             ms0 = sh.res[0];
             ms1 = sh.res[1];
             if (resid / a.sqrtn <= a.lin_tol) break;
@@ -477,13 +580,13 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
             double v3[1] = {0.0};
             for (int64_t i = gtid; i < a.n; i += gstride) {
                 double jd;
-                const double Ay = row_apply(a, v.ynew, i, jd);
+                const double Ay = row_apply(a, XView{v.ynew, a.ynew_lo, a.ynew_hi}, i, jd);
                 const double w = (dyn.c * Ay - v.psi[i] - v.d[i]) * v.ps[i];
                 v.w[i] = w;
                 v3[0] = fma(w, w, v3[0]);
             }
             rhs_evals++;
-            reduce_all<1, MULTI>(v3, 1, a, parity, sh);
+            reduce_all<1, MULTI>(v3, 1, a, sy, sh);
             beta = sqrt(fmax(sh.res[0], 0.0));
             if (!(beta > 0.0)) break;
         }
@@ -492,7 +595,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
     StepResult* res = a.res;
     if (!lin_ok) {
         if (publish && blockIdx.x == 0 && threadIdx.x == 0) {
-            res->lin_ok = 0;
+            res->lin_ok = (a.P > 1 && *((volatile unsigned int*)&a.flags[a.me]->error)) ? -1 : 0;
             res->accepted = 0;
             res->kiters = kiters;
             res->rhs_evals = rhs_evals;
@@ -514,7 +617,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
     // 1^T A = 0, so an exact step has sum_all(d + psi) = 0; the defect is removed by the relative rescaling
     // d_i -= defect |ynew_i| / sum|ynew| (see bdf.cu).  The sink rows are linear in ynew: S(ynew + delta) follows from
     // S(ynew) and S(|ynew|) without a second pass.
-    sink_rows<MULTI>(a, v.ynew, sh);
+    sink_rows<MULTI>(a, v.ynew, sh, sy);
     double ms2 = 0.0;
     for (int r = 0; r < a.R; ++r) ms2 += dyn.c * sh.sinkS[r];
     const double defect = ms0 + ms2;
@@ -539,7 +642,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
         const double S = sh.sinkS[r] + fixfac * sh.sinkA[r];
         sh.sink_d[r] = dyn.c * S - v.psi[a.n + r];
     }
-    reduce_all<1, MULTI>(v4, 1, a, parity, sh);
+    reduce_all<1, MULTI>(v4, 1, a, sy, sh);
     double sumsq = sh.res[0];
     for (int r = 0; r < a.R; ++r) {
         const double ds = sh.sink_d[r], yn = v.ypred[a.n + r] + ds;
@@ -571,7 +674,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
                 v5[1] = fma(qp, qp, v5[1]);
             }
         }
-        reduce_all<2, MULTI>(v5, 2, a, parity, sh);
+        reduce_all<2, MULTI>(v5, 2, a, sy, sh);
         ord_sm = sh.res[0];
         ord_sp = sh.res[1];
         // new sink tails for the host's event function (rows n..n+R were updated before the barrier above)
@@ -580,7 +683,7 @@ __device__ __forceinline__ StepOut step_body(const StepArgs& a, const Vecs& v, c
     }
     __syncthreads();
     if (publish && blockIdx.x == 0 && threadIdx.x == 0) {
-        res->lin_ok = 1;
+        res->lin_ok = (a.P > 1 && *((volatile unsigned int*)&a.flags[a.me]->error)) ? -1 : 1;   // -1: a peer was lost
         res->accepted = accept ? 1 : 0;
         res->kiters = kiters;
         res->rhs_evals = rhs_evals;
@@ -639,9 +742,13 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         v.V = a.V;
         v.vs = a.stride;
     }
-    int parity = 0;
+    SyncState sy;
+    sy.parity = 0;
+    sy.xe = (a.P > 1) ? a.flags[a.me]->fz_epoch : 0u;
     if (MULTI || a.ctl == nullptr) {   // one step attempt per launch, the host keeps the controller
-        step_body<MULTI>(a, v, a.dyn, sh, parity, true);
+        step_body<MULTI>(a, v, a.dyn, sh, sy, true);
+        // every CTA read fz_epoch before its first grid barrier: safe to store the advanced value now
+        if (MULTI && a.P > 1 && blockIdx.x == 0 && threadIdx.x == 0) a.flags[a.me]->fz_epoch = sy.xe;
         return;
     }
     // ---- multi-step mode (single CTA): the controller of bdf_ctl.h runs here, thread 0 holds its state in shared memory
@@ -680,7 +787,7 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
         }
         __syncthreads();
         if (ctl.status != BDF_RUN) break;
-        const StepOut o = step_body<false>(a, v, dyn, sh, parity, false);
+        const StepOut o = step_body<false>(a, v, dyn, sh, sy, false);
         if (threadIdx.x < 32) {   // warp 0: reaction of the controller
             const int lane = threadIdx.x;
             if (!o.lin_ok) {
@@ -779,6 +886,35 @@ struct LazySaver {
     size_t len = 0;
     int nslots = 0;
     std::vector<std::pair<double, int>> pending;
+    // sharded: a slice handed to the callback is the GLOBAL vector [all state rows | R sinks] on every rank (as
+    // SliceSaver of solve.cu delivers it): all-gather of the ranks' rows; the sink entries are already replicated
+    ncme_comm* comm = nullptr;
+    int64_t n_local = 0, n_global = 0;
+    int R = 0;
+    double* full = nullptr;
+    std::vector<int64_t> counts, displs;
+    int init_sharded(ncme_comm* cm, int64_t nloc, int64_t nglob, int nr) {
+        comm = cm;
+        n_local = nloc;
+        n_global = nglob;
+        R = nr;
+        if (!fn) return NCME_OK;
+        NCME_TRY(cache_reserve(&ctx->solve_full, &ctx->solve_full_bytes, (size_t)(nglob + nr) * sizeof(double), false));
+        full = ctx->solve_full;
+        counts.assign((size_t)cm->nranks, 0);
+        displs.assign((size_t)cm->nranks, 0);
+        for (int r = 0; r < cm->nranks; ++r) {   // the row cuts of matrix_build (multiples of 64)
+            auto cut = [&](int q) -> int64_t {
+                if (q <= 0) return 0;
+                if (q >= cm->nranks) return nglob;
+                return std::min<int64_t>(nglob, round_up<int64_t>((int64_t)((__int128)nglob * q / cm->nranks), 64));
+            };
+            displs[(size_t)r] = cut(r);
+            counts[(size_t)r] = cut(r + 1) - cut(r);
+        }
+        NCME_REQUIRE(counts[(size_t)cm->rank] == nloc, "fused BDF step (sharded): unexpected row partition");
+        return NCME_OK;
+    }
     int init(ncme_ctx* c, size_t n, ncme_save_fn f, void* u, ncme_solve_stats* stats) {
         ctx = c;
         fn = f;
@@ -808,25 +944,46 @@ struct LazySaver {
         if (!fn) return NCME_OK;
         if ((int)pending.size() == nslots) NCME_TRY(flush());
         const int slot = (int)pending.size();
-        NCME_CUDA(cudaMemcpyAsync(pinned + (size_t)slot * len, v_dev, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        const double* src = v_dev;
+        if (comm) {
+            NCME_TRY(comm_allgatherv(comm, v_dev, full, counts.data(), displs.data(), ctx->stream));
+            NCME_CUDA(cudaMemcpyAsync(full + n_global, v_dev + n_local, (size_t)R * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            src = full;
+        }
+        NCME_CUDA(cudaMemcpyAsync(pinned + (size_t)slot * len, src, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         pending.emplace_back(t, slot);
+        if (comm) NCME_TRY(flush());   // `full` is reused by the next slice
         return NCME_OK;
     }
 };
 
 }  // namespace
 
+// Sharded matrices: the ranks' cooperative grids exchange halos, barriers and all-reduces through peer memory
+// (CUDA IPC); needs the peer-memory transport, a halo that lives on the two neighbouring ranks, and room in the
+// exchange slots.  The answer must be the same on every rank: it only depends on replicated facts.
+static bool fused_sharded_ok(const ncme_matrix* A) {
+    const ncme_comm* c = A->comm;
+    static const bool off = getenv("NCME_BDF_NO_SHARDED_FUSED") != nullptr;
+    return !off && c && c->nranks > 1 && c->nranks <= NCME_RED_RANKS && c->p2p_ok && c->my_flags && A->p2p_eligible &&
+           2 * A->nr <= NCME_FZ_VALS && comm_hostreduce_available(c);
+}
 bool bdf_fused_eligible(const ncme_matrix* A) {
-    return A->comm == nullptr && A->hl == 0 && A->hh == 0 && A->n >= 1 && A->nr <= MAXR;
+    if (A->n_global < 1 || A->nr > MAXR) return false;
+    if (A->comm == nullptr) return A->hl == 0 && A->hh == 0 && A->n >= 1;
+    return fused_sharded_ok(A);
 }
 
 int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0, double t1,
                     double* u, const ncme_solve_opts* o, ncme_solve_stats* st) {
     ncme_ctx* ctx = A->ctx;
     cudaStream_t s = ctx->stream;
-    NCME_REQUIRE(bdf_fused_eligible(A), "fused BDF step kernel: single-GPU FSP matrices only");
-    const int64_t n = A->n, N = A->N;
+    NCME_REQUIRE(bdf_fused_eligible(A), "fused BDF step kernel: needs a single-GPU matrix or the peer-memory transport");
+    ncme_comm* comm = A->comm;            // non-null: row-sharded, one cooperative grid per rank
+    const bool sharded = comm != nullptr;
+    const int64_t n = A->n, N = A->N;     // local rows, local vector length (rows + R sink entries, sinks replicated)
     const int R = A->nr;
+    const int64_t Nglob = A->n_global + R;
     const int64_t launches0 = ctx->launches;
 
     // ---- grid: one CTA up to 2 rows per thread, a cooperative grid above (bounded by co-residency)
@@ -841,21 +998,31 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>(maxG, (n + (int64_t)FBT * 2 - 1) / ((int64_t)FBT * 2)));
     // tiny systems: work vectors + Krylov basis in shared memory (8 + GM + 1 vectors of round_up(N, 8) doubles)
     const size_t smem_need = (size_t)(8 + GM + 1) * (size_t)((N + 7) / 8 * 8) * sizeof(double);
-    const size_t smem_bytes = (G == 1 && smem_need <= (size_t)SMEM_MAX_BYTES && !getenv("NCME_BDF_NO_SMEM")) ? smem_need : 0;
+    const size_t smem_bytes = (!sharded && G == 1 && smem_need <= (size_t)SMEM_MAX_BYTES && !getenv("NCME_BDF_NO_SMEM")) ? smem_need : 0;
     // multi-step launches: time-invariant matrix (no host callback per step), one CTA, no saveat list
     bool need_coef = false;
     for (int r = 0; r < R; ++r) need_coef |= (A->kind[r] != NCME_TIME_INVARIANT);
-    const bool multi = G == 1 && !need_coef && o->nsave == 0 && !getenv("NCME_BDF_SINGLE_STEP");
+    const bool multi = !sharded && G == 1 && !need_coef && o->nsave == 0 && !getenv("NCME_BDF_SINGLE_STEP");
 
     // ---- workspace
-    const size_t stride = round_up<size_t>((size_t)N, 32);
+    // sharded: every vector carries the halo margins a matvec input needs and the workspace is exposed to the
+    // neighbours (CUDA IPC, collective registration), exactly as in bdf.cu
+    const size_t hlp = sharded ? round_up<size_t>((size_t)A->hl, 32) : 0, hhp = sharded ? round_up<size_t>((size_t)A->hh, 32) : 0;
+    const size_t stride = hlp + round_up<size_t>((size_t)N, 32) + hhp;
     const int NV = (MAXO + 3) + 8 + (GM + 1) + (multi ? BDF_RING : 0);
-    const size_t extra = (size_t)2 * G * NSLOT + 2 * MAXR + 64;
-    NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, (stride * NV + extra) * sizeof(double), false));
-    double* base = ctx->solve_ws;
+    const int Gmax_all = 2 * ctx->sm_count;   // the scratch size must not depend on this rank's row count
+    const size_t extra = (size_t)2 * (sharded ? Gmax_all : G) * NSLOT + 2 * MAXR + 64;
+    double* base = nullptr;
+    if (sharded) {
+        const int peers[2] = {A->plo, A->phi};
+        NCME_TRY(comm_workspace(comm, (stride * NV + extra) * sizeof(double), (int64_t)hlp, (int64_t)stride, NV, peers, 2, &base));
+    } else {
+        NCME_TRY(cache_reserve(&ctx->solve_ws, &ctx->solve_ws_bytes, (stride * NV + extra) * sizeof(double), false));
+        base = ctx->solve_ws;
+    }
     NCME_CUDA(cudaMemsetAsync(base, 0, (stride * ((MAXO + 3) + 8 + (GM + 1)) + extra) * sizeof(double), s));
     int slot = 0;
-    auto vec = [&]() { return base + stride * (slot++); };
+    auto vec = [&]() { return base + stride * (slot++) + hlp; };
     double* D[MAXO + 3];
     for (int j = 0; j < MAXO + 3; ++j) D[j] = vec();
     double* ypred = vec();
@@ -866,9 +1033,9 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     double* ps = vec();
     double* w = vec();
     double* d = vec();
-    double* V = base + stride * slot;
+    double* V = base + stride * slot + hlp;
     slot += GM + 1;
-    double* ring = base + stride * slot;       // multi-step mode only
+    double* ring = base + stride * slot;       // multi-step mode only (never sharded: hlp == 0)
     double* partials = base + stride * NV;
     double* sinkbuf = partials + (size_t)2 * G * NSLOT;
     // pinned scalars of the context: [StepResult | BdfCtl]
@@ -883,7 +1050,8 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     res_host->seq = 0;
 
     LazySaver saver;
-    NCME_TRY(saver.init(ctx, (size_t)N, save_fn, user, st));
+    NCME_TRY(saver.init(ctx, (size_t)(sharded ? Nglob : N), save_fn, user, st));
+    if (sharded) NCME_TRY(saver.init_sharded(comm, n, A->n_global, R));
     double* ring_pinned = nullptr;
     if (multi && save_fn) {   // the lazy saver's pinned block is at least 4 MB: the ring's host image lives behind its slots
         const size_t need = ((size_t)saver.nslots + BDF_RING) * (size_t)N * sizeof(double);
@@ -899,7 +1067,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     bdf_constants(kc);
     kc.atol = atol;
     kc.rtol = rtol;
-    kc.Nglob = (double)N;
+    kc.Nglob = (double)Nglob;
 
     double coef[NCME_MAX_REACTIONS];
     for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
@@ -907,6 +1075,14 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     auto finish = [&](const double* src) -> int {
         if (src != u) NCME_CUDA(cudaMemcpyAsync(u, src, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         NCME_CUDA(cudaStreamSynchronize(s));
+        if (sharded) {   // sink entries are replicated (all-reduced inside the kernel): nothing to combine here
+            unsigned int perr = 0;
+            NCME_CUDA(cudaMemcpy(&perr, &comm->my_flags->error, sizeof(perr), cudaMemcpyDeviceToHost));
+            if (perr) {
+                set_error("fused BDF step (sharded): a peer rank did not arrive at an exchange within 2 s");
+                return NCME_ERR_COMM;
+            }
+        }
         saver.delivered();
         st->steps = c.steps;
         st->rejected = c.rejected;
@@ -942,14 +1118,42 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     // ---- initial step size (Hairer's rule on the WRMS norms of u and f(t0, u)), D_1 = h f(t0, u)
     if (coef_fn) coef_fn(t0, coef, user);
     if (abort_requested()) return abort_status();
-    NCME_TRY(matvec_dist(A, coef, D[0], ynew, 0.0, 0));
+    if (sharded) {
+        // The ranks' exchange counters must agree before the first cooperative launch (they do unless an earlier
+        // segment failed half way): everybody continues from the largest one.
+        unsigned int mine = 0;
+        NCME_CUDA(cudaMemsetAsync(&comm->my_flags->error, 0, sizeof(unsigned int), s));   // (only this rank ever sets it)
+        NCME_CUDA(cudaMemcpyAsync(&mine, &comm->my_flags->fz_epoch, sizeof(mine), cudaMemcpyDeviceToHost, s));
+        NCME_CUDA(cudaStreamSynchronize(s));
+        double all[NCME_RED_RANKS] = {0.0};
+        all[comm->rank] = (double)mine;
+        NCME_TRY(comm_hostreduce_sum(comm, all, (size_t)comm->nranks));
+        double mx = 0.0, mn = 1e300;
+        for (int q = 0; q < comm->nranks; ++q) {
+            mx = std::max(mx, all[q]);
+            mn = std::min(mn, all[q]);
+        }
+        if (mx != mn) {
+            const unsigned int next = (unsigned int)mx + 1024u;
+            NCME_CUDA(cudaMemcpyAsync(&comm->my_flags->fz_epoch, &next, sizeof(next), cudaMemcpyHostToDevice, s));
+            NCME_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    NCME_TRY(matvec_dist(A, coef, D[0], ynew, 0.0, sharded ? 1 : 0));   // sharded: all-reduced (replicated) sink rows
     c.rhs_evals++;
     c.h_abs = o->h_init;
     if (!(c.h_abs > 0)) {
         double d0 = 0, d1 = 0;
-        NCME_TRY(ncme_vec_wrms(ctx, N, D[0], D[0], D[0], atol, rtol, &d0));
-        NCME_TRY(ncme_vec_wrms(ctx, N, ynew, D[0], D[0], atol, rtol, &d1));
+        const int64_t nn = sharded ? n : N;   // sharded: state rows only (the sinks are replicated), summed over the ranks
+        NCME_TRY(ncme_vec_wrms(ctx, nn > 0 ? nn : 1, D[0], D[0], D[0], atol, rtol, &d0));
+        NCME_TRY(ncme_vec_wrms(ctx, nn > 0 ? nn : 1, ynew, D[0], D[0], atol, rtol, &d1));
         saver.delivered();
+        if (sharded) {
+            double ss[2] = {d0 * d0 * (double)nn, d1 * d1 * (double)nn};
+            NCME_TRY(comm_hostreduce_sum(comm, ss, 2));
+            d0 = sqrt(ss[0] / (double)Nglob);
+            d1 = sqrt(ss[1] / (double)Nglob);
+        }
         c.h_abs = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         c.h_abs = std::min(c.h_abs, tspan);
     }
@@ -989,9 +1193,30 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
     sa.atol = atol;
     sa.rtol = rtol;
     sa.lin_tol = lin_tol;
-    sa.sqrtn = sqrt((double)std::max<int64_t>(1, n));
+    sa.sqrtn = sqrt((double)std::max<int64_t>(1, A->n_global));
     sa.massfix_limit = 10.0 * rtol;
-    sa.Nglob = (double)N;
+    sa.Nglob = (double)Nglob;
+    sa.P = 1;
+    if (sharded) {
+        sa.P = comm->nranks;
+        sa.me = comm->rank;
+        sa.self_off = (uint32_t)A->hl;
+        sa.lo_end = (uint32_t)A->hl;
+        sa.hi_begin = (uint32_t)(A->hl + A->n + A->nr);
+        for (int q = 0; q < comm->nranks; ++q) sa.flags[q] = (q == comm->rank) ? comm->my_flags : comm->peer_flags[q];
+        // peer views of the matvec inputs: view[c] = entry at padded position c (see matvec_dist_p2p)
+        auto views = [&](const double* x, const double** lo, const double** hi) -> int {
+            const double* xlo = A->plo >= 0 ? comm_peer_vector(comm, x, A->plo) : nullptr;
+            const double* xhi = A->phi >= 0 ? comm_peer_vector(comm, x, A->phi) : nullptr;
+            NCME_REQUIRE((A->plo < 0 || xlo) && (A->phi < 0 || xhi), "fused BDF step (sharded): workspace is not registered on a neighbour");
+            *lo = xlo ? xlo + (A->ext_lo - A->plo_row_lo) : x - A->hl;
+            *hi = xhi ? xhi + (A->row_hi - A->phi_row_lo) - (int64_t)sa.hi_begin : x - A->hl;
+            return NCME_OK;
+        };
+        NCME_TRY(views(ypred, &sa.ypred_lo, &sa.ypred_hi));
+        NCME_TRY(views(z, &sa.z_lo, &sa.z_hi));
+        NCME_TRY(views(ynew, &sa.ynew_lo, &sa.ynew_hi));
+    }
     sa.partials = partials;
     sa.sinkbuf = sinkbuf;
     sa.res = res_dev;
@@ -1011,7 +1236,7 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
         sa.seq = ++seq;
         if (smem_bytes) {
             k_bdf_step<false, true><<<1, FBT, smem_bytes, s>>>(sa);
-        } else if (G == 1) {
+        } else if (G == 1 && !sharded) {
             k_bdf_step<false, false><<<1, FBT, 0, s>>>(sa);
         } else {
             void* kargs[1] = {(void*)&sa};
@@ -1062,6 +1287,10 @@ int solve_bdf_fused(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, 
             }
             NCME_TRY(launch_and_wait());
             c.rhs_evals += res_host->rhs_evals;
+            if (res_host->lin_ok < 0) {
+                set_error("fused BDF step (sharded): a peer rank did not arrive at an exchange within 2 s");
+                return NCME_ERR_COMM;
+            }
             if (!res_host->lin_ok) {
                 bdf_after_linfail(c, ctl_ws);
                 continue;

@@ -12,6 +12,7 @@ constexpr int NCME_HOSTREDUCE_MAX = 320;   // doubles per host-side all-reduce (
 constexpr int NCME_RED_RANKS = 16;         // device-side all-reduce of small scalar sets: ranks, buffers, values
 constexpr int NCME_RED_BUFS = 4;
 constexpr int NCME_RED_VALS = 32;
+constexpr int NCME_FZ_VALS = 64;           // widest in-kernel all-reduce of the fused BDF step (2 R sink sums, R <= 32)
 
 // Flags each rank exposes to its peers through CUDA IPC (peer GPUs store into them over NVLink).
 struct PeerFlags {
@@ -22,6 +23,11 @@ struct PeerFlags {
     // red_slot[e % BUFS][q][..] of EVERY rank and then publishes red_flag[e % BUFS][q] = e there
     unsigned int red_flag[NCME_RED_BUFS][NCME_RED_RANKS];
     double red_slot[NCME_RED_BUFS][NCME_RED_RANKS][NCME_RED_VALS];
+    // the same exchange driven from INSIDE the persistent fused BDF step kernel (bdf_fused.cu, sharded mode): barriers
+    // and all-reduces between the ranks' cooperative grids; fz_epoch is this rank's running sequence number (local use)
+    unsigned int fz_flag[NCME_RED_BUFS][NCME_RED_RANKS];
+    double fz_slot[NCME_RED_BUFS][NCME_RED_RANKS][NCME_FZ_VALS];
+    unsigned int fz_epoch;
 };
 
 // By-value kernel argument of the in-kernel all-reduce.  nranks == 1: no exchange.

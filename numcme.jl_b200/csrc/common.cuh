@@ -10,7 +10,11 @@
 
 #include "ncme.h"
 
+#include <chrono>
 namespace ncme {
+inline double wall_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 void set_error(const char* fmt, ...);
 bool abort_requested();   // a host callback called ncme_request_abort() (context.cu)

@@ -811,7 +811,10 @@ static int matvec_dist_p2p(ncme_matrix* A, MatvecArgs a, const double* xlo, cons
     a.x_lo = xlo ? xlo + (A->ext_lo - A->plo_row_lo) : a.x;
     a.x_hi = xhi ? xhi + (A->row_hi - A->phi_row_lo) - (int64_t)a.hi_begin : a.x;
     const bool interior = A->b1 > A->b0;
-    static const bool two_launch = getenv("NCME_P2P_TWO_LAUNCH") != nullptr;   // experiments: the round-1 control path
+    // One launch (k_fsp_matvec_sharded) or two (halo-free rows on the compute stream + boundary rows on the priority
+    // stream).  Measured on B200 (profiles/README.md, round 2): the two-launch path is 3-9 % faster at 2 and 4 GPUs
+    // (84 vs 87-90 us and 44 vs 48 us per matvec), so it stays the default; NCME_P2P_ONE_LAUNCH=1 selects the other.
+    static const bool two_launch = getenv("NCME_P2P_ONE_LAUNCH") == nullptr;
     static const int bd_mode = getenv("NCME_P2P_BD_MODE") ? atoi(getenv("NCME_P2P_BD_MODE")) : 4;   // 0 last, 1 first, >= 2 interleave stride
     const bool handshake = !(flags & 2);
     if (!two_launch && sig_in_kernel && a.nslots <= 16 && done.nsig <= 4 && done.nwait <= 4 && a.nwait > 0) {

@@ -518,6 +518,15 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     clear_abort();
     double coef[NCME_MAX_REACTIONS];
     for (int r = 0; r < NCME_MAX_REACTIONS; ++r) coef[r] = 1.0;
+    // time factors are pure functions of t (the reference evaluates them in every matvec!, fspsparsematrix.jl:204): one
+    // host callback per DISTINCT time -- all right-hand sides of a BDF step share t_new
+    double coef_t = NAN;
+    auto refresh_coef = [&](double t) {
+        if (coef_fn && !(t == coef_t)) {
+            coef_fn(t, coef, user);
+            coef_t = t;
+        }
+    };
     OdeSystem sys;
     sys.ctx = A->ctx;
     sys.comm = A->comm;
@@ -531,23 +540,23 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
     sys.peers[0] = A->plo;
     sys.peers[1] = A->phi;
     sys.rhs = [&](double t, const double* x, double* y) -> int {
-        if (coef_fn) coef_fn(t, coef, user);
+        refresh_coef(t);
         if (abort_requested()) return abort_status();
         return matvec_dist(A, coef, x, y, 0.0, /*no sink reduction, inputs alternate buffers*/ 2);
     };
     sys.rhs_safe = [&](double t, const double* x, double* y) -> int {
-        if (coef_fn) coef_fn(t, coef, user);
+        refresh_coef(t);
         if (abort_requested()) return abort_status();
         return matvec_dist(A, coef, x, y, 0.0, 0);
     };
     sys.n_impl = A->n;
     sys.jac_diag = [&](double t, double* out) -> int {
-        if (coef_fn) coef_fn(t, coef, user);
+        refresh_coef(t);
         if (abort_requested()) return abort_status();
         return matrix_diag(A, coef, out);
     };
     sys.rhs_sinks = [&](double t, const double* x, double* y) -> int {
-        if (coef_fn) coef_fn(t, coef, user);
+        refresh_coef(t);
         if (abort_requested()) return abort_status();
         return matvec_sinks_only(A, coef, x, y);
     };
@@ -557,14 +566,20 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
         // launch-per-operation integrator (bdf.cu) for sharded matrices and for very large state spaces
         bool fused = false;
         if (opts->method == 3) {
-            NCME_REQUIRE(bdf_fused_eligible(A), "method 3 (fused BDF step kernel) needs an unsharded matrix");
+            NCME_REQUIRE(bdf_fused_eligible(A), "method 3 (fused BDF step kernel) needs an unsharded matrix or the peer-memory transport");
             fused = true;
         } else if (opts->method == 1 && bdf_fused_eligible(A)) {
             static const long long max_rows = [] {
                 const char* e = getenv("NCME_BDF_FUSED_MAX_ROWS");
                 return e ? atoll(e) : 2000000LL;   // measured cross-over on B200 (tools/bdf_crossover.py)
             }();
-            fused = (long long)A->n <= max_rows;
+            static const long long max_rows_sharded = [] {
+                const char* e = getenv("NCME_BDF_FUSED_MAX_ROWS_SHARDED");
+                return e ? atoll(e) : 4000000LL;   // per rank; the launch-per-operation path pays a host round trip
+            }();                                   // + host all-reduce per reduction when sharded
+            // decided from replicated facts only: every rank must take the same branch
+            const int P = A->comm ? A->comm->nranks : 1;
+            fused = (long long)(A->n_global / P) <= (A->comm ? max_rows_sharded : max_rows);
         }
         if (fused) return solve_bdf_fused(A, coef_fn, save_fn, user, t0, t1, u_dev, opts, stats);
         return solve_bdf(sys, save_fn, user, t0, t1, u_dev, opts, stats);

@@ -1,5 +1,6 @@
 """Multi-rank parity check, launched by tests/test_gpu_multi.py through torchrun (one rank per GPU):
 row-sharded matvec / solve against the single-GPU path computed on the same rank."""
+import faulthandler
 import os
 import sys
 
@@ -10,6 +11,7 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    faulthandler.enable()
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
@@ -107,8 +109,14 @@ def main():
     b1 = pkg.solve(model, pfull, (0.0, 0.5), pkg.NativeBDF(), saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-7, ctx=ctx)
     b2 = pkg.solve(model, pfull, (0.0, 0.5), pkg.NativeBDF(), saveat=[0.25, 0.5], odeatol=1e-12, odertol=1e-7, comm=comm)
     for a, b, c3 in zip(b1.p, b2.p, f1.p):
-        assert np.abs(a.values - b.values).max() < 1e-9, "sharded BDF differs from single-GPU BDF"
-        assert np.abs(a.values - c3.values).max() < 1e-6, "BDF differs from the explicit integrator"
+        d_ab, d_ac, d_bc = (float(np.abs(x.values - y.values).max()) for x, y in ((a, b), (a, c3), (b, c3)))
+        if rank == 0:
+            print(f"BDF single vs sharded {d_ab:.3e}; single vs explicit {d_ac:.3e}; sharded vs explicit {d_bc:.3e}; "
+                  f"steps {b1.stats['steps']} / {b2.stats['steps']}, rhs {b1.stats['rhs_evals']} / {b2.stats['rhs_evals']}")
+        # two BDF runs whose reductions are summed in different orders may take different step sequences: both must
+        # sit within the solver tolerance (odertol = 1e-7) of the tight explicit solution, and of each other
+        assert d_ab < 2e-7, "sharded BDF differs from single-GPU BDF"
+        assert d_ac < 1e-6 and d_bc < 1e-6, "BDF differs from the explicit integrator"
     dist.barrier()
     if rank == 0:
         print(f"DIST_CHECK_OK world={world} n={n} comm={comm.info()} halo=({info['halo_lo']},{info['halo_hi']}) "
