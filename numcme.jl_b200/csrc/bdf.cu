@@ -24,7 +24,8 @@ constexpr int BT = 256;
 constexpr int MAX_ORDER = 5;
 constexpr int GM_M = 24;          // Krylov dimension before restart
 constexpr int RED_SLOTS = GM_M + 2;
-constexpr int RED_BLOCKS = 512;   // RED_BLOCKS * RED_SLOTS doubles fit the context's partials buffer (16384)
+constexpr int RED_BLOCKS = 1184;  // 148 SMs x 8 CTAs: the reductions of a step (<= 2 values per CTA; the context's partials buffer
+                                  // holds 16384 doubles) ran at 0.3-0.65 of the HBM rate with 512 CTAs (ncu launch list, round 2)
 
 struct PtrList {
     const double* p[GM_M + 2];

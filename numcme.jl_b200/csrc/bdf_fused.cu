@@ -863,7 +863,11 @@ __global__ void __launch_bounds__(FBT) k_bdf_step(const __grid_constant__ StepAr
             if (threadIdx.x == 0 && ++ctl.ring_count == BDF_RING && ctl.status == BDF_RUN) ctl.status = BDF_YIELD;
             __syncthreads();
         }
-        if (ctl.status != BDF_RUN) break;
+        // racecheck (round 2): thread 0 rewrites ctl.status at the top of the next attempt -- every thread must have
+        // read it before that, or a slow warp could leave the loop on the NEXT attempt's status
+        const bool keep_going = (ctl.status == BDF_RUN);
+        __syncthreads();
+        if (!keep_going) break;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (int)(sizeof(BdfCtl) / 8); i += FBT)

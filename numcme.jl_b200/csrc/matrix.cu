@@ -1384,7 +1384,11 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     // ---- row chunks of the host-buffer pipeline (single GPU): how far ahead each chunk's gathers reach
     A->pipe_chunks = 0;
     if (!A->comm && n >= 16 * 4096 && nslots > 0) {
-        const int NC = 16;
+        static const int NC = [] {   // experiments: NCME_HOST_PIPE_CHUNKS = 2..16 (default 16)
+            const char* e = getenv("NCME_HOST_PIPE_CHUNKS");
+            const int v = e ? atoi(e) : 16;
+            return v < 2 ? 2 : (v > 16 ? 16 : v);
+        }();
         const int64_t chunk_rows = round_up<int64_t>((n + NC - 1) / NC, 64);
         unsigned int* d_reach = nullptr;
         NCME_CUDA(cudaMalloc(&d_reach, 16 * sizeof(unsigned int)));

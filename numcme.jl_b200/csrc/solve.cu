@@ -575,8 +575,9 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
             }();
             static const long long max_rows_sharded = [] {
                 const char* e = getenv("NCME_BDF_FUSED_MAX_ROWS_SHARDED");
-                return e ? atoll(e) : 4000000LL;   // per rank; the launch-per-operation path pays a host round trip
-            }();                                   // + host all-reduce per reduction when sharded
+                return e ? atoll(e) : 500000LL;    // per rank.  Measured on 4 B200 (profiles/README.md): at 1.27e6 rows per
+            }();                                   // rank the launch-per-operation path wins (0.085 vs 0.116 s), at 2.5e6
+                                                   // 0.122 vs 0.201 s; the one-kernel step pays off for small shards only
             // decided from replicated facts only: every rank must take the same branch
             const int P = A->comm ? A->comm->nranks : 1;
             fused = (long long)(A->n_global / P) <= (A->comm ? max_rows_sharded : max_rows);
