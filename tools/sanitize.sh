@@ -4,7 +4,7 @@
 # Usage (on a GPU box):  tools/sanitize.sh [outdir]      logs -> <outdir>/sanitizer_<tool>.log
 OUT=${1:-gpurun_out}
 mkdir -p "$OUT"
-SEL='test_fspmat_jl_on_gpu or test_rectangular_telegraph_all_kernel_variants or test_device_resident_and_matvecadd or test_reference_kats or test_expand_delete_sequence_index_exact or test_sens_telegraph or test_sens_poisson or test_fixed_space_solve or test_adaptive_solve_reference_tests or test_bdf_fused or test_prune_by_mass_matches_oracle or test_telegraph_example'
+SEL=${SAN_SEL:-'test_fspmat_jl_on_gpu or test_rectangular_telegraph_all_kernel_variants or test_device_resident_and_matvecadd or test_reference_kats or test_expand_delete_sequence_index_exact or test_sens_telegraph or test_sens_poisson or test_fixed_space_solve or test_adaptive_solve_reference_tests or test_bdf_fused or test_prune_by_mass_matches_oracle or test_telegraph_example'}
 for tool in ${SAN_TOOLS:-memcheck synccheck racecheck}; do
   extra=""
   [ "$tool" = memcheck ] && extra="--leak-check no"
