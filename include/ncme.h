@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define NCME_VERSION 100
-#define NCME_MAX_REACTIONS 32
+#define NCME_MAX_REACTIONS 64
 #define NCME_MAX_SPECIES 16
 
 typedef enum {

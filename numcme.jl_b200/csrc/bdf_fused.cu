@@ -47,7 +47,9 @@ constexpr int FW = FBT / 32;          // warps per CTA
 constexpr int MAXO = BDF_MAXO;        // maximum BDF order
 constexpr int GM = 24;                // Krylov dimension before restart
 constexpr int NSLOT = GM + 2;         // widest reduction (k+1 inner products + <w,w>)
-constexpr int MAXR = NCME_MAX_REACTIONS;
+constexpr int MAXR = 32;              // reactions the fused step kernel handles (its shared-memory staging is sized by it);
+                                      // models with 33..NCME_MAX_REACTIONS reactions use the launch-per-operation path (bdf.cu)
+static_assert(MAXR <= NCME_MAX_REACTIONS, "fused BDF reaction limit");
 constexpr int SMEM_MAX_BYTES = 211 * 1024;   // dynamic shared memory of the SMEMV variant (+ ~15 KB static <= 227 KB)
 
 struct StepResult {                   // written by CTA 0 straight into pinned (device-mapped) host memory

@@ -7,12 +7,12 @@
 #include "common.cuh"
 
 constexpr int NCME_MAX_RANKS = 64;
-constexpr int NCME_HOSTREDUCE_MAX = 320;   // doubles per host-side all-reduce (1 + 9 R sink tails, R <= 32)
+constexpr int NCME_HOSTREDUCE_MAX = 320;   // doubles per host-side all-reduce (1 + 9 R sink tails for R <= 35; wider sets fall back to the device all-reduce)
 
 constexpr int NCME_RED_RANKS = 16;         // device-side all-reduce of small scalar sets: ranks, buffers, values
 constexpr int NCME_RED_BUFS = 4;
 constexpr int NCME_RED_VALS = 32;
-constexpr int NCME_FZ_VALS = 64;           // widest in-kernel all-reduce of the fused BDF step (2 R sink sums, R <= 32)
+constexpr int NCME_FZ_VALS = 64;           // widest in-kernel all-reduce of the fused BDF step (2 R sink sums; the fused kernel handles R <= 32)
 
 // Flags each rank exposes to its peers through CUDA IPC (peer GPUs store into them over NVLink).
 struct PeerFlags {

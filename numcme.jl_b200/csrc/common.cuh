@@ -46,6 +46,10 @@ int abort_status();        // sets the message, returns NCME_ERR_ABORTED
 
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+// one bit per reaction (sink_connectivity of a state, sets of reactions): NCME_MAX_REACTIONS <= 64
+typedef unsigned long long smask_t;
+#define SMASK1(r) ((ncme::smask_t)1 << (r))
+static_assert(NCME_MAX_REACTIONS <= 64, "sink masks hold one bit per reaction");
 
 template <typename T>
 static inline T round_up(T a, T b) {

@@ -1114,14 +1114,14 @@ __global__ void k_chunk_reach(const uint32_t* __restrict__ col, int64_t ld, int6
 
 // counts[r] = rows with a predecessor through reaction r; counts[NCME_MAX_REACTIONS + r] = rows whose sink flag r is set
 __global__ void __launch_bounds__(256) k_count_structure(const uint32_t* __restrict__ pred, int64_t ld, int64_t row_lo,
-                                                         const uint32_t* __restrict__ sinkmask, int64_t n, int nr,
-                                                         uint32_t validmask, unsigned long long* __restrict__ counts) {
+                                                         const smask_t* __restrict__ sinkmask, int64_t n, int nr,
+                                                         smask_t validmask, unsigned long long* __restrict__ counts) {
     __shared__ unsigned int sh[2 * NCME_MAX_REACTIONS];
     if (threadIdx.x < 2 * NCME_MAX_REACTIONS) sh[threadIdx.x] = 0u;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < n;
-    const uint32_t m = in ? (sinkmask[row_lo + i] & validmask) : 0u;
+    const smask_t m = in ? (sinkmask[row_lo + i] & validmask) : 0;
     for (int r = 0; r < nr; ++r) {
         const bool hp = in && pred[(int64_t)r * ld + row_lo + i] != NONE32;
         const unsigned bp = __ballot_sync(0xffffffffu, hp), bs = __ballot_sync(0xffffffffu, (m >> r) & 1u);
@@ -1135,13 +1135,13 @@ __global__ void __launch_bounds__(256) k_count_structure(const uint32_t* __restr
 }
 
 // flags[q * n + i] = sink flag of reaction r0 + q at local row i
-__global__ void k_sink_flags_group(const uint32_t* __restrict__ mask, int64_t n, int r0, int g, uint32_t validmask,
+__global__ void k_sink_flags_group(const smask_t* __restrict__ mask, int64_t n, int r0, int g, smask_t validmask,
                                    uint32_t* __restrict__ flags) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)g * n) return;
     const int q = (int)(t / n);
     const int64_t i = t - (int64_t)q * n;
-    flags[t] = ((mask[i] & validmask) >> (r0 + q)) & 1u;
+    flags[t] = (uint32_t)(((mask[i] & validmask) >> (r0 + q)) & 1u);
 }
 
 __global__ void k_fill_sinks_group(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n, int g,
@@ -1469,9 +1469,9 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
     // ---- structural counts (one kernel, one device->host fetch) and sink lists (rows ascending inside each reaction)
     int64_t npred[NCME_MAX_REACTIONS] = {0};
     std::vector<uint64_t> nsink_r((size_t)nr, 0);
-    uint32_t validmask = 0;
+    smask_t validmask = 0;
     for (int r = 0; r < nr; ++r)
-        if (!zero_stoich(sp, r)) validmask |= 1u << r;
+        if (!zero_stoich(sp, r)) validmask |= SMASK1(r);
     A->sink_ptr[0] = 0;
     if (n > 0) {
         unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->red_result_dev);

@@ -10,19 +10,23 @@
 // dA_e has the sparsity of reaction r's slot, so it shares col[slot(r)] with A.
 #include "matrix.cuh"
 
+// (reaction, parameter) entries of the sparsity pattern a sensitivity matrix may hold (Hog1p: 14); bounded by the
+// 4 KB kernel parameter block of K2, which carries c_r(t) and dc_r/dtheta(t) of every entry by value
+#define NCME_SENS_MAX_ENTRIES 96
+
 struct ncme_sensmatrix {
     ncme_matrix* A = nullptr;
     int npar = 0;
     int nent = 0;
-    int ent_reaction[NCME_MAX_REACTIONS * 4];   // internal order: sorted by parameter
-    int ent_param[NCME_MAX_REACTIONS * 4];
-    int ent_user[NCME_MAX_REACTIONS * 4];       // internal -> user entry index
-    int user_ent[NCME_MAX_REACTIONS * 4];       // user -> internal
-    int ent_ptr[NCME_MAX_REACTIONS * 4 + 2];    // entries of parameter ip: [ent_ptr[ip], ent_ptr[ip+1])
+    int ent_reaction[NCME_SENS_MAX_ENTRIES];   // internal order: sorted by parameter
+    int ent_param[NCME_SENS_MAX_ENTRIES];
+    int ent_user[NCME_SENS_MAX_ENTRIES];       // internal -> user entry index
+    int user_ent[NCME_SENS_MAX_ENTRIES];       // user -> internal
+    int ent_ptr[NCME_SENS_MAX_ENTRIES + 2];    // entries of parameter ip: [ent_ptr[ip], ent_ptr[ip+1])
     ncme::DevArray<double> dval;    // [nent][ld]  d(state factor)/d theta at the predecessor
     ncme::DevArray<double> ddiag;   // [nent][ld]  minus d(state factor)/d theta at the state itself
     ncme::DevArray<double> dsink;   // per entry: values along the sink list of its reaction
-    int64_t dsink_ptr[NCME_MAX_REACTIONS * 4 + 1];
+    int64_t dsink_ptr[NCME_SENS_MAX_ENTRIES + 1];
     ncme::DevArray<double> partial;   // [ntasks][P+1]
     ncme::DevArray<double> dpartial;  // [ntasks][nent]
     unsigned int* counter = nullptr;
@@ -32,7 +36,7 @@ struct ncme_sensmatrix {
 
 namespace ncme {
 
-constexpr int SMAX_ENT = NCME_MAX_REACTIONS * 4;
+constexpr int SMAX_ENT = NCME_SENS_MAX_ENTRIES;
 constexpr int SV_THREADS = 256;
 
 struct SensArgs {

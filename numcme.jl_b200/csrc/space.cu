@@ -104,19 +104,19 @@ __global__ void k_mark_winners(HashView h, const uint32_t* __restrict__ cand_slo
 __global__ void k_commit_new(HashView h, const uint64_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_slot,
                              const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t ncand,
                              uint32_t n_old, uint64_t* __restrict__ keys, uint32_t* __restrict__ pred, int64_t ld, int nr,
-                             uint32_t* __restrict__ sinkmask) {
+                             smask_t* __restrict__ sinkmask) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand || !flags[c]) return;
     const uint32_t i = n_old + pos[c];
     keys[i] = cand_key[c];
     h.vals[cand_slot[c]] = i;
-    sinkmask[i] = 0u;
+    sinkmask[i] = 0;
     for (int r = 0; r < nr; ++r) pred[(int64_t)r * ld + i] = NONE32;
 }
 
 // _addstates! connectivity loops (:241-266), one thread per (new state, reaction).
 __global__ void k_connect_new(HashView h, KeyLayout L, StoichDev S, const uint64_t* __restrict__ keys, int64_t n_old,
-                              int64_t n_new, uint32_t* __restrict__ pred, int64_t ld, uint32_t* __restrict__ sinkmask) {
+                              int64_t n_new, uint32_t* __restrict__ pred, int64_t ld, smask_t* __restrict__ sinkmask) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nr = S.nr;
     if (t >= (n_new - n_old) * nr) return;
@@ -128,23 +128,23 @@ __global__ void k_connect_new(HashView h, KeyLayout L, StoichDev S, const uint64
         uint32_t j = hash_lookup(h, k2);
         if (j != NONE32) {
             pred[(int64_t)r * ld + i] = j;
-            atomicAnd(&sinkmask[j], ~(1u << r));
+            atomicAnd(&sinkmask[j], ~SMASK1(r));
         }
     }
     const int rc = shifted_key(L, S, key, r, +1, &k2);  // successor x_i + s_r
     if (rc == 0) {
         uint32_t j = hash_lookup(h, k2);
         if (j == NONE32)
-            atomicOr(&sinkmask[i], 1u << r);
+            atomicOr(&sinkmask[i], SMASK1(r));
         else
             pred[(int64_t)r * ld + j] = (uint32_t)i;
     } else if (rc == 2) {
         // successor is non-negative but does not fit the key: it cannot be in the space => it is a sink
-        atomicOr(&sinkmask[i], 1u << r);
+        atomicOr(&sinkmask[i], SMASK1(r));
     }
 }
 
-__global__ void k_frontier_flags(const uint32_t* __restrict__ sinkmask, int64_t n, uint32_t reactmask,
+__global__ void k_frontier_flags(const smask_t* __restrict__ sinkmask, int64_t n, smask_t reactmask,
                                  uint32_t* __restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = (sinkmask[i] & reactmask) ? 1u : 0u;
@@ -164,8 +164,8 @@ __global__ void k_clear_flags_at(const uint32_t* __restrict__ ids0 /*0-based*/, 
 
 __global__ void k_compact_space(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, int64_t n,
                                 const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pred, int64_t ld,
-                                const uint32_t* __restrict__ sinkmask, int nr, uint64_t* __restrict__ keys2,
-                                uint32_t* __restrict__ pred2, int64_t ld2, uint32_t* __restrict__ sinkmask2,
+                                const smask_t* __restrict__ sinkmask, int nr, uint64_t* __restrict__ keys2,
+                                uint32_t* __restrict__ pred2, int64_t ld2, smask_t* __restrict__ sinkmask2,
                                 const uint32_t* __restrict__ origin, uint32_t* __restrict__ origin2) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !keep[i]) return;
@@ -181,16 +181,16 @@ __global__ void k_compact_space(const uint32_t* __restrict__ keep, const uint32_
 
 // deleteat! :318-329 -- re-derive sink flags of the surviving states.
 __global__ void k_rederive_sinks(HashView h, KeyLayout L, StoichDev S, const uint64_t* __restrict__ keys, int64_t n,
-                                 uint32_t* __restrict__ sinkmask) {
+                                 smask_t* __restrict__ sinkmask) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nr = S.nr;
     if (t >= n * nr) return;
     const int64_t i = t / nr;
     const int r = (int)(t % nr);
-    if (sinkmask[i] & (1u << r)) return;
+    if (sinkmask[i] & SMASK1(r)) return;
     uint64_t k2;
     const int rc = shifted_key(L, S, keys[i], r, +1, &k2);
-    if ((rc == 0 && hash_lookup(h, k2) == NONE32) || rc == 2) atomicOr(&sinkmask[i], 1u << r);
+    if ((rc == 0 && hash_lookup(h, k2) == NONE32) || rc == 2) atomicOr(&sinkmask[i], SMASK1(r));
 }
 
 __global__ void k_lookup(HashView h, const uint64_t* __restrict__ q, int64_t m, uint32_t* __restrict__ out) {
@@ -236,11 +236,11 @@ struct ExpandSmallArgs {
     KeyLayout L;
     StoichDev S;
     ReactList reacts;
-    uint32_t reactmask;
+    smask_t reactmask;
     uint64_t* keys;
     uint32_t* pred;
     int64_t ld;
-    uint32_t* sinkmask;
+    smask_t* sinkmask;
     uint64_t* cand_key;
     uint32_t* cand_slot;
     uint32_t* frontier;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(XS_THREADS) k_expand_small(const __grid_consta
                 const uint32_t i = n_old + running + pos;
                 a.keys[i] = a.cand_key[c];
                 a.h.vals[slot] = i;
-                a.sinkmask[i] = 0u;
+                a.sinkmask[i] = 0;
                 for (int r = 0; r < nr; ++r) a.pred[(int64_t)r * a.ld + i] = NONE32;
             }
             running += total;
@@ -357,18 +357,18 @@ __global__ void __launch_bounds__(XS_THREADS) k_expand_small(const __grid_consta
                 const uint32_t j = hash_lookup(a.h, k2);
                 if (j != NONE32) {
                     a.pred[(int64_t)r * a.ld + i] = j;
-                    atomicAnd(&a.sinkmask[j], ~(1u << r));
+                    atomicAnd(&a.sinkmask[j], ~SMASK1(r));
                 }
             }
             const int rc = shifted_key(a.L, a.S, key, r, +1, &k2);
             if (rc == 0) {
                 const uint32_t j = hash_lookup(a.h, k2);
                 if (j == NONE32)
-                    atomicOr(&a.sinkmask[i], 1u << r);
+                    atomicOr(&a.sinkmask[i], SMASK1(r));
                 else
                     a.pred[(int64_t)r * a.ld + j] = (uint32_t)i;
             } else if (rc == 2) {
-                atomicOr(&a.sinkmask[i], 1u << r);
+                atomicOr(&a.sinkmask[i], SMASK1(r));
             }
         }
         __syncthreads();
@@ -536,7 +536,8 @@ int space_delete_flagged(ncme_space* sp) {
     sp->last_delete_nnew = (int64_t)m;
     if ((int64_t)m == n) return NCME_OK;
     DevArray<uint64_t> k2;
-    DevArray<uint32_t> p2, m2, o2;
+    DevArray<uint32_t> p2, o2;
+    DevArray<smask_t> m2;
     // keep head-room for the expansion that follows every prune (adapt!, rstepadapters.jl:44-49) instead of shrinking
     // to fit and re-growing (re-layout of the slot-major predecessor table) a moment later
     const int64_t ld2 = round_up<int64_t>(std::max<int64_t>(1024, std::min<int64_t>(sp->ld, 2 * (int64_t)m + 8192)), 64);
@@ -808,7 +809,8 @@ int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, i
             if ((st = space_ensure_key_room(sp, zero)) != NCME_OK) break;
         }
         std::vector<uint64_t> hk((size_t)n);
-        std::vector<uint32_t> hm((size_t)n, 0u), hp((size_t)n * nr);
+        std::vector<smask_t> hm((size_t)n, 0);
+        std::vector<uint32_t> hp((size_t)n * nr);
         for (int64_t i = 0; i < n && st == NCME_OK; ++i) {
             int rc = space_pack_host(sp, states + (size_t)i * ns, &hk[(size_t)i]);
             if (rc != 0) {
@@ -822,7 +824,7 @@ int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, i
                     st = NCME_ERR_ARG;
                 }
                 hp[(size_t)r * n + i] = c ? c - 1 : NONE32;
-                if (sink_connectivity[(size_t)i * nr + r]) hm[(size_t)i] |= 1u << r;
+                if (sink_connectivity[(size_t)i * nr + r]) hm[(size_t)i] |= SMASK1(r);
             }
         }
         if (st != NCME_OK) break;
@@ -830,7 +832,7 @@ int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, i
         bool ok = true;
         if (n > 0) {
             ok &= cudaMemcpyAsync(sp->keys.p, hk.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s) == cudaSuccess;
-            ok &= cudaMemcpyAsync(sp->sinkmask.p, hm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+            ok &= cudaMemcpyAsync(sp->sinkmask.p, hm.data(), (size_t)n * sizeof(smask_t), cudaMemcpyHostToDevice, s) == cudaSuccess;
             for (int r = 0; r < nr; ++r)
                 ok &= cudaMemcpyAsync(sp->pred.p + (size_t)r * sp->ld, hp.data() + (size_t)r * n, (size_t)n * 4,
                                       cudaMemcpyHostToDevice, s) == cudaSuccess;
@@ -874,7 +876,7 @@ int ncme_space_destroy(ncme_space* sp) {
 
 // small spaces: run as many levels as fit the (generously pre-reserved) capacities in one single-CTA launch.
 // Returns the levels done and the size of the last level's batch of new states (the next frontier).
-static int expand_small(ncme_space* sp, int levels, const ReactList& reacts, uint32_t reactmask, const int64_t* inc,
+static int expand_small(ncme_space* sp, int levels, const ReactList& reacts, smask_t reactmask, const int64_t* inc,
                         int* levels_done, int64_t* last_added, bool* frontier_empty) {
     ncme_ctx* ctx = sp->ctx;
     cudaStream_t s = ctx->stream;
@@ -948,7 +950,7 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
     ncme_ctx* ctx = sp->ctx;
     sp->last_delete_nold = -1;
     ReactList reacts{};
-    uint32_t reactmask = 0;
+    smask_t reactmask = 0;
     if (nonly <= 0) {
         for (int r = 0; r < sp->nr; ++r) reacts.r[reacts.n++] = r;
     } else {
@@ -959,7 +961,7 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
         }
     }
     const int nreact = reacts.n;
-    for (int k = 0; k < nreact; ++k) reactmask |= 1u << reacts.r[k];
+    for (int k = 0; k < nreact; ++k) reactmask |= SMASK1(reacts.r[k]);
     int64_t inc[NCME_MAX_SPECIES] = {0};   // largest possible growth of each species in one level
     for (int k = 0; k < nreact; ++k)
         for (int s2 = 0; s2 < sp->ns; ++s2) inc[s2] = std::max(inc[s2], sp->stoich[(size_t)reacts.r[k] * sp->ns + s2]);
@@ -1101,17 +1103,18 @@ int ncme_space_download_connectivity(ncme_space* sp, int64_t first, int64_t coun
     if (count == 0) return NCME_OK;
     cudaStream_t s = sp->ctx->stream;
     const int nr = sp->nr;
-    std::vector<uint32_t> hp((size_t)count * nr), hm((size_t)count);
+    std::vector<uint32_t> hp((size_t)count * nr);
+    std::vector<smask_t> hm((size_t)count);
     for (int r = 0; r < nr; ++r)
         NCME_CUDA(cudaMemcpyAsync(hp.data() + (size_t)r * count, sp->pred.p + (size_t)r * sp->ld + first, (size_t)count * 4,
                                   cudaMemcpyDeviceToHost, s));
-    NCME_CUDA(cudaMemcpyAsync(hm.data(), sp->sinkmask.p + first, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
+    NCME_CUDA(cudaMemcpyAsync(hm.data(), sp->sinkmask.p + first, (size_t)count * sizeof(smask_t), cudaMemcpyDeviceToHost, s));
     NCME_CUDA(cudaStreamSynchronize(s));
     for (int64_t i = 0; i < count; ++i)
         for (int r = 0; r < nr; ++r) {
             uint32_t p = hp[(size_t)r * count + i];
             if (sc_out) sc_out[(size_t)i * nr + r] = (p == NONE32) ? 0u : p + 1u;
-            if (kc_out) kc_out[(size_t)i * nr + r] = (hm[(size_t)i] >> r & 1u) ? (uint32_t)(r + 1) : 0u;
+            if (kc_out) kc_out[(size_t)i * nr + r] = ((hm[(size_t)i] >> r) & 1u) ? (uint32_t)(r + 1) : 0u;
         }
     return NCME_OK;
 }

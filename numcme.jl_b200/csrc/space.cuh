@@ -63,7 +63,7 @@ struct ncme_space {
 
     ncme::DevArray<uint64_t> keys;      // [ld]      packed state of index i (insertion order)
     ncme::DevArray<uint32_t> pred;      // [nr][ld]  pred[r][i] = j with x_i = x_j + s_r, NONE32 if absent
-    ncme::DevArray<uint32_t> sinkmask;  // [ld]      bit r set <=> x_i + s_r >= 0 and not in the space
+    ncme::DevArray<ncme::smask_t> sinkmask;  // [ld]      bit r set <=> x_i + s_r >= 0 and not in the space
     // incremental matrix assembly (H8): origin[i] = index state i had when the space was last marked (by a matrix
     // build), NONE32 for states added since.  Deletions compact it with the states, expansions append NONE32 -- the
     // surviving old states therefore always form a prefix and the new ones the tail.

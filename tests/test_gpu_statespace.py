@@ -171,8 +171,51 @@ def test_small_to_general_handover_index_exact(pkg):
         _same(sp2, osp2)
 
 
+@pytest.mark.parametrize("R", [33, 48, 64])
+def test_more_than_32_reactions(pkg, R):
+    """33..64 reactions (NCME_MAX_REACTIONS = 64, 64-bit sink masks): state space index-exact incl. expand with
+    onlyreactions above bit 31 and deleteat!, matvec <= 1e-12 (generic > 16-slot kernel), sink rows of reactions >= 32,
+    and a BDF solve on the launch-per-operation path (the fused step kernel handles R <= 32) against DP5."""
+    from oracle.fspmatrix import FspMatrixOracle, OProp
+    from test_gpu_matvec import _to_pkg_props
+    rng = np.random.default_rng(100 + R)
+    S = rng.integers(-1, 2, size=(6, R))
+    S[:, R - 1] = [1, 0, 0, 0, 0, -1]          # make sure the highest reaction has a non-trivial stoichiometry
+    S[:, 36 % R] = S[:, 2]                     # duplicate stoichiometry across the 32-bit boundary
+    x0 = [2, 2, 2, 2, 2, 2]
+    sp, osp = pkg.StateSpaceSparse(S, x0), StateSpaceOracleFast(S, x0)
+    sp.expand_(1)
+    osp.expand(1)
+    _same(sp, osp)
+    hi = [r for r in (R, R - 1, 34, 2) if r <= R]
+    sp.expand_(1, onlyreactions=hi)
+    osp.expand(1, onlyreactions=hi)
+    _same(sp, osp)
+    n = sp.get_state_count()
+    drop = sorted(rng.choice(np.arange(2, n + 1), size=n // 5, replace=False).tolist())
+    sp.deleteat_(drop)
+    osp.deleteat(drop)
+    _same(sp, osp)
+    props = [OProp("ti", f=(lambda x, p, r=r: (0.05 + 0.003 * r) * (1.0 + x[r % 6]))) for r in range(R)]
+    props[R - 2] = OProp("sep", tfactor=lambda t, p: 1.0 + 0.5 * np.sin(t), statefactor=lambda x, p: 0.3 * x[2])
+    A = pkg.FspMatrixSparse(sp, _to_pkg_props(pkg, props), parameters=[])
+    OA = FspMatrixOracle(osp, props, [])
+    v = rng.random(A.size(1))
+    for t in (0.0, 1.3):
+        w, wr = pkg.matvec(t, A, v), OA.matvec(t, v)
+        assert np.abs(w - wr).max() <= 1e-12 * np.abs(wr).max()
+        assert np.abs(wr[-R:]).min() >= 0.0 and np.abs(wr[-(R - 32):]).max() > 0.0   # sink rows above bit 31 are populated
+    p0 = pkg.FspVectorSparse.from_pairs(sp, [(x0, 1.0)])
+    model = pkg.CmeModel(S, _to_pkg_props(pkg, props), [])
+    a = pkg.solve(model, p0, (0.0, 0.3), None, saveat=[0.3], odertol=1e-8, odeatol=1e-13)
+    b = pkg.solve(model, p0, (0.0, 0.3), pkg.NativeRK45(), saveat=[0.3], odertol=1e-9, odeatol=1e-13)
+    assert np.abs(a.p[0].values - b.p[0].values).max() < 1e-7 and np.abs(a.sinks[0] - b.sinks[0]).max() < 1e-7
+    with pytest.raises(pkg.ArgumentError):      # 65 reactions: a clean error, not a truncated mask
+        pkg.StateSpaceSparse(rng.integers(-1, 2, size=(3, 65)), [1, 1, 1])
+
+
 def test_maximum_reaction_count_and_degenerate_spaces(pkg):
-    """R = 32 (NCME_MAX_REACTIONS) over 8 species incl. a zero-stoichiometry reaction and two reactions with identical
+    """R = 32 (the most the fused BDF step kernel handles) over 8 species incl. a zero-stoichiometry reaction and two reactions with identical
     stoichiometry; a one-state space; a space emptied by deleteat!."""
     from oracle.fspmatrix import FspMatrixOracle, OProp
     rng = np.random.default_rng(17)
