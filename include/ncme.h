@@ -128,7 +128,9 @@ int ncme_matrix_destroy(ncme_matrix* mat);
 /* size(A)                                          fspsparsematrix.jl:174-186 */
 int ncme_matrix_size(ncme_matrix* mat, int64_t* rows, int64_t* cols);
 /* _update_sparsematrix!(A_joint[r], states, prop, t, theta)   fspsparsematrix.jl:154-166
- * vals[i] = f(t, x_i, theta) evaluated by the host for the 1-based joint reaction `reaction`. */
+ * vals[i] = f(t, x_i, theta) evaluated by the host for the 1-based joint reaction `reaction`.
+ * Row-sharded matrices take the values over this rank's rows and predecessor window only: states
+ * [row_lo - halo_lo, row_hi + halo_hi) of ncme_matrix_shard_info, in that order. */
 int ncme_matrix_set_joint_values(ncme_matrix* mat, int reaction, const double* vals);
 /* matvec!(out,t,A,v) (beta=0) / matvecadd!(out,t,A,v) (beta=1)   fspsparsematrix.jl:196-247
  * coef[r] (host, nr entries) = tfactor_r(t,theta) for separable reactions; entries of time-invariant

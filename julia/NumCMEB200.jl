@@ -404,7 +404,7 @@ mutable struct FspMatrixSparseB200{NS,NR} <: NumCME.AbstractFspMatrix
     coef::Vector{Float64}
     tfactors::Dict{Int,Any}      # reaction => t -> c_r(t) for every reaction the library treats as separable
 end
-# comm !== nothing: this rank's row block only (K8).  Without joint propensities the host evaluates the state factors
+# comm !== nothing: this rank's row block only (K8).  The host evaluates the state factors
 # of its own rows + predecessor window only (ncme_matrix_shard_window / ncme_matrix_create_window): evaluation and
 # upload shrink with the number of ranks.
 function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, props::Vector{<:Propensity}; parameters = [],
@@ -412,7 +412,7 @@ function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, props::Vector{<
     states = get_states(space)                      # the host copy the reference keeps (`deepcopy(space.states)`, :97)
     n = length(states)
     kinds = Int32[!istimevarying(a) ? 0 : (istimeseparable(a) ? 1 : 2) for a in props]
-    windowed = comm !== nothing && comm.nranks > 1 && n > 0 && all(k -> k != 2, kinds)
+    windowed = comm !== nothing && comm.nranks > 1 && n > 0
     lo, hi = 0, n
     if windowed
         w = zeros(Int64, 4)
@@ -429,7 +429,7 @@ function FspMatrixSparseB200(space::StateSpaceSparseB200{NS,NR}, props::Vector{<
             found = detect_rank1(a.f, states, parameters)
             if found !== nothing
                 g, sent = found
-                G[:, r] .= g; kinds[r] = 1
+                G[1:nw, r] .= g[lo+1:hi]; kinds[r] = 1
                 tfactors[r] = function (t)
                     c = a.f(t, states[sent[1]], parameters) / g[sent[1]]
                     for k in sent[2:end]
@@ -504,9 +504,14 @@ function _prepare!(A::FspMatrixSparseB200, t::Real)
     end
     if t != A.t_cache
         A.t_cache = t
+        lo, hi = 0, length(A.states)
+        if A.comm !== nothing                      # row-sharded: this rank's rows + predecessor window only
+            i = shard_info(A)
+            lo, hi = Int(i[1] - i[3]), Int(i[2] + i[4])
+        end
         for (r, a) in enumerate(A.propensities)
             if A.kinds[r] == 2
-                vals = Float64[a.f(t, x, θ) for x in A.states]
+                vals = Float64[a.f(t, A.states[k], θ) for k in lo+1:hi]
                 check(ccall((:ncme_matrix_set_joint_values, libncme), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), A.h, r, vals))
             end
         end

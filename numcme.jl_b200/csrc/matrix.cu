@@ -1159,20 +1159,24 @@ __global__ void k_fill_sinks_group(const uint32_t* __restrict__ flags, const uin
 
 
 
-// _update_sparsematrix! (:154-166) for one joint reaction: vals[i] = f(t, x_i, theta).
-__global__ void k_set_joint(const double* __restrict__ vals, int64_t n, const uint32_t* __restrict__ col,
-                            double* __restrict__ val, double* __restrict__ diag) {
+// _update_sparsematrix! (:154-166) for one joint reaction.  vals holds f(t, x, theta) over the states this rank's
+// rows can reach: the window [ext_lo, ext_hi) = [low halo (hl) | local rows (n) | high halo]; on a single GPU that is
+// the whole state list (hl = 0, no halo).  Column indices are positions in the padded matvec input
+// [low halo | local rows | nr sinks | high halo], so positions behind the local rows skip the nr sink entries.
+__global__ void k_set_joint(const double* __restrict__ vals, int64_t n, uint32_t hl, uint32_t nr,
+                            const uint32_t* __restrict__ col, double* __restrict__ val, double* __restrict__ diag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t c = col[i];   // single-GPU matrices only: padded position == global index
-    val[i] = (c == (uint32_t)i) ? 0.0 : vals[c];
-    diag[i] = -vals[i];
+    const uint32_t c = col[i], self = hl + (uint32_t)i;
+    const uint32_t w = (c < hl + (uint32_t)n) ? c : c - nr;
+    val[i] = (c == self) ? 0.0 : vals[w];
+    diag[i] = -vals[self];
 }
 
-__global__ void k_set_joint_sinks(const double* __restrict__ vals, const uint32_t* __restrict__ sink_row, int64_t begin,
-                                  int64_t end, double* __restrict__ sink_val) {
+__global__ void k_set_joint_sinks(const double* __restrict__ vals, uint32_t hl, const uint32_t* __restrict__ sink_row,
+                                  int64_t begin, int64_t end, double* __restrict__ sink_val) {
     int64_t k = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < end) sink_val[k] = vals[sink_row[k]];
+    if (k < end) sink_val[k] = vals[hl + sink_row[k]];
 }
 
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -1578,9 +1582,6 @@ int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t
                                ncme_matrix** out) {
     NCME_REQUIRE(space && kind && out, "null argument");
     NCME_REQUIRE(propvals || space->n == 0, "propvals is null");
-    if (comm && comm->nranks > 1)
-        for (int r = 0; r < space->nr; ++r)
-            NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
     ncme_matrix* A = new ncme_matrix();
     int st = matrix_build(space, kind, propvals, A, comm);
     if (st != NCME_OK) {
@@ -1632,9 +1633,6 @@ int ncme_matrix_create_window(ncme_space* space, ncme_comm* comm, const int32_t*
     NCME_REQUIRE(space && kind && out, "null argument");
     NCME_REQUIRE(win_lo >= 0 && win_lo <= win_hi && win_hi <= space->n, "bad window");
     NCME_REQUIRE(propvals_window || win_hi == win_lo, "propvals is null");
-    if (comm && comm->nranks > 1)
-        for (int r = 0; r < space->nr; ++r)
-            NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
     ncme_matrix* A = new ncme_matrix();
     int st = matrix_build(space, kind, propvals_window, A, comm, nullptr, 0, win_lo, win_hi);
     if (st != NCME_OK) {
@@ -1665,9 +1663,6 @@ int ncme_matrix_create_incremental(ncme_space* space, ncme_comm* comm, ncme_matr
     NCME_REQUIRE(!prev->g_window, "incremental build: `prev` was built from a state-factor window (sharded build)");
     NCME_REQUIRE(prev->nr == space->nr, "incremental build: reaction count changed");
     for (int r = 0; r < space->nr; ++r) NCME_REQUIRE(prev->kind[r] == kind[r], "incremental build: reaction kinds changed");
-    if (comm && comm->nranks > 1)
-        for (int r = 0; r < space->nr; ++r)
-            NCME_REQUIRE(kind[r] != NCME_JOINT_TV, "joint time-varying reactions are not supported on row-sharded matrices");
     int64_t nkept = 0;
     NCME_TRY(space_count_kept(space, &nkept));
     NCME_REQUIRE(propvals_new || space->n == nkept, "propvals_new is null");
@@ -1762,19 +1757,20 @@ int ncme_matrix_set_joint_values(ncme_matrix* A, int reaction, const double* val
                  "reaction %d is not a joint time-varying reaction", reaction);
     const int r = reaction - 1;
     const int s = A->reaction_slot[r], d = A->reaction_diag[r];
-    NCME_REQUIRE(!A->comm, "joint reactions are single-GPU only");
     if (s < 0 || A->n == 0) return NCME_OK;
     ncme_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
+    // sharded matrices take the values over this rank's window [ext_lo, ext_hi) (ncme_matrix_shard_info), see k_set_joint
+    const int64_t nw = A->hl + A->n + A->hh;
     DevArray<double> tmp;
-    NCME_TRY(tmp.reserve((size_t)A->n, st, false));
-    NCME_CUDA(cudaMemcpyAsync(tmp.p, vals, (size_t)A->n * 8, cudaMemcpyHostToDevice, st));
-    k_set_joint<<<nblk(A->n), 256, 0, st>>>(tmp.p, A->n, A->col.p + (size_t)s * A->ld, A->val.p + (size_t)s * A->ld,
-                                            A->diag.p + (size_t)d * A->ld);
+    NCME_TRY(tmp.reserve((size_t)nw, st, false));
+    NCME_CUDA(cudaMemcpyAsync(tmp.p, vals, (size_t)nw * 8, cudaMemcpyHostToDevice, st));
+    k_set_joint<<<nblk(A->n), 256, 0, st>>>(tmp.p, A->n, (uint32_t)A->hl, (uint32_t)A->nr, A->col.p + (size_t)s * A->ld,
+                                            A->val.p + (size_t)s * A->ld, A->diag.p + (size_t)d * A->ld);
     ctx->launches++;
     const int64_t b = A->sink_ptr[r], e = A->sink_ptr[r + 1];
     if (e > b) {
-        k_set_joint_sinks<<<nblk(e - b), 256, 0, st>>>(tmp.p, A->sink_row.p, b, e, A->sink_val.p);
+        k_set_joint_sinks<<<nblk(e - b), 256, 0, st>>>(tmp.p, (uint32_t)A->hl, A->sink_row.p, b, e, A->sink_val.p);
         ctx->launches++;
     }
     NCME_CUDA(cudaGetLastError());

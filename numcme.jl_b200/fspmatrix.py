@@ -164,10 +164,11 @@ class FspMatrixSparse:
         self._tfactor = {}                 # 1-based reaction id -> callable t -> c(t)
         self._rank1 = {}                   # 1-based reaction id -> factorisation info of detected reactions
         lib = L.load()
-        # Row-sharded build: without joint propensities every rank evaluates the state factors of its own
-        # rows + predecessor window only -- host evaluation and upload shrink with the number of ranks.
+        # Row-sharded build: every rank evaluates the state factors of its own rows + predecessor window
+        # only -- host evaluation and upload shrink with the number of ranks.  Joint propensities are refreshed over the
+        # same window at every distinct t (_refresh_joint).
         lo, hi = 0, n
-        windowed = comm is not None and comm.nranks > 1 and n > 0 and all(a.kind != "joint" for a in self.propensities)
+        windowed = comm is not None and comm.nranks > 1 and n > 0
         if windowed:
             w = (C.c_int64 * 4)()
             L.check(lib.ncme_matrix_shard_window(space.handle, comm.handle, w))
@@ -201,7 +202,7 @@ class FspMatrixSparse:
                 info = _rank1_info(a.f, self.states, parameters)
                 if info is not None:
                     g = info.pop("g")
-                    propvals[r, :n] = g
+                    propvals[r, :nw] = g[lo:hi]
                     self.kinds[r] = SEPARABLE_TV
                     info["sent_states"] = [[int(v) for v in self.states[i]] for i in info["sent"]]
                     info["zero_states"] = [[int(v) for v in self.states[i]] for i in info["zero_sent"]]
@@ -323,8 +324,16 @@ class FspMatrixSparse:
         if t == self.t_cache:
             return
         self.t_cache = t
+        if not self.device_joint_ids:
+            return
+        states = self.states
+        if self.comm is not None and self.comm.nranks > 1:
+            # row-sharded: this rank's rows + predecessor window [row_lo - halo_lo, row_hi + halo_hi)
+            info = self.shard_info()
+            states = states[info["row_lo"] - info["halo_lo"]: info["row_hi"] + info["halo_hi"]]
         for r in self.device_joint_ids:
-            vals = eval_over_states(self.propensities[r - 1].f, self.states, self.parameters, t=t)
+            vals = np.ascontiguousarray(eval_over_states(self.propensities[r - 1].f, states, self.parameters, t=t),
+                                        dtype=np.float64)
             L.check(L.load().ncme_matrix_set_joint_values(self._h, r, L.ptr(vals, C.c_double)))
 
     def _apply(self, out, t, v, beta: float):
