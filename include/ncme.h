@@ -168,6 +168,14 @@ int ncme_matrix_compression_info(ncme_matrix* mat, int64_t info[4]);
  *                 (d f / d theta for time-invariant; d statefactor / d theta for separable; ignored for joint) */
 int ncme_sensmatrix_create(ncme_matrix* mat, int npar, int nentries, const int32_t* ent_reaction,
                            const int32_t* ent_param, const double* dpropvals, ncme_sensmatrix** out);
+/* The rebuild after an adapt! (src/forwardsenscme/sparse/forwardsenscmesparse.jl:140 rebuilds from scratch inside the loop).  `mat` must have been built with
+ * ncme_matrix_create_incremental from the matrix `prev` sits on; dpropvals_new then holds the derivative factors of
+ * the states appended since (entry-major nentries x n_new, n_new as ncme_space_new_count reported before `mat` was
+ * built); the rows of the surviving states are carried over on the device.  The (reaction, parameter) pattern must be
+ * the one of `prev`.  Same result, bit for bit, as ncme_sensmatrix_create on all states. */
+int ncme_sensmatrix_create_incremental(ncme_matrix* mat, ncme_sensmatrix* prev, int npar, int nentries,
+                                       const int32_t* ent_reaction, const int32_t* ent_param,
+                                       const double* dpropvals_new, ncme_sensmatrix** out);
 int ncme_sensmatrix_destroy(ncme_sensmatrix* smat);
 /* joint-TV entries: host evaluates d f / d theta_param (t, x_i, theta) and uploads (entry is 0-based). */
 int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* smat, int entry, const double* vals);

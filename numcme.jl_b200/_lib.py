@@ -103,6 +103,7 @@ SIGNATURES = {
     "ncme_matvec_host": (cint, [p_void, p_f64, p_void, p_void, f64]),
     "ncme_matrix_stats": (cint, [p_void, C.POINTER(cint), p_i64, p_i64, p_i64]),
     "ncme_sensmatrix_create": (cint, [p_void, cint, cint, p_i32, p_i32, p_f64, C.POINTER(p_void)]),
+    "ncme_sensmatrix_create_incremental": (cint, [p_void, p_void, cint, cint, p_i32, p_i32, p_f64, C.POINTER(p_void)]),
     "ncme_sensmatrix_destroy": (cint, [p_void]),
     "ncme_sensmatrix_set_joint_values": (cint, [p_void, cint, p_f64]),
     "ncme_sens_matvec": (cint, [p_void, p_f64, p_f64, p_void, p_void]),

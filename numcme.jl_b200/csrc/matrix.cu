@@ -1229,6 +1229,15 @@ __global__ void k_carry_factors(const double* __restrict__ Gprev, int64_t ngprev
     G[t] = i < nkept ? Gprev[(int64_t)r * ngprev + origin[i]] : Gnew_tail[(int64_t)r * nnew + (i - nkept)];
 }
 
+int carry_rows(ncme_ctx* ctx, const double* prev, int64_t ngprev, const uint32_t* origin, int64_t nkept, const double* tail,
+               int64_t nnew, int nrows, double* out, int64_t ng) {
+    if (ng <= 0 || nrows <= 0) return NCME_OK;
+    k_carry_factors<<<nblk(ng * nrows), 256, 0, ctx->stream>>>(prev, ngprev, origin, nkept, tail, nnew, nrows, out, ng);
+    ctx->launches++;
+    NCME_CUDA(cudaGetLastError());
+    return NCME_OK;
+}
+
 // prev != nullptr: incremental build -- `propvals` then holds the factors of the nnew = n - nkept states appended since
 // prev was built (reaction-major nnew x nr), everything else is carried over on the device.
 // win_lo >= 0: windowed build of a row shard -- `propvals` holds the factors of the states [win_lo, win_hi) only
@@ -1320,10 +1329,12 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
             else
                 NCME_CUDA(cudaMemcpyAsync(tail.p + (size_t)r * nnew, propvals + (size_t)r * nnew, (size_t)nnew * 8, cudaMemcpyHostToDevice, st));
         }
-        k_carry_factors<<<nblk(ng * nr), 256, 0, st>>>(prev->G.p, prev->n_global, sp->origin.p, nkept, tail.p, nnew, nr, G.p, ng);
-        ctx->launches++;
-        NCME_CUDA(cudaGetLastError());
+        NCME_TRY(carry_rows(ctx, prev->G.p, prev->n_global, sp->origin.p, nkept, tail.p, nnew, nr, G.p, ng));
         tail.release();
+        NCME_TRY(A->carry_origin.reserve((size_t)(nkept > 0 ? nkept : 1), st, false));
+        if (nkept > 0) NCME_CUDA(cudaMemcpyAsync(A->carry_origin.p, sp->origin.p, (size_t)nkept * 4, cudaMemcpyDeviceToDevice, st));
+        A->carry_nkept = nkept;
+        A->carry_prev = prev;
     } else if (win_lo >= 0) {
         NCME_REQUIRE(win_lo <= row_lo && row_hi <= win_hi && win_hi <= ng, "state-factor window does not cover this rank's rows");
         const int64_t nw = win_hi - win_lo;
@@ -1719,6 +1730,7 @@ int ncme_matrix_destroy(ncme_matrix* A) {
     A->val.release();
     A->diag.release();
     A->G.release();
+    A->carry_origin.release();
     A->sink_row.release();
     A->sink_val.release();
     A->tasks.release();

@@ -57,6 +57,12 @@ struct ncme_matrix {
     // state factors G[r][i] of ALL states (reaction-major, stride n_global), kept for the incremental constructor of the
     // matrix that follows an adapt! (H8): only the states added since are evaluated on the host
     ncme::DevArray<double> G;
+    // origin map the incremental constructor used (old index of the surviving states, a prefix of length carry_nkept) and
+    // the matrix it carried the factors from (identity only, never dereferenced): the sensitivity matrix built on top
+    // of this matrix carries its derivative factors over through the same map (ncme_sensmatrix_create_incremental)
+    ncme::DevArray<uint32_t> carry_origin;
+    int64_t carry_nkept = -1;
+    const ncme_matrix* carry_prev = nullptr;
     bool g_window = false;          // G only holds the factors of this rank's rows + halo window (ncme_matrix_create_window)
     uint64_t space_mark = 0;        // mark of the space this matrix was built at
     // compressed column indices (K1 fast path): one byte per (slot,row) relative to a per-(slot, 64-row chunk)
@@ -158,5 +164,8 @@ int halo_exchange(ncme_matrix* A, const double* x_local, cudaStream_t st);
 int matrix_diag(ncme_matrix* A, const double* coef, double* out);                                 // out[0..n) = diag(A(t))
 int matvec_sinks_only(ncme_matrix* A, const double* coef, const double* x_local, double* y_local);  // the nr sink rows only
 int sens_describe(ncme_sensmatrix* SA, ncme_matrix** A, int* npar, int* nent);
+// out[r][i] = i < nkept ? prev[r][origin[i]] : tail[r][i - nkept]   (nrows arrays of length ng; prev has stride ngprev)
+int carry_rows(ncme_ctx* ctx, const double* prev, int64_t ngprev, const uint32_t* origin, int64_t nkept, const double* tail,
+               int64_t nnew, int nrows, double* out, int64_t ng);
 
 }  // namespace ncme

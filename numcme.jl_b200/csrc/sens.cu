@@ -16,6 +16,7 @@
 
 struct ncme_sensmatrix {
     ncme_matrix* A = nullptr;
+    int64_t A_n = 0;   // states of A at build time (stride of dG)
     int npar = 0;
     int nent = 0;
     int ent_reaction[NCME_SENS_MAX_ENTRIES];   // internal order: sorted by parameter
@@ -26,6 +27,9 @@ struct ncme_sensmatrix {
     ncme::DevArray<double> dval;    // [nent][ld]  d(state factor)/d theta at the predecessor
     ncme::DevArray<double> ddiag;   // [nent][ld]  minus d(state factor)/d theta at the state itself
     ncme::DevArray<double> dsink;   // per entry: values along the sink list of its reaction
+    // d(state factor)/d theta of ALL states per entry (internal entry order, stride A->n), kept for the incremental
+    // constructor of the sensitivity matrix that follows an adapt! (only the appended states are evaluated on the host)
+    ncme::DevArray<double> dG;
     int64_t dsink_ptr[NCME_SENS_MAX_ENTRIES + 1];
     ncme::DevArray<double> partial;   // [ntasks][P+1]
     ncme::DevArray<double> dpartial;  // [ntasks][nent]
@@ -287,25 +291,20 @@ __global__ void k_sens_sink_fill(const uint32_t* __restrict__ sink_row, int64_t 
 
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
-static int sens_fill_entry(ncme_sensmatrix* SA, int e, const double* dG_host) {
+// dval / ddiag / dsink of entry e from its derivative factors dG_row (DEVICE, length A->n)
+static int sens_fill_entry(ncme_sensmatrix* SA, int e, const double* dG_row) {
     ncme_matrix* A = SA->A;
     ncme_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
     const int r = SA->ent_reaction[e];
     const int s = A->reaction_slot[r];
-    DevArray<double> tmp;
-    NCME_TRY(tmp.reserve((size_t)(A->n > 0 ? A->n : 1), st, false));
-    if (dG_host)
-        NCME_CUDA(cudaMemcpyAsync(tmp.p, dG_host, (size_t)A->n * 8, cudaMemcpyHostToDevice, st));
-    else
-        NCME_CUDA(cudaMemsetAsync(tmp.p, 0, (size_t)A->n * 8, st));
     if (s >= 0) {
-        k_sens_entry_fill<<<nblk(A->ld), 256, 0, st>>>(A->col.p + (size_t)s * A->ld, tmp.p, A->n, A->ld,
+        k_sens_entry_fill<<<nblk(A->ld), 256, 0, st>>>(A->col.p + (size_t)s * A->ld, dG_row, A->n, A->ld,
                                                        SA->dval.p + (size_t)e * A->ld, SA->ddiag.p + (size_t)e * A->ld);
         ctx->launches++;
         const int64_t b = A->sink_ptr[r], en = A->sink_ptr[r + 1];
         if (en > b) {
-            k_sens_sink_fill<<<nblk(en - b), 256, 0, st>>>(A->sink_row.p, b, en, tmp.p, SA->dsink.p + SA->dsink_ptr[e]);
+            k_sens_sink_fill<<<nblk(en - b), 256, 0, st>>>(A->sink_row.p, b, en, dG_row, SA->dsink.p + SA->dsink_ptr[e]);
             ctx->launches++;
         }
     } else {
@@ -313,8 +312,6 @@ static int sens_fill_entry(ncme_sensmatrix* SA, int e, const double* dG_host) {
         NCME_CUDA(cudaMemsetAsync(SA->ddiag.p + (size_t)e * A->ld, 0, (size_t)A->ld * 8, st));
     }
     NCME_CUDA(cudaGetLastError());
-    NCME_CUDA(cudaStreamSynchronize(st));
-    tmp.release();
     return NCME_OK;
 }
 
@@ -338,6 +335,7 @@ int ncme_sensmatrix_destroy(ncme_sensmatrix* SA) {
     SA->dval.release();
     SA->ddiag.release();
     SA->dsink.release();
+    SA->dG.release();
     SA->partial.release();
     SA->dpartial.release();
     if (SA->counter) cudaFree(SA->counter);
@@ -346,8 +344,11 @@ int ncme_sensmatrix_destroy(ncme_sensmatrix* SA) {
     return NCME_OK;
 }
 
-int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t* ent_reaction, const int32_t* ent_param,
-                           const double* dpropvals, ncme_sensmatrix** out) {
+// prev != nullptr: incremental build after an adapt! -- dpropvals then holds the derivative factors of the
+// nnew = A->n - A->carry_nkept appended states only (entry-major nentries x nnew); the rows of the surviving states are
+// carried over on the device through the origin map A's own incremental constructor used.
+static int sens_build(ncme_matrix* A, const ncme_sensmatrix* prev, int npar, int nentries, const int32_t* ent_reaction,
+                      const int32_t* ent_param, const double* dpropvals, ncme_sensmatrix** out) {
     NCME_REQUIRE(A && out && npar >= 0 && nentries >= 0, "bad arguments");
     NCME_REQUIRE(!A->comm, "the sensitivity matrix is single-GPU only");
     NCME_REQUIRE(nentries <= SMAX_ENT, "too many (reaction, parameter) entries (max %d)", SMAX_ENT);
@@ -355,6 +356,7 @@ int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t
     NCME_REQUIRE(nentries == 0 || (ent_reaction && ent_param && dpropvals), "null entry arrays");
     ncme_sensmatrix* SA = new ncme_sensmatrix();
     SA->A = A;
+    SA->A_n = A->n;
     SA->npar = npar;
     SA->nent = nentries;
     ncme_ctx* ctx = A->ctx;
@@ -396,11 +398,56 @@ int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t
         if ((rc = SA->dsink.reserve((size_t)SA->dsink_ptr[nentries] + 1, st, false)) != NCME_OK) break;
         if ((rc = SA->partial.reserve((size_t)A->ntasks * (npar + 1), st, false)) != NCME_OK) break;
         if ((rc = SA->dpartial.reserve((size_t)A->ntasks * ne, st, false)) != NCME_OK) break;
-        for (int e = 0; e < nentries && rc == NCME_OK; ++e) {
-            const int r = SA->ent_reaction[e];
-            const double* src = (A->kind[r] == NCME_JOINT_TV) ? nullptr : dpropvals + (size_t)SA->ent_user[e] * A->n;
-            rc = sens_fill_entry(SA, e, src);
+        const int64_t n = A->n;
+        if ((rc = SA->dG.reserve(ne * (size_t)(n > 0 ? n : 1), st, false)) != NCME_OK) break;
+        if (prev) {
+            bool same = prev->nent == nentries && prev->npar == npar;
+            for (int e = 0; same && e < nentries; ++e)
+                same = prev->ent_reaction[e] == SA->ent_reaction[e] && prev->ent_param[e] == SA->ent_param[e] &&
+                       prev->ent_user[e] == SA->ent_user[e];
+            if (!same) {
+                set_error("incremental sensitivity build: the (reaction, parameter) pattern changed");
+                rc = NCME_ERR_ARG;
+                break;
+            }
+            const int64_t nkept = A->carry_nkept, nnew = n - nkept;
+            DevArray<double> tail;
+            if ((rc = tail.reserve(ne * (size_t)(nnew > 0 ? nnew : 1), st, false)) != NCME_OK) break;
+            bool ok = true;
+            for (int e = 0; e < nentries && nnew > 0; ++e) {
+                const int r = SA->ent_reaction[e];
+                if (A->kind[r] == NCME_JOINT_TV)
+                    ok &= cudaMemsetAsync(tail.p + (size_t)e * nnew, 0, (size_t)nnew * 8, st) == cudaSuccess;
+                else
+                    ok &= cudaMemcpyAsync(tail.p + (size_t)e * nnew, dpropvals + (size_t)SA->ent_user[e] * nnew, (size_t)nnew * 8,
+                                          cudaMemcpyHostToDevice, st) == cudaSuccess;
+            }
+            if (ok && nentries > 0)
+                rc = carry_rows(ctx, prev->dG.p, prev->A_n, A->carry_origin.p, nkept, tail.p, nnew, nentries, SA->dG.p, n);
+            ok &= cudaStreamSynchronize(st) == cudaSuccess;   // `tail` is released right below
+            tail.release();
+            if (!ok) {
+                set_error("incremental sensitivity build: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = NCME_ERR_CUDA;
+            }
+            if (rc != NCME_OK) break;
+        } else {
+            bool ok = true;
+            for (int e = 0; e < nentries && n > 0; ++e) {
+                const int r = SA->ent_reaction[e];
+                if (A->kind[r] == NCME_JOINT_TV)
+                    ok &= cudaMemsetAsync(SA->dG.p + (size_t)e * n, 0, (size_t)n * 8, st) == cudaSuccess;
+                else
+                    ok &= cudaMemcpyAsync(SA->dG.p + (size_t)e * n, dpropvals + (size_t)SA->ent_user[e] * n, (size_t)n * 8,
+                                          cudaMemcpyHostToDevice, st) == cudaSuccess;
+            }
+            if (!ok) {
+                set_error("sensitivity build: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = NCME_ERR_CUDA;
+                break;
+            }
         }
+        for (int e = 0; e < nentries && rc == NCME_OK; ++e) rc = sens_fill_entry(SA, e, SA->dG.p + (size_t)e * n);
         if (rc != NCME_OK) break;
         // device meta: ent_reaction | ent_param | ent_slot | ent_diag | ent_ptr(npar+1) ; then dsink_ptr (int64) ; then 2*nent doubles
         std::vector<int> meta((size_t)4 * SMAX_ENT + SMAX_ENT + 2, 0);
@@ -433,6 +480,21 @@ int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t
     }
     *out = SA;
     return NCME_OK;
+}
+
+int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t* ent_reaction, const int32_t* ent_param,
+                           const double* dpropvals, ncme_sensmatrix** out) {
+    return sens_build(A, nullptr, npar, nentries, ent_reaction, ent_param, dpropvals, out);
+}
+
+int ncme_sensmatrix_create_incremental(ncme_matrix* A, ncme_sensmatrix* prev, int npar, int nentries,
+                                       const int32_t* ent_reaction, const int32_t* ent_param, const double* dpropvals_new,
+                                       ncme_sensmatrix** out) {
+    NCME_REQUIRE(A && prev && out, "null argument");
+    NCME_REQUIRE(A->carry_nkept >= 0 && A->carry_prev == prev->A && prev->dG.p,
+                 "incremental sensitivity build: `mat` was not built incrementally from the matrix of `prev`");
+    NCME_REQUIRE(dpropvals_new || nentries == 0 || A->n == A->carry_nkept, "dpropvals_new is null");
+    return sens_build(A, prev, npar, nentries, ent_reaction, ent_param, dpropvals_new, out);
 }
 
 // Reference-structure statistics of the derivative terms ("Algorithmic bytes, sensitivity matvec"):
@@ -486,7 +548,14 @@ int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* SA, int entry, const doubl
     NCME_REQUIRE(SA && vals && entry >= 0 && entry < SA->nent, "bad arguments");
     const int e = SA->user_ent[entry];
     NCME_REQUIRE(SA->A->kind[SA->ent_reaction[e]] == NCME_JOINT_TV, "entry %d does not belong to a joint reaction", entry);
-    return sens_fill_entry(SA, e, vals);
+    ncme_matrix* A = SA->A;
+    if (A->n == 0) return NCME_OK;
+    cudaStream_t st = A->ctx->stream;
+    double* row = SA->dG.p + (size_t)e * A->n;
+    NCME_CUDA(cudaMemcpyAsync(row, vals, (size_t)A->n * 8, cudaMemcpyHostToDevice, st));
+    NCME_TRY(sens_fill_entry(SA, e, row));
+    NCME_CUDA(cudaStreamSynchronize(st));   // `vals` is caller memory
+    return NCME_OK;
 }
 
 int ncme_sens_matvec(ncme_sensmatrix* SA, const double* coef, const double* dcoef, const double* X, double* Y) {

@@ -164,10 +164,17 @@ def solve_sens(model: CmeModelWithSensitivity, initial_condition: ForwardSensFsp
     sinks = np.zeros(R)
     dsinks = [np.zeros(R) for _ in range(P)]
     out = ForwardSensFspOutputSparse()
-    tot = {"steps": 0, "rejected": 0, "rhs_evals": 0, "launches": 0, "adapts": 0}
+    tot = {"steps": 0, "rejected": 0, "rhs_evals": 0, "launches": 0, "adapts": 0, "incremental_builds": 0}
     tnow = tstart
+    prev_SA = None
     while tnow < tend:
-        SA = ForwardSensFspMatrixSparse(model, space)
+        # after an adapt! only the appended states are evaluated (propensities and their parameter derivatives); the
+        # rows of the survivors are carried over on the device (the reference rebuilds from scratch, :140)
+        SA = ForwardSensFspMatrixSparse(model, space, previous=prev_SA)
+        if prev_SA is not None:
+            prev_SA.close()
+            prev_SA = None
+        tot["incremental_builds"] += int(SA.incremental)
         n = space.get_state_count()
         N = n + R
         U = DeviceVector.zeros(ctx, N * (P + 1))
@@ -214,7 +221,7 @@ def solve_sens(model: CmeModelWithSensitivity, initial_condition: ForwardSensFsp
             vecs = [U.view(b * N, n).clone() for b in range(P + 1)]
             sinks = U.to_host(n, R)
             dsinks = [U.to_host((ip + 1) * N + n, R) for ip in range(P)]
-            SA.close()
+            prev_SA = SA
             vecs = sens_adapt_(space, adapter, vecs, tnow, tend, fsptol)
             tot["adapts"] += 1
             if sinks.sum() >= tnow * fsptol / tend:      # forwardsenscmesparse.jl:187-189

@@ -23,10 +23,17 @@ from .statespace import StateSpaceSparse
 
 
 class ForwardSensFspMatrixSparse:
-    def __init__(self, model: CmeModelWithSensitivity, space: StateSpaceSparse):
+    def __init__(self, model: CmeModelWithSensitivity, space: StateSpaceSparse,
+                 previous: "ForwardSensFspMatrixSparse | None" = None):
+        """``previous``: the sensitivity matrix this space was assembled into before its last prune / expand (the
+        rebuild after an ``adapt!``, forwardsenscmesparse.jl:140).  Propensities AND their parameter derivatives are then
+        evaluated on the appended states only; the rows of the surviving states are carried over on the device
+        (``ncme_matrix_create_incremental`` + ``ncme_sensmatrix_create_incremental``).  Falls back to the full build
+        whenever the plain matrix does (other model, too few states, a space assembled elsewhere in between)."""
         # the derivative entries below follow the user's classification of every reaction: no separability detection
+        prevA = previous.fspmatrix if previous is not None and getattr(previous, "_h", None) else None
         self.fspmatrix = A = FspMatrixSparse(space, get_propensities(model), parameters=get_parameters(model),
-                                             detect_separable=False)
+                                             detect_separable=False, previous=prevA)
         self.ctx = A.ctx
         self.parameters = get_parameters(model)
         self.parameter_count = P = len(self.parameters)
@@ -36,21 +43,39 @@ class ForwardSensFspMatrixSparse:
         ents = [(r, ip) for ip in range(P) for r in range(A.nr) if pattern[r, ip]]
         self.entries = ents
         n = A.n
-        dvals = np.zeros((max(len(ents), 1), max(n, 1)), dtype=np.float64)
+        self.incremental = bool(prevA is not None and A.incremental and previous.entries == ents and
+                                previous.propensity_gradients is self.propensity_gradients)
+        if self.incremental:
+            n_new = A.new_state_count
+            states = space.get_states(n - n_new, n_new) if n_new else np.zeros((0, space.ns), dtype=np.int64)
+        else:
+            n_new, states = n, A.states
+        dvals = np.zeros((max(len(ents), 1), max(n_new, 1)), dtype=np.float64)
         for e, (r, ip) in enumerate(ents):
             g = self.propensity_gradients[r]
             kind = A.propensities[r].kind
             if kind == "ti":
-                dvals[e, :n] = eval_over_states(g.pardiffs[ip], A.states, self.parameters)
+                dvals[e, :n_new] = eval_over_states(g.pardiffs[ip], states, self.parameters)
             elif kind == "sep":
-                dvals[e, :n] = eval_over_states(g.statefactor_pardiffs[ip], A.states, self.parameters)
-        dvals = np.ascontiguousarray(dvals[:, :n]) if n else dvals
+                dvals[e, :n_new] = eval_over_states(g.statefactor_pardiffs[ip], states, self.parameters)
+        dvals = np.ascontiguousarray(dvals[:, :n_new]) if n_new else dvals
         er = np.array([r + 1 for r, _ in ents], dtype=np.int32)
         ep = np.array([ip + 1 for _, ip in ents], dtype=np.int32)
         h = L.p_void()
-        L.check(L.load().ncme_sensmatrix_create(A.handle, P, len(ents), L.ptr(er, C.c_int32) if ents else None,
-                                                L.ptr(ep, C.c_int32) if ents else None,
-                                                L.ptr(dvals, C.c_double), C.byref(h)))
+        lib = L.load()
+        if self.incremental:
+            st = lib.ncme_sensmatrix_create_incremental(A.handle, previous._h, P, len(ents),
+                                                        L.ptr(er, C.c_int32) if ents else None,
+                                                        L.ptr(ep, C.c_int32) if ents else None,
+                                                        L.ptr(dvals, C.c_double), C.byref(h))
+            if st != 0:                      # should not happen once A was built incrementally; be safe, not wrong
+                A.close()
+                self.__init__(model, space)
+                return
+        else:
+            L.check(lib.ncme_sensmatrix_create(A.handle, P, len(ents), L.ptr(er, C.c_int32) if ents else None,
+                                               L.ptr(ep, C.c_int32) if ents else None,
+                                               L.ptr(dvals, C.c_double), C.byref(h)))
         self._h = h
         self._dcoef = np.zeros(max(len(ents), 1), dtype=np.float64)
         self._joint_entries = [e for e, (r, _) in enumerate(ents) if A.propensities[r].kind == "joint"]

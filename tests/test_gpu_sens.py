@@ -246,3 +246,62 @@ def test_sens_solve_vs_oracle(pkg, method):
             scale = max(np.abs(s_ref).max(), 1e-2)
             assert np.abs(_on_states(sol.S[k][ip].states, sol.S[k][ip].values, st) - s_ref).max() <= tol * scale, (k, ip)
             assert np.abs(sol.dsinks[k][ip] - ref["dsinks"][k][ip]).max() <= tol * scale, (k, ip)
+
+
+def test_sens_incremental_rebuild_after_adapt(pkg, ctx):
+    """The sensitivity matrix after a prune + expand built from its predecessor -- propensities and parameter derivatives
+    evaluated on the appended states only, the survivors' rows carried over on the device -- is bit-for-bit the matrix
+    built from scratch (Hog1p, 14 entries, two adapt rounds), falls back when the pattern's model changes, and the
+    adaptive sensitivity solve uses it (forwardsenscmesparse.jl:140 rebuilds from scratch)."""
+    rng = np.random.default_rng(12)
+    th = list(pkg.workloads.HOG1P_THETA)
+    th[2] = 3.2e4
+    model = pkg.workloads.hog1p_sens_model(th)
+    cm = model.cmemodel
+    sp = pkg.StateSpaceSparse(cm.stoich_matrix, [1, 0, 0, 0, 0, 0], ctx=ctx)
+    sp.expand_(40)
+    assert sp.get_state_count() >= 2048                      # (below INCREMENTAL_MIN_STATES matrices are rebuilt from scratch)
+    SA = pkg.ForwardSensFspMatrixSparse(model, sp)
+    assert not SA.incremental
+    for rnd in range(2):
+        n = sp.get_state_count()
+        drop = np.sort(rng.choice(np.arange(2, n + 1), size=n // 6, replace=False))
+        sp.deleteat_(drop)
+        sp.expand_(3 + rnd)
+        SB = pkg.ForwardSensFspMatrixSparse(model, sp, previous=SA)
+        assert SB.incremental and SB.fspmatrix.incremental and 0 < SB.fspmatrix.new_state_count < sp.get_state_count()
+        SF = pkg.ForwardSensFspMatrixSparse(model, sp)       # from scratch (re-marks the space)
+        assert not SF.incremental and SB.stats() == SF.stats()
+        N = SB.fspmatrix.rowcount
+        v = rng.random(15 * N)
+        a, b = np.empty_like(v), np.empty_like(v)
+        for t in (0.0, 45.0, 900.0):
+            pkg.matvec_(a, t, SB, v)
+            pkg.matvec_(b, t, SF, v)
+            assert np.array_equal(a, b), (rnd, t)
+        SA.close()
+        SB.close()
+        SA = SF
+    # another model object (other gradient closures) -> full build, never a stale carry-over
+    other = pkg.workloads.hog1p_sens_model(th)
+    sp.expand_(1)
+    assert not pkg.ForwardSensFspMatrixSparse(other, sp, previous=SA).incremental
+    # the adaptive sensitivity solve goes through it: identical results with and without the carry-over
+    import numcme_jl_b200.fspmatrix as FM
+    props, grads, pattern, _ = sens_telegraph()
+    tm = _sensmodel(pkg, TELEGRAPH_S, props, grads, pattern, SENS_THETA)
+    ic = pkg.forwardsens_initial_condition([[1, 0, 0]], [1.0], [[0.0] for _ in range(5)])
+    alg = pkg.AdaptiveForwardSensFspSparse(ode_method=pkg.NativeRK45(), space_adapter=pkg.ForwardSensRStepAdapter(10, 10, True))
+    saved = FM.INCREMENTAL_MIN_STATES
+    try:
+        FM.INCREMENTAL_MIN_STATES = 0
+        s1 = pkg.solve(tm, ic, (0.0, 40.0), alg, saveat=[40.0], fsptol=1e-8, odeatol=1e-12, odertol=1e-8)
+        assert s1.stats["adapts"] >= 1 and s1.stats["incremental_builds"] >= 1
+        FM.INCREMENTAL_MIN_STATES = 1 << 60
+        s0 = pkg.solve(tm, ic, (0.0, 40.0), alg, saveat=[40.0], fsptol=1e-8, odeatol=1e-12, odertol=1e-8)
+        assert s0.stats["incremental_builds"] == 0 and s0.stats["adapts"] == s1.stats["adapts"]
+        assert np.array_equal(s0.p[0].values, s1.p[0].values)
+        for x, y in zip(s0.S[0], s1.S[0]):
+            assert np.array_equal(x.values, y.values)
+    finally:
+        FM.INCREMENTAL_MIN_STATES = saved
