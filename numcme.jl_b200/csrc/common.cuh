@@ -10,8 +10,19 @@
 
 #include "ncme.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: a no-op (one predictable branch) unless a profiler injects itself
+
 #include <chrono>
 namespace ncme {
+// NVTX range around an ABI entry point (named ranges for nsys / ncu --nvtx): NCME_RANGE("ncme_matvec");
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NCME_RANGE(name) ncme::NvtxRange _ncme_nvtx_range(name)
+
 inline double wall_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }

@@ -1591,6 +1591,7 @@ int ncme_matrix_create(ncme_space* space, const int32_t* kind, const double* pro
 
 int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals,
                                ncme_matrix** out) {
+    NCME_RANGE("ncme_matrix_create_sharded");
     NCME_REQUIRE(space && kind && out, "null argument");
     NCME_REQUIRE(propvals || space->n == 0, "propvals is null");
     ncme_matrix* A = new ncme_matrix();
@@ -1607,6 +1608,7 @@ int ncme_matrix_create_sharded(ncme_space* space, ncme_comm* comm, const int32_t
 // state factors of the states [ext_lo, ext_hi) only and builds with ncme_matrix_create_window (sharded build: host
 // evaluation and upload shrink with the number of ranks).  out = {row_lo, row_hi, ext_lo, ext_hi}.
 int ncme_matrix_shard_window(ncme_space* sp, ncme_comm* comm, int64_t out[4]) {
+    NCME_RANGE("ncme_matrix_shard_window");
     NCME_REQUIRE(sp && out, "null argument");
     ncme_ctx* ctx = sp->ctx;
     cudaStream_t st = ctx->stream;
@@ -1641,6 +1643,7 @@ int ncme_matrix_shard_window(ncme_space* sp, ncme_comm* comm, int64_t out[4]) {
 
 int ncme_matrix_create_window(ncme_space* space, ncme_comm* comm, const int32_t* kind, const double* propvals_window,
                               int64_t win_lo, int64_t win_hi, ncme_matrix** out) {
+    NCME_RANGE("ncme_matrix_create_window");
     NCME_REQUIRE(space && kind && out, "null argument");
     NCME_REQUIRE(win_lo >= 0 && win_lo <= win_hi && win_hi <= space->n, "bad window");
     NCME_REQUIRE(propvals_window || win_hi == win_lo, "propvals is null");
@@ -1668,6 +1671,7 @@ int ncme_space_new_count(ncme_space* space, int64_t* n_kept, int64_t* n_new) {
 
 int ncme_matrix_create_incremental(ncme_space* space, ncme_comm* comm, ncme_matrix* prev, const int32_t* kind,
                                    const double* propvals_new, ncme_matrix** out) {
+    NCME_RANGE("ncme_matrix_create_incremental");
     NCME_REQUIRE(space && prev && kind && out, "null argument");
     NCME_REQUIRE(prev->space_mark == space->mark_id && space->mark_n >= 0 && prev->G.p,
                  "incremental build: `prev` is not the matrix this space was last assembled into");
@@ -1764,6 +1768,7 @@ int ncme_matrix_set_tuning(ncme_matrix* A, int rows_per_thread) {
 }
 
 int ncme_matrix_set_joint_values(ncme_matrix* A, int reaction, const double* vals) {
+    NCME_RANGE("ncme_matrix_set_joint_values");
     NCME_REQUIRE(A && vals, "null argument");
     NCME_REQUIRE(reaction >= 1 && reaction <= A->nr && A->kind[reaction - 1] == NCME_JOINT_TV,
                  "reaction %d is not a joint time-varying reaction", reaction);
@@ -1792,6 +1797,7 @@ int ncme_matrix_set_joint_values(ncme_matrix* A, int reaction, const double* val
 }
 
 int ncme_matvec(ncme_matrix* A, const double* coef, const double* x_dev, double* y_dev, double beta) {
+    NCME_RANGE("ncme_matvec");
     NCME_REQUIRE(A && x_dev && y_dev, "null argument");
     NCME_REQUIRE(x_dev != y_dev, "matvec!: input and output must not alias");
     bool need_coef = false;
@@ -1810,6 +1816,7 @@ int ncme_matvec_local(ncme_matrix* A, const double* coef, const double* x_dev, d
 }
 
 int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, double* y_host, double beta) {
+    NCME_RANGE("ncme_matvec_host");
     NCME_REQUIRE(A && x_host && y_host, "null argument");
     NCME_REQUIRE(!A->comm, "the host-buffer matvec is single-GPU only");
     ncme_ctx* ctx = A->ctx;

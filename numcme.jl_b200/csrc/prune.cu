@@ -139,6 +139,7 @@ using namespace ncme;
 
 extern "C" int ncme_space_prune_by_mass(ncme_space* sp, const double* p_dev, double threshold, int strict,
                                         int64_t* dropcount) {
+    NCME_RANGE("ncme_space_prune_by_mass");
     NCME_REQUIRE(sp && p_dev && dropcount, "null argument");
     *dropcount = 0;
     const int64_t n = sp->n;

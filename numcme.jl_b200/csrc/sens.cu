@@ -484,12 +484,14 @@ static int sens_build(ncme_matrix* A, const ncme_sensmatrix* prev, int npar, int
 
 int ncme_sensmatrix_create(ncme_matrix* A, int npar, int nentries, const int32_t* ent_reaction, const int32_t* ent_param,
                            const double* dpropvals, ncme_sensmatrix** out) {
+    NCME_RANGE("ncme_sensmatrix_create");
     return sens_build(A, nullptr, npar, nentries, ent_reaction, ent_param, dpropvals, out);
 }
 
 int ncme_sensmatrix_create_incremental(ncme_matrix* A, ncme_sensmatrix* prev, int npar, int nentries,
                                        const int32_t* ent_reaction, const int32_t* ent_param, const double* dpropvals_new,
                                        ncme_sensmatrix** out) {
+    NCME_RANGE("ncme_sensmatrix_create_incremental");
     NCME_REQUIRE(A && prev && out, "null argument");
     NCME_REQUIRE(A->carry_nkept >= 0 && A->carry_prev == prev->A && prev->dG.p,
                  "incremental sensitivity build: `mat` was not built incrementally from the matrix of `prev`");
@@ -559,6 +561,7 @@ int ncme_sensmatrix_set_joint_values(ncme_sensmatrix* SA, int entry, const doubl
 }
 
 int ncme_sens_matvec(ncme_sensmatrix* SA, const double* coef, const double* dcoef, const double* X, double* Y) {
+    NCME_RANGE("ncme_sens_matvec");
     NCME_REQUIRE(SA && X && Y && X != Y, "bad arguments");
     ncme_matrix* A = SA->A;
     ncme_ctx* ctx = A->ctx;

@@ -508,6 +508,7 @@ using namespace ncme;
 
 extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user, double t0,
                                   double t1, double* u_dev, const ncme_solve_opts* opts, ncme_solve_stats* stats) {
+    NCME_RANGE("ncme_solve_segment");
     NCME_REQUIRE(A && u_dev && opts && stats, "null argument");
     NCME_REQUIRE(t1 >= t0, "solve_segment: t1 < t0");
     NCME_REQUIRE(opts->nsave == 0 || opts->save_t, "save_t is null");
@@ -596,6 +597,7 @@ extern "C" int ncme_solve_segment(ncme_matrix* A, ncme_coef_fn coef_fn, ncme_sav
 extern "C" int ncme_sens_solve_segment(ncme_sensmatrix* SA, ncme_coef_fn coef_fn, ncme_save_fn save_fn, void* user,
                                        double t0, double t1, double* U_dev, const ncme_solve_opts* opts,
                                        ncme_solve_stats* stats) {
+    NCME_RANGE("ncme_sens_solve_segment");
     NCME_REQUIRE(SA && U_dev && opts && stats && coef_fn, "null argument");
     NCME_REQUIRE(t1 >= t0, "solve_segment: t1 < t0");
     NCME_REQUIRE(opts->nsave == 0 || opts->save_t, "save_t is null");

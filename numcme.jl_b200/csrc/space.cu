@@ -749,6 +749,7 @@ extern "C" {
 
 int ncme_space_create(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int64_t n0, const int64_t* states0,
                       ncme_space** out) {
+    NCME_RANGE("ncme_space_create");
     NCME_REQUIRE(n0 >= 0 && (n0 == 0 || states0), "bad initial state list");
     ncme_space* sp = nullptr;
     NCME_TRY(space_alloc(ctx, ns, nr, stoich, &sp));
@@ -795,6 +796,7 @@ int ncme_space_create(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int6
 
 int ncme_space_from_host(ncme_ctx* ctx, int ns, int nr, const int64_t* stoich, int64_t n, const int64_t* states,
                          const uint32_t* state_connectivity, const uint32_t* sink_connectivity, ncme_space** out) {
+    NCME_RANGE("ncme_space_from_host");
     NCME_REQUIRE(n >= 0 && (n == 0 || (states && state_connectivity && sink_connectivity)), "bad arguments");
     ncme_space* sp = nullptr;
     NCME_TRY(space_alloc(ctx, ns, nr, stoich, &sp));
@@ -945,6 +947,7 @@ static int expand_small(ncme_space* sp, int levels, const ReactList& reacts, sma
 }
 
 int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32_t* onlyreactions) {
+    NCME_RANGE("ncme_space_expand");
     NCME_REQUIRE(sp, "null space");
     if (expansionlevel <= 0 || sp->n == 0) return NCME_OK;
     ncme_ctx* ctx = sp->ctx;
@@ -1033,6 +1036,7 @@ int ncme_space_expand(ncme_space* sp, int expansionlevel, int nonly, const int32
 }
 
 int ncme_space_delete(ncme_space* sp, int64_t nids, const int64_t* ids) {
+    NCME_RANGE("ncme_space_delete");
     NCME_REQUIRE(sp && (nids == 0 || ids), "bad arguments");
     if (nids <= 0 || sp->n == 0) return NCME_OK;
     ncme_ctx* ctx = sp->ctx;
@@ -1145,6 +1149,7 @@ int ncme_space_lookup(ncme_space* sp, int64_t m, const int64_t* states, uint32_t
 
 int ncme_space_marginal(ncme_space* sp, const double* p_dev, int ndims, const int32_t* dims, int64_t cap, int64_t* nred,
                         int64_t* states_out, double* vals_out) {
+    NCME_RANGE("ncme_space_marginal");
     NCME_REQUIRE(sp && p_dev && nred && ndims >= 1 && dims, "null argument");
     uint32_t drop = 0;
     for (int k = 0; k < ndims; ++k) {
