@@ -603,6 +603,34 @@ function ForwardSensFspMatrixSparseB200(model::CmeModelWithSensitivity, space::S
     SA = ForwardSensFspMatrixSparseB200{NS,NR}(A, ref[], grads, ents, zeros(max(length(ents), 1)))
     finalizer(x -> ccall((:ncme_sensmatrix_destroy, libncme), Cint, (Ptr{Cvoid},), x.h), SA)
 end
+# Rebuild after an adapt! (forwardsenscmesparse.jl:140 rebuilds from scratch inside the loop): the plain matrix is rebuilt
+# incrementally from `previous.fspmatrix`, the parameter derivatives are evaluated on the appended states only and the
+# survivors' rows are carried over on the device (ncme_sensmatrix_create_incremental).  Falls back to the full
+# constructor whenever the plain matrix did (too few kept states, a space assembled elsewhere in between).
+function ForwardSensFspMatrixSparseB200(model::CmeModelWithSensitivity, space::StateSpaceSparseB200{NS,NR},
+                                        previous::ForwardSensFspMatrixSparseB200{NS,NR}) where {NS,NR}
+    full() = ForwardSensFspMatrixSparseB200(model, space)
+    grads = get_propensity_gradients(model)
+    grads === previous.propensity_gradients || return full()
+    nk = Ref{Int64}(0); nn = Ref{Int64}(0)
+    check(ccall((:ncme_space_new_count, libncme), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), space.h, nk, nn))
+    nkept, nnew = Int(nk[]), Int(nn[])
+    nkept == 0 && return full()
+    A = FspMatrixSparseB200(space, previous.fspmatrix; detect_separable = false)
+    θ = get_parameters(model); P = get_parameter_count(model); ents = previous.entries
+    dvals = zeros(Float64, max(nnew, 1), max(length(ents), 1))            # entry-major nentries x n_new for the ABI
+    for (e, (r, ip)) in enumerate(ents), i in 1:nnew
+        A.kinds[r] == 0 && (dvals[i, e] = grads[r].pardiffs[ip](A.states[nkept+i], θ))
+        A.kinds[r] == 1 && (dvals[i, e] = grads[r].statefactor_pardiffs[ip](A.states[nkept+i], θ))
+    end
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    code = ccall((:ncme_sensmatrix_create_incremental, libncme), Cint,
+                 (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                 A.h, previous.h, P, length(ents), Int32[r for (r, _) in ents], Int32[ip for (_, ip) in ents], dvals, ref)
+    code == 0 || return full()               # `A` was built from scratch (not from previous.fspmatrix): start over
+    SA = ForwardSensFspMatrixSparseB200{NS,NR}(A, ref[], grads, ents, zeros(max(length(ents), 1)))
+    finalizer(x -> ccall((:ncme_sensmatrix_destroy, libncme), Cint, (Ptr{Cvoid},), x.h), SA)
+end
 get_propensity_gradients(SA::ForwardSensFspMatrixSparseB200) = SA.propensity_gradients
 
 # time factors of A and of the derivative entries at t (sensfspmatrixsparse.jl:124-139)
@@ -919,8 +947,9 @@ function solve(model::CmeModelWithSensitivity, ic::ForwardSensFspInitialConditio
         push!(out.dsinks, AbstractVector{Float64}[uu[ip*N+n+1:(ip+1)*N] for ip in 1:P])
     end
     tnow = tstart
+    SA = nothing
     while tnow < tend
-        SA = ForwardSensFspMatrixSparseB200(model, space)
+        SA = SA === nothing ? ForwardSensFspMatrixSparseB200(model, space) : ForwardSensFspMatrixSparseB200(model, space, SA)
         n = get_state_count(space); N = n + R
         U = fill!(DeviceVector(ctx, N * (P + 1)), 0.0)
         for (b, v) in enumerate(vecs); copyto!(view(U, (b-1)*N+1:(b-1)*N+n), v); end
