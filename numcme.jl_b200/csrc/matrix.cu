@@ -1103,13 +1103,20 @@ __global__ void k_compress_cols(const uint32_t* __restrict__ col, int64_t ld, in
 }
 
 // per row chunk: the highest padded x position its gathers touch (host-buffer pipeline)
-__global__ void k_chunk_reach(const uint32_t* __restrict__ col, int64_t ld, int64_t n, int nslots, int64_t chunk_rows,
-                              unsigned int* __restrict__ reach /*[nchunks]*/) {
+// row chunks of the host-buffer pipeline: chunk c = rows [row[c], row[c+1])
+struct PipeChunks {
+    int nc;
+    int64_t row[17];
+};
+__global__ void k_chunk_reach(const uint32_t* __restrict__ col, int64_t ld, int64_t n, int nslots, PipeChunks pc,
+                              unsigned int* __restrict__ reach /*[16]*/) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned int m = 0;
     for (int s = 0; s < nslots; ++s) m = max(m, col[(int64_t)s * ld + i]);
-    atomicMax(&reach[i / chunk_rows], m);
+    int c = 0;
+    while (c < pc.nc - 1 && i >= pc.row[c + 1]) ++c;
+    atomicMax(&reach[c], m);
 }
 
 // counts[r] = rows with a predecessor through reaction r; counts[NCME_MAX_REACTIONS + r] = rows whose sink flag r is set
@@ -1404,24 +1411,49 @@ static int matrix_build(ncme_space* sp, const int32_t* kind, const double* propv
             const int v = e ? atoi(e) : 16;
             return v < 2 ? 2 : (v > 16 ? 16 : v);
         }();
-        const int64_t chunk_rows = round_up<int64_t>((n + NC - 1) / NC, 64);
+        // Chunk sizes ramp up and down (1 : 2 : 4 : 8 ... 8 : 4 : 2 : 1): the first download can start after ~3 % of the
+        // upload instead of 2/NC of it, and what is left after the last upload is ~3 % of the download.  Both directions
+        // of the link then overlap for almost the whole call (measured floor of this link for 80 MB each way at once:
+        // 1.80 ms, tools/pcie_ceiling.py).  NCME_HOST_PIPE_UNIFORM=1: equal chunks (round 1).
+        static const bool uniform = getenv("NCME_HOST_PIPE_UNIFORM") != nullptr;
+        PipeChunks pc;
+        {
+            static const int ramp[4] = {1, 2, 4, 8};
+            double w[16], wsum = 0.0;
+            for (int c = 0; c < NC; ++c) {
+                const int d = std::min(c, NC - 1 - c);
+                w[c] = uniform ? 1.0 : (double)ramp[std::min(d, 3)];
+                wsum += w[c];
+            }
+            int nc = 0;
+            int64_t r0 = 0;
+            double acc = 0.0;
+            pc.row[0] = 0;
+            for (int c = 0; c < NC && r0 < n; ++c) {
+                acc += w[c];
+                int64_t r1 = (c == NC - 1) ? n : std::min<int64_t>(n, round_up<int64_t>((int64_t)((double)n * acc / wsum), 512));
+                if (r1 <= r0) continue;
+                pc.row[++nc] = r1;
+                r0 = r1;
+            }
+            pc.row[nc] = n;
+            pc.nc = nc;
+        }
         unsigned int* d_reach = nullptr;
         NCME_CUDA(cudaMalloc(&d_reach, 16 * sizeof(unsigned int)));
         NCME_CUDA(cudaMemsetAsync(d_reach, 0, 16 * sizeof(unsigned int), st));
-        k_chunk_reach<<<nblk(n), 256, 0, st>>>(A->col.p, A->ld, n, nslots, chunk_rows, d_reach);
+        k_chunk_reach<<<nblk(n), 256, 0, st>>>(A->col.p, A->ld, n, nslots, pc, d_reach);
         ctx->launches++;
         unsigned int h_reach[16];
         NCME_CUDA(cudaMemcpyAsync(h_reach, d_reach, sizeof(h_reach), cudaMemcpyDeviceToHost, st));
         NCME_CUDA(cudaStreamSynchronize(st));
         cudaFree(d_reach);
-        int nc = 0;
-        for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
-            A->pipe_row[nc] = r0;
-            A->pipe_need_hi[nc] = (int64_t)h_reach[nc] + 1;
-            ++nc;
+        for (int c = 0; c < pc.nc; ++c) {
+            A->pipe_row[c] = pc.row[c];
+            A->pipe_need_hi[c] = (int64_t)h_reach[c] + 1;
         }
-        A->pipe_row[nc] = n;
-        A->pipe_chunks = nc;
+        A->pipe_row[pc.nc] = n;
+        A->pipe_chunks = pc.nc;
     }
     // byte-compressed column indices (experimental kernel variants) are built on demand: matrix_ensure_compressed
     A->nchunks = A->ld / 64;

@@ -259,7 +259,7 @@ def test_sens_incremental_rebuild_after_adapt(pkg, ctx):
     model = pkg.workloads.hog1p_sens_model(th)
     cm = model.cmemodel
     sp = pkg.StateSpaceSparse(cm.stoich_matrix, [1, 0, 0, 0, 0, 0], ctx=ctx)
-    sp.expand_(40)
+    sp.expand_(60)
     assert sp.get_state_count() >= 2048                      # (below INCREMENTAL_MIN_STATES matrices are rebuilt from scratch)
     SA = pkg.ForwardSensFspMatrixSparse(model, sp)
     assert not SA.incremental

@@ -1,8 +1,14 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L
-( time timeout 600 python -m pytest tests -m gpu -x -q --durations=15 ) > gpurun_out/r2b_pytest_gpu.log 2>&1
-tail -30 gpurun_out/r2b_pytest_gpu.log
-timeout 120 python tools/pcie_ceiling.py > gpurun_out/r2b_pcie_ceiling.json 2> gpurun_out/r2b_pcie_ceiling.err; cat gpurun_out/r2b_pcie_ceiling.json
-( time timeout 420 python bench.py --steps 20 --warmup 5 ) > gpurun_out/r2b_bench_n1.json 2> gpurun_out/r2b_bench_n1.err
-tail -c 1500 gpurun_out/r2b_bench_n1.json; tail -5 gpurun_out/r2b_bench_n1.err
+( time timeout 600 python -m pytest tests -m gpu -q --durations=8 ) > gpurun_out/r2c_pytest_gpu.log 2>&1
+tail -25 gpurun_out/r2c_pytest_gpu.log
+for mode in ramp uniform ramp8 ; do
+  case $mode in
+    ramp) export -n NCME_HOST_PIPE_UNIFORM; unset NCME_HOST_PIPE_UNIFORM; unset NCME_HOST_PIPE_CHUNKS;;
+    uniform) export NCME_HOST_PIPE_UNIFORM=1; unset NCME_HOST_PIPE_CHUNKS;;
+    ramp8) unset NCME_HOST_PIPE_UNIFORM; export NCME_HOST_PIPE_CHUNKS=8;;
+  esac
+  timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu --no-solve > gpurun_out/r2c_e2e_$mode.json 2>gpurun_out/r2c_e2e_$mode.err
+  python -c "
+import json; d=json.loads(open('gpurun_out/r2c_e2e_$mode.json').read().strip().splitlines()[-1]); print('$mode e2e ms', d['e2e']['ms_per_step'], 'GB/s', d['e2e']['value'], 'matvec ms', d['ms_per_step'], 'checksum', d['e2e'].get('checksum_sum_y_states'))"
+done
