@@ -1885,6 +1885,22 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
     const int nc = A->pipe_chunks;
     double* xd = ctx->stage_dev_x;
     double* yd = ctx->stage_dev_y;
+    // Page-locked (mapped) output buffer: the row kernels store y straight into host memory over the link -- no
+    // device->host copy stage, so the download of chunk c is emitted by kernel c itself while chunk c+2 uploads, and
+    // what is left after the last upload is the last two (small) kernels.  Pageable buffers keep the copy stage.
+    // NCME_HOST_ZEROCOPY=0 forces the copy stage (A/B measurements).
+    static const bool zc_enabled = [] {
+        const char* e = getenv("NCME_HOST_ZEROCOPY");
+        return !(e && e[0] == '0');
+    }();
+    double* y_map = nullptr;
+    if (zc_enabled) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, y_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            y_map = static_cast<double*>(at.devicePointer);
+        else
+            cudaGetLastError();   // pageable memory: not an error
+    }
     NCME_CUDA(cudaEventRecord(ctx->ev_start, st));                       // order after earlier work on the context
     NCME_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_start, 0));
     NCME_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_start, 0));
@@ -1898,7 +1914,7 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
     matvec_fill_args(A, coef, &a);
     a.xd = xd;
     a.x = xd;
-    a.y = yd;
+    a.y = y_map ? y_map : yd;
     a.beta = 0.0;
     for (int c = 0; c < nc; ++c) {
         int need = c;
@@ -1909,6 +1925,7 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
         ac.row_end = A->pipe_row[c + 1];
         ac.do_sinks = (c == nc - 1) ? 1 : 0;                             // sink rows read x everywhere: last
         NCME_TRY(matvec_launch(A, ac));
+        if (y_map) continue;                                             // y already went to the host buffer
         NCME_CUDA(cudaEventRecord(ctx->ev_comp[c], st));
         NCME_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_comp[c], 0));
         const int64_t r0 = A->pipe_row[c];

@@ -64,5 +64,11 @@ def test_headline_size_matvec_vs_oracle(pkg, ctx, name):
         A.set_tuning(0)
         pkg.matvec_(host, t, A, v)                      # ncme_matvec_host (pipelined H2D / kernel / D2H)
         assert np.array_equal(host, first)
+        # page-locked buffers: the row kernels store y straight into the host buffer (no D2H copy stage)
+        import torch
+        xp, yp = torch.from_numpy(v.copy()).pin_memory(), torch.full((N,), float("nan"), dtype=torch.float64).pin_memory()
+        pkg.matvec_(yp.numpy(), t, A, xp.numpy())
+        assert np.array_equal(yp.numpy(), first)
+        del xp, yp
         assert abs(first.sum()) <= 1e-12 * np.abs(first).sum()           # column sums vanish
     A.close()
