@@ -64,7 +64,7 @@ def test_headline_size_matvec_vs_oracle(pkg, ctx, name):
         A.set_tuning(0)
         pkg.matvec_(host, t, A, v)                      # ncme_matvec_host (pipelined H2D / kernel / D2H)
         assert np.array_equal(host, first)
-        # page-locked buffers: the row kernels store y straight into the host buffer (no D2H copy stage)
+        # page-locked buffers (what bench.py's e2e leg and a Julia binding with pinned arrays pass)
         import torch
         xp, yp = torch.from_numpy(v.copy()).pin_memory(), torch.full((N,), float("nan"), dtype=torch.float64).pin_memory()
         pkg.matvec_(yp.numpy(), t, A, xp.numpy())
