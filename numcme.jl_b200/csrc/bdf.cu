@@ -34,6 +34,32 @@ struct PtrListRW {
     double* p[MAX_ORDER + 3];
 };
 
+// Ordered, PARALLEL combine of the per-CTA partials by the CTA that finished last (call with the whole CTA, after the
+// fence that follows the completion counter).  Thread t sums the CTAs b = t / SP, t / SP + BT / SP, ... for value slot
+// t % SP; the slot threads then add the BT / SP group sums in group order.  Fixed order => the same bits on every
+// rank and in every run.  Round 2: this stage used one thread per slot walking all gridDim.x partials (1 184 dependent
+// L2 round trips): k_bdf_errnorm ran at 0.30 and k_gm_apply_dots at 0.65-0.70 of the HBM rate because of that tail
+// (profiles/README.md, per-kernel roofline of the BDF).
+template <int NS>
+__device__ __forceinline__ double final_combine(const double* partials, int nslot) {
+    constexpr int SP = NS <= 1 ? 1 : NS <= 2 ? 2 : NS <= 4 ? 4 : NS <= 8 ? 8 : NS <= 16 ? 16 : 32;
+    constexpr int NG = BT / SP;
+    static_assert(NS <= 32, "final_combine handles up to 32 value slots");
+    __shared__ double gsum[NG][SP];
+    const int sl = threadIdx.x % SP, g = threadIdx.x / SP;
+    double t = 0.0;
+    if (sl < nslot)
+        for (unsigned b = g; b < gridDim.x; b += NG) t += __ldcg(partials + (size_t)b * NS + sl);
+    gsum[g][sl] = t;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x < nslot) {
+#pragma unroll 8
+        for (int q = 0; q < NG; ++q) tot += gsum[q][threadIdx.x];
+    }
+    return tot;   // valid in threads [0, nslot)
+}
+
 // ---- deterministic multi-value block reduction: value slots [0, nslot) ------------------------------------------
 template <int NS>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NS], int nslot, double* partials, unsigned int* counter,
@@ -65,12 +91,8 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NS], int nslot, d
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (threadIdx.x < nslot) {
-        const volatile double* p = partials;
-        double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += p[(size_t)b * NS + threadIdx.x];
-        result[threadIdx.x] = t;
-    }
+    const double t = final_combine<NS>(partials, nslot);
+    if (threadIdx.x < nslot) result[threadIdx.x] = t;
     if (threadIdx.x == 0) *counter = 0u;
 }
 
@@ -112,11 +134,7 @@ __device__ __forceinline__ void block_reduce_allreduce(double (&v)[NS], double* 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    double t = 0.0;
-    if (threadIdx.x < NS) {
-        const volatile double* p = partials;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += p[(size_t)b * NS + threadIdx.x];
-    }
+    double t = final_combine<NS>(partials, NS);
     if (threadIdx.x == 0) *counter = 0u;
     if (ar.nranks > 1) {
         const int buf = (int)(ar.epoch % NCME_RED_BUFS);
