@@ -199,7 +199,31 @@ struct SetupArgs {
 };
 __global__ void __launch_bounds__(BT) k_bdf_setup(const __grid_constant__ SetupArgs a) {
     double v[1] = {0.0};
-    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * BT) {
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+    // four grid strides per trip, all loads first (the stores through the struct's plain pointers would otherwise keep
+    // the compiler from hoisting the next element's loads): enough bytes in flight per SM for the HBM latency
+    for (; i + 3 * stride < a.n; i += 4 * stride) {
+        double yp[4], jd[4], ay[4], ps[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            yp[u] = a.ypred[i + u * stride];
+            jd[u] = a.jdiag[i + u * stride];
+            ay[u] = a.Ay[i + u * stride];
+            ps[u] = a.psi[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double sc = a.atol + a.rtol * fabs(yp[u]);
+            const double p = 1.0 / ((1.0 - a.c * jd[u]) * sc);
+            const double w = (a.c * ay[u] - ps[u]) * p;
+            a.scale[i + u * stride] = sc;
+            a.ps[i + u * stride] = p;
+            a.w0[i + u * stride] = w;
+            v[0] = fma(w, w, v[0]);
+        }
+    }
+    for (; i < a.n; i += stride) {
         const double sc = a.atol + a.rtol * fabs(a.ypred[i]);
         const double p = 1.0 / ((1.0 - a.c * a.jdiag[i]) * sc);
         const double w = (a.c * a.Ay[i] - a.psi[i]) * p;
@@ -303,19 +327,39 @@ __host__ __device__ __forceinline__ double gm_hk1(const double* hh, int k) {
     if (!(hk1sq > 1e-10 * ww)) hk1sq = hk1sq > 0.0 ? hk1sq : 0.0;
     return sqrt(hk1sq > 0.0 ? hk1sq : 0.0);
 }
+// KB = basis vectors subtracted, k + 1 rounded up to a multiple of 4 (surplus pointers alias V_0 with a zero
+// coefficient: fma(-0, v, x) == x): fully unrolled, every load of an element independent and issued before first use
+template <int KB>
 __global__ void __launch_bounds__(BT) k_gm_ortho(const __grid_constant__ OrthoArgs a) {
     __shared__ double sh[RED_SLOTS + 1];
     if (threadIdx.x < RED_SLOTS) sh[threadIdx.x] = a.hcol[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) sh[RED_SLOTS] = 1.0 / gm_hk1(sh, a.k);
     __syncthreads();
+    if (threadIdx.x > a.k && threadIdx.x < RED_SLOTS) sh[threadIdx.x] = 0.0;   // (after gm_hk1 read <w,w> in the last slot)
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
     if (i >= a.n) return;
+    double vj[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) vj[j] = a.V.p[j][i];
     double x = a.w[i];
-    for (int j = 0; j <= a.k; ++j) x = fma(-sh[j], a.V.p[j][i], x);
+    const double sc = a.scale[i];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) x = fma(-sh[j], vj[j], x);
     x *= sh[RED_SLOTS];
     a.vout[i] = x;
-    a.z[i] = x * a.scale[i];
+    a.z[i] = x * sc;
+}
+static void launch_ortho(const OrthoArgs& oa, unsigned grid, cudaStream_t s) {
+    switch (((oa.k + 1 + 3) / 4) * 4) {
+        case 4: k_gm_ortho<4><<<grid, BT, 0, s>>>(oa); break;
+        case 8: k_gm_ortho<8><<<grid, BT, 0, s>>>(oa); break;
+        case 12: k_gm_ortho<12><<<grid, BT, 0, s>>>(oa); break;
+        case 16: k_gm_ortho<16><<<grid, BT, 0, s>>>(oa); break;
+        case 20: k_gm_ortho<20><<<grid, BT, 0, s>>>(oa); break;
+        default: k_gm_ortho<24><<<grid, BT, 0, s>>>(oa); break;
+    }
 }
 
 // d = scale * sum_j y_j V_j ;  ynew = ypred + d     (state rows)
@@ -367,7 +411,23 @@ struct MassArgs {
 };
 __global__ void __launch_bounds__(BT) k_bdf_massdefect(const __grid_constant__ MassArgs a) {
     double v[2] = {0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * BT) {
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+    for (; i + 3 * stride < a.n; i += 4 * stride) {   // loads of four grid strides in flight, same summation order
+        double dd[4], pp[4], yy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dd[u] = a.d[i + u * stride];
+            pp[u] = a.psi[i + u * stride];
+            yy[u] = a.ynew[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[0] += dd[u] + pp[u];
+            v[1] += fabs(yy[u]);
+        }
+    }
+    for (; i < a.n; i += stride) {
         v[0] += a.d[i] + a.psi[i];
         v[1] += fabs(a.ynew[i]);
     }
@@ -407,7 +467,22 @@ struct ErrArgs {
 };
 __global__ void __launch_bounds__(BT) k_bdf_errnorm(const __grid_constant__ ErrArgs a) {
     double v[1] = {0.0};
-    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * BT) {
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+    for (; i + 3 * stride < a.n; i += 4 * stride) {   // loads of four grid strides in flight, same summation order
+        double dd[4], yy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dd[u] = a.d[i + u * stride];
+            yy[u] = a.ynew[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double q = dd[u] / (a.atol + a.rtol * fabs(yy[u]));
+            v[0] = fma(q, q, v[0]);
+        }
+    }
+    for (; i < a.n; i += stride) {
         const double q = a.d[i] / (a.atol + a.rtol * fabs(a.ynew[i]));
         v[0] = fma(q, q, v[0]);
     }
@@ -429,7 +504,25 @@ struct OrdArgs {
 };
 __global__ void __launch_bounds__(BT) k_bdf_ordnorms(const __grid_constant__ OrdArgs a) {
     double v[2] = {0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * BT) {
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x;
+    for (; i + 3 * stride < a.n; i += 4 * stride) {   // loads of four grid strides in flight, same summation order
+        double yy[4], dm[4], dp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            yy[u] = a.y[i + u * stride];
+            dm[u] = a.Dm ? a.Dm[i + u * stride] : 0.0;
+            dp[u] = a.Dp ? a.Dp[i + u * stride] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double inv = 1.0 / (a.atol + a.rtol * fabs(yy[u]));
+            const double qm = dm[u] * inv, qp = dp[u] * inv;
+            v[0] = fma(qm, qm, v[0]);
+            v[1] = fma(qp, qp, v[1]);
+        }
+    }
+    for (; i < a.n; i += stride) {
         const double inv = 1.0 / (a.atol + a.rtol * fabs(a.y[i]));
         const double qm = a.Dm ? a.Dm[i] * inv : 0.0, qp = a.Dp ? a.Dp[i] * inv : 0.0;
         v[0] = fma(qm, qm, v[0]);
@@ -775,11 +868,12 @@ int solve_bdf(const OdeSystem& sys, ncme_save_fn save_fn, void* user, double t0,
                             oa.k = kk - 1;
                             oa.w = w;
                             for (int j = 0; j <= kk - 1; ++j) oa.V.p[j] = V[j];
+                            for (int j = kk; j < GM_M + 2; ++j) oa.V.p[j] = V[0];
                             oa.hcol = hcol_dev(kk - 1);
                             oa.scale = scale;
                             oa.vout = V[kk];
                             oa.z = z;
-                            k_gm_ortho<<<grid_for(n), BT, 0, s>>>(oa);
+                            launch_ortho(oa, grid_for(n), s);
                             ctx->launches++;
                         }
                         NCME_TRY(rhs(t_new, z, Ay));
