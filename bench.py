@@ -491,6 +491,36 @@ def main():
     barrier()
     ms_e2e = (time.perf_counter() - t0) / Ke * 1e3
     checksum = float(yp.numpy()[:nloc].sum())
+    # what the host link of THIS box sustains for the same traffic (one pinned H2D and one D2H of the vector's size in
+    # flight at once, plain copies): the floor of any host-buffer matvec, so the e2e number can be read against it
+    link = None
+    if world == 1:
+        d_a = torch.empty(nloc + R, dtype=torch.float64, device=f"cuda:{local_rank}")
+        d_b = torch.empty(nloc + R, dtype=torch.float64, device=f"cuda:{local_rank}")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def both():
+            cur = torch.cuda.current_stream()
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                d_a.copy_(xp, non_blocking=True)
+            with torch.cuda.stream(s2):
+                yp.copy_(d_b, non_blocking=True)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+        for _ in range(3):
+            both()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            both()
+        torch.cuda.synchronize()
+        floor_ms = (time.perf_counter() - t0) / 10 * 1e3
+        link = {"both_directions_floor_ms": floor_ms, "gbs_per_direction": 8 * (nloc + R) / (floor_ms * 1e-3) / 1e9,
+                "e2e_frac_of_link_floor": floor_ms / ms_e2e,
+                "note": "plain pinned copies of the vector's size, H2D and D2H at once on two streams, this box"}
+        del d_a, d_b
 
     # ---- second half of the metric: full FSP solve wall time (fixed M-3D space, p0 = delta at the origin)
     solve_info = None
@@ -593,6 +623,8 @@ def main():
                          "note": "achieved = algorithmic bytes (SURVEY 8(d)) / CUDA-event time per launch, per GPU"}}
     if abs(per_gpu / peak) > 1.5:
         line["roofline"]["timing_suspect"] = True
+    if link:
+        line["e2e"]["link"] = link
     if solve_info:
         line["solve"] = solve_info
     tr = os.path.join(ROOT, "profiles", "traffic.json")
