@@ -1904,12 +1904,18 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
     NCME_CUDA(cudaEventRecord(ctx->ev_start, st));                       // order after earlier work on the context
     NCME_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_start, 0));
     NCME_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_start, 0));
-    for (int c = 0; c < nc; ++c) {
-        const int64_t r0 = A->pipe_row[c];
-        const int64_t r1 = (c == nc - 1) ? A->N : A->pipe_row[c + 1];  // the last chunk carries the sink entries
-        NCME_CUDA(cudaMemcpyAsync(xd + r0, x_host + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
-        NCME_CUDA(cudaEventRecord(ctx->ev_h2d[c], ctx->h2d_stream));
-    }
+    // Uploads are ISSUED in dependency order, interleaved with the kernels and downloads below (issuing all 16 uploads
+    // first kept the host busy for ~130 us before the first kernel / download could even be queued).
+    int issued = 0;
+    auto issue_uploads = [&](int upto) -> int {   // chunks [issued, upto]
+        for (; issued <= upto && issued < nc; ++issued) {
+            const int64_t r0 = A->pipe_row[issued];
+            const int64_t r1 = (issued == nc - 1) ? A->N : A->pipe_row[issued + 1];  // the last chunk carries the sink entries
+            NCME_CUDA(cudaMemcpyAsync(xd + r0, x_host + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            NCME_CUDA(cudaEventRecord(ctx->ev_h2d[issued], ctx->h2d_stream));
+        }
+        return NCME_OK;
+    };
     MatvecArgs a;
     matvec_fill_args(A, coef, &a);
     a.xd = xd;
@@ -1919,6 +1925,7 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
     for (int c = 0; c < nc; ++c) {
         int need = c;
         while (need < nc - 1 && A->pipe_row[need + 1] < A->pipe_need_hi[c]) ++need;
+        NCME_TRY(issue_uploads(std::min(nc - 1, need + 2)));             // keep the upload queue two chunks ahead
         NCME_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[need], 0));
         MatvecArgs ac = a;
         ac.row_begin = A->pipe_row[c];

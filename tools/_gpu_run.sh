@@ -1,11 +1,9 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest tests -m gpu -q --durations=6 ) > gpurun_out/r2g_pytest_gpu.log 2>&1
-tail -14 gpurun_out/r2g_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-( time timeout 420 python bench.py --steps 20 --warmup 5 ) > gpurun_out/r2g_bench_n1.json 2> gpurun_out/r2g_bench_n1.err
-tail -3 gpurun_out/r2g_bench_n1.err
+( time timeout 300 python -m pytest tests/test_gpu_headline.py tests/test_gpu_matvec.py -m gpu -q -x ) > gpurun_out/r2h_pytest.log 2>&1
+tail -4 gpurun_out/r2h_pytest.log
+for rep in 1 2; do
+timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu --no-solve > gpurun_out/r2h_e2e_$rep.json 2>gpurun_out/r2h_e2e_$rep.err
 python -c "
-import json; d=json.loads(open('gpurun_out/r2g_bench_n1.json').read().strip().splitlines()[-1]); s=d['solve']; print('matvec', d['ms_per_step'], d['value'], d['roofline']['frac'], 'e2e', d['e2e']['ms_per_step'], d['e2e']['value'], d['e2e'].get('link'), 'bdf', s['wall_s'], 'dp5', s['all_methods']['dp5']['wall_s'], 'api', s['solve_api_wall_s'], s['solve_api']['breakdown_s'], 'cpu', d['cpu_baseline']['value'], 'tele', d['parity_configs']['telegraph_adaptive_solve_ms']['best'])"
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_bdf|k_gm|k_matrix_diag' -c 2600 --csv --log-file gpurun_out/r2g_launches_bdf.csv python bench.py --steps 3 --warmup 3 --no-cpu --solve-method bdf > gpurun_out/r2g_ncu_bench.log 2>&1
-python tools/summarize_launches.py gpurun_out/r2g_launches_bdf.csv | head -24
+import json; d=json.loads(open('gpurun_out/r2h_e2e_$rep.json').read().strip().splitlines()[-1]); print('rep $rep e2e ms', d['e2e']['ms_per_step'], 'GB/s', d['e2e']['value'], d['e2e']['link']['both_directions_floor_ms'], d['e2e']['link']['e2e_frac_of_link_floor'], 'checksum', d['e2e'].get('checksum_sum_y_states'))"
+done
