@@ -1871,16 +1871,23 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
         NCME_CUDA(cudaStreamSynchronize(st));
         return NCME_OK;
     }
+    // NCME_HOST_PIPE_TRACE=1 (diagnostics): events carry timestamps and the 5th call prints, per chunk, when its upload,
+    // kernel and download finished relative to the start of the call
+    static const bool pipe_trace = getenv("NCME_HOST_PIPE_TRACE") != nullptr;
+    static cudaEvent_t trace_d2h[16];
+    static int trace_calls = 0;
     // ---- pipelined: H2D of x (chunk c+1), rows of chunk c, D2H of y (chunk c-1) overlap on three streams.
     // Chunk c may start once x is on the device up to the furthest entry its gathers reach (pipe_need_hi).
     if (!ctx->h2d_stream) {
         NCME_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
         NCME_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        const unsigned evflags = pipe_trace ? cudaEventDefault : cudaEventDisableTiming;
         for (int k = 0; k < 16; ++k) {
-            NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
-            NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+            NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[k], evflags));
+            NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[k], evflags));
+            if (pipe_trace) NCME_CUDA(cudaEventCreate(&trace_d2h[k]));
         }
-        NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+        NCME_CUDA(cudaEventCreateWithFlags(&ctx->ev_start, evflags));
     }
     const int nc = A->pipe_chunks;
     double* xd = ctx->stage_dev_x;
@@ -1931,16 +1938,29 @@ int ncme_matvec_host(ncme_matrix* A, const double* coef, const double* x_host, d
         ac.row_begin = A->pipe_row[c];
         ac.row_end = A->pipe_row[c + 1];
         ac.do_sinks = (c == nc - 1) ? 1 : 0;                             // sink rows read x everywhere: last
-        NCME_TRY(matvec_launch(A, ac));
+        static const bool trace_nokernel = getenv("NCME_HOST_PIPE_NOKERNEL") != nullptr;   // diagnostics: copies only
+        if (!(pipe_trace && trace_nokernel)) NCME_TRY(matvec_launch(A, ac));
         if (y_map) continue;                                             // y already went to the host buffer
         NCME_CUDA(cudaEventRecord(ctx->ev_comp[c], st));
         NCME_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_comp[c], 0));
         const int64_t r0 = A->pipe_row[c];
         const int64_t r1 = (c == nc - 1) ? A->N : A->pipe_row[c + 1];
         NCME_CUDA(cudaMemcpyAsync(y_host + r0, yd + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (pipe_trace) NCME_CUDA(cudaEventRecord(trace_d2h[c], ctx->d2h_stream));
     }
     NCME_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
     NCME_CUDA(cudaStreamSynchronize(st));
+    if (pipe_trace && !y_map && ++trace_calls == 5) {
+        fprintf(stderr, "[ncme host pipe] chunk rows MB | upload done | kernel done | download done (ms after the call's start)\n");
+        for (int c = 0; c < nc; ++c) {
+            float a_ms = 0, b_ms = 0, c_ms = 0;
+            cudaEventElapsedTime(&a_ms, ctx->ev_start, ctx->ev_h2d[c]);
+            cudaEventElapsedTime(&b_ms, ctx->ev_start, ctx->ev_comp[c]);
+            cudaEventElapsedTime(&c_ms, ctx->ev_start, trace_d2h[c]);
+            const int64_t rows = A->pipe_row[c + 1] - A->pipe_row[c];
+            fprintf(stderr, "[ncme host pipe] %2d %9lld %6.2f | %7.3f | %7.3f | %7.3f\n", c, (long long)rows, rows * 8e-6, a_ms, b_ms, c_ms);
+        }
+    }
     return NCME_OK;
 }
 
