@@ -288,18 +288,36 @@ __global__ void __launch_bounds__(BT) k_gm_apply_dots(const __grid_constant__ Ap
     block_reduce_allreduce<RED_SLOTS>(full, a.partials, a.counter, a.result, a.ar);
 }
 
+// One wave: the grid-stride kernel is launched with at most as many CTAs as are resident at once (SMs x occupancy of the
+// instantiation).  With the former fixed 1 184 CTAs the instantiations that fit 3-5 CTAs per SM (48-128 registers) ran
+// 1.6-2.7 waves, i.e. a last wave that left 30-40 % of the SMs idle while it drained.
+template <int KB>
+static unsigned apply_dots_wave(ncme_ctx* ctx) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gm_apply_dots<KB>, BT, 0) != cudaSuccess || nb < 1) {
+            cudaGetLastError();
+            nb = 1;
+        }
+        per_sm = nb;
+    }
+    return (unsigned)(ctx->sm_count * per_sm);
+}
 static int launch_apply_dots(ncme_ctx* ctx, const ApplyArgs& aa, unsigned grid) {
     cudaStream_t s = ctx->stream;
     const int kb = aa.k < 0 ? 0 : ((aa.k + 1 + 3) / 4) * 4;
+#define NCME_AD(KB) k_gm_apply_dots<KB><<<std::min(grid, apply_dots_wave<KB>(ctx)), BT, 0, s>>>(aa)
     switch (kb) {
-        case 0: k_gm_apply_dots<0><<<grid, BT, 0, s>>>(aa); break;
-        case 4: k_gm_apply_dots<4><<<grid, BT, 0, s>>>(aa); break;
-        case 8: k_gm_apply_dots<8><<<grid, BT, 0, s>>>(aa); break;
-        case 12: k_gm_apply_dots<12><<<grid, BT, 0, s>>>(aa); break;
-        case 16: k_gm_apply_dots<16><<<grid, BT, 0, s>>>(aa); break;
-        case 20: k_gm_apply_dots<20><<<grid, BT, 0, s>>>(aa); break;
-        default: k_gm_apply_dots<24><<<grid, BT, 0, s>>>(aa); break;
+        case 0: NCME_AD(0); break;
+        case 4: NCME_AD(4); break;
+        case 8: NCME_AD(8); break;
+        case 12: NCME_AD(12); break;
+        case 16: NCME_AD(16); break;
+        case 20: NCME_AD(20); break;
+        default: NCME_AD(24); break;
     }
+#undef NCME_AD
     ctx->launches++;
     NCME_CUDA(cudaGetLastError());
     return NCME_OK;

@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
-for q in 1 2; do
-NCME_HOST_PIPE_QUEUES=$q timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu --no-solve > gpurun_out/r2k_q$q.json 2>gpurun_out/r2k_q$q.err
+( time timeout 300 python -m pytest tests/test_gpu_solve.py -m gpu -q -x ) > gpurun_out/r2l_pytest.log 2>&1
+tail -4 gpurun_out/r2l_pytest.log
+for rep in 1 2; do
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu --solve-method bdf > gpurun_out/r2l_bench_bdf_$rep.json 2>gpurun_out/r2l_bench_bdf_$rep.err
 python -c "
-import json; d=json.loads(open('gpurun_out/r2k_q$q.json').read().strip().splitlines()[-1]); print('queues $q e2e ms', d['e2e']['ms_per_step'], d['e2e']['value'], 'floor', d['e2e']['link']['both_directions_floor_ms'], 'checksum', d['e2e']['checksum_sum_y_states'])"
+import json; d=json.loads(open('gpurun_out/r2l_bench_bdf_$rep.json').read().strip().splitlines()[-1]); s=d['solve']; print('bdf wall', s['wall_s'], s['steps'], s['rhs_evals'], s['launches'], 'api integrate', s['solve_api']['breakdown_s']['integrate'], s['mean_x'])"
 done
-NCME_HOST_PIPE_QUEUES=2 NCME_HOST_PIPE_TRACE=1 timeout 200 python bench.py --steps 10 --warmup 5 --no-cpu --no-solve 2>&1 >/dev/null | grep "host pipe"
