@@ -537,14 +537,20 @@ def main():
             seg = _Segment(A, 1e-4, 1e-8, code)
             # untimed warm-up segment (workspace allocation, lazy kernel loading), like the matvec's warm-up steps
             seg.run(d.u.v, 0.0, min(0.02, args.solve_t), saveat=[min(0.02, args.solve_t)])
-            d.load(pfull, np.zeros(R))
-            barrier()
-            tw = time.perf_counter()
-            sstats = seg.run(d.u.v, 0.0, args.solve_t, saveat=[args.solve_t])
-            barrier()
-            wall = time.perf_counter() - tw
+            # two full solves from p0, the faster one is reported (the first may still grow the Krylov workspace: the short
+            # warm-up segment needs fewer basis vectors than the late steps of the full horizon); both are listed
+            walls = []
+            for _rep in range(2):
+                d.load(pfull, np.zeros(R))
+                seg.saved_u = []
+                barrier()
+                tw = time.perf_counter()
+                sstats = seg.run(d.u.v, 0.0, args.solve_t, saveat=[args.solve_t])
+                barrier()
+                walls.append(time.perf_counter() - tw)
+            wall = min(walls)
             uu = seg.saved_u[-1]
-            runs[name] = {"wall_s": wall, "steps": int(sstats.steps), "rejected": int(sstats.rejected),
+            runs[name] = {"wall_s": wall, "wall_s_runs": walls, "steps": int(sstats.steps), "rejected": int(sstats.rejected),
                           "rhs_evals": int(sstats.rhs_evals), "launches": int(sstats.launches),
                           "mass": float(uu.sum()), "sinks": float(uu[n:].sum()),
                           "mean_x": [float((uu[:n] * space.get_states()[:, k]).sum()) for k in range(3)] if rank == 0 else None}
@@ -552,7 +558,7 @@ def main():
         best = min(runs, key=lambda k: runs[k]["wall_s"])
         solve_info = dict(runs[best])
         solve_info.update({"tspan": [0.0, args.solve_t], "odertol": 1e-4, "odeatol": 1e-8,
-                           "warmup": "one untimed segment of horizon 0.02 per method",
+                           "warmup": "one untimed segment of horizon 0.02 per method, then two full solves from p0: the faster is wall_s, both in wall_s_runs",
                            "method": {"dp5": "native Dormand-Prince 5(4)", "bdf": "native BDF/NDF + Jacobi-GMRES"}[best] +
                                      ", device-resident", "all_methods": runs})
 
