@@ -1,3 +1,8 @@
-SAN_SEL="test_bdf_fixed_space or test_sens_incremental_rebuild_after_adapt" SAN_TOOLS=racecheck SAN_TIMEOUT=95 tools/sanitize.sh gpurun_out
-head -12 gpurun_out/sanitizer_racecheck.log
-tail -3 gpurun_out/sanitizer_racecheck.pytest.log
+# the command of the last `gpurun` call: full validation on one GPU
+set -x
+mkdir -p gpurun_out
+( time timeout 600 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+( time timeout 420 python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+tail -c 600 gpurun_out/bench_n1.json
